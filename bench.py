@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""Benchmark of the joint-step hot path (fused front-end x3 + CTC + 41-step AttLoc loop, fwd + bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[2]/[3] per-GPU shape -- B=32 utterances, T=800 STFT
+frames x 257 bins -> 40 mel, encoder length Th=200, U=40 labels (41 decoder steps), vocab 4233,
+D=A=320, Z=300, C=10, K=201, mtlalpha=0.5; synthetic seeded tensors (robust_e2e_gan_b200/synth.py).
+Metric: utterances/sec = (N * 32) / step time.  One process per GPU (torchrun for N > 1): every rank
+runs its own 32 utterances and the hot-path parameter gradients are all-reduced (NCCL) -> weak scaling.
+
+JSON keys beyond the base contract: ``roofline`` (dominant kernel, CUDA-event timed), ``kernels``
+(every kernel of ours with achieved GB/s), ``cpu_baseline`` (the oracle port timed on the host cores),
+``e2e`` (public nn.Module API, pinned host inputs copied in and the loss read back every step),
+``gpu_launches``, ``clocks``.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "utterances/sec (joint step fwd/bwd)"
+UNIT = "utt/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index=0, period=0.02):
+        super().__init__(daemon=True)
+        self.period, self.index = period, index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_step_time(cfg, batch, sd, reps, warm):
+    """Oracle (port of the reference's CPU path) fwd+bwd on the host cores."""
+    from oracle.hotpath_oracle import oracle_step
+    for _ in range(warm):
+        oracle_step(cfg, batch, sd)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle_step(cfg, batch, sd)
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def sub_batch(batch, cfg, nb):
+    """First nb utterances of a host batch (bounded CPU sample of the same workload)."""
+    from robust_e2e_gan_b200.hotpath import Batch
+    d = {}
+    for k in Batch.FIELDS:
+        v = getattr(batch, k)
+        if k in ("dec_z", "g_c"):
+            d[k] = v[:, :nb].contiguous()
+        elif k == "cmvn":
+            d[k] = v
+        else:
+            d[k] = v[:nb].contiguous()
+    c2 = dict(cfg)
+    c2["B"] = nb
+    return Batch(ys=batch.ys[:nb], hlens_list=batch.hlens_list[:nb], targets=None, **d), c2
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is
+    Python/PyTorch and cannot travel), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from robust_e2e_gan_b200.hotpath import DEFAULT_CFG, HotPath, make_batch
+    cfg = dict(DEFAULT_CFG)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = make_batch(cfg, seed=4000)
+    sd = HotPath(cfg, seed=4000).state_dict_cpu()
+    nb = 8
+    sb, scfg = sub_batch(batch, cfg, nb)
+    from oracle.hotpath_oracle import oracle_step
+    for _ in range(args.warmup):
+        oracle_step(scfg, sb, sd)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_step(scfg, sb, sd)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = nb / dt
+    sample = "%d of %d utterances of the step's batch, all %d decoder steps, per step" % (nb, cfg["B"], cfg["steps"])
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": workload_config(cfg, world),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, world):
+    return {"workload": "joint hot path, BASELINE configs[2]/[3] per-GPU shape: B=%d/GPU T=%d F=%d M=%d Th=%d U=%d "
+                        "(%d AttLoc steps) V=%d D=A=%d Z=%d" % (cfg["B"], cfg["T"], cfg["F"], cfg["M"], cfg["Th"],
+                                                                  cfg["U"], cfg["steps"], cfg["V"], cfg["D"], cfg["Z"]),
+            "global_batch": cfg["B"] * world, "parallelism": "dp%d (utterance-sharded, grad all-reduce)" % world,
+            "l2": "256 MiB scratch write between timed steps (excluded from step time)"}
+
+
+def kernel_rooflines(hp, db, cfg, peak, dev):
+    """Per-kernel CUDA-event timings of OUR kernels on the bench tensors: each kernel (through the same
+    C-ABI call the step makes) is captured R times into a CUDA graph and replayed, so the events see
+    back-to-back launches without Python gaps.  achieved = algorithmic bytes / average launch time."""
+    from robust_e2e_gan_b200 import _lib
+    L = _lib.lib()
+    B, T, F, M, Th, D, A, Z, C, V, U = (cfg[k] for k in ("B", "T", "F", "M", "Th", "D", "A", "Z", "C", "V", "U"))
+    K = 2 * cfg["filts"] + 1
+    N = B * T
+    sp = _lib.stream_ptr
+    P = _lib.ptr
+    res = {}
+    f32 = dict(device=dev, dtype=torch.float32)
+    fc = hp.feat.fc.detach()
+    Y, G, dY, din = (torch.empty(B, T, M, **f32), torch.empty(B, T, M, **f32), torch.randn(B, T, M, **f32),
+                     torch.empty(B, T, F, **f32))
+    lens = db.lens.to(torch.int32)
+    att = hp.att
+    W_dec, W_att = att.mlp_dec.weight.detach().contiguous(), att.mlp_att.weight.detach().contiguous()
+    W_conv = att.loc_conv.weight.detach().view(C, K).contiguous()
+    gv, gb = att.gvec.weight.detach().view(A).contiguous(), att.gvec.bias.detach().contiguous()
+    enc = db.hpad.contiguous()
+    pre = torch.addmm(att.mlp_enc.bias.detach(), enc.view(B * Th, D), att.mlp_enc.weight.detach().t()).view(B, Th, A)
+    ap = torch.softmax(torch.randn(B, Th, **f32), 1)
+    c, w, dproj, conv = torch.empty(B, D, **f32), torch.empty(B, Th, **f32), torch.empty(B, A, **f32), torch.empty(B, Th, C, **f32)
+    dz = db.dec_z[0].contiguous()
+    dc, dw = torch.randn(B, D, **f32), torch.randn(B, Th, **f32)
+    d_pre, ddp, dprev = torch.zeros(B, Th, A, **f32), torch.empty(B, A, **f32), torch.empty(B, Th, **f32)
+    acc = [torch.zeros(A * C, **f32), torch.zeros(C * K, **f32), torch.zeros(A, **f32), torch.zeros(1, **f32)]
+    logits = torch.randn(B, Th, V, **f32)
+    grad = torch.empty_like(logits)
+    tg = db.targets
+    hl = db.hlens.to(torch.int32)
+    nb = int(L.re2e_ctc_ws_bytes(B, Th, V, tg.umax))
+    ws = torch.empty(nb, device=dev, dtype=torch.uint8)
+    nll, loss = torch.empty(B, **f32), torch.empty(1, **f32)
+    valid_frames = int(hl.sum())
+
+    def k_fb_fwd():
+        _lib.check(L.re2e_fbank_fwd(P(db.mask_logits), 1, P(db.mix), P(fc), P(db.cmvn), P(lens), P(Y), P(G), None,
+                                    B, T, F, M, sp()))
+
+    def k_fb_fwd_plain():
+        _lib.check(L.re2e_fbank_fwd(None, 0, P(db.clean), P(fc), P(db.cmvn), None, P(Y), None, None, B, T, F, M, sp()))
+
+    def k_fb_bwd():
+        _lib.check(L.re2e_fbank_bwd(P(dY), P(G), P(db.mask_logits), 1, P(db.mix), P(fc), P(lens), P(din), None,
+                                    B, T, F, M, sp()))
+
+    def k_att_fwd():
+        _lib.check(L.re2e_attloc_step_fwd(P(pre), P(enc), P(dz), P(ap), P(W_dec), P(W_att), P(W_conv), P(gv), P(gb),
+                                          2.0, P(c), P(w), P(dproj), P(conv), B, Th, D, A, Z, C, K, sp()))
+
+    def k_att_bwd():
+        _lib.check(L.re2e_attloc_step_bwd(P(dc), P(dw), P(pre), P(enc), P(ap), P(w), P(dproj), P(conv), P(W_att),
+                                          P(W_conv), P(gv), 2.0, P(d_pre), 1, P(ddp), P(dprev), P(acc[0]), P(acc[1]),
+                                          P(acc[2]), P(acc[3]), B, Th, D, A, C, K, sp()))
+
+    def k_ctc_fwd():
+        _lib.check(L.re2e_ctc_loss_fwd(P(logits), Th * V, V, P(tg.labels), P(tg.offs), P(tg.lens), P(hl), 0, P(nll),
+                                       P(loss), P(ws), nb, B, Th, V, tg.umax, sp()))
+
+    def k_ctc_bwd():
+        _lib.check(L.re2e_ctc_loss_bwd(P(logits), Th * V, V, P(tg.labels), P(tg.offs), P(tg.lens), P(hl), 0, P(nll),
+                                       None, P(ws), nb, P(grad), B, Th, V, tg.umax, sp()))
+
+    S = 2 * tg.umax + 1
+    specs = [
+        ("fbank_fwd(mask,mag->Y,G)", k_fb_fwd, 4.0 * N * (2 * F + 2 * M), 4),
+        ("fbank_fwd(mag->Y)", k_fb_fwd_plain, 4.0 * N * (F + M), 4),
+        ("fbank_bwd(->d mask)", k_fb_bwd, 4.0 * N * (2 * M + 3 * F), 4),
+        ("attloc_step_fwd", k_att_fwd, 4.0 * B * Th * (A + D) + 4.0 * B * (Z + Th * (2 + C) + D + A), 20),
+        ("attloc_step_bwd", k_att_bwd, 4.0 * B * Th * (A + D) + 4.0 * B * Th * A + 4.0 * B * Th * (4 + C), 20),
+        ("ctc_fwd(lse+alpha/beta)", k_ctc_fwd, 4.0 * valid_frames * V + 4.0 * 3 * valid_frames * S, 4),
+        ("ctc_bwd(grad)", k_ctc_bwd, 4.0 * valid_frames * V + 4.0 * B * Th * V, 4),
+    ]
+    flush = torch.empty(64 * 1024 * 1024, **f32)
+    for name, fn, nbytes, reps in specs:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        ts = []
+        for _ in range(5):
+            if not name.startswith("attloc"):      # AttLoc's working set is L2-resident in the real loop too
+                flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3 / reps)
+        ts.sort()
+        us = ts[len(ts) // 2]
+        ach = nbytes / (us * 1e-6) / 1e9
+        res[name] = {"us_per_launch": round(us, 2), "algorithmic_MB": round(nbytes / 1e6, 2),
+                     "achieved_GBps": round(ach, 1), "frac_of_hbm_peak": round(ach / peak, 3)}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernels", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    from robust_e2e_gan_b200.parallel import GradBuckets, init_distributed
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, int(os.environ.get("RANK", "0")), world_env)
+        return
+
+    import torch.distributed as dist
+    rank, world = init_distributed()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    from robust_e2e_gan_b200 import _lib
+    from robust_e2e_gan_b200.hotpath import DEFAULT_CFG, HotPath, make_batch
+    cfg = dict(DEFAULT_CFG)
+    peak, peak_src = load_peaks()
+
+    hp = HotPath(cfg, seed=4000).to(dev)                 # identical init on every rank
+    hb = make_batch(cfg, seed=4000 + rank).pin()         # distinct utterances per rank
+    db = hb.to(dev)
+    torch.cuda.synchronize()
+    buckets = GradBuckets(hp.trainable(), bucket_mb=25.0) if world > 1 else None
+    flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)   # 256 MiB > 126 MB L2
+
+    def eager_step(batch):
+        if buckets is not None:
+            buckets.zero()
+        else:
+            for p in hp.parameters():
+                p.grad = None
+        out = hp.step(batch, hlens_for_att=batch.hlens)
+        if buckets is not None:
+            buckets.finish()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (eager), launch count of one step
+    n0 = _lib.launch_count()
+    eager_step(db)
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - n0
+    for _ in range(max(0, args.warmup - 1)):
+        eager_step(db)
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing: CUDA-graph replay of the whole step when capture works
+    mode = "eager"
+    graph = None
+    if not args.no_graph:
+        try:
+            for p in hp.parameters():
+                p.grad = None
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                hp.step(db, hlens_for_att=db.hlens)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            for p in hp.parameters():
+                p.grad = None
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                hp.step(db, hlens_for_att=db.hlens)
+            graph.replay()
+            torch.cuda.synchronize()
+            mode = "cuda_graph"
+        except Exception as e:  # capture not possible: keep the eager path, say so
+            graph = None
+            mode = "eager (graph capture failed: %s)" % (str(e).splitlines()[0][:120])
+            torch.cuda.synchronize()
+
+    def timed_step():
+        if graph is not None:
+            graph.replay()
+            if world > 1:
+                grads = [p.grad for p in hp.trainable() if p.grad is not None]
+                flat = torch.cat([g.reshape(-1) for g in grads])
+                dist.all_reduce(flat)
+                flat.div_(world)
+        else:
+            eager_step(db)
+
+    for _ in range(3):
+        timed_step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(0.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        timed_step()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop()
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = cfg["B"] * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public nn.Module API: pinned host inputs in, loss out, every step
+    for _ in range(2):
+        eager_step(hb.to(dev))
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        out = eager_step(hb.to(dev))
+        lv = out["loss_ctc"].cpu()          # D2H read of the step's result (synchronises)
+        d2h = lv.numel() * 4
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e = {"value": cfg["B"] * world / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": hb.h2d_bytes(),
+           "d2h_bytes_per_step": d2h, "ms_per_step": float(e2e_s.item()) * 1e3}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": workload_config(cfg, world),
+            "mode": mode, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks}
+
+    if rank == 0:
+        if not args.no_kernels:
+            ks = kernel_rooflines(hp, db, cfg, peak, dev)
+            line["kernels"] = ks
+            per_step = {"attloc_step_fwd": cfg["steps"], "attloc_step_bwd": cfg["steps"], "fbank_fwd(mag->Y)": 2}
+            dom = max(ks, key=lambda k: ks[k]["us_per_launch"] * per_step.get(k, 1))
+            line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ks[dom]["achieved_GBps"], "peak": peak,
+                                "unit": "GB/s", "frac": ks[dom]["frac_of_hbm_peak"], "peak_source": peak_src,
+                                "launches_per_step": per_step.get(dom, 1), "us_per_launch": ks[dom]["us_per_launch"],
+                                "traffic": None}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            nb = 8
+            sb, scfg = sub_batch(hb, cfg, nb)
+            dt = cpu_step_time(scfg, sb, hp.state_dict_cpu(), reps=3, warm=1)
+            line["cpu_baseline"] = {"value": nb / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d of %d utterances of the same batch, all %d decoder steps; "
+                                              "1 warm-up + median of 3" % (nb, cfg["B"], cfg["steps"]),
+                                    "ms_per_step": dt * 1e3}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

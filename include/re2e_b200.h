@@ -1,0 +1,164 @@
+/*
+ * re2e_b200.h -- C ABI of the B200-native hot path for Robust_e2e_gan.
+ *
+ * The reference (bliunlpr/Robust_e2e_gan) has no FFI of its own: its hot path
+ * is three Python nn.Modules that dispatch to ATen / cuDNN / warp-ctc.  This
+ * header is the boundary a maintainer binds instead (ctypes stub shown in
+ * INTEGRATION.md).  Each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - fp32, row-major, contiguous unless a stride argument says otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - no entry point allocates, frees or synchronises; scratch comes in as `ws`;
+ *   - return value: 0 = ok; < 0 = argument error (RE2E_E_*); > 0 = cudaError_t.
+ *   - NULL for an optional pointer disables that input / output.
+ */
+#ifndef RE2E_B200_H_
+#define RE2E_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RE2E_OK 0
+#define RE2E_E_ARG (-1)        /* bad size / null pointer / misaligned buffer */
+#define RE2E_E_UNSUPPORTED (-2) /* shape outside what the kernels were built for */
+#define RE2E_E_WORKSPACE (-3)   /* ws_bytes too small; call the *_ws_bytes query */
+
+/* ABI / build identification. */
+int re2e_abi_version(void);              /* bumps on any signature change */
+const char *re2e_build_info(void);       /* "sm_100a nvcc 12.9 ..." */
+const char *re2e_error_string(int code); /* static string for RE2E_E_* or cudaGetErrorString */
+/* Number of kernel launches this library has issued in this process (monotonic). */
+unsigned long long re2e_launch_count(void);
+
+/* --------------------------------------------------------------------------------------------
+ * Front-end.  Replaces model/enhance_model.py:157-164 (mask tail) fused with
+ * model/feat_model.py:118-135 (FbankModel.forward) and its autograd backward.
+ *
+ *   x[n,f]  = mask ? act(mask[n,f]) * [t < lens[b]] * mag[n,f] : mag[n,f]        n = b*T + t
+ *   P[n,m]  = sum_f x[n,f]^2 * fc[f,m]
+ *   Y[n,m]  = (log(max(P, 1e-7)) + cmvn[0,m]) * cmvn[1,m]            (cmvn optional)
+ *   G[n,m]  = P > 1e-7 ? cmvn[1,m] / P : 0          (dY/dP; saved for the backward, optional)
+ *
+ * mask_is_logit: 1 -> act = sigmoid (mask holds linear_out), 0 -> act = identity.
+ * enh_out (optional): receives x (the reference's `enhance_out`, (B,T,F)).
+ * ------------------------------------------------------------------------------------------ */
+int re2e_fbank_fwd(const float *mask, int mask_is_logit, const float *mag, const float *fc,
+                   const float *cmvn, const int32_t *lens, float *Y, float *G, float *enh_out,
+                   int B, int T, int F, int M, void *stream);
+
+/* dY (N,M) -> d_in (N,F): gradient w.r.t. `mask` when mask != NULL (through act and *mag),
+ * else w.r.t. `mag` (the single-input FbankModel form).  G is the tensor saved by fwd.
+ * dfc (optional, (F,M), ACCUMULATED into): gradient of a trainable filter bank
+ * (feat_model.py:105-109 `fbank_opti_type == 'train'`). */
+int re2e_fbank_bwd(const float *dY, const float *G, const float *mask, int mask_is_logit,
+                   const float *mag, const float *fc, const int32_t *lens, float *d_in, float *dfc,
+                   int B, int T, int F, int M, void *stream);
+
+/* Stand-alone mask tail (enhance_model.py:157-164) forward / backward, for callers that
+ * need `enhance_out` itself (e.g. the L1 mask loss at :166-172). */
+int re2e_mask_apply_fwd(const float *logits, const float *mag, const int32_t *lens, float *enh,
+                        int B, int T, int F, void *stream);
+int re2e_mask_apply_bwd(const float *d_enh, const float *logits, const float *mag,
+                        const int32_t *lens, float *d_logits, int B, int T, int F, void *stream);
+
+/* CMVN statistics (feat_model.py:62-90 compute_cmvn): per-mel sum and sum of squares over the
+ * valid frames t < lens[b] of Y (B,T,M); ACCUMULATES into sum[M], sumsq[M] (fp64 on device)
+ * and frames[1] (int64).  Next-row N3 of SURVEY.md section 8f. */
+int re2e_cmvn_stats(const float *Y, const int32_t *lens, double *sum, double *sumsq,
+                    long long *frames, int B, int T, int M, void *stream);
+
+/* --------------------------------------------------------------------------------------------
+ * AttLoc.  Replaces model/e2e_attention.py:236-299 (forward) and its autograd backward.
+ * Shapes: enc_h (B,Th,D)  pre (B,Th,A)  dec_z (B,Z)  att_prev,w (B,Th)  c (B,D)
+ *         W_enc (A,D) b_enc (A)  W_dec (A,Z)  W_att (A,C)  W_conv (C,K) K = 2*filts+1
+ *         gvec (A)  gvec_b (1)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Uniform initial alignment, zero padded (e2e_attention.py:264-268). hlens on device. */
+int re2e_attloc_init_att(const int32_t *hlens, float *att_prev, int B, int Th, void *stream);
+
+/* One attention step (e2e_attention.py:258-299).  dec_z == NULL means zeros (:258-259).
+ * Saved for backward: dec_proj (B,A) = dec_z @ W_dec^T, conv (B,Th,C) = loc_conv(att_prev). */
+int re2e_attloc_step_fwd(const float *pre, const float *enc_h, const float *dec_z,
+                         const float *att_prev, const float *W_dec, const float *W_att,
+                         const float *W_conv, const float *gvec, const float *gvec_b,
+                         float scaling, float *c, float *w, float *dec_proj, float *conv,
+                         int B, int Th, int D, int A, int Z, int C, int K, void *stream);
+
+/* Backward of one step.  Inputs dc (B,D) / dw (B,Th) may be NULL (= zero).
+ *   d_pre (B,Th,A)       (+)= dE/dpre   accumulate_pre != 0: TMA reduce-add into d_pre (accumulated
+ *                             across steps); == 0: plain store (first backward step, no zero-fill)
+ *   d_decproj (B,A)       = dE/d(dec_z @ W_dec^T)        (caller derives d_dec_z, dW_dec)
+ *   d_att_prev (B,Th)     = dE/d att_prev                (NULL to skip, e.g. first decoder step)
+ *   dW_att (A,C), dW_conv (C,K), dgvec (A), dgvec_b (1)  += (accumulated across steps)
+ * d enc_h is NOT produced here: sum_i w_i (x) dc_i is a rank-(#steps) update applied once by
+ * re2e_attloc_enc_grad after the loop (no per-step read-modify-write of (B,Th,D)). */
+int re2e_attloc_step_bwd(const float *dc, const float *dw, const float *pre, const float *enc_h,
+                         const float *att_prev, const float *w, const float *dec_proj,
+                         const float *conv, const float *W_att, const float *W_conv,
+                         const float *gvec, float scaling, float *d_pre, int accumulate_pre,
+                         float *d_decproj, float *d_att_prev, float *dW_att, float *dW_conv,
+                         float *dgvec, float *dgvec_b, int B, int Th, int D, int A, int C, int K,
+                         void *stream);
+
+/* d_enc_h[b,t,:] (+)= sum_i w_all[i,b,t] * dc_all[i,b,:]   (i < steps); accumulate != 0 adds. */
+int re2e_attloc_enc_grad(const float *w_all, const float *dc_all, float *d_enc_h, int steps,
+                         int B, int Th, int D, int accumulate, void *stream);
+
+/* Batch-sized ("skinny", M <= a few hundred rows) fp32 products on the per-step path:
+ *   out[M,N] (+)= X[M,K] @ W[N,K]^T   (re2e_skinny_nt)   dec_proj = dec_z @ W_dec^T  (mlp_dec, :278)
+ *   out[M,N] (+)= X[M,K] @ W[K,N]     (re2e_skinny_nn)   d_dec_z  = d_decproj @ W_dec */
+int re2e_skinny_nt(const float *X, const float *W, float *out, int M, int N, int K, int accumulate,
+                   void *stream);
+int re2e_skinny_nn(const float *X, const float *W, float *out, int M, int N, int K, int accumulate,
+                   void *stream);
+
+/* --------------------------------------------------------------------------------------------
+ * CTC.  Replaces the warp_ctc.CTCLoss call at model/e2e_ctc.py:30,63 (softmax + alpha/beta +
+ * gradient; arithmetic of the un-vendored warpctc_pytorch) and F.log_softmax at :75.
+ * logits: raw activations, element (b,t,v) at logits[b*stride_b + t*stride_t + v]
+ *         ((B,Th,V) contiguous: stride_b = Th*V, stride_t = V; warp-ctc's (Th,B,V): stride_b = V,
+ *         stride_t = B*V).  labels: flat int32, utterance b at labels[label_offs[b] ..+label_lens[b]).
+ * blank = 0 in the reference.  Smax = 2*max(label_lens)+1.
+ * ------------------------------------------------------------------------------------------ */
+size_t re2e_ctc_ws_bytes(int B, int Th, int V, int Umax);
+
+/* Forward: nll[b] = -log p(y_b | x_b[:input_lens[b]]), loss[0] = sum_b nll[b] / B  (size_average
+ * over the batch, e2e_ctc.py:30).  Fills ws with lse (B,Th), alpha/beta (B,Th,Smax) for bwd. */
+int re2e_ctc_loss_fwd(const float *logits, long long stride_b, long long stride_t,
+                      const int32_t *labels, const int32_t *label_offs, const int32_t *label_lens,
+                      const int32_t *input_lens, int blank, float *nll, float *loss, void *ws,
+                      size_t ws_bytes, int B, int Th, int V, int Umax, void *stream);
+
+/* Backward: grad[b,t,v] = gscale * (softmax(x)[v] - occupancy[b,t,v]) for t < input_lens[b], else 0,
+ * gscale = (grad_out ? grad_out[0] : 1) / B.   grad has the same strides as logits. */
+int re2e_ctc_loss_bwd(const float *logits, long long stride_b, long long stride_t,
+                      const int32_t *labels, const int32_t *label_offs, const int32_t *label_lens,
+                      const int32_t *input_lens, int blank, const float *nll, const float *grad_out,
+                      const void *ws, size_t ws_bytes, float *grad, int B, int Th, int V, int Umax,
+                      void *stream);
+
+/* out = log_softmax(logits, dim=-1) over rows of length V (e2e_ctc.py:68-75 after ctc_lo);
+ * best (optional, int32 per row) = argmax_v  ("CTC best-path alignment", lowest index on ties). */
+int re2e_log_softmax(const float *logits, float *out, int32_t *best, long long rows, int V,
+                     void *stream);
+
+/* Batched CTC prefix scoring (model/e2e_ctc.py:109-155, one call per live hypothesis there).
+ * lpz (T,V) log-probs of one utterance; H hypotheses x Ccand candidates each.
+ *   r_prev (H,T,2); cs (H,Ccand) int32 candidate ids; last (H) int32 = y[-1]; out_len (H) = len(y)-1
+ *   log_psi (H,Ccand); r_new (H,Ccand,T,2)  (rows < max(out_len,1)-1 are set to logzero). */
+int re2e_ctc_prefix_score(const float *lpz, const float *r_prev, const int32_t *cs,
+                          const int32_t *last, const int32_t *out_len, float *log_psi,
+                          float *r_new, int T, int V, int H, int Ccand, int blank, int eos,
+                          void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RE2E_B200_H_ */

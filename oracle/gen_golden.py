@@ -1,0 +1,201 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules (build container only).
+
+    python -m oracle.gen_golden
+
+Imports model/feat_model.py, model/e2e_attention.py and model/e2e_ctc.py from /root/reference through
+oracle/refshim.py (stubs listed there), feeds them small seeded inputs and stores inputs, outputs and
+autograd gradients.  The committed fixtures pin (a) the oracle restatement (tests/test_oracle.py, CPU)
+and (b) the CUDA path (tests/test_gpu_golden.py).  TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import refshim  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def gen_fbank(ns):
+    torch.manual_seed(11)
+    B, T, F = 2, 13, 257
+    model = ns.FbankModel(refshim.fbank_args(fbank_dim=80, fbank_opti_type='train'))
+    g = torch.Generator().manual_seed(12)
+    mag = (torch.randn(B, T, F, generator=g).abs() * torch.exp(1.5 * torch.randn(B, T, F, generator=g)) * 300).clamp(0, 3e5)
+    mag[0, 3] = 0.0                      # a silent frame: exercises the <= 1e-7 clamp (zero gradient)
+    mag[1, 10:] = 0.0                    # collate padding
+    logits = 2.0 * torch.randn(B, T, F, generator=g)
+    lens = torch.tensor([13, 10], dtype=torch.int32)
+    cmvn = torch.stack([-(5 + 10 * torch.rand(80, generator=g)), 0.3 + 0.7 * torch.rand(80, generator=g)])
+    dY = torch.randn(B, T, 80, generator=g)
+    out = {}
+    # (a) single-input form, with and without CMVN
+    x = mag.clone().requires_grad_(True)
+    y = model(x, cmvn)
+    y.backward(dY)
+    out.update(mag=npy(mag), cmvn=npy(cmvn), dY=npy(dY), fc=npy(model.fc), y_cmvn=npy(y), dmag=npy(x.grad),
+               dfc=npy(model.fc.grad))
+    out["y_plain"] = npy(model(mag))
+    # (b) mask tail of EnhanceModel.forward (enhance_model.py:157-164; torch.bool mask, see refshim notes)
+    lo = logits.clone().requires_grad_(True)
+    s = torch.sigmoid(lo)
+    pad = torch.zeros(B, T, 1, dtype=torch.bool)
+    for i, l in enumerate(lens):
+        pad[i, int(l):] = True
+    enh = s.masked_fill(pad, 0) * mag
+    model.fc.grad = None
+    y2 = model(enh, cmvn)
+    y2.backward(dY)
+    out.update(logits=npy(logits), lens=npy(lens), enh=npy(enh), y_masked=npy(y2), dlogits=npy(lo.grad))
+    # (c) compute_cmvn over two batches
+    m2 = ns.FbankModel(refshim.fbank_args(fbank_dim=80, train_dataset_len=2, num_utt_cmvn=2))
+    r1 = m2.compute_cmvn(mag, lens)
+    r2 = m2.compute_cmvn(mag, lens)
+    assert r1 is None
+    out["cmvn_est"] = np.asarray(r2).copy()
+    np.savez_compressed(os.path.join(OUT, "fbank.npz"), **out)
+
+
+ATT_PARAM_SHAPES = lambda e, d, a, c, f: [  # registration order of AttLoc.__init__ (e2e_attention.py:212-219)
+    ("mlp_enc.weight", (a, e)), ("mlp_enc.bias", (a,)), ("mlp_dec.weight", (a, d)), ("mlp_att.weight", (a, c)),
+    ("loc_conv.weight", (c, 1, 1, 2 * f + 1)), ("gvec.weight", (1, a)), ("gvec.bias", (1,))]
+
+
+def make_attloc_inputs(eprojs, dunits, att_dim, chans, filts, B, Th, steps, seed):
+    """Seeded parameters and inputs for an AttLoc case; shared by the generator and the tests."""
+    g = torch.Generator().manual_seed(seed + 1)
+    params = {}
+    for name, shape in ATT_PARAM_SHAPES(eprojs, dunits, att_dim, chans, filts):
+        fan = 1
+        for v in shape[1:]:
+            fan *= v
+        params[name] = torch.randn(shape, generator=g) * (1.5 / max(1, fan) ** 0.5)
+    enc = torch.tanh(torch.randn(B, Th, eprojs, generator=g))
+    hlens = sorted([int(v) for v in torch.randint(Th // 2, Th + 1, (B,), generator=g)], reverse=True)
+    hlens[0] = Th
+    for b in range(B):
+        enc[b, hlens[b]:] = 0
+    zs = [None] + [0.5 * torch.randn(B, dunits, generator=g) for _ in range(steps - 1)]
+    gc = [torch.randn(B, eprojs, generator=g) for _ in range(steps)]
+    gw = torch.randn(B, Th, generator=g)
+    return params, enc, hlens, zs, gc, gw
+
+
+def gen_attloc(ns, name, eprojs, dunits, att_dim, chans, filts, B, Th, steps, seed, full):
+    att = ns.AttLoc(eprojs, dunits, att_dim, chans, filts, 'softmax')
+    params, enc, hlens, zs, gc, gw = make_attloc_inputs(eprojs, dunits, att_dim, chans, filts, B, Th, steps, seed)
+    att.load_state_dict(params)
+    enc.requires_grad_(True)
+    zs = [None] + [z.requires_grad_(True) for z in zs[1:]]
+    att.reset()
+    a = None
+    cs, ws = [], []
+    for i in range(steps):
+        c, a = att(enc, hlens, zs[i], a)
+        cs.append(c)
+        ws.append(a)
+    loss = sum((c * gci).sum() for c, gci in zip(cs, gc)) + (ws[-1] * gw).sum()
+    loss.backward()
+    out = dict(hlens=np.array(hlens, dtype=np.int32), dims=np.array([eprojs, dunits, att_dim, chans, filts, B, Th, steps, seed]),
+               c=np.stack([npy(c) for c in cs]), w=np.stack([npy(w) for w in ws]))
+    small = {"d_" + k.replace('.', '_'): npy(p.grad) for k, p in att.named_parameters()
+             if full or p.numel() <= 4096}
+    out.update(small)
+    out["d_dec_z"] = np.stack([npy(z.grad) for z in zs[1:]])
+    if full:
+        out.update(enc=npy(enc), gc=np.stack([npy(t) for t in gc]), gw=npy(gw), d_enc=npy(enc.grad),
+                   dec_z=np.stack([npy(z) for z in zs[1:]]))
+        out.update({"p_" + k.replace('.', '_'): npy(p) for k, p in att.named_parameters()})
+    else:
+        # inputs are regenerated from the seed by the test; keep checksums + a slice of the big grads
+        out.update(enc_sum=np.float64(enc.double().sum().item()), d_enc_slice=npy(enc.grad[:, ::7, ::9]),
+                   d_mlp_enc_weight_slice=npy(att.mlp_enc.weight.grad[::11, ::13]),
+                   d_mlp_dec_weight_slice=npy(att.mlp_dec.weight.grad[::11, ::13]),
+                   d_mlp_att_weight=npy(att.mlp_att.weight.grad), d_loc_conv_weight=npy(att.loc_conv.weight.grad))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
+def gen_ctc(ns):
+    torch.manual_seed(21)
+    B, Th, D, V = 4, 17, 12, 13
+    ctc = ns.CTC(V, D, 0.0)
+    g = torch.Generator().manual_seed(22)
+    hs = torch.tanh(torch.randn(B, Th, D, generator=g)).requires_grad_(True)
+    hlens = [17, 15, 12, 9]
+    ys = [torch.tensor([3, 3, 5, 1]), torch.tensor([7, 2, 2, 2, 9, 4]), torch.tensor([11]), torch.tensor([6, 6, 1])]
+    ys_pad = torch.full((B, 6), -1, dtype=torch.long)
+    for i, y in enumerate(ys):
+        ys_pad[i, :len(y)] = y
+    loss = ctc(hs, hlens, ys_pad)
+    (0.5 * loss).sum().backward()          # mtlalpha-style scaling: checks grad_output is honoured
+    lsm = ctc.log_softmax(hs)
+    out = dict(hs=npy(hs), hlens=np.array(hlens, np.int32), ys_pad=npy(ys_pad), W=npy(ctc.ctc_lo.weight),
+               b=npy(ctc.ctc_lo.bias), loss=npy(loss), d_hs=npy(hs.grad), d_W=npy(ctc.ctc_lo.weight.grad),
+               d_b=npy(ctc.ctc_lo.bias.grad), log_softmax=npy(lsm), best=npy(lsm.argmax(2)).astype(np.int32))
+    # gradient w.r.t. the logits themselves (what the kernel emits)
+    logits = (torch.randn(B, Th, V, generator=g) * 2).requires_grad_(True)
+    l2 = ctc.loss_fn(logits.transpose(0, 1), torch.cat(ys).int(), torch.tensor(hlens, dtype=torch.int32),
+                     torch.tensor([len(y) for y in ys], dtype=torch.int32))
+    l2.sum().backward()
+    out.update(logits=npy(logits), loss_logits=npy(l2), d_logits=npy(logits.grad))
+    np.savez_compressed(os.path.join(OUT, "ctc.npz"), **out)
+
+
+def gen_prefix(ns):
+    g = torch.Generator().manual_seed(31)
+    T, V = 14, 9
+    lpz = torch.log_softmax(torch.randn(T, V, generator=g) * 2, dim=1).numpy()
+    eos = V - 1
+    sc = ns.CTCPrefixScore(lpz, 0, eos, np)
+    r0 = sc.initial_state()
+    out = dict(lpz=lpz, r0=r0)
+    y = [eos]
+    r = r0
+    # walk a hypothesis 4 labels deep, scoring candidate sets that include y[-1] and eos
+    for step, (cs, pick) in enumerate([([1, 2, 3, eos], 1), ([2, 5, 1, 0 + 4], 2), ([1, eos, 6, 7], 0),
+                                       ([1, 3, eos], 0)]):
+        cs = np.array(cs)
+        psi, rs = sc(y, torch.from_numpy(cs), r)
+        start = max(len(y) - 1, 1)
+        out["y_%d" % step] = np.array(y)
+        out["cs_%d" % step] = cs
+        out["rprev_%d" % step] = r.copy()
+        out["psi_%d" % step] = psi.copy()
+        out["r_%d" % step] = rs[:, start - 1:].copy()      # rows below start-1 are uninitialised in the reference
+        out["start_%d" % step] = np.int64(start)
+        y = y + [int(cs[pick])]
+        r = rs[pick]
+        if start - 1 > 0:
+            r = r.copy()
+            r[:start - 1] = sc.logzero
+    np.savez_compressed(os.path.join(OUT, "prefix.npz"), **out)
+
+
+def main():
+    if not refshim.available():
+        raise SystemExit("reference tree not available; fixtures can only be generated in the build container")
+    os.makedirs(OUT, exist_ok=True)
+    ns = refshim.load()
+    gen_fbank(ns)
+    gen_attloc(ns, "attloc_small", eprojs=32, dunits=24, att_dim=64, chans=10, filts=5, B=3, Th=21, steps=4,
+               seed=41, full=True)
+    gen_attloc(ns, "attloc_default", eprojs=320, dunits=300, att_dim=320, chans=10, filts=100, B=2, Th=45,
+               steps=3, seed=43, full=False)
+    gen_ctc(ns)
+    gen_prefix(ns)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,128 @@
+"""Utterance-sharded data parallelism for the hot path.
+
+The reference is single-process / single-GPU (only ``gpu_ids[0]`` is used, joint_train.py:55).
+Every op on the hot path is independent across utterances, so the step shards by utterance with
+ONE exchange: the parameter gradients.  One process per GPU; gradients live as views into a few
+flat buckets and each bucket is all-reduced (NCCL over NVLink 5 / NVSwitch; gloo in the CPU tests)
+as soon as its last gradient has been accumulated, overlapping the rest of the backward.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend=None):
+    """Join the torchrun rendezvous (RANK / WORLD_SIZE / MASTER_* from the env). Returns (rank, world)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous shard [lo, hi) of ``n_items`` utterances for ``rank`` (remainder to the low ranks)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GradBuckets(object):
+    """Flat gradient buckets with asynchronous all-reduce overlapped with the backward pass.
+
+    ``params`` keep being ordinary nn.Parameters (the reference's optimisers and
+    ``clip_grad_norm_`` see them unchanged, joint_train.py:127-140,188); their ``.grad`` tensors are
+    views into the buckets.  Usage per step::
+
+        buckets.zero()            # instead of optimizer.zero_grad()
+        loss.backward()           # hooks launch all-reduces bucket by bucket
+        buckets.finish()          # wait + average; .grad now holds the mean over ranks
+    """
+
+    def __init__(self, params, bucket_mb=25.0, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        cap = int(bucket_mb * 1024 * 1024)
+        # reverse order: gradients become ready roughly last-parameter-first
+        order = list(reversed(self.params))
+        self.buckets = []
+        cur, cur_bytes = [], 0
+        for p in order:
+            nbytes = p.numel() * p.element_size()
+            if cur and (cur_bytes + nbytes > cap or p.dtype != cur[0].dtype or p.device != cur[0].device):
+                self.buckets.append(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nbytes
+        if cur:
+            self.buckets.append(cur)
+        self.flat, self._bucket_of, self._pending, self._handles = [], {}, [], []
+        self._hooks = []
+        for bi, bucket in enumerate(self.buckets):
+            total = sum(p.numel() for p in bucket)
+            flat = torch.zeros(total, dtype=bucket[0].dtype, device=bucket[0].device)
+            o = 0
+            for p in bucket:
+                p.grad = flat[o:o + p.numel()].view_as(p)
+                o += p.numel()
+                self._bucket_of[p] = bi
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(p)))
+            self.flat.append(flat)
+            self._pending.append(len(bucket))
+        self._launched = [False] * len(self.buckets)
+
+    def _make_hook(self, p):
+        def hook(param):
+            bi = self._bucket_of[p]
+            self._pending[bi] -= 1
+            if self._pending[bi] == 0:
+                self._launch(bi)
+        return hook
+
+    def _launch(self, bi):
+        if self.world > 1:
+            self._handles.append(dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group,
+                                                 async_op=True))
+        self._launched[bi] = True
+
+    def zero(self):
+        for bi, flat in enumerate(self.flat):
+            flat.zero_()
+            self._pending[bi] = len(self.buckets[bi])
+        self._launched = [False] * len(self.buckets)
+        self._handles = []
+        # re-attach views (an optimizer.zero_grad(set_to_none=True) would have dropped them)
+        for bi, bucket in enumerate(self.buckets):
+            o = 0
+            for p in bucket:
+                if p.grad is None or p.grad.data_ptr() != self.flat[bi][o:o + 1].data_ptr():
+                    p.grad = self.flat[bi][o:o + p.numel()].view_as(p)
+                o += p.numel()
+
+    def finish(self):
+        """Reduce any bucket whose hooks did not all fire (unused parameters), wait, average."""
+        for bi in range(len(self.buckets)):
+            if not self._launched[bi]:
+                self._launch(bi)
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+        if self.world > 1:
+            for flat in self.flat:
+                flat.div_(self.world)
+
+    def nbytes(self):
+        return sum(f.numel() * f.element_size() for f in self.flat)
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

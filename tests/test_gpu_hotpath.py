@@ -1,0 +1,33 @@
+"""GPU: the composed hot-path step (what bench.py times and smoke() runs) against the oracle."""
+import pytest
+import torch
+
+from helpers import assert_close
+from oracle.hotpath_oracle import oracle_step
+from robust_e2e_gan_b200 import _lib
+from robust_e2e_gan_b200.hotpath import HotPath, make_batch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_smoke_entry():
+    import __graft_entry__
+    __graft_entry__.smoke()
+
+
+def test_config1_step_matches_oracle():
+    """BASELINE config 1: B=8, T=400, 257 bins, 40 mel, vocab 4233, Th=100."""
+    cfg = dict(B=8, T=400, F=257, M=40, Th=100, D=320, A=320, Z=300, C=10, filts=100, V=4233, U=16, steps=9)
+    batch = make_batch(cfg, seed=1234)
+    hp = HotPath(cfg, seed=1234).to(DEV)
+    n0 = _lib.launch_count()
+    out = hp.step(batch.to(DEV))
+    torch.cuda.synchronize()
+    assert _lib.launch_count() - n0 >= 3 + 3 + 2 * cfg["steps"]
+    ref = oracle_step(cfg, batch, hp.state_dict_cpu())
+    ref64 = oracle_step(cfg, batch, hp.state_dict_cpu(), dtype=torch.float64)
+    for k in ref:
+        if k == "d_att.gvec.bias":
+            continue
+        assert_close(out[k], ref[k], truth=ref64[k], what=k)

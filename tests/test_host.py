@@ -1,0 +1,103 @@
+"""CPU: host-side logic -- target preparation, filter banks, sharding, gradient buckets over gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from robust_e2e_gan_b200 import synth
+from robust_e2e_gan_b200.e2e_ctc import prepare_targets
+from robust_e2e_gan_b200.feat_model import generic_mel_banks, kaldi_mel_banks
+from robust_e2e_gan_b200.parallel import GradBuckets, shard_range
+
+
+def test_prepare_targets_padded_and_list_agree():
+    ys = [torch.tensor([3, 3, 5]), torch.tensor([], dtype=torch.long), torch.tensor([7, 2, 9, 4])]
+    pad = torch.full((3, 5), -1, dtype=torch.long)
+    for i, y in enumerate(ys):
+        pad[i, :len(y)] = y
+    a = prepare_targets(ys, "cpu")
+    b = prepare_targets(pad, "cpu")
+    for t in (a, b):
+        assert t.lens.tolist() == [3, 0, 4] and t.offs.tolist() == [0, 3, 3] and t.umax == 4 and t.nutt == 3
+        assert t.labels.tolist() == [3, 3, 5, 7, 2, 9, 4] and t.labels.dtype == torch.int32
+
+
+def test_mel_banks_shapes_and_support():
+    k = kaldi_mel_banks(80)
+    assert k.shape == (80, 257) and (k >= 0).all() and (k > 0).sum() == 501
+    assert k[:, 0].sum() == 0 and k[:, 256].sum() == 0          # bins 0 and 256 unused
+    g = generic_mel_banks(40)
+    assert g.shape == (40, 257) and ((g > 0).sum(0) <= 2).all()
+    assert synth.mel_fc(257, 40).shape == (257, 40)
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 32, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synth_targets_are_ctc_feasible():
+    h, hl = synth.encoder_batch(B=6, Th=20, D=8, seed=3)
+    ys = synth.targets(B=6, V=30, hlens=hl, umin=8, umax=24, seed=3)
+    for y, l in zip(ys, hl):
+        rep = int((y[1:] == y[:-1]).sum()) if len(y) > 1 else 0
+        assert len(y) + rep <= l
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                                   # identical init on every rank
+    model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4))
+    unused = torch.nn.Parameter(torch.ones(5))             # never touched by the loss
+    params = list(model.parameters()) + [unused]
+    buckets = GradBuckets(params, bucket_mb=0.001)         # tiny buckets -> several all-reduces
+    g = torch.Generator().manual_seed(100)
+    x_all, y_all = torch.randn(8, 16, generator=g), torch.randn(8, 4, generator=g)
+    lo, hi = shard_range(8, rank, world)
+    out = []
+    for _ in range(2):                                     # two steps: views survive zero()
+        buckets.zero()
+        loss = ((model(x_all[lo:hi]) - y_all[lo:hi]) ** 2).mean()
+        loss.backward()
+        buckets.finish()
+        out.append([p.grad.clone() for p in params])
+    # single-process truth: mean over the equal-sized shards == grad of the mean over all rows
+    model.zero_grad()
+    for p in params:
+        p.grad = None
+    ((model(x_all) - y_all) ** 2).mean().backward()
+    ok = all(torch.allclose(a, p.grad, atol=1e-6) for a, p in zip(out[1][:-1], params[:-1]))
+    ok = ok and torch.equal(out[1][-1], torch.zeros(5)) and len(buckets.buckets) > 1
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_grad_buckets_allreduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
