@@ -171,7 +171,7 @@ def kernel_rooflines(hp, db, cfg, peak, dev):
     res = {}
     f32 = dict(device=dev, dtype=torch.float32)
     fc = hp.feat.fc.detach()
-    Y, G, dY, din = (torch.empty(B, T, M, **f32), torch.empty(B, T, M, **f32), torch.randn(B, T, M, **f32),
+    Y, G, dY, din = (torch.empty(B, T, M, **f32), torch.empty(B, T, M, **f32), torch.randn(B, T, M).to(dev),
                      torch.empty(B, T, F, **f32))
     lens = db.lens.to(torch.int32)
     att = hp.att
@@ -180,13 +180,13 @@ def kernel_rooflines(hp, db, cfg, peak, dev):
     gv, gb = att.gvec.weight.detach().view(A).contiguous(), att.gvec.bias.detach().contiguous()
     enc = db.hpad.contiguous()
     pre = torch.addmm(att.mlp_enc.bias.detach(), enc.view(B * Th, D), att.mlp_enc.weight.detach().t()).view(B, Th, A)
-    ap = torch.softmax(torch.randn(B, Th, **f32), 1)
+    ap = torch.softmax(torch.randn(B, Th), 1).to(dev)
     c, w, dproj, conv = torch.empty(B, D, **f32), torch.empty(B, Th, **f32), torch.empty(B, A, **f32), torch.empty(B, Th, C, **f32)
     dz = db.dec_z[0].contiguous()
-    dc, dw = torch.randn(B, D, **f32), torch.randn(B, Th, **f32)
+    dc, dw = torch.randn(B, D).to(dev), torch.randn(B, Th).to(dev)
     d_pre, ddp, dprev = torch.zeros(B, Th, A, **f32), torch.empty(B, A, **f32), torch.empty(B, Th, **f32)
     acc = [torch.zeros(A * C, **f32), torch.zeros(C * K, **f32), torch.zeros(A, **f32), torch.zeros(1, **f32)]
-    logits = torch.randn(B, Th, V, **f32)
+    logits = torch.randn(B, Th, V).to(dev)
     grad = torch.empty_like(logits)
     tg = db.targets
     hl = db.hlens.to(torch.int32)
@@ -329,26 +329,39 @@ def main():
     graph = None
     if not args.no_graph:
         try:
-            for p in hp.parameters():
-                p.grad = None
+            import gc
+
+            def drop_graph_refs():
+                # the modules keep the last loss / pre-compute (and so last step's autograd graph and its
+                # AccumulateGrad nodes, created on the default stream) alive: release before capturing
+                hp.att.reset()
+                hp.ctc.loss = None
+                hp.ctc.nll = None
+                for p in hp.parameters():
+                    p.grad = None
+                gc.collect()
+
+            drop_graph_refs()
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                hp.step(db, hlens_for_att=db.hlens)
+                for _ in range(2):
+                    hp.step(db, hlens_for_att=db.hlens)
+                    drop_graph_refs()
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
-            for p in hp.parameters():
-                p.grad = None
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                hp.step(db, hlens_for_att=db.hlens)
+            with torch.cuda.graph(graph, stream=s):
+                graph_out = hp.step(db, hlens_for_att=db.hlens)
             graph.replay()
             torch.cuda.synchronize()
             mode = "cuda_graph"
         except Exception as e:  # capture not possible: keep the eager path, say so
             graph = None
-            mode = "eager (graph capture failed: %s)" % (str(e).splitlines()[0][:120])
+            mode = "eager (graph capture failed: %s)" % (str(e).splitlines()[0][:160])
             torch.cuda.synchronize()
+    if rank == 0:
+        sys.stderr.write("[bench] timing mode: %s; launches/step %d\n" % (mode, launches_per_step))
 
     def timed_step():
         if graph is not None:

@@ -568,7 +568,6 @@ extern "C" int re2e_fbank_bwd(const float *dY, const float *G, const float *mask
     if ((rc = launch_status()) != RE2E_OK) return rc;
   }
   if (dfc) {
-    if ((size_t)F * M > 48u * kThreads) return RE2E_E_UNSUPPORTED;
     int ctas = num_sms();
     int rows_per_cta = (N + ctas - 1) / ctas;
     rows_per_cta = (rows_per_cta + 15) & ~15;

@@ -1,0 +1,333 @@
+// fp32-accurate dense GEMM on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), 3xTF32 split.
+//
+//   C[M,N] (+)= Aop[M,K] * Bop[N,K]^T (+ bias[N])
+//
+// used for the dense layers on the hot path whose fp32 parity (1e-4) rules out a single TF32/BF16
+// pass: ctc_lo (model/e2e_ctc.py:51), mlp_enc (model/e2e_attention.py:256) and their backward
+// products.  Each fp32 operand x is split as x = hi + lo with hi = the TF32 the tensor core sees
+// when it reads x (top 19 bits) and lo = tf32_rn(x - hi); three MMAs accumulate
+// hi*hi + lo*hi + hi*lo in an fp32 TMEM accumulator (the dropped lo*lo term is ~2^-22 relative).
+//
+// Structure (one CTA per 128 x BN output tile, 192 threads):
+//   warp 0      : TMA producer  -- cp.async.bulk.tensor.2d (SWIZZLE_128B boxes) into a smem ring
+//   warp 1      : MMA issuer    -- one elected lane issues tcgen05.mma.cta_group::1.kind::tf32
+//   warps 2..5  : converters    -- read each landed stage, write the `lo` copies (same swizzled layout)
+//                 then epilogue -- tcgen05.ld the accumulator, add bias, store C
+// Operands may be K-major ([rows][K], the nn.Linear layout) or MN-major ([K][rows]); the latter is
+// what the backward products need (dX = g W, dW = g^T X) and is expressed purely through the TMA box
+// shape and the UMMA descriptors -- no transposed copies.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace re2e {
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 32;                 // fp32 elements per k-block = one 128 B swizzle row
+constexpr int kGemmThreads = 192;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements; box 32 x box_outer,
+// 128 B swizzle, out-of-bounds elements read as zero.
+int make_tmap(CUtensorMap *tm, const float *ptr, long long inner, long long outer, long long ld, int box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return RE2E_E_UNSUPPORTED;
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? RE2E_OK : RE2E_E_ARG;
+}
+
+// ---- device helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor, SWIZZLE_128B, descriptor version 1 (Blackwell)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tf32_lo(float x) {
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);  // what the tensor core keeps of x
+  float lo = x - hi;                                                   // exact
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(lo));
+  return __uint_as_float(r);
+}
+
+struct GemmParams {
+  float *C;
+  const float *bias;
+  int M, N, K, ldc, accumulate;
+};
+
+template <bool A_MN, bool B_MN, int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const GemmParams p) {
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  constexpr int A_BYTES = kBM * kBK * 4;         // 16 KB
+  constexpr int B_BYTES = BN * kBK * 4;
+  constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+  // smem: [stages][A_hi | B_hi | A_lo | B_lo] then barriers
+  unsigned char *stage0 = smraw;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smraw + (size_t)STAGES * STAGE_BYTES);
+  uint64_t *conv = full + STAGES;
+  uint64_t *empty = conv + STAGES;
+  uint64_t *tmem_full = empty + STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+  const int nkb = (p.K + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&conv[s], 4);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {  // TMEM allocation by one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        if (kb >= STAGES) mbar_wait(&empty[s], (uint32_t)(((kb / STAGES) - 1) & 1));
+        unsigned char *st = stage0 + (size_t)s * STAGE_BYTES;
+        mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+        const int k0 = kb * kBK;
+        if (!A_MN) {
+          tma_load_2d(st, &tmA, k0, m0, &full[s]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kBM / 32; ++j) tma_load_2d(st + j * 4096, &tmA, m0 + 32 * j, k0, &full[s]);
+        }
+        if (!B_MN) {
+          tma_load_2d(st + A_BYTES, &tmB, k0, n0, &full[s]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(st + A_BYTES + j * 4096, &tmB, n0 + 32 * j, k0, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(&conv[s], (uint32_t)((kb / STAGES) & 1));
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(stage0 + (size_t)s * STAGE_BYTES);
+        const uint32_t b_hi = a_hi + A_BYTES;
+        const uint32_t a_lo = b_hi + B_BYTES;
+        const uint32_t b_lo = a_lo + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < kBK / 8; ++k) {
+          // K-major: 8 tf32 = 32 B further along the swizzled 128 B row; MN-major: next 8-row group (1 KB)
+          const uint32_t ao = A_MN ? k * 1024 : k * 32;
+          const uint32_t bo = B_MN ? k * 1024 : k * 32;
+          const uint64_t dah = umma_desc(a_hi + ao, A_MN ? 4096 : 16, 1024);
+          const uint64_t dal = umma_desc(a_lo + ao, A_MN ? 4096 : 16, 1024);
+          const uint64_t dbh = umma_desc(b_hi + bo, B_MN ? 4096 : 16, 1024);
+          const uint64_t dbl = umma_desc(b_lo + bo, B_MN ? 4096 : 16, 1024);
+          umma_tf32(tmem_base, dah, dbh, IDESC, (kb | k) ? 1u : 0u);
+          umma_tf32(tmem_base, dal, dbh, IDESC, 1u);
+          umma_tf32(tmem_base, dah, dbl, IDESC, 1u);
+        }
+        umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+      }
+      umma_commit(tmem_full);    // accumulator complete
+    }
+  } else {
+    // ===== converters (lo = tf32(x - hi)), then epilogue =====
+    const int ctid = threadIdx.x - 64;  // 0..127
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(&full[s], (uint32_t)((kb / STAGES) & 1));
+      const float4 *hi = reinterpret_cast<const float4 *>(stage0 + (size_t)s * STAGE_BYTES);
+      float4 *lo = reinterpret_cast<float4 *>(stage0 + (size_t)s * STAGE_BYTES + A_BYTES + B_BYTES);
+      constexpr int N4 = (A_BYTES + B_BYTES) / 16;
+#pragma unroll 4
+      for (int i = ctid; i < N4; i += 128) {
+        const float4 x = hi[i];
+        lo[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+      }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&conv[s]);
+    }
+    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = m0 + 32 * q + lane;
+    const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32), v);
+      const int col0 = n0 + c * 32;
+      if (row < p.M && col0 < p.N) {
+        float *dst = p.C + (size_t)row * p.ldc + col0;
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+        }
+        if (vec && col0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (p.accumulate) {
+              const float4 old = *reinterpret_cast<const float4 *>(dst + j);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *reinterpret_cast<float4 *>(dst + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <bool A_MN, bool B_MN, int BN, int STAGES>
+int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &prm, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * 2 * (kBM * kBK * 4 + BN * kBK * 4) + 1024;
+  auto kern = gemm_tf32x3_kernel<A_MN, B_MN, BN, STAGES>;
+  int rc = ensure_smem(reinterpret_cast<const void *>(kern), smem);
+  if (rc != RE2E_OK) return rc;
+  dim3 grid((prm.M + kBM - 1) / kBM, (prm.N + BN - 1) / BN);
+  kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, prm);
+  count_launch();
+  return launch_status();
+}
+
+template <int BN, int STAGES>
+int dispatch_major(int a_mn, int b_mn, const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &prm,
+                   cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_gemm<false, false, BN, STAGES>(ta, tb, prm, st);
+  if (!a_mn && b_mn) return launch_gemm<false, true, BN, STAGES>(ta, tb, prm, st);
+  if (a_mn && !b_mn) return launch_gemm<true, false, BN, STAGES>(ta, tb, prm, st);
+  return launch_gemm<true, true, BN, STAGES>(ta, tb, prm, st);
+}
+
+}  // namespace
+}  // namespace re2e
+
+using namespace re2e;
+
+// C[M,N] (+)= Aop[M,K] * Bop[N,K]^T (+ bias[N]);  a_mn = 0: A is [M][lda>=K] (K contiguous), a_mn = 1: A is
+// stored [K][lda>=M] (M contiguous).  Same for B with N.  lda, ldb multiples of 4; A, B 16 B aligned.
+extern "C" int re2e_gemm_tf32x3(const float *A, int lda, int a_mn, const float *B, int ldb, int b_mn, float *C,
+                                int ldc, const float *bias, int M, int N, int K, int accumulate, void *stream) {
+  RE2E_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0 && ldc >= N);
+  RE2E_CHECK_ARG((lda & 3) == 0 && (ldb & 3) == 0 && aligned16(A) && aligned16(B));
+  RE2E_CHECK_ARG(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K));
+  CUtensorMap ta, tb;
+  int rc;
+  const int BN = (N % 256 == 0 || N > 1024) ? 256 : 160;
+  if (!a_mn) rc = make_tmap(&ta, A, K, M, lda, kBM);
+  else rc = make_tmap(&ta, A, M, K, lda, kBK);
+  if (rc != RE2E_OK) return rc;
+  if (!b_mn) rc = make_tmap(&tb, B, K, N, ldb, BN);
+  else rc = make_tmap(&tb, B, N, K, ldb, kBK);
+  if (rc != RE2E_OK) return rc;
+  GemmParams prm;
+  prm.C = C; prm.bias = bias; prm.M = M; prm.N = N; prm.K = K; prm.ldc = ldc; prm.accumulate = accumulate;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (BN == 256) return dispatch_major<256, 2>(a_mn, b_mn, ta, tb, prm, st);
+  return dispatch_major<160, 3>(a_mn, b_mn, ta, tb, prm, st);
+}

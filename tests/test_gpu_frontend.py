@@ -71,11 +71,11 @@ def test_oracle_parity_shapes(B, T_, M, seed):
     dY = torch.randn(B, T_, M, generator=g)
     outs = {}
     for dt in (torch.float32, torch.float64):
-        lo = d["mask_logits"].to(dt).requires_grad_(True)
+        lo = d["mask_logits"].detach().clone().to(dt).requires_grad_(True)
         y = o_fe.masked_fbank_forward(lo, d["mix"].to(dt), d["lens"], fc.to(dt), cm.to(dt))
         y.backward(dY.to(dt))
         outs[dt] = (y.detach(), lo.grad)
-    lo = d["mask_logits"].to(DEV).requires_grad_(True)
+    lo = d["mask_logits"].detach().clone().to(DEV).requires_grad_(True)
     y = masked_fbank(lo, d["mix"].to(DEV), d["lens"], fc.to(DEV), cm.to(DEV))
     y.backward(dY.to(DEV))
     assert_close(y, outs[torch.float32][0], truth=outs[torch.float64][0], what="Y")
