@@ -157,10 +157,9 @@ def workload_config(cfg, world):
             "l2": "256 MiB scratch write between timed steps (excluded from step time)"}
 
 
-def kernel_rooflines(hp, db, cfg, peak, dev):
-    """Per-kernel CUDA-event timings of OUR kernels on the bench tensors: each kernel (through the same
-    C-ABI call the step makes) is captured R times into a CUDA graph and replayed, so the events see
-    back-to-back launches without Python gaps.  achieved = algorithmic bytes / average launch time."""
+def kernel_specs(hp, db, cfg, dev):
+    """(name, callable, algorithmic bytes per launch, repetitions) for each of OUR kernels, on the bench
+    tensors and through the same C-ABI calls the step makes."""
     from robust_e2e_gan_b200 import _lib
     L = _lib.lib()
     B, T, F, M, Th, D, A, Z, C, V, U = (cfg[k] for k in ("B", "T", "F", "M", "Th", "D", "A", "Z", "C", "V", "U"))
@@ -233,8 +232,16 @@ def kernel_rooflines(hp, db, cfg, peak, dev):
         ("ctc_fwd(lse+alpha/beta)", k_ctc_fwd, 4.0 * valid_frames * V + 4.0 * 3 * valid_frames * S, 4),
         ("ctc_bwd(grad)", k_ctc_bwd, 4.0 * valid_frames * V + 4.0 * B * Th * V, 4),
     ]
+    return specs
+
+
+def kernel_rooflines(hp, db, cfg, peak, dev):
+    """Per-kernel CUDA-event timings: each kernel is captured R times into a CUDA graph and replayed, so
+    the events see back-to-back launches without Python gaps.  achieved = algorithmic bytes / avg launch."""
+    res = {}
+    f32 = dict(device=dev, dtype=torch.float32)
     flush = torch.empty(64 * 1024 * 1024, **f32)
-    for name, fn, nbytes, reps in specs:
+    for name, fn, nbytes, reps in kernel_specs(hp, db, cfg, dev):
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

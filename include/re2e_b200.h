@@ -119,6 +119,15 @@ int re2e_skinny_nt(const float *X, const float *W, float *out, int M, int N, int
 int re2e_skinny_nn(const float *X, const float *W, float *out, int M, int N, int K, int accumulate,
                    void *stream);
 
+/* fp32-accurate dense GEMM on tcgen05 tensor cores (3xTF32 split, fp32 TMEM accumulator; csrc/gemm_tc.cu):
+ *   C[M,N] (+)= Aop[M,K] * Bop[N,K]^T (+ bias[N])
+ * a_mn = 0: A stored [M][lda] (K contiguous)   a_mn = 1: A stored [K][lda] (M contiguous);  same for B / N.
+ * Replaces the cuBLAS sgemm behind nn.Linear on the path: ctc_lo (model/e2e_ctc.py:51), mlp_enc
+ * (model/e2e_attention.py:256) and their backward products (dX = g W : b_mn = 1;  dW = g^T X : a_mn = b_mn = 1).
+ * lda, ldb multiples of 4 elements, A and B 16 B aligned (TMA); ldc >= N. */
+int re2e_gemm_tf32x3(const float *A, int lda, int a_mn, const float *B, int ldb, int b_mn, float *C,
+                     int ldc, const float *bias, int M, int N, int K, int accumulate, void *stream);
+
 /* --------------------------------------------------------------------------------------------
  * CTC.  Replaces the warp_ctc.CTCLoss call at model/e2e_ctc.py:30,63 (softmax + alpha/beta +
  * gradient; arithmetic of the un-vendored warpctc_pytorch) and F.log_softmax at :75.

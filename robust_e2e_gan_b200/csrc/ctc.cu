@@ -27,6 +27,7 @@ constexpr int kRenorm = 8;
 struct CtcWs {
   unsigned int *counter;
   float *lse;      // (B,Th)
+  float *lpmax;    // (B,Th)  max_s lp[b,t,s]: per-frame normaliser of the lattice column
   double *offA;    // (B,Th)
   double *offB;    // (B,Th)
   float *lpc;      // (B,Th,Smax)
@@ -45,6 +46,7 @@ inline CtcWs carve(void *ws, int B, int Th, int Smax) {
   w.offA = reinterpret_cast<double *>(p + off); off += align_up(sizeof(double) * (size_t)B * Th, 256);
   w.offB = reinterpret_cast<double *>(p + off); off += align_up(sizeof(double) * (size_t)B * Th, 256);
   w.lse = reinterpret_cast<float *>(p + off); off += align_up(sizeof(float) * (size_t)B * Th, 256);
+  w.lpmax = reinterpret_cast<float *>(p + off); off += align_up(sizeof(float) * (size_t)B * Th, 256);
   size_t lat = align_up(sizeof(float) * (size_t)B * Th * Smax, 256);
   w.lpc = reinterpret_cast<float *>(p + off); off += lat;
   w.alpha = reinterpret_cast<float *>(p + off); off += lat;
@@ -98,7 +100,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 ctc_lse_kernel(const float *__restrict__ logits, long long stride_b, long long stride_t,
                const int32_t *__restrict__ labels, const int32_t *__restrict__ label_offs,
                const int32_t *__restrict__ label_lens, const int32_t *__restrict__ input_lens, int blank,
-               float *__restrict__ lse, float *__restrict__ lpc, int B, int Th, int V, int Smax) {
+               float *__restrict__ lse, float *__restrict__ lpmax, float *__restrict__ lpc, int B, int Th,
+               int V, int Smax) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (row >= (long long)B * Th) return;
@@ -112,10 +115,15 @@ ctc_lse_kernel(const float *__restrict__ logits, long long stride_b, long long s
   const int U = __ldg(label_lens + b), S = 2 * U + 1;
   const int32_t *lab = labels + __ldg(label_offs + b);
   float *out = lpc + row * Smax;
+  float mx = -CUDART_INF_F;
   for (int i = lane; i < S; i += 32) {
     int v = (i & 1) ? __ldg(lab + (i >> 1)) : blank;
-    out[i] = __ldg(x + v) - l;   // row was just streamed: L2 hit
+    const float lpv = __ldg(x + v) - l;   // row was just streamed: L2 hit
+    out[i] = lpv;
+    mx = fmaxf(mx, lpv);
   }
+  mx = warp_max(mx);
+  if (lane == 0) lpmax[row] = mx;
 }
 
 // log(e^a + e^b + e^c) with -inf handling
@@ -131,7 +139,8 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
 
 // one CTA per utterance; blockDim = 2*Sp (Sp = Smax rounded to 32): first half alpha, second beta
 __global__ void __launch_bounds__(1024)
-ctc_ab_kernel(const float *__restrict__ lpc, const int32_t *__restrict__ labels,
+ctc_ab_kernel(const float *__restrict__ lpc, const float *__restrict__ lpmax,
+              const int32_t *__restrict__ labels,
               const int32_t *__restrict__ label_offs, const int32_t *__restrict__ label_lens,
               const int32_t *__restrict__ input_lens, int blank, float *__restrict__ alpha,
               float *__restrict__ beta, double *__restrict__ offA, double *__restrict__ offB,
@@ -162,11 +171,13 @@ ctc_ab_kernel(const float *__restrict__ lpc, const int32_t *__restrict__ labels,
   const int nwarps = Sp >> 5;
   const int barid = 1 + half;
 
-  float pf[kRenorm];
+  const float *lpm_b = lpmax + (size_t)b * Th;
+  float pf[kRenorm], pm[kRenorm];
 #pragma unroll
   for (int j = 0; j < kRenorm; ++j) {
     int t = half ? T - 1 - j : j;
     pf[j] = (live && j < T) ? __ldg(lp_b + (size_t)t * Smax + s) : NEG;
+    pm[j] = j < T ? __ldg(lpm_b + t) : 0.0f;
   }
   double off = 0.0;
   int cur = 0;
@@ -176,11 +187,16 @@ ctc_ab_kernel(const float *__restrict__ lpc, const int32_t *__restrict__ labels,
       const int i = i0 + j;
       if (i >= T) break;
       const int t = half ? T - 1 - i : i;
-      const float lpv = pf[j];
+      // every frame is shifted by its own max label log-prob (kept in `off`), so a column only drifts
+      // by the gap to the best label between the exact renormalisations below
+      const float lpm = pm[j];
+      const float lpv = pf[j] - lpm;
+      off += (double)lpm;
       {  // prefetch frame i + kRenorm
         const int i2 = i + kRenorm;
         const int t2 = half ? T - 1 - i2 : i2;
         pf[j] = (live && i2 < T) ? __ldg(lp_b + (size_t)t2 * Smax + s) : NEG;
+        pm[j] = i2 < T ? __ldg(lpm_b + t2) : 0.0f;
       }
       float v;
       if (i == 0) {
@@ -397,13 +413,13 @@ extern "C" int re2e_ctc_loss_fwd(const float *logits, long long stride_b, long l
   const long long rows = (long long)B * Th;
   const int grid = (int)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
   ctc_lse_kernel<<<grid, kWarpsPerCta * 32, 0, st>>>(logits, stride_b, stride_t, labels, label_offs,
-                                                     label_lens, input_lens, blank, w.lse, w.lpc, B, Th, V,
-                                                     Smax);
+                                                     label_lens, input_lens, blank, w.lse, w.lpmax, w.lpc, B,
+                                                     Th, V, Smax);
   count_launch();
   int rc = launch_status();
   if (rc != RE2E_OK) return rc;
   const size_t smem = sizeof(float) * (4 * (size_t)(Sp + 4) + 64);
-  ctc_ab_kernel<<<B, 2 * Sp, smem, st>>>(w.lpc, labels, label_offs, label_lens, input_lens, blank, w.alpha,
+  ctc_ab_kernel<<<B, 2 * Sp, smem, st>>>(w.lpc, w.lpmax, labels, label_offs, label_lens, input_lens, blank, w.alpha,
                                          w.beta, w.offA, w.offB, nll, loss, w.counter, B, Th, Smax, Sp);
   count_launch();
   return launch_status();
