@@ -181,6 +181,7 @@ def kernel_specs(hp, db, cfg, dev):
     pre = torch.addmm(att.mlp_enc.bias.detach(), enc.view(B * Th, D), att.mlp_enc.weight.detach().t()).view(B, Th, A)
     ap = torch.softmax(torch.randn(B, Th), 1).to(dev)
     c, w, dproj, conv = torch.empty(B, D, **f32), torch.empty(B, Th, **f32), torch.empty(B, A, **f32), torch.empty(B, Th, C, **f32)
+    xsave = torch.empty(B, Th, A, **f32)
     dz = db.dec_z[0].contiguous()
     dc, dw = torch.randn(B, D).to(dev), torch.randn(B, Th).to(dev)
     d_pre, ddp, dprev = torch.zeros(B, Th, A, **f32), torch.empty(B, A, **f32), torch.empty(B, Th, **f32)
@@ -207,10 +208,10 @@ def kernel_specs(hp, db, cfg, dev):
 
     def k_att_fwd():
         _lib.check(L.re2e_attloc_step_fwd(P(pre), P(enc), P(dz), P(ap), P(W_dec), P(W_att), P(W_conv), P(gv), P(gb),
-                                          2.0, P(c), P(w), P(dproj), P(conv), B, Th, D, A, Z, C, K, sp()))
+                                          2.0, P(c), P(w), P(dproj), P(conv), P(xsave), B, Th, D, A, Z, C, K, sp()))
 
     def k_att_bwd():
-        _lib.check(L.re2e_attloc_step_bwd(P(dc), P(dw), P(pre), P(enc), P(ap), P(w), P(dproj), P(conv), P(W_att),
+        _lib.check(L.re2e_attloc_step_bwd(P(dc), P(dw), P(xsave), P(enc), P(ap), P(w), P(conv), P(W_att),
                                           P(W_conv), P(gv), 2.0, P(d_pre), 1, P(ddp), P(dprev), P(acc[0]), P(acc[1]),
                                           P(acc[2]), P(acc[3]), B, Th, D, A, C, K, sp()))
 
@@ -227,7 +228,7 @@ def kernel_specs(hp, db, cfg, dev):
         ("fbank_fwd(mask,mag->Y,G)", k_fb_fwd, 4.0 * N * (2 * F + 2 * M), 4),
         ("fbank_fwd(mag->Y)", k_fb_fwd_plain, 4.0 * N * (F + M), 4),
         ("fbank_bwd(->d mask)", k_fb_bwd, 4.0 * N * (2 * M + 3 * F), 4),
-        ("attloc_step_fwd", k_att_fwd, 4.0 * B * Th * (A + D) + 4.0 * B * (Z + Th * (2 + C) + D + A), 20),
+        ("attloc_step_fwd", k_att_fwd, 4.0 * B * Th * (2 * A + D) + 4.0 * B * (Z + Th * (2 + C) + D + A), 20),
         ("attloc_step_bwd", k_att_bwd, 4.0 * B * Th * (A + D) + 4.0 * B * Th * A + 4.0 * B * Th * (4 + C), 20),
         ("ctc_fwd(lse+alpha/beta)", k_ctc_fwd, 4.0 * valid_frames * V + 4.0 * 3 * valid_frames * S, 4),
         ("ctc_bwd(grad)", k_ctc_bwd, 4.0 * valid_frames * V + 4.0 * B * Th * V, 4),

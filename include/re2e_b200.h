@@ -84,14 +84,18 @@ int re2e_cmvn_stats(const float *Y, const int32_t *lens, double *sum, double *su
 int re2e_attloc_init_att(const int32_t *hlens, float *att_prev, int B, int Th, void *stream);
 
 /* One attention step (e2e_attention.py:258-299).  dec_z == NULL means zeros (:258-259).
- * Saved for backward: dec_proj (B,A) = dec_z @ W_dec^T, conv (B,Th,C) = loc_conv(att_prev). */
+ * Saved for backward (all optional outputs may be NULL when no gradient is needed):
+ *   dec_proj (B,A) = dec_z @ W_dec^T   (always written: scratch of the step)
+ *   conv (B,Th,C)  = loc_conv(att_prev)
+ *   xsave (B,Th,A) = tanh(mlp_att(conv) + pre + dec_proj), written by the TMA unit from the smem ring */
 int re2e_attloc_step_fwd(const float *pre, const float *enc_h, const float *dec_z,
                          const float *att_prev, const float *W_dec, const float *W_att,
                          const float *W_conv, const float *gvec, const float *gvec_b,
-                         float scaling, float *c, float *w, float *dec_proj, float *conv,
+                         float scaling, float *c, float *w, float *dec_proj, float *conv, float *xsave,
                          int B, int Th, int D, int A, int Z, int C, int K, void *stream);
 
-/* Backward of one step.  Inputs dc (B,D) / dw (B,Th) may be NULL (= zero).
+/* Backward of one step.  Inputs dc (B,D) / dw (B,Th) may be NULL (= zero); xsave / conv / w are the
+ * tensors saved by the forward.
  *   d_pre (B,Th,A)       (+)= dE/dpre   accumulate_pre != 0: TMA reduce-add into d_pre (accumulated
  *                             across steps); == 0: plain store (first backward step, no zero-fill)
  *   d_decproj (B,A)       = dE/d(dec_z @ W_dec^T)        (caller derives d_dec_z, dW_dec)
@@ -99,13 +103,12 @@ int re2e_attloc_step_fwd(const float *pre, const float *enc_h, const float *dec_
  *   dW_att (A,C), dW_conv (C,K), dgvec (A), dgvec_b (1)  += (accumulated across steps)
  * d enc_h is NOT produced here: sum_i w_i (x) dc_i is a rank-(#steps) update applied once by
  * re2e_attloc_enc_grad after the loop (no per-step read-modify-write of (B,Th,D)). */
-int re2e_attloc_step_bwd(const float *dc, const float *dw, const float *pre, const float *enc_h,
-                         const float *att_prev, const float *w, const float *dec_proj,
-                         const float *conv, const float *W_att, const float *W_conv,
-                         const float *gvec, float scaling, float *d_pre, int accumulate_pre,
-                         float *d_decproj, float *d_att_prev, float *dW_att, float *dW_conv,
-                         float *dgvec, float *dgvec_b, int B, int Th, int D, int A, int C, int K,
-                         void *stream);
+int re2e_attloc_step_bwd(const float *dc, const float *dw, const float *xsave, const float *enc_h,
+                         const float *att_prev, const float *w, const float *conv,
+                         const float *W_att, const float *W_conv, const float *gvec, float scaling,
+                         float *d_pre, int accumulate_pre, float *d_decproj, float *d_att_prev,
+                         float *dW_att, float *dW_conv, float *dgvec, float *dgvec_b, int B, int Th,
+                         int D, int A, int C, int K, void *stream);
 
 /* d_enc_h[b,t,:] (+)= sum_i w_all[i,b,t] * dc_all[i,b,:]   (i < steps); accumulate != 0 adds. */
 int re2e_attloc_enc_grad(const float *w_all, const float *dc_all, float *d_enc_h, int steps,

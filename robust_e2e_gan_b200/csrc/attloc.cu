@@ -2,19 +2,23 @@
 // forward and backward, one thread-block-cluster kernel each.
 //
 // Mapping.  One CLUSTER of CL CTAs per utterance b; CTA `rank` owns the encoder frames
-// [t0,t1) = rank*ceil(Th/CL) ....  The two big operands of a step, pre[b,t0:t1,:] and
-// enc_h[b,t0:t1,:], are contiguous in HBM, so they are fetched with 1-D bulk async copies (TMA,
-// cp.async.bulk -> SASS UBLKCP) in chunks of 8 frames into a shared-memory ring, each chunk
-// signalled on its own mbarrier; the loads are all in flight while the CTA computes the location
-// convolution.  Softmax statistics and the context vector are combined across the CTAs of the
-// cluster through distributed shared memory (ld.shared::cluster) -- no global round trip and no
-// second kernel.  In the backward the gradient w.r.t. pre is formed in place in the ring and
-// accumulated into HBM by the TMA unit itself (cp.reduce.async.bulk .add.f32): the SM never reads
-// d_pre.  Algorithmic bytes per step (fp32): fwd 4*B*Th*(A+D); bwd 4*B*Th*(A+D) + 4*B*Th*A.
+// [t0,t1) = rank*ceil(Th/CL) ....  The big per-step operands pre[b,t0:t1,:] / enc_h[b,t0:t1,:] (and in
+// the backward the saved tanh activations) are contiguous in HBM, so they are fetched with 1-D bulk
+// async copies (TMA, cp.async.bulk -> SASS UBLKCP) in chunks of NW frames into a shared-memory ring,
+// each chunk signalled on its own mbarrier; all loads are in flight while the CTA computes the location
+// convolution.  Softmax statistics and the context vector are combined across the CTAs of the cluster
+// through distributed shared memory (ld.shared::cluster) -- no global round trip, no second kernel.
+// The forward writes tanh(.) in place into the ring and hands the chunk back to the TMA unit (bulk
+// store) so the backward does not recompute W_att*conv + tanh; the backward forms d pre in place in
+// the ring and lets the TMA unit accumulate it into HBM (cp.reduce.async.bulk.add.f32 -> UBLKRED): the
+// SM never reads d_pre.
+// Algorithmic bytes per step (fp32): fwd 4*B*Th*(A+D) read (+4*B*Th*A activation save when training);
+// bwd 4*B*Th*(A+D) read + 4*B*Th*A reduce.
 //
-// Thread mapping inside a CTA (256 threads = 8 warps): for the energy part a row (frame) is
-// handled by a PAIR of warps, each owning half of the A attention channels, lane <-> channel
-// (a = half*A/2 + lane + 32j): W_att (A x C) then lives in registers (APL*CP floats per lane).
+// Thread mapping (NW warps): for the energy part a frame is handled by a PAIR of warps, each owning
+// half of the A attention channels, lane <-> channel (a = half*A/2 + lane + 32j): W_att (A x C) lives in
+// registers (APL*CP floats per lane).  The 1 x K location convolution and its two transposes in the
+// backward are register-blocked sliding-window FMAs (5 outputs per thread, K split 4 ways).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -22,28 +26,29 @@
 namespace re2e {
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = 8;
-constexpr int kChunkRows = 8;
+constexpr int kNWF = 16;      // warps per CTA, forward
+constexpr int kNWB = 12;      // warps per CTA, backward (register budget: W_att + dW_att accumulators)
 constexpr int kDplMax = 16;   // D <= 512
 constexpr int kMaxStages = 30;
+constexpr int kTG = 5;        // conv outputs per thread (sliding window)
+constexpr int kKQ = 4;        // K split
 
 __host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
 
 struct AttGeom {
-  int tloc_max, nch, ns, stage_floats, Thp, CKp;
+  int tloc_max, nch, ns, stage_floats, Thp, CKp, App;  // App: padded alignment row Th + 2*filts + 8
 };
 
 struct AttFwdParams {
   const float *pre, *enc, *att_prev, *dec_proj, *W_att, *W_conv, *gvec, *gvec_b;
   float scaling;
-  float *c, *w, *conv;
+  float *c, *w, *conv, *xsave;
   int B, Th, D, A, C, K;
   AttGeom g;
 };
 
 struct AttBwdParams {
-  const float *dc, *dw, *pre, *enc, *att_prev, *w, *dec_proj, *conv, *W_att, *W_conv, *gvec;
+  const float *dc, *dw, *xsave, *enc, *att_prev, *w, *conv, *W_att, *W_conv, *gvec;
   float scaling;
   float *d_pre, *d_decproj, *d_att_prev, *dW_att, *dW_conv, *dgvec, *dgvec_b;
   int accumulate_pre;
@@ -52,14 +57,15 @@ struct AttBwdParams {
 };
 
 // issue chunk `q` of the [first | second] operand sequence into ring stage q % ns
-__device__ __forceinline__ void issue_chunk(int q, const AttGeom &g, const float *first, int wfirst,
-                                            const float *second, int wsecond, int b, int Th, int t0,
-                                            int t1, float *stages, uint64_t *full) {
+template <int NW>
+__device__ __forceinline__ void issue_chunk(int q, int nch, const AttGeom &g, const float *first, int wfirst,
+                                            const float *second, int wsecond, int b, int Th, int t0, int t1,
+                                            float *stages, uint64_t *full) {
   const int st = q % g.ns;
-  const bool is_first = q < g.nch;
-  const int qq = is_first ? q : q - g.nch;
-  const int r0 = t0 + kChunkRows * qq;
-  const int rows = min(kChunkRows, t1 - r0);
+  const bool is_first = q < nch;
+  const int qq = is_first ? q : q - nch;
+  const int r0 = t0 + NW * qq;
+  const int rows = min(NW, t1 - r0);
   const int width = is_first ? wfirst : wsecond;
   const float *src = (is_first ? first : second) + ((size_t)b * Th + r0) * width;
   const uint32_t bytes = (uint32_t)rows * width * 4u;
@@ -67,43 +73,75 @@ __device__ __forceinline__ void issue_chunk(int q, const AttGeom &g, const float
   bulk_g2s(stages + (size_t)st * g.stage_floats, src, bytes, &full[st]);
 }
 
+// sum 16 per-lane values across the warp with recursive halving (16 shuffles instead of 80); on return
+// lane L (L even) holds in v[0] the total of value index  bit4*8 + bit3*4 + bit2*2 + bit1  of L.
+__device__ __forceinline__ void warp_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 16;
+    const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 8;
+    const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
 template <int APL, int CP>
-__global__ void __launch_bounds__(kThreads, 1) attloc_fwd_kernel(const AttFwdParams p) {
+__global__ void __launch_bounds__(kNWF * 32, 1) attloc_fwd_kernel(const AttFwdParams p) {
+  constexpr int NW = kNWF, NT = NW * 32;
   extern __shared__ __align__(128) unsigned char smraw[];
   const AttGeom g = p.g;
   const int Th = p.Th, D = p.D, A = p.A, C = p.C, K = p.K, filts = (p.K - 1) / 2;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = warp & 1, rw = warp >> 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = warp & 1, pair = warp >> 1;
   const int CL = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
   const int b = blockIdx.x / CL;
   const int t0 = min(Th, rank * g.tloc_max), t1 = min(Th, t0 + g.tloc_max), tloc = t1 - t0;
-  const int nch = (tloc + kChunkRows - 1) / kChunkRows;  // chunks actually used by this CTA
-  AttGeom gl = g;
-  gl.nch = nch;
+  const int nch = (tloc + NW - 1) / NW;  // chunks actually used by this CTA
   const int total = 2 * nch;
 
   uint64_t *full = reinterpret_cast<uint64_t *>(smraw);
   float *stages = reinterpret_cast<float *>(smraw + 256);
-  float *ap_s = stages + (size_t)g.ns * g.stage_floats;
-  float *wc_s = ap_s + g.Thp;
-  float *conv_s = wc_s + g.CKp;
-  float *e_s = conv_s + g.tloc_max * CP;
-  float *p_s = e_s + 2 * g.tloc_max;
-  float *cred = p_s + g.tloc_max;
-  float *cpart = cred + kWarps * D;
-  float *xch = cpart + round4(D);
+  float *app = stages + (size_t)g.ns * g.stage_floats;     // App   zero padded alignment row, ap[i] at filts+i
+  float *wc_s = app + g.App;                               // CKp
+  float *convp = wc_s + g.CKp;                             // kKQ*tloc_max*CP  conv partials
+  float *conv_s = convp + kKQ * g.tloc_max * CP;           // tloc_max*CP
+  float *e_part = conv_s + g.tloc_max * CP;                // tloc_max*65
+  float *p_s = e_part + g.tloc_max * 65;                   // tloc_max
+  float *cpart = p_s + round4(g.tloc_max);                 // round4(D)
+  float *xch = cpart + round4(D);                          // 4
+  float *cred = stages;                                    // NW*D, aliases stage 0 after the ring is drained
 
   if (tid == 0) {
     for (int i = 0; i < g.ns; ++i) mbar_init(&full[i], 1);
     mbar_fence_init();
     const int first = total < g.ns ? total : g.ns;
-    for (int q = 0; q < first; ++q) issue_chunk(q, gl, p.pre, A, p.enc, D, b, Th, t0, t1, stages, full);
+    for (int q = 0; q < first; ++q) issue_chunk<NW>(q, nch, g, p.pre, A, p.enc, D, b, Th, t0, t1, stages, full);
   }
-  // stage the small operands
-  for (int i = tid; i < Th; i += kThreads) ap_s[i] = __ldg(p.att_prev + (size_t)b * Th + i);
-  for (int i = tid; i < C * K; i += kThreads) wc_s[i] = __ldg(p.W_conv + i);
+  // stage the small operands (issued back to back: one round trip)
+  for (int i = tid; i < g.App; i += NT) {
+    const int t = i - filts;
+    app[i] = (t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
+  }
+  for (int i = tid; i < C * K; i += NT) wc_s[i] = __ldg(p.W_conv + i);
   float Watt[APL][CP], dp[APL], gv[APL];
 #pragma unroll
   for (int j = 0; j < APL; ++j) {
@@ -115,28 +153,45 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_fwd_kernel(const AttFwdPar
   }
   __syncthreads();
 
-  // ---- location convolution: conv[t,c] = sum_k Wc[c,k] * att_prev[t + k - filts]  (zero padded)
-  for (int item = tid; item < tloc * CP; item += kThreads) {
-    const int tl = item / CP, c = item - tl * CP;
-    float acc = 0.0f;
-    if (c < C) {
-      const int t = t0 + tl;
-      const int klo = max(0, filts - t), khi = min(K, Th + filts - t);
+  // ---- location convolution: conv[t,c] = sum_k Wc[c,k] * att_prev[t + k - filts]  (zero padded).
+  //      item = (k quarter, channel, group of 5 frames): 2 shared loads per 5 FMAs
+  {
+    const int ntg = (tloc + kTG - 1) / kTG;
+    const int Kq = (K + kKQ - 1) / kKQ;
+    const int nitems = ntg * C * kKQ;
+    for (int item = tid; item < nitems; item += NT) {
+      const int tg = item % ntg, rest = item / ntg, c = rest % C, kq = rest / C;
+      const int k0 = kq * Kq, k1 = min(K, k0 + Kq);
       const float *wr = wc_s + c * K;
-      const float *ar = ap_s + (t - filts);
-      int k = klo;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (; k + 3 < khi; k += 4) {
-        a0 = fmaf(wr[k], ar[k], a0);
-        a1 = fmaf(wr[k + 1], ar[k + 1], a1);
-        a2 = fmaf(wr[k + 2], ar[k + 2], a2);
-        a3 = fmaf(wr[k + 3], ar[k + 3], a3);
+      const float *ar = app + t0 + kTG * tg;  // element (t, k) = ar[(t - 5tg) + k]
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+      float x0 = ar[k0], x1 = ar[k0 + 1], x2 = ar[k0 + 2], x3 = ar[k0 + 3];
+#pragma unroll 5
+      for (int k = k0; k < k1; ++k) {
+        const float x4 = ar[k + 4], wv = wr[k];
+        a0 = fmaf(wv, x0, a0); a1 = fmaf(wv, x1, a1); a2 = fmaf(wv, x2, a2);
+        a3 = fmaf(wv, x3, a3); a4 = fmaf(wv, x4, a4);
+        x0 = x1; x1 = x2; x2 = x3; x3 = x4;
       }
-      for (; k < khi; ++k) a0 = fmaf(wr[k], ar[k], a0);
-      acc = (a0 + a1) + (a2 + a3);
-      if (p.conv) p.conv[((size_t)b * Th + t) * C + c] = acc;
+      float *o = convp + ((size_t)kq * g.tloc_max + kTG * tg) * CP + c;
+      const int nv = min(kTG, tloc - kTG * tg);
+      o[0] = a0;
+      if (nv > 1) o[CP] = a1;
+      if (nv > 2) o[2 * CP] = a2;
+      if (nv > 3) o[3 * CP] = a3;
+      if (nv > 4) o[4 * CP] = a4;
     }
-    conv_s[item] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < tloc * CP; i += NT) {
+    const int tl = i / CP, c = i - tl * CP;
+    float v = 0.0f;
+    if (c < C) {
+#pragma unroll
+      for (int kq = 0; kq < kKQ; ++kq) v += convp[(size_t)kq * g.tloc_max * CP + i];
+      if (p.conv) p.conv[((size_t)b * Th + t0 + tl) * C + c] = v;
+    }
+    conv_s[i] = v;
   }
   __syncthreads();
 
@@ -144,50 +199,68 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_fwd_kernel(const AttFwdPar
   for (int q = 0; q < nch; ++q) {
     const int st = q % g.ns;
     mbar_wait(&full[st], (uint32_t)((q / g.ns) & 1));
-    const float *tile = stages + (size_t)st * g.stage_floats;
-    const int rows = min(kChunkRows, tloc - kChunkRows * q);
+    float *tile = stages + (size_t)st * g.stage_floats;
+    const int rows = min(NW, tloc - NW * q);
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
-      const int r = rw + 4 * rr;
+      const int r = pair + (NW / 2) * rr;
       if (r < rows) {
-        const int tl = kChunkRows * q + r;
+        const int tl = NW * q + r;
         float cv[CP];
 #pragma unroll
         for (int c = 0; c < CP; ++c) cv[c] = conv_s[tl * CP + c];
-        const float *row = tile + r * A + half * (A / 2) + lane;
+        float *row = tile + r * A + half * (A / 2) + lane;
         float part = 0.0f;
 #pragma unroll
         for (int j = 0; j < APL; ++j) {
           float u = dp[j] + row[32 * j];
 #pragma unroll
           for (int c = 0; c < CP; ++c) u = fmaf(Watt[j][c], cv[c], u);
-          part = fmaf(gv[j], tanh_fast(u), part);
+          const float x = tanh_fast(u);
+          if (p.xsave) row[32 * j] = x;  // activation kept for the backward, stored by the TMA unit below
+          part = fmaf(gv[j], x, part);
         }
-        part = warp_sum(part);
-        if (lane == 0) e_s[half * g.tloc_max + tl] = part;
+        e_part[tl * 65 + half * 32 + lane] = part;
       }
     }
-    if (q + g.ns < total) {  // ring wrap: everyone is done with this stage, refill it
+    const bool refill = q + g.ns < total;
+    if (p.xsave || refill) {
+      if (p.xsave) fence_proxy_async_smem();
       __syncthreads();
-      if (tid == 0) issue_chunk(q + g.ns, gl, p.pre, A, p.enc, D, b, Th, t0, t1, stages, full);
+      if (tid == 0) {
+        if (p.xsave) {
+          bulk_s2g(p.xsave + ((size_t)b * Th + t0 + NW * q) * A, tile, (uint32_t)rows * A * 4u);
+          bulk_commit();
+        }
+        if (refill) {
+          if (p.xsave) bulk_wait_read<0>();
+          issue_chunk<NW>(q + g.ns, nch, g, p.pre, A, p.enc, D, b, Th, t0, t1, stages, full);
+        }
+      }
     }
   }
   __syncthreads();
 
-  // ---- local softmax statistics over this CTA's frames (the softmax spans ALL Th frames,
-  //      padding included: e2e_attention.py:282-288 applies no length mask)
-  if (warp == 0) {
+  // ---- local softmax statistics over this CTA's frames (the softmax spans ALL Th frames, padding
+  //      included: e2e_attention.py:282-288 applies no length mask)
+  {
     const float gb = __ldg(p.gvec_b);
-    float m = -CUDART_INF_F;
-    for (int tl = lane; tl < tloc; tl += 32) {
-      float ev = p.scaling * (e_s[tl] + e_s[g.tloc_max + tl] + gb);
-      e_s[tl] = ev;
-      m = fmaxf(m, ev);
+    for (int tl = tid; tl < tloc; tl += NT) {
+      const float *ep = e_part + tl * 65;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) { s0 += ep[i]; s1 += ep[i + 1]; s2 += ep[i + 2]; s3 += ep[i + 3]; }
+      p_s[tl] = p.scaling * ((s0 + s1) + (s2 + s3) + gb);
     }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float m = -CUDART_INF_F;
+    for (int tl = lane; tl < tloc; tl += 32) m = fmaxf(m, p_s[tl]);
     m = warp_max(m);
     float s = 0.0f;
     for (int tl = lane; tl < tloc; tl += 32) {
-      float pv = expf(e_s[tl] - m);
+      const float pv = expf(p_s[tl] - m);
       p_s[tl] = pv;
       s += pv;
     }
@@ -205,9 +278,9 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_fwd_kernel(const AttFwdPar
     mbar_wait(&full[st], (uint32_t)((q / g.ns) & 1));
     const float *tile = stages + (size_t)st * g.stage_floats;
     const int qq = q - nch;
-    const int rows = min(kChunkRows, tloc - kChunkRows * qq);
+    const int rows = min(NW, tloc - NW * qq);
     if (warp < rows) {
-      const float pw = p_s[kChunkRows * qq + warp];
+      const float pw = p_s[NW * qq + warp];
       const float *row = tile + warp * D + lane;
 #pragma unroll
       for (int j = 0; j < kDplMax; ++j)
@@ -215,17 +288,19 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_fwd_kernel(const AttFwdPar
     }
     if (q + g.ns < total) {
       __syncthreads();
-      if (tid == 0) issue_chunk(q + g.ns, gl, p.pre, A, p.enc, D, b, Th, t0, t1, stages, full);
+      if (tid == 0) issue_chunk<NW>(q + g.ns, nch, g, p.pre, A, p.enc, D, b, Th, t0, t1, stages, full);
     }
   }
+  if (tid == 0) bulk_wait_read<0>();  // activation stores have drained stage 0 before it is reused below
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < kDplMax; ++j)
     if (lane + 32 * j < D) cred[warp * D + lane + 32 * j] = acc[j];
   __syncthreads();
-  for (int d = tid; d < D; d += kThreads) {
+  for (int d = tid; d < D; d += NT) {
     float s = 0.0f;
 #pragma unroll
-    for (int w8 = 0; w8 < kWarps; ++w8) s += cred[w8 * D + d];
+    for (int w8 = 0; w8 < NW; ++w8) s += cred[w8 * D + d];
     cpart[d] = s;
   }
   // ---- combine across the cluster through distributed shared memory
@@ -239,9 +314,9 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_fwd_kernel(const AttFwdPar
   }
   const float inv = 1.0f / S;
   const float mine = expf(xch[0] - M) * inv;
-  for (int tl = tid; tl < tloc; tl += kThreads) p.w[(size_t)b * Th + t0 + tl] = p_s[tl] * mine;
+  for (int tl = tid; tl < tloc; tl += NT) p.w[(size_t)b * Th + t0 + tl] = p_s[tl] * mine;
   const int dper = (D + CL - 1) / CL;
-  for (int d = rank * dper + tid; d < min(D, (rank + 1) * dper); d += kThreads) {
+  for (int d = rank * dper + tid; d < min(D, (rank + 1) * dper); d += NT) {
     float s = 0.0f;
     for (int r = 0; r < CL; ++r) {
       const float mr = dsmem_ld(dsmem_addr(xch, r));
@@ -249,6 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_fwd_kernel(const AttFwdPar
     }
     p.c[(size_t)b * D + d] = s * inv;
   }
+  if (tid == 0) bulk_wait<0>();
   cluster_sync_all();  // nobody leaves while a peer may still read its shared memory
 }
 
@@ -256,63 +332,68 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_fwd_kernel(const AttFwdPar
 // backward
 // ------------------------------------------------------------------------------------------------
 template <int APL, int CP>
-__global__ void __launch_bounds__(kThreads, 1) attloc_bwd_kernel(const AttBwdParams p) {
+__global__ void __launch_bounds__(kNWB * 32, 1) attloc_bwd_kernel(const AttBwdParams p) {
+  constexpr int NW = kNWB, NT = NW * 32;
   extern __shared__ __align__(128) unsigned char smraw[];
   const AttGeom g = p.g;
   const int Th = p.Th, D = p.D, A = p.A, C = p.C, K = p.K, filts = (p.K - 1) / 2;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = warp & 1, rw = warp >> 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = warp & 1, pair = warp >> 1;
   const int CL = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
   const int b = blockIdx.x / CL;
   const int t0 = min(Th, rank * g.tloc_max), t1 = min(Th, t0 + g.tloc_max), tloc = t1 - t0;
-  const int nch = (tloc + kChunkRows - 1) / kChunkRows;
-  AttGeom gl = g;
-  gl.nch = nch;
+  const int nch = (tloc + NW - 1) / NW;
   const int total = 2 * nch;
 
   uint64_t *full = reinterpret_cast<uint64_t *>(smraw);
   float *stages = reinterpret_cast<float *>(smraw + 256);
-  float *ap_s = stages + (size_t)g.ns * g.stage_floats;   // Thp
-  float *wc_s = ap_s + g.Thp;                             // CKp
+  float *app = stages + (size_t)g.ns * g.stage_floats;    // App      padded att_prev row
+  float *wc_s = app + g.App;                              // CKp
   float *conv_s = wc_s + g.CKp;                           // tloc_max*CP
   float *w_s = conv_s + g.tloc_max * CP;                  // tloc_max
-  float *dwt_s = w_s + g.tloc_max;                        // tloc_max
-  float *de_s = dwt_s + g.tloc_max;                       // tloc_max
-  float *dcv_p = de_s + g.tloc_max;                       // 2*tloc_max*CP
-  float *dcvT = dcv_p + 2 * g.tloc_max * CP;              // CP*Thp   (filled by every CTA of the cluster)
-  float *dWatt_s = dcvT + CP * g.Thp;                     // A*CP
+  float *dwt_s = w_s + round4(g.tloc_max);                // tloc_max
+  float *de_s = dwt_s + round4(g.tloc_max);               // tloc_max
+  float *dcv_p = de_s + round4(g.tloc_max);               // 2*tloc_max*16   per-half d conv partials
+  float *dcvT = dcv_p + 2 * g.tloc_max * 16;              // CP*App  channel-major, zero padded, cluster-wide
+  float *dWatt_s = dcvT + CP * g.App;                     // A*CP
   float *ddp_s = dWatt_s + A * CP;                        // A
   float *dgv_s = ddp_s + A;                               // A
-  float *xch = dgv_s + A;                                 // 4
+  float *scr = dgv_s + A;                                 // kKQ*C*tloc_max  d att_prev partials
+  float *xch = scr + kKQ * CP * g.tloc_max;               // 4
 
   if (tid == 0) {
     for (int i = 0; i < g.ns; ++i) mbar_init(&full[i], 1);
     mbar_fence_init();
     const int first = total < g.ns ? total : g.ns;
-    for (int q = 0; q < first; ++q) issue_chunk(q, gl, p.enc, D, p.pre, A, b, Th, t0, t1, stages, full);
+    for (int q = 0; q < first; ++q) issue_chunk<NW>(q, nch, g, p.enc, D, p.xsave, A, b, Th, t0, t1, stages, full);
   }
-  for (int i = tid; i < Th; i += kThreads) ap_s[i] = __ldg(p.att_prev + (size_t)b * Th + i);
-  for (int i = tid; i < C * K; i += kThreads) wc_s[i] = __ldg(p.W_conv + i);
-  for (int i = tid; i < tloc * CP; i += kThreads) {
+  for (int i = tid; i < g.App; i += NT) {
+    const int t = i - filts;
+    app[i] = (t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
+  }
+  for (int i = tid; i < C * K; i += NT) wc_s[i] = __ldg(p.W_conv + i);
+  for (int i = tid; i < tloc * CP; i += NT) {
     const int tl = i / CP, c = i - tl * CP;
     conv_s[i] = c < C ? __ldg(p.conv + ((size_t)b * Th + t0 + tl) * C + c) : 0.0f;
   }
-  for (int i = tid; i < tloc; i += kThreads) w_s[i] = __ldg(p.w + (size_t)b * Th + t0 + i);
-  for (int i = tid; i < A * CP; i += kThreads) dWatt_s[i] = 0.0f;
-  for (int i = tid; i < A; i += kThreads) { ddp_s[i] = 0.0f; dgv_s[i] = 0.0f; }
+  for (int i = tid; i < tloc; i += NT) w_s[i] = __ldg(p.w + (size_t)b * Th + t0 + i);
+  for (int i = tid; i < CP * g.App; i += NT) dcvT[i] = 0.0f;
+  for (int i = tid; i < A * CP; i += NT) dWatt_s[i] = 0.0f;
+  for (int i = tid; i < A; i += NT) { ddp_s[i] = 0.0f; dgv_s[i] = 0.0f; }
   float dcr[kDplMax];
 #pragma unroll
   for (int j = 0; j < kDplMax; ++j)
     dcr[j] = (p.dc && lane + 32 * j < D) ? __ldg(p.dc + (size_t)b * D + lane + 32 * j) : 0.0f;
-  __syncthreads();
+  // (peers write into this CTA's dcvT only after the cluster barrier of the softmax reduction below,
+  //  which orders those remote stores after the zero-fill above)
 
   // ---- dwt[t] = dw[t] + enc_h[t,:] . dc      (gradient reaching w[t])
   for (int q = 0; q < nch; ++q) {
     const int st = q % g.ns;
     mbar_wait(&full[st], (uint32_t)((q / g.ns) & 1));
     const float *tile = stages + (size_t)st * g.stage_floats;
-    const int rows = min(kChunkRows, tloc - kChunkRows * q);
+    const int rows = min(NW, tloc - NW * q);
     if (warp < rows) {
-      const int tl = kChunkRows * q + warp;
+      const int tl = NW * q + warp;
       const float *row = tile + warp * D + lane;
       float dot = 0.0f;
 #pragma unroll
@@ -323,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_bwd_kernel(const AttBwdPar
     }
     if (q + g.ns < total) {
       __syncthreads();
-      if (tid == 0) issue_chunk(q + g.ns, gl, p.enc, D, p.pre, A, b, Th, t0, t1, stages, full);
+      if (tid == 0) issue_chunk<NW>(q + g.ns, nch, g, p.enc, D, p.xsave, A, b, Th, t0, t1, stages, full);
     }
   }
   __syncthreads();
@@ -337,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_bwd_kernel(const AttBwdPar
   cluster_sync_all();
   float Stot = 0.0f;
   for (int r = 0; r < CL; ++r) Stot += dsmem_ld(dsmem_addr(xch, r));
-  for (int tl = tid; tl < tloc; tl += kThreads) de_s[tl] = p.scaling * w_s[tl] * (dwt_s[tl] - Stot);
+  for (int tl = tid; tl < tloc; tl += NT) de_s[tl] = p.scaling * w_s[tl] * (dwt_s[tl] - Stot);
   __syncthreads();
   if (warp == 0) {
     float s = 0.0f;
@@ -346,12 +427,11 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_bwd_kernel(const AttBwdPar
     if (lane == 0 && tloc > 0) atomicAdd(p.dgvec_b, s);
   }
 
-  // ---- through tanh: two warps per frame, lane <-> attention channel
-  float Watt[APL][CP], dWatt[APL][CP], dp[APL], gv[APL], dgv[APL], ddp[APL];
+  // ---- through tanh (activations x saved by the forward): two warps per frame, lane <-> channel
+  float Watt[APL][CP], dWatt[APL][CP], gv[APL], dgv[APL], ddp[APL];
 #pragma unroll
   for (int j = 0; j < APL; ++j) {
     const int a = half * (A / 2) + lane + 32 * j;
-    dp[j] = __ldg(p.dec_proj + (size_t)b * A + a);
     gv[j] = __ldg(p.gvec + a);
     dgv[j] = 0.0f;
     ddp[j] = 0.0f;
@@ -366,23 +446,22 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_bwd_kernel(const AttBwdPar
     mbar_wait(&full[st], (uint32_t)((q / g.ns) & 1));
     float *tile = stages + (size_t)st * g.stage_floats;
     const int qq = q - nch;
-    const int rows = min(kChunkRows, tloc - kChunkRows * qq);
+    const int rows = min(NW, tloc - NW * qq);
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
-      const int r = rw + 4 * rr;
+      const int r = pair + (NW / 2) * rr;
       if (r < rows) {
-        const int tl = kChunkRows * qq + r;
+        const int tl = NW * qq + r;
         const float de = de_s[tl];
-        float cv[CP], dcv[CP];
+        float cv[CP], dcv[16];
 #pragma unroll
-        for (int c = 0; c < CP; ++c) { cv[c] = conv_s[tl * CP + c]; dcv[c] = 0.0f; }
+        for (int c = 0; c < CP; ++c) cv[c] = conv_s[tl * CP + c];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) dcv[c] = 0.0f;
         float *row = tile + r * A + half * (A / 2) + lane;
 #pragma unroll
         for (int j = 0; j < APL; ++j) {
-          float u = dp[j] + row[32 * j];
-#pragma unroll
-          for (int c = 0; c < CP; ++c) u = fmaf(Watt[j][c], cv[c], u);
-          const float x = tanh_fast(u);
+          const float x = row[32 * j];
           dgv[j] = fmaf(de, x, dgv[j]);
           const float dt = de * gv[j] * (1.0f - x * x);
           ddp[j] += dt;
@@ -393,11 +472,10 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_bwd_kernel(const AttBwdPar
             dcv[c] = fmaf(dt, Watt[j][c], dcv[c]);
           }
         }
-#pragma unroll
-        for (int c = 0; c < CP; ++c) dcv[c] = warp_sum(dcv[c]);
-        if (lane == 0) {
-#pragma unroll
-          for (int c = 0; c < CP; ++c) dcv_p[(half * g.tloc_max + tl) * CP + c] = dcv[c];
+        warp_reduce16(dcv, lane);
+        if ((lane & 1) == 0) {
+          const int ci = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          dcv_p[(half * g.tloc_max + tl) * 16 + ci] = dcv[0];
         }
       }
     }
@@ -405,19 +483,19 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_bwd_kernel(const AttBwdPar
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
-      float *dst = p.d_pre + ((size_t)b * Th + t0 + kChunkRows * qq) * A;
+      float *dst = p.d_pre + ((size_t)b * Th + t0 + NW * qq) * A;
       const uint32_t bytes = (uint32_t)rows * A * 4u;
       if (p.accumulate_pre) bulk_red_add_s2g(dst, tile, bytes);
       else bulk_s2g(dst, tile, bytes);
       bulk_commit();
       if (q + g.ns < total) {
         bulk_wait_read<0>();  // the store has drained the stage before it is refilled
-        issue_chunk(q + g.ns, gl, p.enc, D, p.pre, A, b, Th, t0, t1, stages, full);
+        issue_chunk<NW>(q + g.ns, nch, g, p.enc, D, p.xsave, A, b, Th, t0, t1, stages, full);
       }
     }
   }
-  // ---- CTA-level reductions of the parameter gradients (shared-memory atomics, then one
-  //      global atomic per element per CTA)
+  // ---- CTA-level reductions of the parameter gradients (shared-memory atomics, then one global
+  //      atomic per element per CTA)
 #pragma unroll
   for (int j = 0; j < APL; ++j) {
     const int a = half * (A / 2) + lane + 32 * j;
@@ -429,60 +507,87 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_bwd_kernel(const AttBwdPar
   }
   __syncthreads();
   if (tloc > 0) {
-    for (int i = tid; i < A * C; i += kThreads) {
+    for (int i = tid; i < A * C; i += NT) {
       const int a = i / C, c = i - a * C;
       atomicAdd(p.dW_att + i, dWatt_s[a * CP + c]);
     }
-    for (int a = tid; a < A; a += kThreads) {
+    for (int a = tid; a < A; a += NT) {
       atomicAdd(p.dgvec + a, dgv_s[a]);
       atomicAdd(p.d_decproj + (size_t)b * A + a, ddp_s[a]);
     }
   }
-  // ---- publish d conv (this CTA's frames) to every CTA of the cluster, channel-major
-  for (int item = tid; item < tloc * C; item += kThreads) {
-    const int tl = item / C, c = item - tl * C;
-    const float v = dcv_p[tl * CP + c] + dcv_p[(g.tloc_max + tl) * CP + c];
-    for (int r = 0; r < CL; ++r) dsmem_st(dsmem_addr(dcvT + c * g.Thp + t0 + tl, r), v);
+  // ---- publish d conv (this CTA's frames) to every CTA of the cluster, channel-major, padded
+  for (int item = tid; item < tloc * C; item += NT) {
+    const int c = item / tloc, tl = item - c * tloc;
+    const float v = dcv_p[tl * 16 + c] + dcv_p[(g.tloc_max + tl) * 16 + c];
+    for (int r = 0; r < CL; ++r) dsmem_st(dsmem_addr(dcvT + c * g.App + filts + t0 + tl, r), v);
   }
   cluster_sync_all();
-  // ---- d att_prev[s] = sum_c sum_k Wc[c,k] * dconv[s - k + filts, c]
+  // ---- d att_prev[s] = sum_c sum_k Wc[c,k] * dconv[s - k + filts, c]   (sliding window, 5 outputs/thread)
   if (p.d_att_prev) {
-    for (int item = tid; item < tloc * C; item += kThreads) {
-      const int tl = item / C, c = item - tl * C;
-      const int s = t0 + tl;
-      const int klo = max(0, s + filts - Th + 1), khi = min(K, s + filts + 1);
+    const int nsg = (tloc + kTG - 1) / kTG;
+    const int Kq = (K + kKQ - 1) / kKQ;
+    const int nitems = nsg * C * kKQ;
+    for (int item = tid; item < nitems; item += NT) {
+      const int sg = item % nsg, rest = item / nsg, c = rest % C, kq = rest / C;
+      const int k0 = kq * Kq, k1 = min(K, k0 + Kq);
       const float *wr = wc_s + c * K;
-      const float *dr = dcvT + c * g.Thp + s + filts;  // index (s + filts - k)
-      float a0 = 0.f, a1 = 0.f;
-      int k = klo;
-      for (; k + 1 < khi; k += 2) {
-        a0 = fmaf(wr[k], dr[-k], a0);
-        a1 = fmaf(wr[k + 1], dr[-k - 1], a1);
+      // padded index of dconv[s - k + filts] is (s - k + 2*filts); outputs s = s0 .. s0+4
+      const float *dr = dcvT + c * g.App + (t0 + kTG * sg) + 2 * filts;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+      float x1 = dr[1 - k0], x2 = dr[2 - k0], x3 = dr[3 - k0], x4 = dr[4 - k0];
+#pragma unroll 5
+      for (int k = k0; k < k1; ++k) {
+        const float x0 = dr[-k], wv = wr[k];
+        a0 = fmaf(wv, x0, a0); a1 = fmaf(wv, x1, a1); a2 = fmaf(wv, x2, a2);
+        a3 = fmaf(wv, x3, a3); a4 = fmaf(wv, x4, a4);
+        x4 = x3; x3 = x2; x2 = x1; x1 = x0;
       }
-      if (k < khi) a0 = fmaf(wr[k], dr[-k], a0);
-      dcv_p[tl * CP + c] = a0 + a1;  // reuse as scratch (this CTA's publish is complete)
+      float *o = scr + ((size_t)(kq * C + c)) * g.tloc_max + kTG * sg;
+      const int nv = min(kTG, tloc - kTG * sg);
+      o[0] = a0;
+      if (nv > 1) o[1] = a1;
+      if (nv > 2) o[2] = a2;
+      if (nv > 3) o[3] = a3;
+      if (nv > 4) o[4] = a4;
     }
     __syncthreads();
-    for (int tl = tid; tl < tloc; tl += kThreads) {
+    for (int tl = tid; tl < tloc; tl += NT) {
       float s = 0.0f;
-      for (int c = 0; c < C; ++c) s += dcv_p[tl * CP + c];
+      for (int i = 0; i < kKQ * C; ++i) s += scr[(size_t)i * g.tloc_max + tl];
       p.d_att_prev[(size_t)b * Th + t0 + tl] = s;
     }
   }
-  // ---- dWc[c,k] += sum_{t in mine} dconv[t,c] * att_prev[t + k - filts]
-  for (int item = tid; item < C * K; item += kThreads) {
-    const int c = item / K, k = item - c * K;
-    const int lo = max(t0, filts - k), hi = min(t1, Th + filts - k);
-    const float *dr = dcvT + c * g.Thp;
-    const float *ar = ap_s + (k - filts);
-    float a0 = 0.f, a1 = 0.f;
-    int t = lo;
-    for (; t + 1 < hi; t += 2) {
-      a0 = fmaf(dr[t], ar[t], a0);
-      a1 = fmaf(dr[t + 1], ar[t + 1], a1);
+  // ---- dWc[c,k] += sum_{t in mine} dconv[t,c] * att_prev[t + k - filts]   (6 taps per thread)
+  {
+    constexpr int KG = 6;
+    const int nkg = (K + KG - 1) / KG;
+    for (int item = tid; item < C * nkg; item += NT) {
+      const int kg = item % nkg, c = item / nkg;
+      const int kb = kg * KG;
+      const float *dr = dcvT + c * g.App + filts;  // dconv[t] at dr[t]
+      const float *ar = app + kb;                  // att_prev[t + k - filts] = app[t + k]
+      float acc6[KG];
+#pragma unroll
+      for (int i = 0; i < KG; ++i) acc6[i] = 0.0f;
+      float x[KG];
+#pragma unroll
+      for (int i = 0; i < KG - 1; ++i) x[i] = ar[t0 + i];
+#pragma unroll 4
+      for (int t = t0; t < t1; ++t) {
+        x[KG - 1] = ar[t + KG - 1];
+        const float dv = dr[t];
+#pragma unroll
+        for (int i = 0; i < KG; ++i) acc6[i] = fmaf(dv, x[i], acc6[i]);
+#pragma unroll
+        for (int i = 0; i < KG - 1; ++i) x[i] = x[i + 1];
+      }
+      if (tloc > 0) {
+#pragma unroll
+        for (int i = 0; i < KG; ++i)
+          if (kb + i < K) atomicAdd(p.dW_conv + c * K + kb + i, acc6[i]);
+      }
     }
-    if (t < hi) a0 = fmaf(dr[t], ar[t], a0);
-    if (hi > lo) atomicAdd(p.dW_conv + item, a0 + a1);
   }
   if (tid == 0) bulk_wait<0>();  // all d_pre traffic of this CTA has left shared memory / landed
 }
@@ -490,30 +595,56 @@ __global__ void __launch_bounds__(kThreads, 1) attloc_bwd_kernel(const AttBwdPar
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
-// out[m,n] (+)= sum_k X[m,k] * W[n,k] (NT) or W[k,n] (NN);  M small (batch), one warp per output
-// column, lane <-> row m.  Used for dec_proj = dec_z W_dec^T and d_dec_z = d_decproj W_dec.
+// out[m,n] (+)= sum_k X[m,k] * W[n,k] (NT) or W[k,n] (NN);  M small (batch).  One warp per output column,
+// lane <-> row m; X and the CTA's slab of W are staged with 128-bit loads issued back to back.
+constexpr int kSkWarps = 16;
 template <bool NN>
-__global__ void __launch_bounds__(128) skinny_gemm_kernel(const float *__restrict__ X,
-                                                          const float *__restrict__ W,
-                                                          float *__restrict__ out, int M, int N, int Kd,
-                                                          int accumulate) {
+__global__ void __launch_bounds__(kSkWarps * 32) skinny_gemm_kernel(const float *__restrict__ X,
+                                                                   const float *__restrict__ W,
+                                                                   float *__restrict__ out, int M, int N, int Kd,
+                                                                   int accumulate, int vec_ok) {
   extern __shared__ __align__(16) float smem[];
+  constexpr int NT = kSkWarps * 32;
   const int Kp = Kd | 1;                   // odd pitch: lane <-> row reads are conflict free
   float *x_s = smem;                       // [M][Kp]
-  float *w_s = smem + (size_t)M * Kp;      // [4][Kd]
+  float *w_s = smem + (size_t)M * Kp;      // [kSkWarps][Kd]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n0 = blockIdx.x * 4;
-  for (int i = tid; i < M * Kd; i += 128) {
-    const int m = i / Kd, k = i - m * Kd;
-    x_s[m * Kp + k] = __ldg(X + i);
+  const int n0 = blockIdx.x * kSkWarps;
+  if (vec_ok) {
+    const int k4n = Kd >> 2;
+    for (int i = tid; i < M * k4n; i += NT) {
+      const int m = i / k4n, k4 = i - m * k4n;
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(X + (size_t)m * Kd) + k4);
+      float *d = x_s + m * Kp + 4 * k4;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+  } else {
+    for (int i = tid; i < M * Kd; i += NT) {
+      const int m = i / Kd, k = i - m * Kd;
+      x_s[m * Kp + k] = __ldg(X + i);
+    }
   }
-  for (int i = tid; i < 4 * Kd; i += 128) {
-    int w4, k;
-    if (NN) { k = i >> 2; w4 = i & 3; } else { w4 = i / Kd; k = i - w4 * Kd; }
-    const int n = n0 + w4;
-    float v = 0.0f;
-    if (n < N) v = NN ? __ldg(W + (size_t)k * N + n) : __ldg(W + (size_t)n * Kd + k);
-    w_s[w4 * Kd + k] = v;
+  if (NN) {
+    for (int i = tid; i < kSkWarps * Kd; i += NT) {
+      const int k = i / kSkWarps, w4 = i - k * kSkWarps;
+      const int n = n0 + w4;
+      w_s[w4 * Kd + k] = n < N ? __ldg(W + (size_t)k * N + n) : 0.0f;
+    }
+  } else if (vec_ok) {
+    const int k4n = Kd >> 2;
+    for (int i = tid; i < kSkWarps * k4n; i += NT) {
+      const int w4 = i / k4n, k4 = i - w4 * k4n;
+      const int n = n0 + w4;
+      float4 v = make_float4(0, 0, 0, 0);
+      if (n < N) v = __ldg(reinterpret_cast<const float4 *>(W + (size_t)n * Kd) + k4);
+      *reinterpret_cast<float4 *>(w_s + w4 * Kd + 4 * k4) = v;
+    }
+  } else {
+    for (int i = tid; i < kSkWarps * Kd; i += NT) {
+      const int w4 = i / Kd, k = i - w4 * Kd;
+      const int n = n0 + w4;
+      w_s[w4 * Kd + k] = n < N ? __ldg(W + (size_t)n * Kd + k) : 0.0f;
+    }
   }
   __syncthreads();
   const int n = n0 + warp;
@@ -544,32 +675,46 @@ __global__ void init_att_kernel(const int32_t *__restrict__ hlens, float *__rest
   att[i] = (t < l) ? 1.0f / (float)l : 0.0f;
 }
 
-// d_enc_h[b,t,:] (+)= sum_i w_all[i,b,t] * dc_all[i,b,:]
-__global__ void __launch_bounds__(kThreads)
+// d_enc_h[b,t,:] (+)= sum_i w_all[i,b,t] * dc_all[i,b,:]   -- 8 frames x (lane <-> d) per warp, steps in smem
+__global__ void __launch_bounds__(256)
 enc_grad_kernel(const float *__restrict__ w_all, const float *__restrict__ dc_all,
                 float *__restrict__ d_enc, int steps, int B, int Th, int D, int tt, int accumulate) {
   extern __shared__ __align__(16) float smem[];
-  float *dc_s = smem;                    // [steps][D]
+  float *dc_s = smem;                     // [steps][D]
   float *w_s = smem + (size_t)steps * D;  // [steps][tt]
   const int tiles = (Th + tt - 1) / tt;
   const int b = blockIdx.x / tiles, t0 = (blockIdx.x - b * tiles) * tt;
   const int rows = min(tt, Th - t0);
   const int tid = threadIdx.x;
-  for (int i = tid; i < steps * D; i += kThreads) {
+  for (int i = tid; i < steps * D; i += 256) {
     const int s = i / D, d = i - s * D;
     dc_s[i] = __ldg(dc_all + ((size_t)s * B + b) * D + d);
   }
-  for (int i = tid; i < steps * tt; i += kThreads) {
+  for (int i = tid; i < steps * tt; i += 256) {
     const int s = i / tt, r = i - s * tt;
     w_s[i] = r < rows ? __ldg(w_all + ((size_t)s * B + b) * Th + t0 + r) : 0.0f;
   }
   __syncthreads();
-  for (int d = tid; d < D; d += kThreads) {
-    for (int r = 0; r < rows; ++r) {
-      float a = 0.0f;
-      for (int s = 0; s < steps; ++s) a = fmaf(w_s[s * tt + r], dc_s[s * D + d], a);
-      float *o = d_enc + ((size_t)b * Th + t0 + r) * D + d;
-      *o = accumulate ? *o + a : a;
+  // thread <-> (d, group of 8 frames): w broadcast from smem, dc conflict free
+  const int ngr = (tt + 7) / 8;
+  for (int item = tid; item < D * ngr; item += 256) {
+    const int d = item % D, gr = item / D;
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 0.0f;
+    for (int s = 0; s < steps; ++s) {
+      const float dv = dc_s[s * D + d];
+      const float *wr = w_s + s * tt + gr * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fmaf(wr[i], dv, a[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = gr * 8 + i;
+      if (r < rows) {
+        float *o = d_enc + ((size_t)b * Th + t0 + r) * D + d;
+        *o = accumulate ? *o + a[i] : a[i];
+      }
     }
   }
 }
@@ -577,24 +722,28 @@ enc_grad_kernel(const float *__restrict__ w_all, const float *__restrict__ dc_al
 inline bool pick_geom(int B, int Th, int D, int A, int C, int K, int CP, bool bwd, int &CL, AttGeom &g,
                       size_t &smem) {
   // cluster size: enough CTAs to cover the SMs once, at most 8 (portable limit)
+  const int NW = bwd ? kNWB : kNWF;
   const int sms = num_sms();
   CL = 1;
   while (CL < 8 && B * CL * 2 <= sms) CL *= 2;
-  while (CL > 1 && (Th + CL - 1) / CL < kChunkRows) CL /= 2;  // tiny Th: do not over-split
-  for (;; ) {
+  while (CL > 1 && (Th + CL - 1) / CL < NW) CL /= 2;  // tiny Th: do not over-split
+  const int filts = (K - 1) / 2;
+  for (;;) {
     g.tloc_max = (Th + CL - 1) / CL;
-    g.nch = (g.tloc_max + kChunkRows - 1) / kChunkRows;
-    g.stage_floats = kChunkRows * (A > D ? A : D);
+    g.nch = (g.tloc_max + NW - 1) / NW;
+    g.stage_floats = NW * (A > D ? A : D);
     g.Thp = round4(Th);
     g.CKp = round4(C * K);
+    g.App = round4(Th + 2 * filts + 8);
     size_t fixed = 256;
     if (!bwd)
-      fixed += sizeof(float) * ((size_t)g.Thp + g.CKp + (size_t)g.tloc_max * (CP + 3) + (size_t)kWarps * D +
-                                round4(D) + 4);
+      fixed += sizeof(float) * ((size_t)g.App + g.CKp + (size_t)(kKQ + 1) * g.tloc_max * CP +
+                                (size_t)g.tloc_max * 65 + round4(g.tloc_max) + round4(D) + 4);
     else
-      fixed += sizeof(float) * ((size_t)g.Thp + g.CKp + (size_t)g.tloc_max * (CP + 3) +
-                                2 * (size_t)g.tloc_max * CP + (size_t)CP * g.Thp + (size_t)A * CP + 2 * A + 4);
-    const size_t budget = 220 * 1024;
+      fixed += sizeof(float) * ((size_t)g.App + g.CKp + (size_t)g.tloc_max * CP + 3 * (size_t)round4(g.tloc_max) +
+                                2 * (size_t)g.tloc_max * 16 + (size_t)CP * g.App + (size_t)A * CP + 2 * A +
+                                (size_t)kKQ * CP * g.tloc_max + 4);
+    const size_t budget = 224 * 1024;
     const size_t stage_bytes = sizeof(float) * (size_t)g.stage_floats;
     if (fixed + 2 * stage_bytes <= budget) {
       int ns = (int)((budget - fixed) / stage_bytes);
@@ -611,13 +760,13 @@ inline bool pick_geom(int B, int Th, int D, int A, int C, int K, int CP, bool bw
 }
 
 template <typename Kern, typename Params>
-int launch_cluster(Kern kern, const Params &prm, int B, int CL, size_t smem, cudaStream_t st) {
+int launch_cluster(Kern kern, const Params &prm, int B, int CL, int threads, size_t smem, cudaStream_t st) {
   int rc0 = ensure_smem(reinterpret_cast<const void *>(kern), smem);
   if (rc0 != RE2E_OK) return rc0;
   cudaError_t e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(B * CL));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3((unsigned)threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -644,11 +793,11 @@ int launch_cluster(Kern kern, const Params &prm, int B, int CL, size_t smem, cud
 
 template <int APL, int CP>
 int run_fwd(const AttFwdParams &prm, int CL, size_t smem, cudaStream_t st) {
-  return launch_cluster(attloc_fwd_kernel<APL, CP>, prm, prm.B, CL, smem, st);
+  return launch_cluster(attloc_fwd_kernel<APL, CP>, prm, prm.B, CL, kNWF * 32, smem, st);
 }
 template <int APL, int CP>
 int run_bwd(const AttBwdParams &prm, int CL, size_t smem, cudaStream_t st) {
-  return launch_cluster(attloc_bwd_kernel<APL, CP>, prm, prm.B, CL, smem, st);
+  return launch_cluster(attloc_bwd_kernel<APL, CP>, prm, prm.B, CL, kNWB * 32, smem, st);
 }
 
 inline int check_dims(int B, int Th, int D, int A, int C, int K) {
@@ -662,15 +811,17 @@ inline int check_dims(int B, int Th, int D, int A, int C, int K) {
 
 int skinny(bool nn, const float *X, const float *W, float *out, int M, int N, int Kd, int accumulate,
            cudaStream_t st) {
-  const size_t smem = sizeof(float) * ((size_t)M * (Kd | 1) + 4 * (size_t)Kd);
+  const size_t smem = sizeof(float) * ((size_t)M * (Kd | 1) + (size_t)kSkWarps * Kd);
   if (smem > 200 * 1024) return RE2E_E_UNSUPPORTED;
+  const int vec_ok = ((Kd & 3) == 0) && aligned16(X) && aligned16(W);
   int rc0;
+  const int grid = (N + kSkWarps - 1) / kSkWarps;
   if (nn) {
     if ((rc0 = ensure_smem(reinterpret_cast<const void *>(skinny_gemm_kernel<true>), smem)) != RE2E_OK) return rc0;
-    skinny_gemm_kernel<true><<<(N + 3) / 4, 128, smem, st>>>(X, W, out, M, N, Kd, accumulate);
+    skinny_gemm_kernel<true><<<grid, kSkWarps * 32, smem, st>>>(X, W, out, M, N, Kd, accumulate, vec_ok);
   } else {
     if ((rc0 = ensure_smem(reinterpret_cast<const void *>(skinny_gemm_kernel<false>), smem)) != RE2E_OK) return rc0;
-    skinny_gemm_kernel<false><<<(N + 3) / 4, 128, smem, st>>>(X, W, out, M, N, Kd, accumulate);
+    skinny_gemm_kernel<false><<<grid, kSkWarps * 32, smem, st>>>(X, W, out, M, N, Kd, accumulate, vec_ok);
   }
   count_launch();
   return launch_status();
@@ -691,12 +842,13 @@ extern "C" int re2e_attloc_init_att(const int32_t *hlens, float *att_prev, int B
 extern "C" int re2e_attloc_step_fwd(const float *pre, const float *enc_h, const float *dec_z,
                                     const float *att_prev, const float *W_dec, const float *W_att,
                                     const float *W_conv, const float *gvec, const float *gvec_b,
-                                    float scaling, float *c, float *w, float *dec_proj, float *conv, int B,
-                                    int Th, int D, int A, int Z, int C, int K, void *stream) {
+                                    float scaling, float *c, float *w, float *dec_proj, float *conv,
+                                    float *xsave, int B, int Th, int D, int A, int Z, int C, int K,
+                                    void *stream) {
   RE2E_CHECK_ARG(pre && enc_h && att_prev && W_dec && W_att && W_conv && gvec && gvec_b && c && w && dec_proj);
   int rc = check_dims(B, Th, D, A, C, K);
   if (rc != RE2E_OK) return rc;
-  RE2E_CHECK_ARG(Z > 0 && aligned16(pre) && aligned16(enc_h));
+  RE2E_CHECK_ARG(Z > 0 && aligned16(pre) && aligned16(enc_h) && (!xsave || aligned16(xsave)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dec_z) {
     rc = skinny(false, dec_z, W_dec, dec_proj, B, A, Z, 0, st);
@@ -708,7 +860,7 @@ extern "C" int re2e_attloc_step_fwd(const float *pre, const float *enc_h, const 
   AttFwdParams prm;
   prm.pre = pre; prm.enc = enc_h; prm.att_prev = att_prev; prm.dec_proj = dec_proj; prm.W_att = W_att;
   prm.W_conv = W_conv; prm.gvec = gvec; prm.gvec_b = gvec_b; prm.scaling = scaling; prm.c = c; prm.w = w;
-  prm.conv = conv; prm.B = B; prm.Th = Th; prm.D = D; prm.A = A; prm.C = C; prm.K = K;
+  prm.conv = conv; prm.xsave = xsave; prm.B = B; prm.Th = Th; prm.D = D; prm.A = A; prm.C = C; prm.K = K;
   int CL;
   size_t smem;
   if (!pick_geom(B, Th, D, A, C, K, CP, false, CL, prm.g, smem)) return RE2E_E_UNSUPPORTED;
@@ -716,24 +868,23 @@ extern "C" int re2e_attloc_step_fwd(const float *pre, const float *enc_h, const 
   return rc;
 }
 
-extern "C" int re2e_attloc_step_bwd(const float *dc, const float *dw, const float *pre, const float *enc_h,
-                                    const float *att_prev, const float *w, const float *dec_proj,
-                                    const float *conv, const float *W_att, const float *W_conv,
-                                    const float *gvec, float scaling, float *d_pre, int accumulate_pre,
-                                    float *d_decproj, float *d_att_prev, float *dW_att, float *dW_conv,
-                                    float *dgvec, float *dgvec_b, int B, int Th, int D, int A, int C, int K,
-                                    void *stream) {
-  RE2E_CHECK_ARG(pre && enc_h && att_prev && w && dec_proj && conv && W_att && W_conv && gvec);
+extern "C" int re2e_attloc_step_bwd(const float *dc, const float *dw, const float *xsave, const float *enc_h,
+                                    const float *att_prev, const float *w, const float *conv,
+                                    const float *W_att, const float *W_conv, const float *gvec, float scaling,
+                                    float *d_pre, int accumulate_pre, float *d_decproj, float *d_att_prev,
+                                    float *dW_att, float *dW_conv, float *dgvec, float *dgvec_b, int B, int Th,
+                                    int D, int A, int C, int K, void *stream) {
+  RE2E_CHECK_ARG(xsave && enc_h && att_prev && w && conv && W_att && W_conv && gvec);
   RE2E_CHECK_ARG(d_pre && d_decproj && dW_att && dW_conv && dgvec && dgvec_b);
   int rc = check_dims(B, Th, D, A, C, K);
   if (rc != RE2E_OK) return rc;
-  RE2E_CHECK_ARG(aligned16(pre) && aligned16(enc_h) && aligned16(d_pre));
+  RE2E_CHECK_ARG(aligned16(xsave) && aligned16(enc_h) && aligned16(d_pre));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   RE2E_CUDA(cudaMemsetAsync(d_decproj, 0, sizeof(float) * (size_t)B * A, st));
   const int CP = C == 10 ? 10 : 16;
   AttBwdParams prm;
-  prm.dc = dc; prm.dw = dw; prm.pre = pre; prm.enc = enc_h; prm.att_prev = att_prev; prm.w = w;
-  prm.dec_proj = dec_proj; prm.conv = conv; prm.W_att = W_att; prm.W_conv = W_conv; prm.gvec = gvec;
+  prm.dc = dc; prm.dw = dw; prm.xsave = xsave; prm.enc = enc_h; prm.att_prev = att_prev; prm.w = w;
+  prm.conv = conv; prm.W_att = W_att; prm.W_conv = W_conv; prm.gvec = gvec;
   prm.scaling = scaling; prm.d_pre = d_pre; prm.d_decproj = d_decproj; prm.d_att_prev = d_att_prev;
   prm.dW_att = dW_att; prm.dW_conv = dW_conv; prm.dgvec = dgvec; prm.dgvec_b = dgvec_b;
   prm.accumulate_pre = accumulate_pre;
@@ -756,8 +907,8 @@ extern "C" int re2e_attloc_enc_grad(const float *w_all, const float *dc_all, flo
     if (rc0 != RE2E_OK) return rc0;
   }
   const int tiles = (Th + tt - 1) / tt;
-  enc_grad_kernel<<<B * tiles, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(w_all, dc_all, d_enc_h,
-                                                                                   steps, B, Th, D, tt, accumulate);
+  enc_grad_kernel<<<B * tiles, 256, smem, static_cast<cudaStream_t>(stream)>>>(w_all, dc_all, d_enc_h, steps, B,
+                                                                              Th, D, tt, accumulate);
   count_launch();
   return launch_status();
 }

@@ -30,6 +30,7 @@ struct CtcWs {
   float *lpmax;    // (B,Th)  max_s lp[b,t,s]: per-frame normaliser of the lattice column
   double *offA;    // (B,Th)
   double *offB;    // (B,Th)
+  double *nll_d;   // (B) negative log-likelihood in fp64 (float nll loses 1e-4 at |nll| ~ 1e3)
   float *lpc;      // (B,Th,Smax)
   float *alpha;    // (B,Th,Smax)
   float *beta;     // (B,Th,Smax)
@@ -45,6 +46,7 @@ inline CtcWs carve(void *ws, int B, int Th, int Smax) {
   w.counter = reinterpret_cast<unsigned int *>(p + off); off += 256;
   w.offA = reinterpret_cast<double *>(p + off); off += align_up(sizeof(double) * (size_t)B * Th, 256);
   w.offB = reinterpret_cast<double *>(p + off); off += align_up(sizeof(double) * (size_t)B * Th, 256);
+  w.nll_d = reinterpret_cast<double *>(p + off); off += align_up(sizeof(double) * (size_t)B, 256);
   w.lse = reinterpret_cast<float *>(p + off); off += align_up(sizeof(float) * (size_t)B * Th, 256);
   w.lpmax = reinterpret_cast<float *>(p + off); off += align_up(sizeof(float) * (size_t)B * Th, 256);
   size_t lat = align_up(sizeof(float) * (size_t)B * Th * Smax, 256);
@@ -144,8 +146,8 @@ ctc_ab_kernel(const float *__restrict__ lpc, const float *__restrict__ lpmax,
               const int32_t *__restrict__ label_offs, const int32_t *__restrict__ label_lens,
               const int32_t *__restrict__ input_lens, int blank, float *__restrict__ alpha,
               float *__restrict__ beta, double *__restrict__ offA, double *__restrict__ offB,
-              float *__restrict__ nll, float *__restrict__ loss, unsigned int *counter, int B, int Th,
-              int Smax, int Sp) {
+              float *__restrict__ nll, double *__restrict__ nll_d, float *__restrict__ loss,
+              unsigned int *counter, int B, int Th, int Smax, int Sp) {
   extern __shared__ __align__(16) float smem[];
   const int b = blockIdx.x;
   const int half = threadIdx.x / Sp;     // warp-uniform (Sp % 32 == 0)
@@ -227,22 +229,23 @@ ctc_ab_kernel(const float *__restrict__ lpc, const float *__restrict__ lpmax,
     }
   }
   if (half == 0 && s == 0) {
-    float r;
-    if (T == 0) r = (U == 0) ? 0.0f : CUDART_INF_F;
+    double r;
+    if (T == 0) r = (U == 0) ? 0.0 : (double)CUDART_INF_F;
     else {
       const float *c = col + cur * pitch + 2;
       float a = c[S - 1], bb = S > 1 ? c[S - 2] : NEG;
       float m = fmaxf(a, bb);
-      if (m == NEG) r = CUDART_INF_F;
-      else r = (float)(-((double)m + (double)logf(expf(a - m) + expf(bb - m)) + off));
+      if (m == NEG) r = (double)CUDART_INF_F;
+      else r = -((double)m + (double)logf(expf(a - m) + expf(bb - m)) + off);
     }
-    nll[b] = r;
+    nll[b] = (float)r;
+    nll_d[b] = r;
     __threadfence();
     unsigned int done = atomicAdd(counter, 1u);
     if (done == (unsigned)B - 1) {      // last utterance to finish: deterministic ordered sum
       __threadfence();
       double acc = 0.0;
-      for (int k = 0; k < B; ++k) acc += (double)(*(volatile float *)(nll + k));
+      for (int k = 0; k < B; ++k) acc += *(volatile double *)(nll_d + k);
       loss[0] = (float)(acc / (double)B);
       *counter = 0u;
     }
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 ctc_grad_kernel(const float *__restrict__ logits, long long stride_b, long long stride_t,
                 const int32_t *__restrict__ labels, const int32_t *__restrict__ label_offs,
                 const int32_t *__restrict__ label_lens, const int32_t *__restrict__ input_lens, int blank,
-                const float *__restrict__ nll, const float *__restrict__ grad_out,
+                const double *__restrict__ nll_d, const float *__restrict__ grad_out,
                 const float *__restrict__ lse, const float *__restrict__ lpc,
                 const float *__restrict__ alpha, const float *__restrict__ beta,
                 const double *__restrict__ offA, const double *__restrict__ offB, float *__restrict__ grad,
@@ -297,12 +300,12 @@ ctc_grad_kernel(const float *__restrict__ logits, long long stride_b, long long 
   }
   for (int i = head + 4 * nvec + lane; i < V; i += 32) g[i] = valid ? gs * __expf(ld_stream1(x + i) - l) : 0.f;
   if (!valid) return;
-  const float nl = __ldg(nll + b);
+  const double nl = nll_d[b];
   if (!isfinite(nl)) return;  // infeasible labelling: leave softmax only
   __syncwarp();               // row stores above are ordered before the corrections below
   const int U = __ldg(label_lens + b), S = 2 * U + 1;
   const int32_t *lab = labels + __ldg(label_offs + b);
-  const double base = offA[row] + offB[row] + (double)nl;
+  const double base = offA[row] + offB[row] + nl;
   const size_t lo = (size_t)row * Smax;
   for (int i = lane; i < S; i += 32) {
     float a = alpha[lo + i], bt = beta[lo + i];
@@ -420,7 +423,7 @@ extern "C" int re2e_ctc_loss_fwd(const float *logits, long long stride_b, long l
   if (rc != RE2E_OK) return rc;
   const size_t smem = sizeof(float) * (4 * (size_t)(Sp + 4) + 64);
   ctc_ab_kernel<<<B, 2 * Sp, smem, st>>>(w.lpc, w.lpmax, labels, label_offs, label_lens, input_lens, blank, w.alpha,
-                                         w.beta, w.offA, w.offB, nll, loss, w.counter, B, Th, Smax, Sp);
+                                         w.beta, w.offA, w.offB, nll, w.nll_d, loss, w.counter, B, Th, Smax, Sp);
   count_launch();
   return launch_status();
 }
@@ -439,7 +442,7 @@ extern "C" int re2e_ctc_loss_bwd(const float *logits, long long stride_b, long l
   const int grid = (int)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
   const int vec_ok = ((reinterpret_cast<uintptr_t>(logits) ^ reinterpret_cast<uintptr_t>(grad)) & 15u) == 0;
   ctc_grad_kernel<<<grid, kWarpsPerCta * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, stride_b, stride_t, labels, label_offs, label_lens, input_lens, blank, nll, grad_out, w.lse,
+      logits, stride_b, stride_t, labels, label_offs, label_lens, input_lens, blank, w.nll_d, grad_out, w.lse,
       w.lpc, w.alpha, w.beta, w.offA, w.offB, grad, B, Th, V, Smax, vec_ok);
   count_launch();
   return launch_status();

@@ -22,6 +22,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
+from .linear import gemm_tf32x3
 
 
 class _State(object):
@@ -61,7 +62,9 @@ class _Precompute(torch.autograd.Function):
         B, Th, D = enc.shape
         A, Z, C, K = W_enc.shape[0], W_dec.shape[1], W_att.shape[1], W_conv.shape[-1]
         # e2e_attention.py:252-256 linear_tensor(mlp_enc, enc_h): a plain dense layer
-        pre = torch.addmm(b_enc.detach(), enc.view(B * Th, D), W_enc.detach().t()).view(B, Th, A)
+        pre = torch.empty(B, Th, A, device=dev, dtype=torch.float32)
+        gemm_tf32x3(enc.view(B * Th, D), False, _lib.f32c(W_enc.detach()), False, pre.view(B * Th, A), B * Th, A, D,
+                    bias=_lib.f32c(b_enc.detach()))
         state.enc, state.pre = enc, pre
         state.dims = (B, Th, D, A, Z, C, K)
         state.weights = (_lib.f32c(W_dec.detach()), _lib.f32c(W_att.detach()),
@@ -88,10 +91,13 @@ class _Precompute(torch.autograd.Function):
         d_enc = dW_enc = db_enc = dW_dec = dW_att = dW_conv = dgw = dgb = None
         if d_pre is not None:
             dp2 = d_pre.view(B * Th, A)
+            We = _lib.f32c(W_enc.detach())
             if need[0]:
-                d_enc = torch.mm(dp2, W_enc.detach()).view(B, Th, D)
+                d_enc = torch.empty(B, Th, D, device=dev, dtype=torch.float32)
+                gemm_tf32x3(dp2, False, We, True, d_enc.view(B * Th, D), B * Th, D, A)      # d_pre @ W_enc
             if need[1]:
-                dW_enc = torch.mm(dp2.t(), st.enc.view(B * Th, D))
+                dW_enc = torch.empty(A, D, device=dev, dtype=torch.float32)
+                gemm_tf32x3(dp2, True, st.enc.view(B * Th, D), True, dW_enc, A, D, B * Th)  # d_pre^T @ enc
             if need[2]:
                 db_enc = dp2.sum(0)
         if need[0] and st.bwd_w:
@@ -106,7 +112,8 @@ class _Precompute(torch.autograd.Function):
         if need[3] and st.bwd_ddp:
             ddp_all = torch.cat(st.bwd_ddp, 0)
             dz_all = torch.cat(st.bwd_decz, 0)
-            dW_dec = torch.mm(ddp_all.t(), dz_all)
+            dW_dec = torch.empty(A, Z, device=dev, dtype=torch.float32)
+            gemm_tf32x3(ddp_all, True, dz_all, True, dW_dec, A, Z, ddp_all.shape[0])
         elif need[3]:
             dW_dec = torch.zeros(A, Z, device=dev, dtype=torch.float32)
         if st.acc is not None:
@@ -133,18 +140,19 @@ class _Step(torch.autograd.Function):
         dec_proj = torch.empty(B, A, device=dev, dtype=torch.float32)
         need_bwd = any(ctx.needs_input_grad[:3])
         conv = torch.empty(B, Th, C, device=dev, dtype=torch.float32) if need_bwd else None
+        xsave = torch.empty(B, Th, A, device=dev, dtype=torch.float32) if need_bwd else None
         with torch.cuda.device(dev):
             _lib.check(L.re2e_attloc_step_fwd(_lib.ptr(st.pre), _lib.ptr(st.enc), _lib.ptr(dz), _lib.ptr(ap),
                                               _lib.ptr(W_dec), _lib.ptr(W_att), _lib.ptr(W_conv), _lib.ptr(gvec),
                                               _lib.ptr(gvec_b), float(scaling), _lib.ptr(c), _lib.ptr(w),
-                                              _lib.ptr(dec_proj), _lib.ptr(conv), B, Th, D, A, Z, C, K,
+                                              _lib.ptr(dec_proj), _lib.ptr(conv), _lib.ptr(xsave), B, Th, D, A, Z, C, K,
                                               _lib.stream_ptr()), "re2e_attloc_step_fwd")
         if need_bwd:
             ctx.state = st
             ctx.scaling = float(scaling)
             ctx.has_dz = dz is not None
             ctx.skip_dprev = bool(att_prev_is_init)
-            ctx.save_for_backward(ap, w, dec_proj, conv, dz if dz is not None else ap)
+            ctx.save_for_backward(ap, w, xsave, conv, dz if dz is not None else ap)
             ctx.set_materialize_grads(False)
         return c, w
 
@@ -152,7 +160,7 @@ class _Step(torch.autograd.Function):
     def backward(ctx, dc, dw):
         L = _lib.lib()
         st = ctx.state
-        ap, w, dec_proj, conv, dz = ctx.saved_tensors
+        ap, w, xsave, conv, dz = ctx.saved_tensors
         B, Th, D, A, Z, C, K = st.dims
         dev = st.enc.device
         W_dec, W_att, W_conv, gvec, gvec_b = st.weights
@@ -170,8 +178,8 @@ class _Step(torch.autograd.Function):
         acc = st.acc
         with torch.cuda.device(dev):
             _lib.check(L.re2e_attloc_step_bwd(
-                _lib.ptr(dc), _lib.ptr(dw), _lib.ptr(st.pre), _lib.ptr(st.enc), _lib.ptr(ap), _lib.ptr(w),
-                _lib.ptr(dec_proj), _lib.ptr(conv), _lib.ptr(W_att), _lib.ptr(W_conv), _lib.ptr(gvec),
+                _lib.ptr(dc), _lib.ptr(dw), _lib.ptr(xsave), _lib.ptr(st.enc), _lib.ptr(ap), _lib.ptr(w),
+                _lib.ptr(conv), _lib.ptr(W_att), _lib.ptr(W_conv), _lib.ptr(gvec),
                 ctx.scaling, _lib.ptr(st.d_pre), 0 if first else 1, _lib.ptr(d_decproj), _lib.ptr(d_prev),
                 _lib.ptr(acc["dW_att"]), _lib.ptr(acc["dW_conv"]), _lib.ptr(acc["dgvec"]),
                 _lib.ptr(acc["dgvec_b"]), B, Th, D, A, C, K, _lib.stream_ptr()), "re2e_attloc_step_bwd")

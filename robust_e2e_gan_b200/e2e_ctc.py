@@ -12,6 +12,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
+from .linear import linear as _linear_tc
 
 
 class PreparedTargets(object):
@@ -49,15 +50,16 @@ class _CTCLossFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, hlens_dev, tgt, blank):
         L = _lib.lib()
-        x = _lib.f32c(logits)
+        x = logits if _strided_ok(logits) else _lib.f32c(logits)
         B, Th, V = x.shape
         dev = x.device
+        sb, st = x.stride(0), x.stride(1)
         nbytes = int(L.re2e_ctc_ws_bytes(B, Th, V, tgt.umax))
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
         nll = torch.empty(B, device=dev, dtype=torch.float32)
         loss = torch.empty(1, device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
-            _lib.check(L.re2e_ctc_loss_fwd(_lib.ptr(x), Th * V, V, _lib.ptr(tgt.labels), _lib.ptr(tgt.offs),
+            _lib.check(L.re2e_ctc_loss_fwd(_lib.ptr(x), sb, st, _lib.ptr(tgt.labels), _lib.ptr(tgt.offs),
                                            _lib.ptr(tgt.lens), _lib.ptr(hlens_dev), int(blank), _lib.ptr(nll),
                                            _lib.ptr(loss), _lib.ptr(ws), nbytes, B, Th, V, tgt.umax,
                                            _lib.stream_ptr()), "re2e_ctc_loss_fwd")
@@ -72,14 +74,22 @@ class _CTCLossFunction(torch.autograd.Function):
         x, hlens_dev, labels, offs, lens, nll, ws = ctx.saved_tensors
         blank, umax = ctx.meta
         B, Th, V = x.shape
-        grad = torch.empty_like(x)
+        sb, st = x.stride(0), x.stride(1)
+        # same (possibly row-padded) layout as the logits: the tcgen05 backward GEMMs read it through TMA
+        grad = torch.empty_strided((B, Th, V), x.stride(), device=x.device, dtype=torch.float32)
         g = _lib.f32c(g.reshape(-1)[:1], x.device)
         with torch.cuda.device(x.device):
-            _lib.check(L.re2e_ctc_loss_bwd(_lib.ptr(x), Th * V, V, _lib.ptr(labels), _lib.ptr(offs),
+            _lib.check(L.re2e_ctc_loss_bwd(_lib.ptr(x), sb, st, _lib.ptr(labels), _lib.ptr(offs),
                                            _lib.ptr(lens), _lib.ptr(hlens_dev), blank, _lib.ptr(nll), _lib.ptr(g),
                                            _lib.ptr(ws), ws.numel(), _lib.ptr(grad), B, Th, V, umax,
                                            _lib.stream_ptr()), "re2e_ctc_loss_bwd")
         return grad, None, None, None
+
+
+def _strided_ok(t):
+    """fp32 CUDA (B,Th,V) with unit inner stride and non-overlapping rows (a row-padded GEMM output)."""
+    return (t.dtype == torch.float32 and t.is_cuda and t.dim() == 3 and t.stride(2) == 1
+            and t.stride(1) >= t.shape[2] and t.stride(0) >= t.stride(1) * t.shape[1])
 
 
 def ctc_loss(logits, hlens, targets, blank=0):
@@ -129,7 +139,7 @@ class CTC(torch.nn.Module):
         if hs_pad.device != dev:
             hs_pad = hs_pad.to(dev)
         # model/e2e_ctc.py:51 -- functional dropout, active regardless of .training (quirk 6)
-        ys_hat = self.ctc_lo(F.dropout(hs_pad, p=self.dropout_rate))
+        ys_hat = _linear_tc(F.dropout(hs_pad, p=self.dropout_rate), self.ctc_lo.weight, self.ctc_lo.bias)
         tgt = ys_pad if isinstance(ys_pad, PreparedTargets) else prepare_targets(ys_pad, dev, self.ignore_id)
         self.loss, self.nll = ctc_loss(ys_hat, hlens, tgt, blank=0)
         return self.loss
@@ -138,13 +148,14 @@ class CTC(torch.nn.Module):
         """model/e2e_ctc.py:68-75 (decode-time only; returned tensor carries no graph)."""
         dev = self.ctc_lo.weight.device
         with torch.no_grad():
-            return log_softmax_rows(self.ctc_lo(hs_pad.to(dev)))
+            return log_softmax_rows(_linear_tc(hs_pad.to(dev), self.ctc_lo.weight, self.ctc_lo.bias))
 
     def best_path(self, hs_pad):
         """argmax_v log_softmax(ctc_lo(h))[b,t,:] -- the 'CTC alignment' of the north star."""
         dev = self.ctc_lo.weight.device
         with torch.no_grad():
-            return log_softmax_rows(self.ctc_lo(hs_pad.to(dev)), want_best=True)[1]
+            return log_softmax_rows(_linear_tc(hs_pad.to(dev), self.ctc_lo.weight, self.ctc_lo.bias),
+                                    want_best=True)[1]
 
 
 def ctc_prefix_score_batch(lpz, r_prev, cs, last, out_len, blank, eos):

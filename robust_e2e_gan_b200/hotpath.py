@@ -96,7 +96,8 @@ class HotPath(torch.nn.Module):
         steps = self.cfg["steps"]
         mask_logits = b.mask_logits.detach().requires_grad_(backward)
         hpad = b.hpad.detach().requires_grad_(backward)
-        dec_z = b.dec_z.detach().requires_grad_(backward)
+        # one leaf per decoder step (as the LSTMCell outputs are separate tensors in Decoder.forward)
+        dec_zs = [b.dec_z[i].detach().requires_grad_(backward) for i in range(steps - 1)]
         # -- front-end (joint_train.py:158-161)
         enhance_feat = self.feat.forward_masked(mask_logits, b.mix, b.lens, b.cmvn)
         with torch.no_grad():
@@ -110,7 +111,7 @@ class HotPath(torch.nn.Module):
         cs = []
         hl = hlens_for_att if hlens_for_att is not None else b.hlens_list
         for i in range(steps):
-            z = None if i == 0 else dec_z[i - 1]
+            z = None if i == 0 else dec_zs[i - 1]
             att_c, att_w = self.att(hpad, hl, z, att_w)
             cs.append(att_c)
         out = {"enhance_feat": enhance_feat, "clean_feat": clean_feat, "mix_feat": mix_feat, "loss_ctc": loss_ctc,
@@ -119,7 +120,7 @@ class HotPath(torch.nn.Module):
             outs = [enhance_feat, loss_ctc, att_w] + cs
             grads = [b.g_feat, torch.full_like(loss_ctc, self.mtlalpha), b.g_w] + [b.g_c[i] for i in range(steps)]
             torch.autograd.backward(outs, grads)
-            out.update(d_mask_logits=mask_logits.grad, d_hpad=hpad.grad, d_dec_z=dec_z.grad)
+            out.update(d_mask_logits=mask_logits.grad, d_hpad=hpad.grad, d_dec_z=[z.grad for z in dec_zs])
             for k, p in self.named_parameters():
                 if p.requires_grad and p.grad is not None:
                     out["d_" + k] = p.grad

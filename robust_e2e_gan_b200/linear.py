@@ -67,5 +67,15 @@ class _LinearTC(torch.autograd.Function):
 def linear(x, weight, bias=None):
     """F.linear on the tcgen05 path; x (..., K) fp32 CUDA, weight (N, K), K % 4 == 0."""
     K = x.shape[-1]
+    N = weight.shape[0]
     y = _LinearTC.apply(x.reshape(-1, K), weight, bias)
-    return y.view(*x.shape[:-1], weight.shape[0]) if y.is_contiguous() else y.unflatten(0, x.shape[:-1])
+    lead = tuple(x.shape[:-1])
+    if y.is_contiguous():
+        return y.view(*lead, N)
+    # row-padded output: expose (..., N) with the padded pitch, no copy
+    ld = y.stride(0)
+    strides, acc = [], ld
+    for n in reversed(lead):
+        strides.append(acc)
+        acc *= n
+    return y.as_strided(lead + (N,), tuple(reversed(strides)) + (1,))

@@ -36,7 +36,7 @@ def test_gemm_matches_fp64(M, N, K, a_mn, b_mn):
     assert torch.all(C[:, N:] == 7.0)                       # nothing written outside the N columns
     e = rel_err(C[:, :N], ref)
     e32 = rel_err((A.to(DEV) @ Bm.to(DEV).t() + bias.to(DEV)), ref)
-    assert e < 2e-6 + 2 * e32, (e, e32)
+    assert e < 1e-5, (e, e32)                               # 3xTF32: ~2^-20 relative to sum |a||b|
     # accumulate
     gemm_tf32x3(As.to(DEV), bool(a_mn), Bs.to(DEV), bool(b_mn), C, M, N, K, accumulate=True)
-    assert rel_err(C[:, :N], 2 * ref - bias.double()) < 4e-6 + 4 * e32
+    assert rel_err(C[:, :N], 2 * ref - bias.double()) < 2e-5

@@ -30,4 +30,5 @@ def test_config1_step_matches_oracle():
     for k in ref:
         if k == "d_att.gvec.bias":
             continue
-        assert_close(out[k], ref[k], truth=ref64[k], what=k)
+        got = torch.stack(out[k]) if isinstance(out[k], (list, tuple)) else out[k]
+        assert_close(got, ref[k], truth=ref64[k], what=k)
