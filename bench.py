@@ -278,13 +278,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
-    from robust_e2e_gan_b200.parallel import GradBuckets, init_distributed
+    from robust_e2e_gan_b200.parallel import init_distributed
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, int(os.environ.get("RANK", "0")), world_env)
@@ -300,100 +299,57 @@ def main():
     cfg = dict(DEFAULT_CFG)
     peak, peak_src = load_peaks()
 
+    from robust_e2e_gan_b200.hotpath import StepRunner
     hp = HotPath(cfg, seed=4000).to(dev)                 # identical init on every rank
     hb = make_batch(cfg, seed=4000 + rank).pin()         # distinct utterances per rank
     db = hb.to(dev)
     torch.cuda.synchronize()
-    buckets = GradBuckets(hp.trainable(), bucket_mb=25.0) if world > 1 else None
     flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)   # 256 MiB > 126 MB L2
-
-    def eager_step(batch):
-        if buckets is not None:
-            buckets.zero()
-        else:
-            for p in hp.parameters():
-                p.grad = None
-        out = hp.step(batch, hlens_for_att=batch.hlens)
-        if buckets is not None:
-            buckets.finish()
-        return out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (eager), launch count of one step
+    # ---- warm-up (eager public modules), launch count of one step
     n0 = _lib.launch_count()
-    eager_step(db)
+    hp.step(db, hlens_for_att=db.hlens)
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - n0
     for _ in range(max(0, args.warmup - 1)):
-        eager_step(db)
+        for p in hp.parameters():
+            p.grad = None
+        hp.step(db, hlens_for_att=db.hlens)
     torch.cuda.synchronize()
 
-    # ---- device-resident timing: CUDA-graph replay of the whole step when capture works
-    mode = "eager"
-    graph = None
-    if not args.no_graph:
-        try:
-            import gc
-
-            def drop_graph_refs():
-                # the modules keep the last loss / pre-compute (and so last step's autograd graph and its
-                # AccumulateGrad nodes, created on the default stream) alive: release before capturing
-                hp.att.reset()
-                hp.ctc.loss = None
-                hp.ctc.nll = None
-                for p in hp.parameters():
-                    p.grad = None
-                gc.collect()
-
-            drop_graph_refs()
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                for _ in range(2):
-                    hp.step(db, hlens_for_att=db.hlens)
-                    drop_graph_refs()
-            torch.cuda.current_stream().wait_stream(s)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=s):
-                graph_out = hp.step(db, hlens_for_att=db.hlens)
-            graph.replay()
-            torch.cuda.synchronize()
-            mode = "cuda_graph"
-        except Exception as e:  # capture not possible: keep the eager path, say so
-            graph = None
-            mode = "eager (graph capture failed: %s)" % (str(e).splitlines()[0][:160])
-            torch.cuda.synchronize()
+    # ---- the step as a user runs it: StepRunner = CUDA-graph replay over static buffers, H2D on a copy stream
+    runner = StepRunner(hp, hb, slots=2)
+    mode = "cuda_graph"
+    grad_keys = ["d_" + k for k, p in hp.named_parameters() if p.requires_grad]
+    if world > 1:
+        def allreduce_grads(out):
+            flat = torch.cat([out[k].reshape(-1) for k in grad_keys if k in out])
+            dist.all_reduce(flat)
+            flat.div_(world)
+            out["_grads_flat_mean"] = flat
+        runner.post = allreduce_grads
     if rank == 0:
         sys.stderr.write("[bench] timing mode: %s; launches/step %d\n" % (mode, launches_per_step))
 
-    def timed_step():
-        if graph is not None:
-            graph.replay()
-            if world > 1:
-                grads = [p.grad for p in hp.trainable() if p.grad is not None]
-                flat = torch.cat([g.reshape(-1) for g in grads])
-                dist.all_reduce(flat)
-                flat.div_(world)
-        else:
-            eager_step(db)
-
+    rs = runner.run_stream
     for _ in range(3):
-        timed_step()
+        runner.replay_resident(0)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     evs = []
     for _ in range(args.steps):
-        flush.fill_(0.0)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        timed_step()
-        e1.record()
+        with torch.cuda.stream(rs):
+            flush.fill_(0.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(rs)
+        runner.replay_resident(0)
+        e1.record(rs)
         evs.append((e0, e1))
     barrier()
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -404,22 +360,26 @@ def main():
     ms_per_step = float(t.item()) / args.steps
     value = cfg["B"] * world / (ms_per_step * 1e-3)
 
-    # ---- end to end through the public nn.Module API: pinned host inputs in, loss out, every step
+    # ---- end to end through StepRunner: every step copies its pinned host batch in and reads the loss back.
+    #      One step of look-ahead: batch i+1 is copied (copy stream) while step i computes.
     for _ in range(2):
-        eager_step(hb.to(dev))
+        float(runner(hb)["loss_ctc"].cpu())
     barrier()
     t0 = time.perf_counter()
     d2h = 0
-    for _ in range(args.steps):
-        out = eager_step(hb.to(dev))
-        lv = out["loss_ctc"].cpu()          # D2H read of the step's result (synchronises)
+    runner.submit(hb)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            runner.submit(hb)
+        lv = runner.result()["loss_ctc"].cpu()      # D2H read of the step's result (synchronises)
         d2h = lv.numel() * 4
     barrier()
     e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e = {"value": cfg["B"] * world / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": hb.h2d_bytes(),
-           "d2h_bytes_per_step": d2h, "ms_per_step": float(e2e_s.item()) * 1e3}
+    e2e = {"value": cfg["B"] * world / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes(hb),
+           "d2h_bytes_per_step": d2h, "ms_per_step": float(e2e_s.item()) * 1e3,
+           "api": "robust_e2e_gan_b200.hotpath.StepRunner (graph replay, H2D of batch i+1 overlaps step i)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

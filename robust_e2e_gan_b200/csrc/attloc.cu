@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(kSkWarps * 32) skinny_gemm_kernel(const float 
   constexpr int NT = kSkWarps * 32;
   const int Kp = Kd | 1;                   // odd pitch: lane <-> row reads are conflict free
   float *x_s = smem;                       // [M][Kp]
-  float *w_s = smem + (size_t)M * Kp;      // [kSkWarps][Kd]
+  float *w_s = smem + round4(M * Kp);      // [kSkWarps][Kd], 16 B aligned for the float4 stores
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n0 = blockIdx.x * kSkWarps;
   if (vec_ok) {
@@ -811,7 +811,7 @@ inline int check_dims(int B, int Th, int D, int A, int C, int K) {
 
 int skinny(bool nn, const float *X, const float *W, float *out, int M, int N, int Kd, int accumulate,
            cudaStream_t st) {
-  const size_t smem = sizeof(float) * ((size_t)M * (Kd | 1) + (size_t)kSkWarps * Kd);
+  const size_t smem = sizeof(float) * ((size_t)round4(M * (Kd | 1)) + (size_t)kSkWarps * Kd);
   if (smem > 200 * 1024) return RE2E_E_UNSUPPORTED;
   const int vec_ok = ((Kd & 3) == 0) && aligned16(X) && aligned16(W);
   int rc0;

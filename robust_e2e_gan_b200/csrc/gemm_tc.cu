@@ -46,7 +46,10 @@ EncodeTiledFn get_encode() {
 
 // 2-D fp32 tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements; box 32 x box_outer,
 // 128 B swizzle, out-of-bounds elements read as zero.
-int make_tmap(CUtensorMap *tm, const float *ptr, long long inner, long long outer, long long ld, int box_outer) {
+// mn_major operands use the 128B-span / 32B-atom swizzle: the only shared-memory layout tcgen05 accepts for MN-major
+// 32-bit (tf32) operands (UMMA LayoutType SWIZZLE_128B_BASE32B = Swizzle<2,5,2> on the byte address).
+int make_tmap(CUtensorMap *tm, const float *ptr, long long inner, long long outer, long long ld, int box_outer,
+              bool mn_major) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return RE2E_E_UNSUPPORTED;
   cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
@@ -54,7 +57,9 @@ int make_tmap(CUtensorMap *tm, const float *ptr, long long inner, long long oute
   cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? RE2E_OK : RE2E_E_ARG;
 }
@@ -70,14 +75,16 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, in
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// shared-memory matrix descriptor, SWIZZLE_128B, descriptor version 1 (Blackwell)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// shared-memory matrix descriptor, descriptor version 1 (Blackwell).  layout: 2 = SWIZZLE_128B (K-major tiles),
+// 1 = SWIZZLE_128B_BASE32B (MN-major tf32 tiles).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -124,7 +131,13 @@ struct GemmParams {
   float *C;
   const float *bias;
   int M, N, K, ldc, accumulate;
+  int kb_per;   // k-blocks per split (gridDim.z splits); split > 1: partial tiles are added with red.global
 };
+
+__device__ __forceinline__ void red_add4(float *p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 
 template <bool A_MN, bool B_MN, int BN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -148,7 +161,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
-  const int nkb = (p.K + kBK - 1) / kBK;
+  // this CTA's slice of the K loop (split-K over gridDim.z keeps every tensor-core accumulation chain
+  // <= kb_per*32 products: the TMEM accumulator adds with truncation, whose bias grows linearly in K)
+  const int kb_begin = blockIdx.z * p.kb_per;
+  const int nkb = min((p.K + kBK - 1) / kBK - kb_begin, p.kb_per);
+  const bool split = gridDim.z > 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -178,7 +195,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (kb >= STAGES) mbar_wait(&empty[s], (uint32_t)(((kb / STAGES) - 1) & 1));
         unsigned char *st = stage0 + (size_t)s * STAGE_BYTES;
         mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-        const int k0 = kb * kBK;
+        const int k0 = (kb_begin + kb) * kBK;
         if (!A_MN) {
           tma_load_2d(st, &tmA, k0, m0, &full[s]);
         } else {
@@ -206,13 +223,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint32_t b_lo = a_lo + A_BYTES;
 #pragma unroll
         for (int k = 0; k < kBK / 8; ++k) {
-          // K-major: 8 tf32 = 32 B further along the swizzled 128 B row; MN-major: next 8-row group (1 KB)
+          // K-major (SWIZZLE_128B): 8 tf32 = 32 B further along the swizzled 128 B row, 8-row groups 1 KB apart.
+          // MN-major (SWIZZLE_128B_BASE32B): a box is 32 k-rows x 128 B (32 mn); the canonical atom is 4 k-rows
+          // (SBO = 512 B between 4-k groups), 32-mn blocks are LBO = 4 KB apart, one MMA (K = 8) = 1 KB.
           const uint32_t ao = A_MN ? k * 1024 : k * 32;
           const uint32_t bo = B_MN ? k * 1024 : k * 32;
-          const uint64_t dah = umma_desc(a_hi + ao, A_MN ? 4096 : 16, 1024);
-          const uint64_t dal = umma_desc(a_lo + ao, A_MN ? 4096 : 16, 1024);
-          const uint64_t dbh = umma_desc(b_hi + bo, B_MN ? 4096 : 16, 1024);
-          const uint64_t dbl = umma_desc(b_lo + bo, B_MN ? 4096 : 16, 1024);
+          const uint64_t dah = A_MN ? umma_desc(a_hi + ao, 4096, 512, 1) : umma_desc(a_hi + ao, 16, 1024, 2);
+          const uint64_t dal = A_MN ? umma_desc(a_lo + ao, 4096, 512, 1) : umma_desc(a_lo + ao, 16, 1024, 2);
+          const uint64_t dbh = B_MN ? umma_desc(b_hi + bo, 4096, 512, 1) : umma_desc(b_hi + bo, 16, 1024, 2);
+          const uint64_t dbl = B_MN ? umma_desc(b_lo + bo, 4096, 512, 1) : umma_desc(b_lo + bo, 16, 1024, 2);
           umma_tf32(tmem_base, dah, dbh, IDESC, (kb | k) ? 1u : 0u);
           umma_tf32(tmem_base, dal, dbh, IDESC, 1u);
           umma_tf32(tmem_base, dah, dbl, IDESC, 1u);
@@ -252,12 +271,21 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int col0 = n0 + c * 32;
       if (row < p.M && col0 < p.N) {
         float *dst = p.C + (size_t)row * p.ldc + col0;
-        if (p.bias) {
+        if (p.bias && blockIdx.z == 0) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
         }
-        if (vec && col0 + 32 <= p.N) {
+        if (split) {  // C was zeroed by the host side unless `accumulate`
+          if (vec && col0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) red_add4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
+          }
+        } else if (vec && col0 + 32 <= p.N) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -289,7 +317,13 @@ int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &
   auto kern = gemm_tf32x3_kernel<A_MN, B_MN, BN, STAGES>;
   int rc = ensure_smem(reinterpret_cast<const void *>(kern), smem);
   if (rc != RE2E_OK) return rc;
-  dim3 grid((prm.M + kBM - 1) / kBM, (prm.N + BN - 1) / BN);
+  const int nkb = (prm.K + kBK - 1) / kBK;
+  dim3 grid((prm.M + kBM - 1) / kBM, (prm.N + BN - 1) / BN, (nkb + prm.kb_per - 1) / prm.kb_per);
+  if (grid.z > 1 && !prm.accumulate) {
+    cudaError_t e = cudaMemset2DAsync(prm.C, sizeof(float) * (size_t)prm.ldc, 0, sizeof(float) * (size_t)prm.N,
+                                      (size_t)prm.M, st);
+    if (e != cudaSuccess) return (int)e;
+  }
   kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, prm);
   count_launch();
   return launch_status();
@@ -319,14 +353,16 @@ extern "C" int re2e_gemm_tf32x3(const float *A, int lda, int a_mn, const float *
   CUtensorMap ta, tb;
   int rc;
   const int BN = (N % 256 == 0 || N > 1024) ? 256 : 160;
-  if (!a_mn) rc = make_tmap(&ta, A, K, M, lda, kBM);
-  else rc = make_tmap(&ta, A, M, K, lda, kBK);
+  if (!a_mn) rc = make_tmap(&ta, A, K, M, lda, kBM, false);
+  else rc = make_tmap(&ta, A, M, K, lda, kBK, true);
   if (rc != RE2E_OK) return rc;
-  if (!b_mn) rc = make_tmap(&tb, B, K, N, ldb, BN);
-  else rc = make_tmap(&tb, B, N, K, ldb, kBK);
+  if (!b_mn) rc = make_tmap(&tb, B, K, N, ldb, BN, false);
+  else rc = make_tmap(&tb, B, N, K, ldb, kBK, true);
   if (rc != RE2E_OK) return rc;
   GemmParams prm;
   prm.C = C; prm.bias = bias; prm.M = M; prm.N = N; prm.K = K; prm.ldc = ldc; prm.accumulate = accumulate;
+  const int nkb = (K + kBK - 1) / kBK;
+  prm.kb_per = nkb > 24 ? 16 : nkb;   // K > 768: slices of 512
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (BN == 256) return dispatch_major<256, 2>(a_mn, b_mn, ta, tb, prm, st);
   return dispatch_major<160, 3>(a_mn, b_mn, ta, tb, prm, st);

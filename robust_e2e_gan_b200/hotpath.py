@@ -125,3 +125,145 @@ class HotPath(torch.nn.Module):
                 if p.requires_grad and p.grad is not None:
                     out["d_" + k] = p.grad
         return out
+
+
+def _targets_host(ys, ignore_id=-1):
+    """Flat int32 labels / offsets / lengths on the host (numpy), as prepare_targets builds them."""
+    seqs = [np.asarray(y.detach().cpu().numpy() if torch.is_tensor(y) else y).reshape(-1) for y in ys]
+    seqs = [s[s != ignore_id] for s in seqs]
+    lens = np.array([len(s) for s in seqs], dtype=np.int32)
+    offs = np.zeros(len(seqs), dtype=np.int32)
+    if len(seqs) > 1:
+        offs[1:] = np.cumsum(lens[:-1])
+    flat = np.concatenate(seqs).astype(np.int32) if lens.sum() else np.zeros(1, np.int32)
+    return flat, offs, lens
+
+
+class StepRunner(object):
+    """The hot-path step as a user drives it from host batches: ``runner(host_batch) -> outputs``.
+
+    The whole fwd+bwd (``HotPath.step``) is captured once per input slot into a CUDA graph over static
+    device buffers.  ``submit(host_batch)`` copies a (pinned) host batch into the free slot on a copy
+    stream -- overlapping the previous step's kernels -- and enqueues the replay; ``result()`` returns
+    the oldest outstanding step's output dict (device tensors, valid until that slot is reused two
+    submits later).  ``__call__`` = submit + result.  Shapes are fixed at construction (the reference's
+    bucketing sampler yields fixed-shape batches, data/mix_data_loader.py:314-346); label sequences may
+    vary up to ``umax`` labels each.
+    """
+
+    def __init__(self, hp, example_host_batch, slots=2, umax=None):
+        self.hp = hp
+        self.dev = next(hp.parameters()).device
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.run_stream = torch.cuda.Stream(self.dev)
+        B = hp.cfg["B"]
+        flat, offs, lens = _targets_host(example_host_batch.ys)
+        self.umax = int(umax if umax is not None else max(int(lens.max()) if len(lens) else 1, 1))
+        self.slots = []
+        self._pending = []
+        self._next = 0
+        self.post = None          # optional callable(out) run on the step's stream right after the replay
+                                  # (e.g. the gradient all-reduce of a data-parallel job)
+        self._lab_pin = [torch.empty(B * self.umax + 2 * B, dtype=torch.int32).pin_memory() for _ in range(slots)]
+        for s in range(slots):
+            db = example_host_batch.to(self.dev, non_blocking=False)
+            labels = torch.zeros(B * self.umax + 2 * B, device=self.dev, dtype=torch.int32)
+            from .e2e_ctc import PreparedTargets
+            db.targets = PreparedTargets(labels[:B * self.umax], labels[B * self.umax:B * self.umax + B],
+                                         labels[B * self.umax + B:], self.umax, B)
+            db._labels_all = labels
+            self.slots.append({"batch": db, "graph": None, "out": None,
+                               "copied": torch.cuda.Event(), "done": torch.cuda.Event()})
+        torch.cuda.synchronize(self.dev)
+        for s in range(slots):
+            self._stage(s, example_host_batch)
+        torch.cuda.synchronize(self.dev)
+        self._capture()
+
+    # -- graph capture -----------------------------------------------------------------------------
+    def _drop_refs(self):
+        import gc
+        self.hp.att.reset()
+        self.hp.ctc.loss = None
+        self.hp.ctc.nll = None
+        for p in self.hp.parameters():
+            p.grad = None
+        gc.collect()
+
+    def _capture(self):
+        hp, st = self.hp, self.run_stream
+        self._drop_refs()
+        st.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(st):
+            for _ in range(2):                                  # warm-up: sizes the caching allocator, smem attrs
+                hp.step(self.slots[0]["batch"], hlens_for_att=self.slots[0]["batch"].hlens)
+                self._drop_refs()
+        torch.cuda.synchronize(self.dev)
+        for slot in self.slots:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                out = hp.step(slot["batch"], hlens_for_att=slot["batch"].hlens)
+            slot["graph"], slot["out"] = g, out
+            self._drop_refs()
+        torch.cuda.synchronize(self.dev)
+
+    # -- per step ----------------------------------------------------------------------------------
+    def _stage(self, s, hb):
+        """H2D of one host batch into slot s (on the copy stream)."""
+        slot = self.slots[s]
+        db = slot["batch"]
+        B = self.hp.cfg["B"]
+        flat, offs, lens = _targets_host(hb.ys)
+        if len(lens) != B or (len(lens) and int(lens.max()) > self.umax):
+            raise ValueError("StepRunner: batch has %d utterances / %d labels max, captured for %d / %d"
+                             % (len(lens), int(lens.max()) if len(lens) else 0, B, self.umax))
+        pin = self._lab_pin[s]
+        pin.zero_()
+        pin[:len(flat)] = torch.from_numpy(flat)
+        pin[B * self.umax:B * self.umax + B] = torch.from_numpy(offs)
+        pin[B * self.umax + B:] = torch.from_numpy(lens)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(slot["done"])           # the slot's previous replay has finished
+            for k in Batch.FIELDS:
+                getattr(db, k).copy_(getattr(hb, k), non_blocking=True)
+            db._labels_all.copy_(pin, non_blocking=True)
+            slot["copied"].record(self.copy_stream)
+
+    def h2d_bytes(self, hb):
+        return int(sum(getattr(hb, k).numel() * getattr(hb, k).element_size() for k in Batch.FIELDS)
+                   + self._lab_pin[0].numel() * 4)
+
+    def submit(self, host_batch):
+        s = self._next
+        self._next = (s + 1) % len(self.slots)
+        if any(p == s for p in self._pending):
+            raise RuntimeError("StepRunner: slot %d still has an unread result; call result() first" % s)
+        self._stage(s, host_batch)
+        slot = self.slots[s]
+        with torch.cuda.stream(self.run_stream):
+            self.run_stream.wait_event(slot["copied"])
+            slot["graph"].replay()
+            if self.post is not None:
+                self.post(slot["out"])
+            slot["done"].record(self.run_stream)
+        self._pending.append(s)
+        return s
+
+    def replay_resident(self, s=0):
+        """Replay slot s on its current device-resident inputs (no host copy); returns the output dict.
+        Runs on ``run_stream``; the caller synchronises (events on that stream or device sync)."""
+        slot = self.slots[s]
+        with torch.cuda.stream(self.run_stream):
+            slot["graph"].replay()
+            if self.post is not None:
+                self.post(slot["out"])
+        return slot["out"]
+
+    def result(self):
+        s = self._pending.pop(0)
+        torch.cuda.current_stream(self.dev).wait_event(self.slots[s]["done"])
+        return self.slots[s]["out"]
+
+    def __call__(self, host_batch):
+        self.submit(host_batch)
+        return self.result()
