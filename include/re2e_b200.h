@@ -84,10 +84,11 @@ int re2e_cmvn_stats(const float *Y, const int32_t *lens, double *sum, double *su
 int re2e_attloc_init_att(const int32_t *hlens, float *att_prev, int B, int Th, void *stream);
 
 /* One attention step (e2e_attention.py:258-299).  dec_z == NULL means zeros (:258-259).
- * Saved for backward (all optional outputs may be NULL when no gradient is needed):
- *   dec_proj (B,A) = dec_z @ W_dec^T   (always written: scratch of the step)
- *   conv (B,Th,C)  = loc_conv(att_prev)
- *   xsave (B,Th,A) = tanh(mlp_att(conv) + pre + dec_proj), written by the TMA unit from the smem ring */
+ * mlp_dec (dec_z @ W_dec^T, :278) is computed inside the kernel (split over the CTAs of a cluster, exchanged
+ * through distributed shared memory).  Optional outputs (NULL when not needed):
+ *   dec_proj (B,A) = dec_z @ W_dec^T
+ *   conv (B,Th,C)  = loc_conv(att_prev)                               (saved for the backward)
+ *   xsave (B,Th,A) = tanh(mlp_att(conv) + pre + dec_proj)             (saved for the backward) */
 int re2e_attloc_step_fwd(const float *pre, const float *enc_h, const float *dec_z,
                          const float *att_prev, const float *W_dec, const float *W_att,
                          const float *W_conv, const float *gvec, const float *gvec_b,

@@ -40,10 +40,10 @@ struct AttGeom {
 };
 
 struct AttFwdParams {
-  const float *pre, *enc, *att_prev, *dec_proj, *W_att, *W_conv, *gvec, *gvec_b;
+  const float *pre, *enc, *att_prev, *dec_z, *W_dec, *W_att, *W_conv, *gvec, *gvec_b;
   float scaling;
-  float *c, *w, *conv, *xsave;
-  int B, Th, D, A, C, K;
+  float *c, *w, *dec_proj, *conv, *xsave;
+  int B, Th, D, A, Z, C, K;
   AttGeom g;
 };
 
@@ -103,55 +103,212 @@ __device__ __forceinline__ void warp_reduce16(float (&v)[16], int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward
+// forward (v3): ONE pass over the CTA's frames with an online softmax.
+//
+//   thread 0         : producer -- initialises the mbarriers and issues the bulk copies of the
+//                      (pre chunk | enc chunk) stages up front (the whole frame range when it fits); a ring
+//                      shorter than the range is refilled once all 16 warps released the stage
+//   warps 0..15      : 8 warp PAIRS; pair p owns frame 8q+p of chunk q; the two warps of a pair split the
+//                      A attention channels (energy) and the D encoder channels (context), lane <-> channel
+//   per frame        : u = W_att conv[t] + pre[t] + dec_proj ; x = tanh(u) (stored for the backward) ;
+//                      e = g.x (warp shuffle + 64-thread named barrier inside the pair) ;
+//                      running (max, sum, context) update -- no CTA-wide barrier inside the frame loop
+//   mlp_dec          : dec_proj = W_dec dec_z is computed INSIDE the kernel: every CTA of the cluster
+//                      produces A/CL channels and pushes them into its peers' shared memory (DSMEM)
+//   cluster combine  : every CTA pushes (max, sum) to all peers and its partial context to rank 0; after
+//                      one cluster barrier all reads are local
 // ------------------------------------------------------------------------------------------------
-template <int APL, int CP>
-__global__ void __launch_bounds__(kNWF * 32, 1) attloc_fwd_kernel(const AttFwdParams p) {
-  constexpr int NW = kNWF, NT = NW * 32;
+constexpr int kFP = 8;                  // warp pairs = frames per chunk
+constexpr int kFW = 2 * kFP;            // compute warps
+constexpr int kFT = kFW * 32;
+constexpr int kDpl = 8;                 // D <= 512: encoder channels per lane per half
+
+__device__ __forceinline__ void mbar_arrive1(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void pair_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+
+template <int APL, int CP, int DPL>
+__global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p) {
+  constexpr int NT = kFT;
+  constexpr int WP = CP + 1;             // odd pitch of the staged W_att rows: conflict-free lane <-> a reads
+  constexpr int CPP = (CP + 3) & ~3;     // pitch of conv rows in shared memory (128-bit broadcast reads)
   extern __shared__ __align__(128) unsigned char smraw[];
   const AttGeom g = p.g;
-  const int Th = p.Th, D = p.D, A = p.A, C = p.C, K = p.K, filts = (p.K - 1) / 2;
+  const int C = CP == 10 ? 10 : p.C;     // the CP == 10 instantiation is only dispatched for C == 10
+  const int Th = p.Th, D = p.D, A = p.A, K = p.K, Z = p.Z, filts = (p.K - 1) / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = warp & 1, pair = warp >> 1;
   const int CL = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
   const int b = blockIdx.x / CL;
   const int t0 = min(Th, rank * g.tloc_max), t1 = min(Th, t0 + g.tloc_max), tloc = t1 - t0;
-  const int nch = (tloc + NW - 1) / NW;  // chunks actually used by this CTA
-  const int total = 2 * nch;
+  const int nch = (tloc + kFP - 1) / kFP;
+  const int Dp = round4(D), Dh = (D + 1) / 2;
 
   uint64_t *full = reinterpret_cast<uint64_t *>(smraw);
-  float *stages = reinterpret_cast<float *>(smraw + 256);
+  uint64_t *empty = full + kMaxStages;
+  float *stages = reinterpret_cast<float *>(smraw + 512);
   float *app = stages + (size_t)g.ns * g.stage_floats;     // App   zero padded alignment row, ap[i] at filts+i
   float *wc_s = app + g.App;                               // CKp
-  float *convp = wc_s + g.CKp;                             // kKQ*tloc_max*CP  conv partials
-  float *conv_s = convp + kKQ * g.tloc_max * CP;           // tloc_max*CP
-  float *e_part = conv_s + g.tloc_max * CP;                // tloc_max*65
-  float *p_s = e_part + g.tloc_max * 65;                   // tloc_max
-  float *cpart = p_s + round4(g.tloc_max);                 // round4(D)
-  float *xch = cpart + round4(D);                          // 4
-  float *cred = stages;                                    // NW*D, aliases stage 0 after the ring is drained
+  float *watt_s = wc_s + g.CKp;                            // A*WP
+  float *dz_s = watt_s + A * WP;                           // round4(Z)
+  float *dp_s = dz_s + round4(Z);                          // A      dec_proj, pushed by the cluster
+  float *convp = dp_s + A;                                 // kKQ*tloc_max*CP  conv partials
+  float *conv_s = convp + round4(kKQ * g.tloc_max * CP);   // tloc_max*CPP
+  float *e_s = conv_s + g.tloc_max * CPP;                  // round4(tloc_max)  scaled energies
+  float *epart = e_s + round4(g.tloc_max);                 // 2*kFP*2
+  float *wstat = epart + 4 * kFP;                          // kFW*2
+  float *cbuf = wstat + 2 * kFW;                           // 8*Dp   partial contexts (used on rank 0)
+  float *xch = cbuf + 8 * Dp;                              // 8*2    (max, sum) of every rank
+  float *cred = stages;                                    // kFP*Dp, aliases the ring once it is drained
 
+  auto issue = [&](int q) {
+    const int st = q % g.ns;
+    const int r0 = t0 + kFP * q;
+    const int rows = min(kFP, t1 - r0);
+    float *dst = stages + (size_t)st * g.stage_floats;
+    mbar_expect_tx(&full[st], (uint32_t)rows * (uint32_t)(A + D) * 4u);
+    bulk_g2s(dst, p.pre + ((size_t)b * Th + r0) * A, (uint32_t)rows * A * 4u, &full[st]);
+    bulk_g2s(dst + kFP * A, p.enc + ((size_t)b * Th + r0) * D, (uint32_t)rows * D * 4u, &full[st]);
+  };
+
+  cluster_arrive_relaxed();  // #0: "this CTA is running" -- peers wait on it before their first DSMEM store
   if (tid == 0) {
-    for (int i = 0; i < g.ns; ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < g.ns; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kFW); }
     mbar_fence_init();
-    const int first = total < g.ns ? total : g.ns;
-    for (int q = 0; q < first; ++q) issue_chunk<NW>(q, nch, g, p.pre, A, p.enc, D, b, Th, t0, t1, stages, full);
+    const int first = nch < g.ns ? nch : g.ns;
+    for (int q = 0; q < first; ++q) issue(q);
   }
-  // stage the small operands (issued back to back: one round trip)
-  for (int i = tid; i < g.App; i += NT) {
-    const int t = i - filts;
-    app[i] = (t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
-  }
-  for (int i = tid; i < C * K; i += NT) wc_s[i] = __ldg(p.W_conv + i);
-  float Watt[APL][CP], dp[APL], gv[APL];
+
+  // ---- every global load of the prologue is issued before the first use: ONE L2 round trip for the small
+  //      operands (alignment row, W_conv, W_att, dec_z, gvec) and this warp's W_dec rows
+  constexpr int kCPW = 5;                              // mlp_dec channels per warp per pass
+  constexpr int kZQ = 3;                               // 128-bit quads per lane per pass (Z <= 384 in one pass)
+  const int apc = A / CL, a_begin = rank * apc;        // this CTA's slice of the A mlp_dec channels
+  const bool wvec = p.dec_z && ((Z & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.W_dec) & 15u) == 0);
+  float4 wv[kCPW][kZQ];
+  if (wvec) {
+    const int zq = Z >> 2;
 #pragma unroll
-  for (int j = 0; j < APL; ++j) {
-    const int a = half * (A / 2) + lane + 32 * j;
-    dp[j] = __ldg(p.dec_proj + (size_t)b * A + a);
-    gv[j] = __ldg(p.gvec + a);
+    for (int u = 0; u < kCPW; ++u) {
+      const int ai = warp + kFW * u;
+      const float4 *wr = reinterpret_cast<const float4 *>(p.W_dec + (size_t)(a_begin + min(ai, apc - 1)) * Z);
 #pragma unroll
-    for (int c = 0; c < CP; ++c) Watt[j][c] = c < C ? __ldg(p.W_att + (size_t)a * C + c) : 0.0f;
+      for (int v = 0; v < kZQ; ++v) {
+        const int z4 = lane + 32 * v;
+        wv[u][v] = (ai < apc && z4 < zq) ? __ldg(wr + z4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
   }
-  __syncthreads();
+  {
+    constexpr int IA = 2, IC = 4, IW = 8;              // first block of every array: loads batched in registers
+    float va[IA], vc[IC], vw[IW], vz;
+#pragma unroll
+    for (int u = 0; u < IA; ++u) {
+      const int i = tid + u * NT, t = i - filts;
+      va[u] = (i < g.App && t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < IC; ++u) {
+      const int i = tid + u * NT;
+      vc[u] = i < C * K ? __ldg(p.W_conv + i) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < IW; ++u) {
+      const int i = tid + u * NT;
+      vw[u] = i < A * C ? __ldg(p.W_att + i) : 0.0f;
+    }
+    vz = (p.dec_z && tid < Z) ? __ldg(p.dec_z + (size_t)b * Z + tid) : 0.0f;
+#pragma unroll
+    for (int u = 0; u < IA; ++u)
+      if (tid + u * NT < g.App) app[tid + u * NT] = va[u];
+#pragma unroll
+    for (int u = 0; u < IC; ++u)
+      if (tid + u * NT < C * K) wc_s[tid + u * NT] = vc[u];
+#pragma unroll
+    for (int u = 0; u < IW; ++u) {
+      const int i = tid + u * NT;
+      if (i < A * C) { const int a = i / C; watt_s[a * WP + (i - a * C)] = vw[u]; }
+    }
+    if (tid < Z) dz_s[tid] = vz;
+    // remainders (shapes beyond the first block)
+    for (int i = tid + IA * NT; i < g.App; i += NT) {
+      const int t = i - filts;
+      app[i] = (t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
+    }
+    for (int i = tid + IC * NT; i < C * K; i += NT) wc_s[i] = __ldg(p.W_conv + i);
+    for (int i = tid + IW * NT; i < A * C; i += NT) { const int a = i / C; watt_s[a * WP + (i - a * C)] = __ldg(p.W_att + i); }
+    for (int i = tid + NT; i < Z; i += NT) dz_s[i] = p.dec_z ? __ldg(p.dec_z + (size_t)b * Z + i) : 0.0f;
+  }
+  float gv[APL];
+#pragma unroll
+  for (int j = 0; j < APL; ++j) gv[j] = __ldg(p.gvec + half * (A / 2) + lane + 32 * j);
+  const float gb = __ldg(p.gvec_b);
+  __syncthreads();  // #1
+
+  // ---- mlp_dec slice of this CTA: channels [rank*A/CL, (rank+1)*A/CL), one warp per channel, lane <-> z
+  for (int base = 0; base < apc; base += kFW * kCPW) {
+    float dots[kCPW];
+#pragma unroll
+    for (int u = 0; u < kCPW; ++u) dots[u] = 0.0f;
+    if (p.dec_z) {
+      if (wvec) {
+        const int zq = Z >> 2;
+        for (int zb = 0; zb < zq; zb += 32 * kZQ) {
+          if (base != 0 || zb != 0) {   // later passes: reload (the first pass was issued in the prologue)
+#pragma unroll
+            for (int u = 0; u < kCPW; ++u) {
+              const int ai = base + warp + kFW * u;
+              const float4 *wr = reinterpret_cast<const float4 *>(p.W_dec + (size_t)(a_begin + min(ai, apc - 1)) * Z);
+#pragma unroll
+              for (int v = 0; v < kZQ; ++v) {
+                const int z4 = zb + lane + 32 * v;
+                wv[u][v] = (ai < apc && z4 < zq) ? __ldg(wr + z4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < kZQ; ++v) {
+            const int z4 = zb + lane + 32 * v;
+            const float4 dz = z4 < zq ? *reinterpret_cast<const float4 *>(dz_s + 4 * z4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < kCPW; ++u)
+              dots[u] = fmaf(wv[u][v].x, dz.x, fmaf(wv[u][v].y, dz.y, fmaf(wv[u][v].z, dz.z, fmaf(wv[u][v].w, dz.w, dots[u]))));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < kCPW; ++u) {
+          const int ai = base + warp + kFW * u;
+          if (ai < apc) {
+            const float *wr = p.W_dec + (size_t)(a_begin + ai) * Z;
+            for (int z = lane; z < Z; z += 32) dots[u] = fmaf(__ldg(wr + z), dz_s[z], dots[u]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kCPW; ++u) dots[u] = warp_sum(dots[u]);
+    if (base == 0) cluster_wait();  // #0 complete: every peer CTA is resident
+#pragma unroll
+    for (int u = 0; u < kCPW; ++u) {
+      const int ai = base + warp + kFW * u;
+      if (ai < apc && lane < CL) dsmem_st(dsmem_addr(dp_s + a_begin + ai, (uint32_t)lane), dots[u]);
+      if (ai < apc && lane == 0 && p.dec_proj) p.dec_proj[(size_t)b * A + a_begin + ai] = dots[u];
+    }
+  }
+  cluster_arrive();  // #1 (release): this CTA's dec_proj slice is in every peer's dp_s
 
   // ---- location convolution: conv[t,c] = sum_k Wc[c,k] * att_prev[t + k - filts]  (zero padded).
   //      item = (k quarter, channel, group of 5 frames): 2 shared loads per 5 FMAs
@@ -168,9 +325,9 @@ __global__ void __launch_bounds__(kNWF * 32, 1) attloc_fwd_kernel(const AttFwdPa
       float x0 = ar[k0], x1 = ar[k0 + 1], x2 = ar[k0 + 2], x3 = ar[k0 + 3];
 #pragma unroll 5
       for (int k = k0; k < k1; ++k) {
-        const float x4 = ar[k + 4], wv = wr[k];
-        a0 = fmaf(wv, x0, a0); a1 = fmaf(wv, x1, a1); a2 = fmaf(wv, x2, a2);
-        a3 = fmaf(wv, x3, a3); a4 = fmaf(wv, x4, a4);
+        const float x4 = ar[k + 4], wv2 = wr[k];
+        a0 = fmaf(wv2, x0, a0); a1 = fmaf(wv2, x1, a1); a2 = fmaf(wv2, x2, a2);
+        a3 = fmaf(wv2, x3, a3); a4 = fmaf(wv2, x4, a4);
         x0 = x1; x1 = x2; x2 = x3; x3 = x4;
       }
       float *o = convp + ((size_t)kq * g.tloc_max + kTG * tg) * CP + c;
@@ -182,34 +339,62 @@ __global__ void __launch_bounds__(kNWF * 32, 1) attloc_fwd_kernel(const AttFwdPa
       if (nv > 4) o[4 * CP] = a4;
     }
   }
-  __syncthreads();
-  for (int i = tid; i < tloc * CP; i += NT) {
-    const int tl = i / CP, c = i - tl * CP;
+  // W_att rows of this lane's channels -> registers (independent of the conv partials)
+  float Watt[APL][CP];
+#pragma unroll
+  for (int j = 0; j < APL; ++j) {
+    const int a = half * (A / 2) + lane + 32 * j;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) Watt[j][c] = c < C ? watt_s[a * WP + c] : 0.0f;
+  }
+  __syncthreads();  // #2
+  for (int i = tid; i < tloc * CPP; i += NT) {
+    const int tl = i / CPP, c = i - tl * CPP;
     float v = 0.0f;
     if (c < C) {
 #pragma unroll
-      for (int kq = 0; kq < kKQ; ++kq) v += convp[(size_t)kq * g.tloc_max * CP + i];
+      for (int kq = 0; kq < kKQ; ++kq) v += convp[((size_t)kq * g.tloc_max + tl) * CP + c];
       if (p.conv) p.conv[((size_t)b * Th + t0 + tl) * C + c] = v;
     }
     conv_s[i] = v;
   }
-  __syncthreads();
+  cluster_wait();   // #1 (acquire): dp_s holds the full dec_proj row
+  __syncthreads();  // #3: conv_s visible
 
-  // ---- energies: e[t] = g . tanh(W_att conv[t] + pre[t] + dec_proj) (+ g_b), two warps per frame
-  for (int q = 0; q < nch; ++q) {
-    const int st = q % g.ns;
-    mbar_wait(&full[st], (uint32_t)((q / g.ns) & 1));
-    float *tile = stages + (size_t)st * g.stage_floats;
-    const int rows = min(NW, tloc - NW * q);
+  float m_run = -CUDART_INF_F, s_run = 0.0f;
+  float acc[DPL];
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int r = pair + (NW / 2) * rr;
-      if (r < rows) {
-        const int tl = NW * q + r;
-        float cv[CP];
+  for (int j = 0; j < DPL; ++j) acc[j] = 0.0f;
+  {
+    float dp[APL];
 #pragma unroll
-        for (int c = 0; c < CP; ++c) cv[c] = conv_s[tl * CP + c];
-        float *row = tile + r * A + half * (A / 2) + lane;
+    for (int j = 0; j < APL; ++j) dp[j] = p.dec_z ? dp_s[half * (A / 2) + lane + 32 * j] : 0.0f;
+    uint32_t dmask = 0;                        // which of this lane's DPL encoder channels exist
+#pragma unroll
+    for (int j = 0; j < DPL; ++j)
+      if (lane + 32 * j < Dh && half * Dh + lane + 32 * j < D) dmask |= 1u << j;
+    const int aoff = half * (A / 2) + lane;
+    const float *tile = stages;
+    const float *cvp = conv_s + pair * CPP;
+    float *xs = p.xsave ? p.xsave + ((size_t)b * Th + t0 + pair) * A + aoff : nullptr;
+    int st = 0;
+    uint32_t ph = 0;
+    for (int q = 0; q < nch; ++q) {
+      if (tid == 0 && q >= 1 && q - 1 + g.ns < nch) {   // ring shorter than the range: refill the stage chunk q-1 used
+        mbar_wait(&empty[(q - 1) % g.ns], (uint32_t)(((q - 1) / g.ns) & 1));
+        issue(q - 1 + g.ns);
+      }
+      __syncwarp();
+      mbar_wait(&full[st], ph);
+      const int tl = kFP * q + pair;
+      if (tl < tloc) {
+        float cv[CPP];
+#pragma unroll
+        for (int c4 = 0; c4 < CPP; c4 += 4) {
+          const float4 t4 = *reinterpret_cast<const float4 *>(cvp + c4);
+          cv[c4] = t4.x; cv[c4 + 1] = t4.y; cv[c4 + 2] = t4.z; cv[c4 + 3] = t4.w;
+        }
+        const float *row = tile + pair * A + aoff;
         float part = 0.0f;
 #pragma unroll
         for (int j = 0; j < APL; ++j) {
@@ -217,115 +402,85 @@ __global__ void __launch_bounds__(kNWF * 32, 1) attloc_fwd_kernel(const AttFwdPa
 #pragma unroll
           for (int c = 0; c < CP; ++c) u = fmaf(Watt[j][c], cv[c], u);
           const float x = tanh_fast(u);
-          if (p.xsave) row[32 * j] = x;  // activation kept for the backward, stored by the TMA unit below
+          if (xs) xs[32 * j] = x;  // activation kept for the backward (coalesced 128 B per warp store)
           part = fmaf(gv[j], x, part);
         }
-        e_part[tl * 65 + half * 32 + lane] = part;
-      }
-    }
-    const bool refill = q + g.ns < total;
-    if (p.xsave || refill) {
-      if (p.xsave) fence_proxy_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        if (p.xsave) {
-          bulk_s2g(p.xsave + ((size_t)b * Th + t0 + NW * q) * A, tile, (uint32_t)rows * A * 4u);
-          bulk_commit();
+        part = warp_sum(part);
+        float *ep = epart + (q & 1) * 2 * kFP + pair * 2;
+        if (lane == 0) ep[half] = part;
+        pair_bar(1 + pair, 64);
+        const float e = p.scaling * ((ep[0] + ep[1]) + gb);
+        if (half == 0 && lane == 0) e_s[tl] = e;
+        // online softmax: running max / sum / context of this warp's frames
+        if (e > m_run) {
+          const float sc = __expf(m_run - e);   // exp(-inf) = 0 on the first frame
+          s_run *= sc;
+#pragma unroll
+          for (int j = 0; j < DPL; ++j) acc[j] *= sc;
+          m_run = e;
         }
-        if (refill) {
-          if (p.xsave) bulk_wait_read<0>();
-          issue_chunk<NW>(q + g.ns, nch, g, p.pre, A, p.enc, D, b, Th, t0, t1, stages, full);
-        }
+        const float pw = __expf(e - m_run);
+        s_run += pw;
+        const float *er = tile + kFP * A + pair * D + half * Dh + lane;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j)
+          if (dmask & (1u << j)) acc[j] = fmaf(pw, er[32 * j], acc[j]);
       }
+      __syncwarp();
+      if (lane == 0 && g.ns < nch) mbar_arrive1(&empty[st]);
+      cvp += kFP * CPP;
+      if (xs) xs += (size_t)kFP * A;
+      if (++st == g.ns) { st = 0; ph ^= 1u; tile = stages; } else tile += g.stage_floats;
     }
+    if (lane == 0) { wstat[2 * warp] = m_run; wstat[2 * warp + 1] = s_run; }
   }
-  __syncthreads();
+  __syncthreads();  // #4: ring drained, per-warp statistics published
 
-  // ---- local softmax statistics over this CTA's frames (the softmax spans ALL Th frames, padding
-  //      included: e2e_attention.py:282-288 applies no length mask)
+  // ---- CTA combine (deterministic order), then push to the cluster
+  float Mc = -CUDART_INF_F;
+#pragma unroll
+  for (int w2 = 0; w2 < kFW; ++w2) Mc = fmaxf(Mc, wstat[2 * w2]);
   {
-    const float gb = __ldg(p.gvec_b);
-    for (int tl = tid; tl < tloc; tl += NT) {
-      const float *ep = e_part + tl * 65;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const float sc = m_run == -CUDART_INF_F ? 0.0f : __expf(m_run - Mc);
 #pragma unroll
-      for (int i = 0; i < 64; i += 4) { s0 += ep[i]; s1 += ep[i + 1]; s2 += ep[i + 2]; s3 += ep[i + 3]; }
-      p_s[tl] = p.scaling * ((s0 + s1) + (s2 + s3) + gb);
-    }
+    for (int j = 0; j < DPL; ++j)
+      if (lane + 32 * j < Dh && half * Dh + lane + 32 * j < D) cred[pair * Dp + half * Dh + lane + 32 * j] = acc[j] * sc;
   }
-  __syncthreads();
-  if (warp == 0) {
-    float m = -CUDART_INF_F;
-    for (int tl = lane; tl < tloc; tl += 32) m = fmaxf(m, p_s[tl]);
-    m = warp_max(m);
-    float s = 0.0f;
-    for (int tl = lane; tl < tloc; tl += 32) {
-      const float pv = expf(p_s[tl] - m);
-      p_s[tl] = pv;
-      s += pv;
-    }
-    s = warp_sum(s);
-    if (lane == 0) { xch[0] = m; xch[1] = s; }
-  }
-  __syncthreads();
-
-  // ---- un-normalised context over this CTA's frames: one warp per frame, lane <-> d
-  float acc[kDplMax];
-#pragma unroll
-  for (int j = 0; j < kDplMax; ++j) acc[j] = 0.0f;
-  for (int q = nch; q < total; ++q) {
-    const int st = q % g.ns;
-    mbar_wait(&full[st], (uint32_t)((q / g.ns) & 1));
-    const float *tile = stages + (size_t)st * g.stage_floats;
-    const int qq = q - nch;
-    const int rows = min(NW, tloc - NW * qq);
-    if (warp < rows) {
-      const float pw = p_s[NW * qq + warp];
-      const float *row = tile + warp * D + lane;
-#pragma unroll
-      for (int j = 0; j < kDplMax; ++j)
-        if (lane + 32 * j < D) acc[j] = fmaf(pw, row[32 * j], acc[j]);
-    }
-    if (q + g.ns < total) {
-      __syncthreads();
-      if (tid == 0) issue_chunk<NW>(q + g.ns, nch, g, p.pre, A, p.enc, D, b, Th, t0, t1, stages, full);
-    }
-  }
-  if (tid == 0) bulk_wait_read<0>();  // activation stores have drained stage 0 before it is reused below
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < kDplMax; ++j)
-    if (lane + 32 * j < D) cred[warp * D + lane + 32 * j] = acc[j];
-  __syncthreads();
+  __syncthreads();  // #5
   for (int d = tid; d < D; d += NT) {
-    float s = 0.0f;
+    float sum = 0.0f;
 #pragma unroll
-    for (int w8 = 0; w8 < NW; ++w8) s += cred[w8 * D + d];
-    cpart[d] = s;
+    for (int pr = 0; pr < kFP; ++pr) sum += cred[pr * Dp + d];
+    dsmem_st(dsmem_addr(cbuf + rank * Dp + d, 0u), sum);
   }
-  // ---- combine across the cluster through distributed shared memory
-  cluster_sync_all();
-  float M = -CUDART_INF_F;
-  for (int r = 0; r < CL; ++r) M = fmaxf(M, dsmem_ld(dsmem_addr(xch, r)));
-  float S = 0.0f;
-  for (int r = 0; r < CL; ++r) {
-    const float mr = dsmem_ld(dsmem_addr(xch, r)), sr = dsmem_ld(dsmem_addr(xch + 1, r));
-    S += sr * expf(mr - M);
-  }
-  const float inv = 1.0f / S;
-  const float mine = expf(xch[0] - M) * inv;
-  for (int tl = tid; tl < tloc; tl += NT) p.w[(size_t)b * Th + t0 + tl] = p_s[tl] * mine;
-  const int dper = (D + CL - 1) / CL;
-  for (int d = rank * dper + tid; d < min(D, (rank + 1) * dper); d += NT) {
-    float s = 0.0f;
-    for (int r = 0; r < CL; ++r) {
-      const float mr = dsmem_ld(dsmem_addr(xch, r));
-      s += dsmem_ld(dsmem_addr(cpart + d, r)) * expf(mr - M);
+  if (tid < CL) {
+    float sc = 0.0f;
+#pragma unroll
+    for (int pr = 0; pr < kFP; ++pr) {
+      const float mw = wstat[4 * pr];
+      if (mw != -CUDART_INF_F) sc += wstat[4 * pr + 1] * __expf(mw - Mc);
     }
-    p.c[(size_t)b * D + d] = s * inv;
+    dsmem_st(dsmem_addr(xch + 2 * rank, (uint32_t)tid), Mc);
+    dsmem_st(dsmem_addr(xch + 2 * rank + 1, (uint32_t)tid), sc);
   }
-  if (tid == 0) bulk_wait<0>();
-  cluster_sync_all();  // nobody leaves while a peer may still read its shared memory
+  cluster_arrive();  // #2
+  cluster_wait();
+  float M = -CUDART_INF_F;
+  for (int r = 0; r < CL; ++r) M = fmaxf(M, xch[2 * r]);
+  float S = 0.0f;
+  for (int r = 0; r < CL; ++r)
+    if (xch[2 * r] != -CUDART_INF_F) S += xch[2 * r + 1] * __expf(xch[2 * r] - M);
+  const float inv = 1.0f / S;
+  for (int tl = tid; tl < tloc; tl += NT) p.w[(size_t)b * Th + t0 + tl] = __expf(e_s[tl] - M) * inv;
+  if (rank == 0) {
+    for (int d = tid; d < D; d += NT) {
+      float sum = 0.0f;
+      for (int r = 0; r < CL; ++r)
+        if (xch[2 * r] != -CUDART_INF_F) sum += cbuf[r * Dp + d] * __expf(xch[2 * r] - M);
+      p.c[(size_t)b * D + d] = sum * inv;
+    }
+  }
+  // no trailing cluster barrier: after #2 nobody touches remote shared memory
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -759,6 +914,36 @@ inline bool pick_geom(int B, int Th, int D, int A, int C, int K, int CP, bool bw
   }
 }
 
+// forward (v3) geometry: stage = kFP frames of (pre | enc); the ring holds the whole frame range when it fits
+inline bool pick_geom_fwd(int B, int Th, int D, int A, int Z, int C, int K, int CP, int &CL, AttGeom &g,
+                          size_t &smem) {
+  const int sms = num_sms();
+  CL = 1;
+  while (CL < 8 && B * CL * 2 <= sms) CL *= 2;
+  while (CL > 1 && (Th + CL - 1) / CL < kFP) CL /= 2;  // tiny Th: do not over-split
+  const int filts = (K - 1) / 2;
+  g.stage_floats = kFP * (A + D);
+  g.Thp = round4(Th);
+  g.CKp = round4(C * K);
+  g.App = round4(Th + 2 * filts + 8);
+  g.tloc_max = (Th + CL - 1) / CL;
+  g.nch = (g.tloc_max + kFP - 1) / kFP;
+  const size_t fixed = 512 + sizeof(float) * ((size_t)g.App + g.CKp + (size_t)A * (CP + 1) + round4(Z) + A +
+                                              (size_t)round4(kKQ * g.tloc_max * CP) + (size_t)g.tloc_max * round4(CP) +
+                                              round4(g.tloc_max) + 4 * kFP +
+                                              2 * kFW + 8 * (size_t)round4(D) + 16);
+  const size_t budget = 224 * 1024;
+  const size_t stage_bytes = sizeof(float) * (size_t)g.stage_floats;
+  if (fixed + 2 * stage_bytes > budget) return false;
+  int ns = (int)((budget - fixed) / stage_bytes);
+  if (ns > g.nch) ns = g.nch;
+  if (ns > kMaxStages) ns = kMaxStages;
+  if (ns < 1) ns = 1;
+  g.ns = ns;
+  smem = fixed + ns * stage_bytes;
+  return true;
+}
+
 template <typename Kern, typename Params>
 int launch_cluster(Kern kern, const Params &prm, int B, int CL, int threads, size_t smem, cudaStream_t st) {
   int rc0 = ensure_smem(reinterpret_cast<const void *>(kern), smem);
@@ -793,7 +978,9 @@ int launch_cluster(Kern kern, const Params &prm, int B, int CL, int threads, siz
 
 template <int APL, int CP>
 int run_fwd(const AttFwdParams &prm, int CL, size_t smem, cudaStream_t st) {
-  return launch_cluster(attloc_fwd_kernel<APL, CP>, prm, prm.B, CL, kNWF * 32, smem, st);
+  // encoder channels per lane: the common D == A case gets an exact instantiation, anything else the general one
+  if (prm.D == prm.A) return launch_cluster(attloc_fwd_kernel<APL, CP, APL>, prm, prm.B, CL, kFT, smem, st);
+  return launch_cluster(attloc_fwd_kernel<APL, CP, kDpl>, prm, prm.B, CL, kFT, smem, st);
 }
 template <int APL, int CP>
 int run_bwd(const AttBwdParams &prm, int CL, size_t smem, cudaStream_t st) {
@@ -845,25 +1032,20 @@ extern "C" int re2e_attloc_step_fwd(const float *pre, const float *enc_h, const 
                                     float scaling, float *c, float *w, float *dec_proj, float *conv,
                                     float *xsave, int B, int Th, int D, int A, int Z, int C, int K,
                                     void *stream) {
-  RE2E_CHECK_ARG(pre && enc_h && att_prev && W_dec && W_att && W_conv && gvec && gvec_b && c && w && dec_proj);
+  RE2E_CHECK_ARG(pre && enc_h && att_prev && W_dec && W_att && W_conv && gvec && gvec_b && c && w);
   int rc = check_dims(B, Th, D, A, C, K);
   if (rc != RE2E_OK) return rc;
-  RE2E_CHECK_ARG(Z > 0 && aligned16(pre) && aligned16(enc_h) && (!xsave || aligned16(xsave)));
+  RE2E_CHECK_ARG(Z > 0 && aligned16(pre) && aligned16(enc_h));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dec_z) {
-    rc = skinny(false, dec_z, W_dec, dec_proj, B, A, Z, 0, st);
-    if (rc != RE2E_OK) return rc;
-  } else {
-    RE2E_CUDA(cudaMemsetAsync(dec_proj, 0, sizeof(float) * (size_t)B * A, st));
-  }
   const int CP = C == 10 ? 10 : 16;
   AttFwdParams prm;
-  prm.pre = pre; prm.enc = enc_h; prm.att_prev = att_prev; prm.dec_proj = dec_proj; prm.W_att = W_att;
+  prm.pre = pre; prm.enc = enc_h; prm.att_prev = att_prev; prm.dec_z = dec_z; prm.W_dec = W_dec; prm.W_att = W_att;
   prm.W_conv = W_conv; prm.gvec = gvec; prm.gvec_b = gvec_b; prm.scaling = scaling; prm.c = c; prm.w = w;
-  prm.conv = conv; prm.xsave = xsave; prm.B = B; prm.Th = Th; prm.D = D; prm.A = A; prm.C = C; prm.K = K;
+  prm.dec_proj = dec_proj; prm.conv = conv; prm.xsave = xsave;
+  prm.B = B; prm.Th = Th; prm.D = D; prm.A = A; prm.Z = Z; prm.C = C; prm.K = K;
   int CL;
   size_t smem;
-  if (!pick_geom(B, Th, D, A, C, K, CP, false, CL, prm.g, smem)) return RE2E_E_UNSUPPORTED;
+  if (!pick_geom_fwd(B, Th, D, A, Z, C, K, CP, CL, prm.g, smem)) return RE2E_E_UNSUPPORTED;
   ATT_DISPATCH(run_fwd, A / 64, CP, (prm, CL, smem, st));
   return rc;
 }

@@ -137,7 +137,6 @@ class _Step(torch.autograd.Function):
         ap = _lib.f32c(att_prev.detach(), dev).view(B, Th)
         c = torch.empty(B, D, device=dev, dtype=torch.float32)
         w = torch.empty(B, Th, device=dev, dtype=torch.float32)
-        dec_proj = torch.empty(B, A, device=dev, dtype=torch.float32)
         need_bwd = any(ctx.needs_input_grad[:3])
         conv = torch.empty(B, Th, C, device=dev, dtype=torch.float32) if need_bwd else None
         xsave = torch.empty(B, Th, A, device=dev, dtype=torch.float32) if need_bwd else None
@@ -145,7 +144,7 @@ class _Step(torch.autograd.Function):
             _lib.check(L.re2e_attloc_step_fwd(_lib.ptr(st.pre), _lib.ptr(st.enc), _lib.ptr(dz), _lib.ptr(ap),
                                               _lib.ptr(W_dec), _lib.ptr(W_att), _lib.ptr(W_conv), _lib.ptr(gvec),
                                               _lib.ptr(gvec_b), float(scaling), _lib.ptr(c), _lib.ptr(w),
-                                              _lib.ptr(dec_proj), _lib.ptr(conv), _lib.ptr(xsave), B, Th, D, A, Z, C, K,
+                                              None, _lib.ptr(conv), _lib.ptr(xsave), B, Th, D, A, Z, C, K,
                                               _lib.stream_ptr()), "re2e_attloc_step_fwd")
         if need_bwd:
             ctx.state = st
