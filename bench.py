@@ -185,7 +185,9 @@ def kernel_specs(hp, db, cfg, dev):
     dz = db.dec_z[0].contiguous()
     dc, dw = torch.randn(B, D).to(dev), torch.randn(B, Th).to(dev)
     d_pre, ddp, dprev = torch.zeros(B, Th, A, **f32), torch.empty(B, A, **f32), torch.empty(B, Th, **f32)
-    acc = [torch.zeros(A * C, **f32), torch.zeros(C * K, **f32), torch.zeros(A, **f32), torch.zeros(1, **f32)]
+    nslots = int(L.re2e_attloc_acc_slots(B))
+    acc = torch.zeros(nslots, int(L.re2e_attloc_acc_floats(A, C, K)), **f32)
+    d_dz = torch.empty(B, Z, **f32)
     logits = torch.randn(B, Th, V).to(dev)
     grad = torch.empty_like(logits)
     tg = db.targets
@@ -211,9 +213,9 @@ def kernel_specs(hp, db, cfg, dev):
                                           2.0, P(c), P(w), P(dproj), P(conv), P(xsave), B, Th, D, A, Z, C, K, sp()))
 
     def k_att_bwd():
-        _lib.check(L.re2e_attloc_step_bwd(P(dc), P(dw), P(xsave), P(enc), P(ap), P(w), P(conv), P(W_att),
-                                          P(W_conv), P(gv), 2.0, P(d_pre), 1, P(ddp), P(dprev), P(acc[0]), P(acc[1]),
-                                          P(acc[2]), P(acc[3]), B, Th, D, A, C, K, sp()))
+        _lib.check(L.re2e_attloc_step_bwd(P(dc), P(dw), P(xsave), P(enc), P(ap), P(w), P(conv), P(W_dec), P(W_att),
+                                          P(W_conv), P(gv), 2.0, P(d_pre), 1, P(ddp), P(d_dz), P(dprev), P(acc),
+                                          nslots, B, Th, D, A, Z, C, K, sp()))
 
     def k_ctc_fwd():
         _lib.check(L.re2e_ctc_loss_fwd(P(logits), Th * V, V, P(tg.labels), P(tg.offs), P(tg.lens), P(hl), 0, P(nll),

@@ -26,8 +26,6 @@
 namespace re2e {
 namespace {
 
-constexpr int kNWF = 16;      // warps per CTA, forward
-constexpr int kNWB = 12;      // warps per CTA, backward (register budget: W_att + dW_att accumulators)
 constexpr int kDplMax = 16;   // D <= 512
 constexpr int kMaxStages = 30;
 constexpr int kTG = 5;        // conv outputs per thread (sliding window)
@@ -37,6 +35,7 @@ __host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
 
 struct AttGeom {
   int tloc_max, nch, ns, stage_floats, Thp, CKp, App;  // App: padded alignment row Th + 2*filts + 8
+  int ring_floats;                                     // backward: floats reserved for the enc_h ring / its aliases
 };
 
 struct AttFwdParams {
@@ -48,11 +47,11 @@ struct AttFwdParams {
 };
 
 struct AttBwdParams {
-  const float *dc, *dw, *xsave, *enc, *att_prev, *w, *conv, *W_att, *W_conv, *gvec;
+  const float *dc, *dw, *xsave, *enc, *att_prev, *w, *conv, *W_dec, *W_att, *W_conv, *gvec;
   float scaling;
-  float *d_pre, *d_decproj, *d_att_prev, *dW_att, *dW_conv, *dgvec, *dgvec_b;
-  int accumulate_pre;
-  int B, Th, D, A, C, K;
+  float *d_pre, *d_decproj, *d_dec_z, *d_att_prev, *acc_slots;
+  int accumulate_pre, slot_stride;
+  int B, Th, D, A, Z, C, K;
   AttGeom g;
 };
 
@@ -136,6 +135,13 @@ __device__ __forceinline__ void pair_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// remote shared-memory store that signals the destination CTA's mbarrier (complete_tx of 4 bytes): the
+// receiver waits on its own barrier -- no cluster-wide barrier, no release fence on the sender
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(__float_as_uint(v)), "r"(remote_bar)
+               : "memory");
+}
 __device__ __forceinline__ void cluster_arrive_relaxed() {
   asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 }
@@ -158,6 +164,8 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
 
   uint64_t *full = reinterpret_cast<uint64_t *>(smraw);
   uint64_t *empty = full + kMaxStages;
+  uint64_t *dpbar = empty + kMaxStages;                    // dec_proj row complete (A floats pushed by the cluster)
+  uint64_t *xbar = dpbar + 1;                              // softmax statistics (+ partial contexts on rank 0) complete
   float *stages = reinterpret_cast<float *>(smraw + 512);
   float *app = stages + (size_t)g.ns * g.stage_floats;     // App   zero padded alignment row, ap[i] at filts+i
   float *wc_s = app + g.App;                               // CKp
@@ -183,13 +191,18 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
     bulk_g2s(dst + kFP * A, p.enc + ((size_t)b * Th + r0) * D, (uint32_t)rows * D * 4u, &full[st]);
   };
 
-  cluster_arrive_relaxed();  // #0: "this CTA is running" -- peers wait on it before their first DSMEM store
   if (tid == 0) {
     for (int i = 0; i < g.ns; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kFW); }
+    mbar_init(dpbar, 1);
+    mbar_init(xbar, 1);
     mbar_fence_init();
+    if (p.dec_z) mbar_expect_tx(dpbar, (uint32_t)A * 4u);
+    mbar_expect_tx(xbar, (uint32_t)CL * 8u + (rank == 0 ? (uint32_t)CL * (uint32_t)D * 4u : 0u));
     const int first = nch < g.ns ? nch : g.ns;
     for (int q = 0; q < first; ++q) issue(q);
   }
+  // "this CTA is running and its barriers exist": peers wait on it before their first remote store
+  cluster_arrive_relaxed();
 
   // ---- every global load of the prologue is issued before the first use: ONE L2 round trip for the small
   //      operands (alignment row, W_conv, W_att, dec_z, gvec) and this warp's W_dec rows
@@ -300,15 +313,17 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
     }
 #pragma unroll
     for (int u = 0; u < kCPW; ++u) dots[u] = warp_sum(dots[u]);
-    if (base == 0) cluster_wait();  // #0 complete: every peer CTA is resident
+    if (base == 0) cluster_wait();  // every peer CTA is resident, its mbarriers initialised
+    if (p.dec_z) {
 #pragma unroll
-    for (int u = 0; u < kCPW; ++u) {
-      const int ai = base + warp + kFW * u;
-      if (ai < apc && lane < CL) dsmem_st(dsmem_addr(dp_s + a_begin + ai, (uint32_t)lane), dots[u]);
-      if (ai < apc && lane == 0 && p.dec_proj) p.dec_proj[(size_t)b * A + a_begin + ai] = dots[u];
+      for (int u = 0; u < kCPW; ++u) {
+        const int ai = base + warp + kFW * u;
+        if (ai < apc && lane < CL)
+          st_async_f32(dsmem_addr(dp_s + a_begin + ai, (uint32_t)lane), dots[u], dsmem_addr(dpbar, (uint32_t)lane));
+        if (ai < apc && lane == 0 && p.dec_proj) p.dec_proj[(size_t)b * A + a_begin + ai] = dots[u];
+      }
     }
   }
-  cluster_arrive();  // #1 (release): this CTA's dec_proj slice is in every peer's dp_s
 
   // ---- location convolution: conv[t,c] = sum_k Wc[c,k] * att_prev[t + k - filts]  (zero padded).
   //      item = (k quarter, channel, group of 5 frames): 2 shared loads per 5 FMAs
@@ -358,7 +373,7 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
     }
     conv_s[i] = v;
   }
-  cluster_wait();   // #1 (acquire): dp_s holds the full dec_proj row
+  if (p.dec_z) mbar_wait(dpbar, 0);   // dp_s holds the full dec_proj row (A floats pushed by the CTAs of the cluster)
   __syncthreads();  // #3: conv_s visible
 
   float m_run = -CUDART_INF_F, s_run = 0.0f;
@@ -451,7 +466,7 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
     float sum = 0.0f;
 #pragma unroll
     for (int pr = 0; pr < kFP; ++pr) sum += cred[pr * Dp + d];
-    dsmem_st(dsmem_addr(cbuf + rank * Dp + d, 0u), sum);
+    st_async_f32(dsmem_addr(cbuf + rank * Dp + d, 0u), sum, dsmem_addr(xbar, 0u));
   }
   if (tid < CL) {
     float sc = 0.0f;
@@ -460,11 +475,10 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
       const float mw = wstat[4 * pr];
       if (mw != -CUDART_INF_F) sc += wstat[4 * pr + 1] * __expf(mw - Mc);
     }
-    dsmem_st(dsmem_addr(xch + 2 * rank, (uint32_t)tid), Mc);
-    dsmem_st(dsmem_addr(xch + 2 * rank + 1, (uint32_t)tid), sc);
+    st_async_f32(dsmem_addr(xch + 2 * rank, (uint32_t)tid), Mc, dsmem_addr(xbar, (uint32_t)tid));
+    st_async_f32(dsmem_addr(xch + 2 * rank + 1, (uint32_t)tid), sc, dsmem_addr(xbar, (uint32_t)tid));
   }
-  cluster_arrive();  // #2
-  cluster_wait();
+  mbar_wait(xbar, 0);   // every rank's (max, sum) -- and on rank 0 every partial context -- has landed here
   float M = -CUDART_INF_F;
   for (int r = 0; r < CL; ++r) M = fmaxf(M, xch[2 * r]);
   float S = 0.0f;
@@ -480,152 +494,253 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
       p.c[(size_t)b * D + d] = sum * inv;
     }
   }
-  // no trailing cluster barrier: after #2 nobody touches remote shared memory
+  // no trailing cluster barrier: a CTA leaves only after everything addressed to it has landed (xbar), and it
+  // never reads remote shared memory
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward
+// backward (v3).  One cluster per utterance, CTA `rank` owns frames [t0,t1).
+//
+//   shared memory : the saved activations x = tanh(.) of ALL the CTA's frames (fetched by bulk copies in 8-frame
+//                   chunks, each on its own mbarrier) stay resident; d pre is formed IN PLACE and handed back to the
+//                   TMA unit chunk by chunk (cp.reduce.async.bulk.add.f32: the SM never reads d_pre).  enc_h streams
+//                   through a small ring (it is only needed for dwt[t] = dw[t] + enc_h[t].dc).
+//   pass 1        : warp per frame, dwt[t]; softmax backward needs sum_t w[t] dwt[t] over the whole utterance:
+//                   every CTA pushes its partial sum to its peers (st.async + mbarrier, no cluster barrier)
+//   pass 2        : warp pair per frame, lane <-> attention channel: dt = de g (1 - x^2) -> d pre (in place),
+//                   d dec_proj, d gvec, d conv (16-value butterfly reduction); no CTA barrier inside the loop
+//   post pass     : dW_att = dt^T conv straight from the resident tile; d conv / d dec_proj partials exchanged over
+//                   DSMEM; d att_prev (transposed conv), dW_conv, and d dec_z = d dec_proj W_dec (split over ranks)
+//   parameter grads: accumulated WITHOUT atomics into this CTA's private slot of `acc_slots` (plain read-modify-write,
+//                   L2 resident across the decoder loop); re2e_attloc_acc_reduce sums the slots once per loop.
 // ------------------------------------------------------------------------------------------------
-template <int APL, int CP>
-__global__ void __launch_bounds__(kNWB * 32, 1) attloc_bwd_kernel(const AttBwdParams p) {
-  constexpr int NW = kNWB, NT = NW * 32;
+constexpr int kBP = 8;                  // warp pairs = frames per activation chunk
+constexpr int kBW = 2 * kBP;            // warps
+constexpr int kBT = kBW * 32;
+constexpr int kMaxXChunks = 16;         // tloc_max <= 128 frames per CTA
+constexpr int kMaxEStages = 8;
+
+template <int APL, int CP, int DPL2>
+__global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p) {
+  constexpr int NT = kBT;
+  constexpr int WP = CP + 1;
+  constexpr int CPP = (CP + 3) & ~3;
   extern __shared__ __align__(128) unsigned char smraw[];
   const AttGeom g = p.g;
-  const int Th = p.Th, D = p.D, A = p.A, C = p.C, K = p.K, filts = (p.K - 1) / 2;
+  const int C = CP == 10 ? 10 : p.C;
+  const int Th = p.Th, D = p.D, A = p.A, K = p.K, Z = p.Z, filts = (p.K - 1) / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = warp & 1, pair = warp >> 1;
   const int CL = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
   const int b = blockIdx.x / CL;
   const int t0 = min(Th, rank * g.tloc_max), t1 = min(Th, t0 + g.tloc_max), tloc = t1 - t0;
-  const int nch = (tloc + NW - 1) / NW;
-  const int total = 2 * nch;
+  const int nchx = (tloc + kBP - 1) / kBP;       // activation chunks (8 frames)
+  const int nche = (tloc + kBW - 1) / kBW;       // enc_h chunks (16 frames)
 
-  uint64_t *full = reinterpret_cast<uint64_t *>(smraw);
-  float *stages = reinterpret_cast<float *>(smraw + 256);
-  float *app = stages + (size_t)g.ns * g.stage_floats;    // App      padded att_prev row
-  float *wc_s = app + g.App;                              // CKp
-  float *conv_s = wc_s + g.CKp;                           // tloc_max*CP
-  float *w_s = conv_s + g.tloc_max * CP;                  // tloc_max
-  float *dwt_s = w_s + round4(g.tloc_max);                // tloc_max
-  float *de_s = dwt_s + round4(g.tloc_max);               // tloc_max
-  float *dcv_p = de_s + round4(g.tloc_max);               // 2*tloc_max*16   per-half d conv partials
-  float *dcvT = dcv_p + 2 * g.tloc_max * 16;              // CP*App  channel-major, zero padded, cluster-wide
-  float *dWatt_s = dcvT + CP * g.App;                     // A*CP
-  float *ddp_s = dWatt_s + A * CP;                        // A
-  float *dgv_s = ddp_s + A;                               // A
-  float *scr = dgv_s + A;                                 // kKQ*C*tloc_max  d att_prev partials
-  float *xch = scr + kKQ * CP * g.tloc_max;               // 4
+  uint64_t *full_x = reinterpret_cast<uint64_t *>(smraw);   // [kMaxXChunks]
+  uint64_t *done_x = full_x + kMaxXChunks;                  // [kMaxXChunks]
+  uint64_t *full_e = done_x + kMaxXChunks;                  // [kMaxEStages]
+  uint64_t *xbar1 = full_e + kMaxEStages;                   // sum_t w dwt partials of every rank
+  uint64_t *xbar2 = xbar1 + 1;                              // d conv of every frame + d dec_proj partials of every rank
+  float *xs = reinterpret_cast<float *>(smraw + 512);       // tloc_max*A   activations, then d pre in place
+  float *ering = xs + (size_t)g.tloc_max * A;               // ns * kBW*D   enc_h ring; reused after pass 1:
+  float *ddp_w = ering;                                     //   kBW*(A/2)  per-warp d dec_proj partials
+  float *dgv_w = ddp_w + kBW * (A / 2);                     //   kBW*(A/2)  per-warp d gvec partials
+  float *scr = dgv_w + kBW * (A / 2);                       //   kKQ*CP*tloc_max  d att_prev partials
+  float *dzp = scr + kKQ * CP * g.tloc_max;                 //   4*round4(Z)  d dec_z partials
+  float *app = ering + (size_t)g.ring_floats;               // App      padded att_prev row
+  float *wc_s = app + g.App;                                // CKp
+  float *watt_s = wc_s + g.CKp;                             // A*WP
+  float *conv_s = watt_s + A * WP;                          // tloc_max*CPP
+  float *w_s = conv_s + g.tloc_max * CPP;                   // round4(tloc_max)
+  float *dwt_s = w_s + round4(g.tloc_max);                  // round4(tloc_max)
+  float *de_s = dwt_s + round4(g.tloc_max);                 // round4(tloc_max)
+  float *dcv_p = de_s + round4(g.tloc_max);                 // 2*tloc_max*16   per-half d conv partials
+  float *dcvT = dcv_p + 2 * g.tloc_max * 16;                // CP*App  channel-major zero padded d conv of ALL frames
+  float *ddp_x = dcvT + CP * g.App;                         // CL*A    d dec_proj partials of every rank
+  float *ddp_t = ddp_x + CL * A;                            // A       d dec_proj total
+  float *xch = ddp_t + A;                                   // 16      sum_t w dwt partials of every rank
+  float *slot = p.acc_slots + (size_t)blockIdx.x * p.slot_stride;   // [dW_att A*C | dW_conv C*K | dgvec A | dgvec_b 1]
 
-  if (tid == 0) {
-    for (int i = 0; i < g.ns; ++i) mbar_init(&full[i], 1);
-    mbar_fence_init();
-    const int first = total < g.ns ? total : g.ns;
-    for (int q = 0; q < first; ++q) issue_chunk<NW>(q, nch, g, p.enc, D, p.xsave, A, b, Th, t0, t1, stages, full);
-  }
-  for (int i = tid; i < g.App; i += NT) {
-    const int t = i - filts;
-    app[i] = (t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
-  }
-  for (int i = tid; i < C * K; i += NT) wc_s[i] = __ldg(p.W_conv + i);
-  for (int i = tid; i < tloc * CP; i += NT) {
-    const int tl = i / CP, c = i - tl * CP;
-    conv_s[i] = c < C ? __ldg(p.conv + ((size_t)b * Th + t0 + tl) * C + c) : 0.0f;
-  }
-  for (int i = tid; i < tloc; i += NT) w_s[i] = __ldg(p.w + (size_t)b * Th + t0 + i);
-  for (int i = tid; i < CP * g.App; i += NT) dcvT[i] = 0.0f;
-  for (int i = tid; i < A * CP; i += NT) dWatt_s[i] = 0.0f;
-  for (int i = tid; i < A; i += NT) { ddp_s[i] = 0.0f; dgv_s[i] = 0.0f; }
-  float dcr[kDplMax];
-#pragma unroll
-  for (int j = 0; j < kDplMax; ++j)
-    dcr[j] = (p.dc && lane + 32 * j < D) ? __ldg(p.dc + (size_t)b * D + lane + 32 * j) : 0.0f;
-  // (peers write into this CTA's dcvT only after the cluster barrier of the softmax reduction below,
-  //  which orders those remote stores after the zero-fill above)
-
-  // ---- dwt[t] = dw[t] + enc_h[t,:] . dc      (gradient reaching w[t])
-  for (int q = 0; q < nch; ++q) {
+  auto issue_e = [&](int q) {
     const int st = q % g.ns;
-    mbar_wait(&full[st], (uint32_t)((q / g.ns) & 1));
-    const float *tile = stages + (size_t)st * g.stage_floats;
-    const int rows = min(NW, tloc - NW * q);
-    if (warp < rows) {
-      const int tl = NW * q + warp;
-      const float *row = tile + warp * D + lane;
-      float dot = 0.0f;
-#pragma unroll
-      for (int j = 0; j < kDplMax; ++j)
-        if (lane + 32 * j < D) dot = fmaf(dcr[j], row[32 * j], dot);
-      dot = warp_sum(dot);
-      if (lane == 0) dwt_s[tl] = dot + (p.dw ? __ldg(p.dw + (size_t)b * Th + t0 + tl) : 0.0f);
+    const int r0 = t0 + kBW * q;
+    const int rows = min(kBW, t1 - r0);
+    mbar_expect_tx(&full_e[st], (uint32_t)rows * D * 4u);
+    bulk_g2s(ering + (size_t)st * g.stage_floats, p.enc + ((size_t)b * Th + r0) * D, (uint32_t)rows * D * 4u, &full_e[st]);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < nchx; ++i) { mbar_init(&full_x[i], 1); mbar_init(&done_x[i], kBW); }
+    for (int i = 0; i < g.ns; ++i) mbar_init(&full_e[i], 1);
+    mbar_init(xbar1, 1);
+    mbar_init(xbar2, 1);
+    mbar_fence_init();
+    mbar_expect_tx(xbar1, (uint32_t)CL * 4u);
+    mbar_expect_tx(xbar2, (uint32_t)Th * (uint32_t)C * 4u + (uint32_t)CL * (uint32_t)A * 4u);
+    const int first = nche < g.ns ? nche : g.ns;
+    for (int q = 0; q < first; ++q) issue_e(q);
+    for (int q = 0; q < nchx; ++q) {
+      const int r0 = t0 + kBP * q;
+      const int rows = min(kBP, t1 - r0);
+      mbar_expect_tx(&full_x[q], (uint32_t)rows * A * 4u);
+      bulk_g2s(xs + (size_t)kBP * q * A, p.xsave + ((size_t)b * Th + r0) * A, (uint32_t)rows * A * 4u, &full_x[q]);
     }
-    if (q + g.ns < total) {
-      __syncthreads();
-      if (tid == 0) issue_chunk<NW>(q + g.ns, nch, g, p.enc, D, p.xsave, A, b, Th, t0, t1, stages, full);
-    }
   }
-  __syncthreads();
-  // ---- softmax backward needs sum_t w[t]*dwt[t] over ALL frames: cluster reduction via DSMEM
-  if (warp == 0) {
-    float s = 0.0f;
-    for (int tl = lane; tl < tloc; tl += 32) s = fmaf(w_s[tl], dwt_s[tl], s);
-    s = warp_sum(s);
-    if (lane == 0) xch[0] = s;
-  }
-  cluster_sync_all();
-  float Stot = 0.0f;
-  for (int r = 0; r < CL; ++r) Stot += dsmem_ld(dsmem_addr(xch, r));
-  for (int tl = tid; tl < tloc; tl += NT) de_s[tl] = p.scaling * w_s[tl] * (dwt_s[tl] - Stot);
-  __syncthreads();
-  if (warp == 0) {
-    float s = 0.0f;
-    for (int tl = lane; tl < tloc; tl += 32) s += de_s[tl];
-    s = warp_sum(s);
-    if (lane == 0 && tloc > 0) atomicAdd(p.dgvec_b, s);
-  }
+  cluster_arrive_relaxed();   // "this CTA is running and its barriers exist"
 
-  // ---- through tanh (activations x saved by the forward): two warps per frame, lane <-> channel
-  float Watt[APL][CP], dWatt[APL][CP], gv[APL], dgv[APL], ddp[APL];
+  // ---- prologue loads, batched in registers: one L2 round trip
+  float dcr[DPL2];
+#pragma unroll
+  for (int j = 0; j < DPL2; ++j) dcr[j] = (p.dc && lane + 32 * j < D) ? __ldg(p.dc + (size_t)b * D + lane + 32 * j) : 0.0f;
+  float gv[APL];
+#pragma unroll
+  for (int j = 0; j < APL; ++j) gv[j] = __ldg(p.gvec + half * (A / 2) + lane + 32 * j);
+  {
+    constexpr int IA = 2, IC = 4, IW = 8, IV = 2;
+    float va[IA], vc[IC], vw[IW], vv[IV], vws, vdw;
+#pragma unroll
+    for (int u = 0; u < IA; ++u) {
+      const int i = tid + u * NT, t = i - filts;
+      va[u] = (i < g.App && t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < IC; ++u) {
+      const int i = tid + u * NT;
+      vc[u] = i < C * K ? __ldg(p.W_conv + i) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < IW; ++u) {
+      const int i = tid + u * NT;
+      vw[u] = i < A * C ? __ldg(p.W_att + i) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < IV; ++u) {
+      const int i = tid + u * NT;
+      vv[u] = i < tloc * C ? __ldg(p.conv + ((size_t)b * Th + t0) * C + i) : 0.0f;
+    }
+    vws = tid < tloc ? __ldg(p.w + (size_t)b * Th + t0 + tid) : 0.0f;
+    vdw = (p.dw && tid < tloc) ? __ldg(p.dw + (size_t)b * Th + t0 + tid) : 0.0f;
+#pragma unroll
+    for (int u = 0; u < IA; ++u)
+      if (tid + u * NT < g.App) app[tid + u * NT] = va[u];
+#pragma unroll
+    for (int u = 0; u < IC; ++u)
+      if (tid + u * NT < C * K) wc_s[tid + u * NT] = vc[u];
+#pragma unroll
+    for (int u = 0; u < IW; ++u) {
+      const int i = tid + u * NT;
+      if (i < A * C) { const int a = i / C; watt_s[a * WP + (i - a * C)] = vw[u]; }
+    }
+#pragma unroll
+    for (int u = 0; u < IV; ++u) {
+      const int i = tid + u * NT;
+      if (i < tloc * C) { const int tl = i / C; conv_s[tl * CPP + (i - tl * C)] = vv[u]; }
+    }
+    if (tid < tloc) { w_s[tid] = vws; dwt_s[tid] = vdw; }
+    for (int i = tid + IA * NT; i < g.App; i += NT) {
+      const int t = i - filts;
+      app[i] = (t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
+    }
+    for (int i = tid + IC * NT; i < C * K; i += NT) wc_s[i] = __ldg(p.W_conv + i);
+    for (int i = tid + IW * NT; i < A * C; i += NT) { const int a = i / C; watt_s[a * WP + (i - a * C)] = __ldg(p.W_att + i); }
+    for (int i = tid + IV * NT; i < tloc * C; i += NT) {
+      const int tl = i / C;
+      conv_s[tl * CPP + (i - tl * C)] = __ldg(p.conv + ((size_t)b * Th + t0) * C + i);
+    }
+    for (int i = tid + NT; i < tloc; i += NT) {
+      w_s[i] = __ldg(p.w + (size_t)b * Th + t0 + i);
+      dwt_s[i] = p.dw ? __ldg(p.dw + (size_t)b * Th + t0 + i) : 0.0f;
+    }
+    // zero the pads of the channel-major d conv rows (the frames themselves are pushed by the cluster)
+    const int padn = g.App - Th;
+    for (int i = tid; i < CP * padn; i += NT) {
+      const int c = i / padn, o = i - c * padn;
+      dcvT[c * g.App + (o < filts ? o : Th + o)] = 0.0f;
+    }
+    if (CPP > CP)
+      for (int i = tid; i < tloc * (CPP - CP); i += NT) conv_s[(i / (CPP - CP)) * CPP + CP + i % (CPP - CP)] = 0.0f;
+  }
+  __syncthreads();  // #1
+
+  // ---- pass 1: dwt[t] = dw[t] + enc_h[t,:] . dc   (warp per frame, lane <-> d)
+  {
+    int st = 0;
+    uint32_t ph = 0;
+    for (int q = 0; q < nche; ++q) {
+      mbar_wait(&full_e[st], ph);
+      const int tl = kBW * q + warp;
+      if (tl < tloc) {
+        const float *row = ering + (size_t)st * g.stage_floats + warp * D + lane;
+        float dot = 0.0f;
+#pragma unroll
+        for (int j = 0; j < DPL2; ++j)
+          if (lane + 32 * j < D) dot = fmaf(dcr[j], row[32 * j], dot);
+        dot = warp_sum(dot);
+        if (lane == 0) dwt_s[tl] += dot;
+      }
+      if (g.ns < nche) {   // ring shorter than the frame range (long utterances): refill behind a CTA barrier
+        __syncthreads();
+        if (tid == 0 && q + g.ns < nche) issue_e(q + g.ns);
+      }
+      if (++st == g.ns) { st = 0; ph ^= 1u; }
+    }
+  }
+  // W_att rows of this lane's channels -> registers
+  float Watt[APL][CP];
 #pragma unroll
   for (int j = 0; j < APL; ++j) {
     const int a = half * (A / 2) + lane + 32 * j;
-    gv[j] = __ldg(p.gvec + a);
-    dgv[j] = 0.0f;
-    ddp[j] = 0.0f;
 #pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      Watt[j][c] = c < C ? __ldg(p.W_att + (size_t)a * C + c) : 0.0f;
-      dWatt[j][c] = 0.0f;
-    }
+    for (int c = 0; c < CP; ++c) Watt[j][c] = c < C ? watt_s[a * WP + c] : 0.0f;
   }
-  for (int q = nch; q < total; ++q) {
-    const int st = q % g.ns;
-    mbar_wait(&full[st], (uint32_t)((q / g.ns) & 1));
-    float *tile = stages + (size_t)st * g.stage_floats;
-    const int qq = q - nch;
-    const int rows = min(NW, tloc - NW * qq);
+  __syncthreads();  // #2: dwt complete; the enc ring is free
+  cluster_wait();   // peers are resident: remote stores may start
+  if (warp == 0) {
+    float s1 = 0.0f;
+    for (int tl = lane; tl < tloc; tl += 32) s1 = fmaf(w_s[tl], dwt_s[tl], s1);
+    s1 = warp_sum(s1);
+    if (lane < CL) st_async_f32(dsmem_addr(xch + rank, (uint32_t)lane), s1, dsmem_addr(xbar1, (uint32_t)lane));
+  }
+  mbar_wait(xbar1, 0);
+  float Stot = 0.0f;
+  for (int r = 0; r < CL; ++r) Stot += xch[r];
+  for (int tl = tid; tl < tloc; tl += NT) de_s[tl] = p.scaling * w_s[tl] * (dwt_s[tl] - Stot);
+  __syncthreads();  // #3
+
+  // ---- pass 2: through tanh.  pair <-> frame, lane <-> channel
+  float dgv[APL], ddp[APL];
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int r = pair + (NW / 2) * rr;
-      if (r < rows) {
-        const int tl = NW * qq + r;
+  for (int j = 0; j < APL; ++j) { dgv[j] = 0.0f; ddp[j] = 0.0f; }
+  {
+    const int aoff = half * (A / 2) + lane;
+    auto flush = [&](int q) {   // hand chunk q (d pre, formed in place) to the TMA unit
+      mbar_wait(&done_x[q], 0);
+      const int r0 = kBP * q;
+      const int rows = min(kBP, tloc - r0);
+      float *dst = p.d_pre + ((size_t)b * Th + t0 + r0) * A;
+      if (p.accumulate_pre) bulk_red_add_s2g(dst, xs + (size_t)r0 * A, (uint32_t)rows * A * 4u);
+      else bulk_s2g(dst, xs + (size_t)r0 * A, (uint32_t)rows * A * 4u);
+      bulk_commit();
+    };
+    for (int q = 0; q < nchx; ++q) {
+      if (tid == 0 && q >= 1) flush(q - 1);
+      __syncwarp();
+      mbar_wait(&full_x[q], 0);
+      const int tl = kBP * q + pair;
+      if (tl < tloc) {
         const float de = de_s[tl];
-        float cv[CP], dcv[16];
-#pragma unroll
-        for (int c = 0; c < CP; ++c) cv[c] = conv_s[tl * CP + c];
+        float dcv[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) dcv[c] = 0.0f;
-        float *row = tile + r * A + half * (A / 2) + lane;
+        float *row = xs + (size_t)tl * A + aoff;
 #pragma unroll
         for (int j = 0; j < APL; ++j) {
           const float x = row[32 * j];
           dgv[j] = fmaf(de, x, dgv[j]);
           const float dt = de * gv[j] * (1.0f - x * x);
           ddp[j] += dt;
-          row[32 * j] = dt;  // d pre, formed in place in the ring
+          row[32 * j] = dt;  // d pre, in place
 #pragma unroll
-          for (int c = 0; c < CP; ++c) {
-            dWatt[j][c] = fmaf(dt, cv[c], dWatt[j][c]);
-            dcv[c] = fmaf(dt, Watt[j][c], dcv[c]);
-          }
+          for (int c = 0; c < CP; ++c) dcv[c] = fmaf(dt, Watt[j][c], dcv[c]);
         }
         warp_reduce16(dcv, lane);
         if ((lane & 1) == 0) {
@@ -633,51 +748,77 @@ __global__ void __launch_bounds__(kNWB * 32, 1) attloc_bwd_kernel(const AttBwdPa
           dcv_p[(half * g.tloc_max + tl) * 16 + ci] = dcv[0];
         }
       }
+      fence_proxy_async_smem();   // this thread's in-place writes -> visible to the bulk (async proxy) read
+      __syncwarp();
+      if (lane == 0) mbar_arrive1(&done_x[q]);
     }
-    // hand the chunk to the TMA unit: d_pre[b, rows, :] (+)= tile
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      float *dst = p.d_pre + ((size_t)b * Th + t0 + NW * qq) * A;
-      const uint32_t bytes = (uint32_t)rows * A * 4u;
-      if (p.accumulate_pre) bulk_red_add_s2g(dst, tile, bytes);
-      else bulk_s2g(dst, tile, bytes);
-      bulk_commit();
-      if (q + g.ns < total) {
-        bulk_wait_read<0>();  // the store has drained the stage before it is refilled
-        issue_chunk<NW>(q + g.ns, nch, g, p.enc, D, p.xsave, A, b, Th, t0, t1, stages, full);
-      }
-    }
-  }
-  // ---- CTA-level reductions of the parameter gradients (shared-memory atomics, then one global
-  //      atomic per element per CTA)
+    if (tid == 0 && nchx > 0) flush(nchx - 1);
 #pragma unroll
-  for (int j = 0; j < APL; ++j) {
-    const int a = half * (A / 2) + lane + 32 * j;
-    atomicAdd(ddp_s + a, ddp[j]);
-    atomicAdd(dgv_s + a, dgv[j]);
-#pragma unroll
-    for (int c = 0; c < CP; ++c)
-      if (c < C) atomicAdd(dWatt_s + a * CP + c, dWatt[j][c]);
-  }
-  __syncthreads();
-  if (tloc > 0) {
-    for (int i = tid; i < A * C; i += NT) {
-      const int a = i / C, c = i - a * C;
-      atomicAdd(p.dW_att + i, dWatt_s[a * CP + c]);
-    }
-    for (int a = tid; a < A; a += NT) {
-      atomicAdd(p.dgvec + a, dgv_s[a]);
-      atomicAdd(p.d_decproj + (size_t)b * A + a, ddp_s[a]);
+    for (int j = 0; j < APL; ++j) {
+      ddp_w[warp * (A / 2) + lane + 32 * j] = ddp[j];
+      dgv_w[warp * (A / 2) + lane + 32 * j] = dgv[j];
     }
   }
-  // ---- publish d conv (this CTA's frames) to every CTA of the cluster, channel-major, padded
+  __syncthreads();  // #4: all d pre tiles written, per-warp partials published
+
+  // ---- post pass A
+  // d conv of this CTA's frames -> every CTA of the cluster (channel-major, padded)
   for (int item = tid; item < tloc * C; item += NT) {
     const int c = item / tloc, tl = item - c * tloc;
     const float v = dcv_p[tl * 16 + c] + dcv_p[(g.tloc_max + tl) * 16 + c];
-    for (int r = 0; r < CL; ++r) dsmem_st(dsmem_addr(dcvT + c * g.App + filts + t0 + tl, r), v);
+    for (int r = 0; r < CL; ++r)
+      st_async_f32(dsmem_addr(dcvT + c * g.App + filts + t0 + tl, (uint32_t)r), v, dsmem_addr(xbar2, (uint32_t)r));
   }
-  cluster_sync_all();
+  // d dec_proj / d gvec of this CTA (fixed summation order), d dec_proj partial -> every CTA
+  for (int a = tid; a < A; a += NT) {
+    const int h = a >= A / 2 ? 1 : 0, ai = a - h * (A / 2);
+    float sd = 0.0f, sg = 0.0f;
+#pragma unroll
+    for (int pr = 0; pr < kBP; ++pr) {
+      sd += ddp_w[(2 * pr + h) * (A / 2) + ai];
+      sg += dgv_w[(2 * pr + h) * (A / 2) + ai];
+    }
+    for (int r = 0; r < CL; ++r)
+      st_async_f32(dsmem_addr(ddp_x + rank * A + a, (uint32_t)r), sd, dsmem_addr(xbar2, (uint32_t)r));
+    if (tloc > 0) slot[A * C + C * K + a] += sg;
+  }
+  if (warp == 0) {   // d gvec.bias = sum_t de[t]  (analytically zero over the utterance; kept for fidelity)
+    float s2 = 0.0f;
+    for (int tl = lane; tl < tloc; tl += 32) s2 += de_s[tl];
+    s2 = warp_sum(s2);
+    if (lane == 0 && tloc > 0) slot[A * C + C * K + A] += s2;
+  }
+  // dW_att[a,c] += sum_t d pre[t,a] conv[t,c]   straight from the resident tile (thread <-> a)
+  for (int a = tid; a < A; a += NT) {
+    float acc[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
+    for (int tl = 0; tl < tloc; ++tl) {
+      const float dt = xs[(size_t)tl * A + a];
+#pragma unroll
+      for (int c4 = 0; c4 < CPP; c4 += 4) {
+        const float4 t4 = *reinterpret_cast<const float4 *>(conv_s + tl * CPP + c4);
+        if (c4 < CP) acc[c4] = fmaf(dt, t4.x, acc[c4]);
+        if (c4 + 1 < CP) acc[c4 + 1] = fmaf(dt, t4.y, acc[c4 + 1]);
+        if (c4 + 2 < CP) acc[c4 + 2] = fmaf(dt, t4.z, acc[c4 + 2]);
+        if (c4 + 3 < CP) acc[c4 + 3] = fmaf(dt, t4.w, acc[c4 + 3]);
+      }
+    }
+    if (tloc > 0) {
+#pragma unroll
+      for (int c = 0; c < CP; ++c)
+        if (c < C) slot[a * C + c] += acc[c];
+    }
+  }
+  mbar_wait(xbar2, 0);   // d conv of all Th frames and every rank's d dec_proj partial have landed here
+  for (int a = tid; a < A; a += NT) {
+    float sd = 0.0f;
+    for (int r = 0; r < CL; ++r) sd += ddp_x[r * A + a];
+    ddp_t[a] = sd;
+    if (rank == 0) p.d_decproj[(size_t)b * A + a] = sd;
+  }
+  __syncthreads();  // #5 (also: scr / dzp alias the per-warp partials read above)
+
   // ---- d att_prev[s] = sum_c sum_k Wc[c,k] * dconv[s - k + filts, c]   (sliding window, 5 outputs/thread)
   if (p.d_att_prev) {
     const int nsg = (tloc + kTG - 1) / kTG;
@@ -706,14 +847,26 @@ __global__ void __launch_bounds__(kNWB * 32, 1) attloc_bwd_kernel(const AttBwdPa
       if (nv > 3) o[3] = a3;
       if (nv > 4) o[4] = a4;
     }
-    __syncthreads();
-    for (int tl = tid; tl < tloc; tl += NT) {
-      float s = 0.0f;
-      for (int i = 0; i < kKQ * C; ++i) s += scr[(size_t)i * g.tloc_max + tl];
-      p.d_att_prev[(size_t)b * Th + t0 + tl] = s;
+  }
+  // ---- d dec_z[z] = sum_a d dec_proj[a] W_dec[a,z]  for this rank's slice of z (thread <-> (z, quarter of A))
+  const int zc = (Z + CL - 1) / CL, z_begin = rank * zc, z_n = max(0, min(zc, Z - z_begin));
+  if (p.d_dec_z) {
+    const int aq = A / 4;
+    for (int item = tid; item < 4 * z_n; item += NT) {
+      const int zi = item % z_n, qa = item / z_n;
+      const float *wcol = p.W_dec + (size_t)(qa * aq) * Z + z_begin + zi;
+      const float *dd = ddp_t + qa * aq;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int a = 0; a < aq; a += 4) {
+        s0 = fmaf(dd[a], __ldg(wcol + (size_t)a * Z), s0);
+        s1 = fmaf(dd[a + 1], __ldg(wcol + (size_t)(a + 1) * Z), s1);
+        s2 = fmaf(dd[a + 2], __ldg(wcol + (size_t)(a + 2) * Z), s2);
+        s3 = fmaf(dd[a + 3], __ldg(wcol + (size_t)(a + 3) * Z), s3);
+      }
+      dzp[qa * round4(Z) + zi] = (s0 + s1) + (s2 + s3);
     }
   }
-  // ---- dWc[c,k] += sum_{t in mine} dconv[t,c] * att_prev[t + k - filts]   (6 taps per thread)
+  // ---- dW_conv[c,k] += sum_{t in mine} dconv[t,c] * att_prev[t + k - filts]   (6 taps per thread, one owner each)
   {
     constexpr int KG = 6;
     const int nkg = (K + KG - 1) / KG;
@@ -740,11 +893,42 @@ __global__ void __launch_bounds__(kNWB * 32, 1) attloc_bwd_kernel(const AttBwdPa
       if (tloc > 0) {
 #pragma unroll
         for (int i = 0; i < KG; ++i)
-          if (kb + i < K) atomicAdd(p.dW_conv + c * K + kb + i, acc6[i]);
+          if (kb + i < K) slot[A * C + c * K + kb + i] += acc6[i];
       }
     }
   }
+  __syncthreads();  // #6
+  if (p.d_att_prev) {
+    for (int tl = tid; tl < tloc; tl += NT) {
+      float sum = 0.0f;
+      for (int i = 0; i < kKQ * C; ++i) sum += scr[(size_t)i * g.tloc_max + tl];
+      p.d_att_prev[(size_t)b * Th + t0 + tl] = sum;
+    }
+  }
+  if (p.d_dec_z) {
+    for (int zi = tid; zi < z_n; zi += NT) {
+      const int rz = round4(Z);
+      p.d_dec_z[(size_t)b * Z + z_begin + zi] = (dzp[zi] + dzp[rz + zi]) + (dzp[2 * rz + zi] + dzp[3 * rz + zi]);
+    }
+  }
   if (tid == 0) bulk_wait<0>();  // all d_pre traffic of this CTA has left shared memory / landed
+}
+
+// out[i] (+)= sum_s slots[s*stride + i]   -- once per decoder loop (deterministic order)
+__global__ void __launch_bounds__(256)
+acc_reduce_kernel(const float *__restrict__ slots, int n_slots, int stride, int n, float *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int s = 0;
+  for (; s + 3 < n_slots; s += 4) {
+    s0 += __ldg(slots + (size_t)s * stride + i);
+    s1 += __ldg(slots + (size_t)(s + 1) * stride + i);
+    s2 += __ldg(slots + (size_t)(s + 2) * stride + i);
+    s3 += __ldg(slots + (size_t)(s + 3) * stride + i);
+  }
+  for (; s < n_slots; ++s) s0 += __ldg(slots + (size_t)s * stride + i);
+  out[i] = (s0 + s1) + (s2 + s3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -874,46 +1058,6 @@ enc_grad_kernel(const float *__restrict__ w_all, const float *__restrict__ dc_al
   }
 }
 
-inline bool pick_geom(int B, int Th, int D, int A, int C, int K, int CP, bool bwd, int &CL, AttGeom &g,
-                      size_t &smem) {
-  // cluster size: enough CTAs to cover the SMs once, at most 8 (portable limit)
-  const int NW = bwd ? kNWB : kNWF;
-  const int sms = num_sms();
-  CL = 1;
-  while (CL < 8 && B * CL * 2 <= sms) CL *= 2;
-  while (CL > 1 && (Th + CL - 1) / CL < NW) CL /= 2;  // tiny Th: do not over-split
-  const int filts = (K - 1) / 2;
-  for (;;) {
-    g.tloc_max = (Th + CL - 1) / CL;
-    g.nch = (g.tloc_max + NW - 1) / NW;
-    g.stage_floats = NW * (A > D ? A : D);
-    g.Thp = round4(Th);
-    g.CKp = round4(C * K);
-    g.App = round4(Th + 2 * filts + 8);
-    size_t fixed = 256;
-    if (!bwd)
-      fixed += sizeof(float) * ((size_t)g.App + g.CKp + (size_t)(kKQ + 1) * g.tloc_max * CP +
-                                (size_t)g.tloc_max * 65 + round4(g.tloc_max) + round4(D) + 4);
-    else
-      fixed += sizeof(float) * ((size_t)g.App + g.CKp + (size_t)g.tloc_max * CP + 3 * (size_t)round4(g.tloc_max) +
-                                2 * (size_t)g.tloc_max * 16 + (size_t)CP * g.App + (size_t)A * CP + 2 * A +
-                                (size_t)kKQ * CP * g.tloc_max + 4);
-    const size_t budget = 224 * 1024;
-    const size_t stage_bytes = sizeof(float) * (size_t)g.stage_floats;
-    if (fixed + 2 * stage_bytes <= budget) {
-      int ns = (int)((budget - fixed) / stage_bytes);
-      if (ns > 2 * g.nch) ns = 2 * g.nch;
-      if (ns > kMaxStages) ns = kMaxStages;
-      if (ns < 2) ns = 2;
-      g.ns = ns;
-      smem = fixed + ns * stage_bytes;
-      return true;
-    }
-    if (CL >= 8) return false;
-    CL *= 2;
-  }
-}
-
 // forward (v3) geometry: stage = kFP frames of (pre | enc); the ring holds the whole frame range when it fits
 inline bool pick_geom_fwd(int B, int Th, int D, int A, int Z, int C, int K, int CP, int &CL, AttGeom &g,
                           size_t &smem) {
@@ -944,11 +1088,57 @@ inline bool pick_geom_fwd(int B, int Th, int D, int A, int Z, int C, int K, int 
   return true;
 }
 
+// backward (v3) geometry: all activations of the CTA resident, enc_h through a ring of kBW-frame stages
+inline bool pick_geom_bwd(int B, int Th, int D, int A, int Z, int C, int K, int CP, int &CL, AttGeom &g,
+                          size_t &smem) {
+  const int sms = num_sms();
+  CL = 1;
+  while (CL < 8 && B * CL * 2 <= sms) CL *= 2;
+  while (CL > 1 && (Th + CL - 1) / CL < kBP) CL /= 2;
+  const int filts = (K - 1) / 2;
+  const int CPP = round4(CP);
+  g.stage_floats = kBW * D;
+  g.Thp = round4(Th);
+  g.CKp = round4(C * K);
+  g.App = round4(Th + 2 * filts + 8);
+  for (;;) {
+    g.tloc_max = (Th + CL - 1) / CL;
+    g.nch = (g.tloc_max + kBW - 1) / kBW;
+    const size_t alias_floats = (size_t)kBW * A + (size_t)kKQ * CP * g.tloc_max + 4 * (size_t)round4(Z);
+    const size_t fixed = 512 + sizeof(float) * ((size_t)g.tloc_max * A + (size_t)g.App + g.CKp + (size_t)A * (CP + 1) +
+                                                (size_t)g.tloc_max * CPP + 3 * (size_t)round4(g.tloc_max) +
+                                                2 * (size_t)g.tloc_max * 16 + (size_t)CP * g.App + (size_t)(CL + 1) * A + 16);
+    const size_t budget = 224 * 1024;
+    const size_t stage_bytes = sizeof(float) * (size_t)g.stage_floats;
+    const size_t alias_bytes = sizeof(float) * ((alias_floats + 3) & ~(size_t)3);
+    const size_t min_ring = stage_bytes > alias_bytes ? stage_bytes : alias_bytes;
+    if (g.tloc_max <= kMaxXChunks * kBP && fixed + min_ring <= budget) {
+      int ns = (int)((budget - fixed) / stage_bytes);
+      if (ns > g.nch) ns = g.nch;
+      if (ns > kMaxEStages) ns = kMaxEStages;
+      if (ns < 1) ns = 1;
+      g.ns = ns;
+      size_t ring = (size_t)ns * stage_bytes;
+      if (ring < alias_bytes) ring = alias_bytes;
+      g.ring_floats = (int)(ring / sizeof(float));
+      smem = fixed + ring;
+      return true;
+    }
+    // long utterances: split further, up to the non-portable cluster size of 16 (B*16 CTAs must be co-resident)
+    if (CL >= 16 || B * CL * 2 > sms) return false;
+    CL *= 2;
+  }
+}
+
 template <typename Kern, typename Params>
 int launch_cluster(Kern kern, const Params &prm, int B, int CL, int threads, size_t smem, cudaStream_t st) {
   int rc0 = ensure_smem(reinterpret_cast<const void *>(kern), smem);
   if (rc0 != RE2E_OK) return rc0;
   cudaError_t e;
+  if (CL > 8) {
+    e = cudaFuncSetAttribute(reinterpret_cast<const void *>(kern), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return (int)e;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(B * CL));
   cfg.blockDim = dim3((unsigned)threads);
@@ -984,7 +1174,8 @@ int run_fwd(const AttFwdParams &prm, int CL, size_t smem, cudaStream_t st) {
 }
 template <int APL, int CP>
 int run_bwd(const AttBwdParams &prm, int CL, size_t smem, cudaStream_t st) {
-  return launch_cluster(attloc_bwd_kernel<APL, CP>, prm, prm.B, CL, kNWB * 32, smem, st);
+  if (prm.D == prm.A) return launch_cluster(attloc_bwd_kernel<APL, CP, 2 * APL>, prm, prm.B, CL, kBT, smem, st);
+  return launch_cluster(attloc_bwd_kernel<APL, CP, 2 * kDpl>, prm, prm.B, CL, kBT, smem, st);
 }
 
 inline int check_dims(int B, int Th, int D, int A, int C, int K) {
@@ -1050,32 +1241,48 @@ extern "C" int re2e_attloc_step_fwd(const float *pre, const float *enc_h, const 
   return rc;
 }
 
+extern "C" size_t re2e_attloc_acc_floats(int A, int C, int K) {
+  return (size_t)round4(A * C + C * K + A + 1);
+}
+extern "C" int re2e_attloc_acc_slots(int B) { return B * 16; }  // one slot per CTA, clusters of at most 16
+
 extern "C" int re2e_attloc_step_bwd(const float *dc, const float *dw, const float *xsave, const float *enc_h,
-                                    const float *att_prev, const float *w, const float *conv,
+                                    const float *att_prev, const float *w, const float *conv, const float *W_dec,
                                     const float *W_att, const float *W_conv, const float *gvec, float scaling,
-                                    float *d_pre, int accumulate_pre, float *d_decproj, float *d_att_prev,
-                                    float *dW_att, float *dW_conv, float *dgvec, float *dgvec_b, int B, int Th,
-                                    int D, int A, int C, int K, void *stream) {
-  RE2E_CHECK_ARG(xsave && enc_h && att_prev && w && conv && W_att && W_conv && gvec);
-  RE2E_CHECK_ARG(d_pre && d_decproj && dW_att && dW_conv && dgvec && dgvec_b);
+                                    float *d_pre, int accumulate_pre, float *d_decproj, float *d_dec_z,
+                                    float *d_att_prev, float *acc_slots, int n_slots, int B, int Th, int D, int A,
+                                    int Z, int C, int K, void *stream) {
+  RE2E_CHECK_ARG(xsave && enc_h && att_prev && w && conv && W_dec && W_att && W_conv && gvec);
+  RE2E_CHECK_ARG(d_pre && d_decproj && acc_slots && Z > 0);
   int rc = check_dims(B, Th, D, A, C, K);
   if (rc != RE2E_OK) return rc;
   RE2E_CHECK_ARG(aligned16(xsave) && aligned16(enc_h) && aligned16(d_pre));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  RE2E_CUDA(cudaMemsetAsync(d_decproj, 0, sizeof(float) * (size_t)B * A, st));
   const int CP = C == 10 ? 10 : 16;
   AttBwdParams prm;
   prm.dc = dc; prm.dw = dw; prm.xsave = xsave; prm.enc = enc_h; prm.att_prev = att_prev; prm.w = w;
-  prm.conv = conv; prm.W_att = W_att; prm.W_conv = W_conv; prm.gvec = gvec;
-  prm.scaling = scaling; prm.d_pre = d_pre; prm.d_decproj = d_decproj; prm.d_att_prev = d_att_prev;
-  prm.dW_att = dW_att; prm.dW_conv = dW_conv; prm.dgvec = dgvec; prm.dgvec_b = dgvec_b;
-  prm.accumulate_pre = accumulate_pre;
-  prm.B = B; prm.Th = Th; prm.D = D; prm.A = A; prm.C = C; prm.K = K;
+  prm.conv = conv; prm.W_dec = W_dec; prm.W_att = W_att; prm.W_conv = W_conv; prm.gvec = gvec;
+  prm.scaling = scaling; prm.d_pre = d_pre; prm.d_decproj = d_decproj; prm.d_dec_z = d_dec_z;
+  prm.d_att_prev = d_att_prev; prm.acc_slots = acc_slots; prm.accumulate_pre = accumulate_pre;
+  prm.slot_stride = (int)re2e_attloc_acc_floats(A, C, K);
+  prm.B = B; prm.Th = Th; prm.D = D; prm.A = A; prm.Z = Z; prm.C = C; prm.K = K;
   int CL;
   size_t smem;
-  if (!pick_geom(B, Th, D, A, C, K, CP, true, CL, prm.g, smem)) return RE2E_E_UNSUPPORTED;
+  if (!pick_geom_bwd(B, Th, D, A, Z, C, K, CP, CL, prm.g, smem)) return RE2E_E_UNSUPPORTED;
+  if (n_slots < B * CL) return RE2E_E_WORKSPACE;
   ATT_DISPATCH(run_bwd, A / 64, CP, (prm, CL, smem, st));
   return rc;
+}
+
+// out[0 .. A*C + C*K + A + 1) = sum over the n_slots private accumulators (layout [dW_att | dW_conv | dgvec | dgvec_b])
+extern "C" int re2e_attloc_acc_reduce(const float *acc_slots, int n_slots, float *out, int A, int C, int K,
+                                      void *stream) {
+  RE2E_CHECK_ARG(acc_slots && out && n_slots > 0 && A > 0 && C > 0 && K > 0);
+  const int n = A * C + C * K + A + 1;
+  acc_reduce_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      acc_slots, n_slots, (int)re2e_attloc_acc_floats(A, C, K), n, out);
+  count_launch();
+  return launch_status();
 }
 
 extern "C" int re2e_attloc_enc_grad(const float *w_all, const float *dc_all, float *d_enc_h, int steps,

@@ -42,15 +42,13 @@ class _State(object):
         self.bwd_w, self.bwd_dc, self.bwd_ddp, self.bwd_decz = [], [], [], []
 
     def ensure_acc(self, dev):
+        """Per-CTA private accumulators of the small parameter gradients (no atomics; summed once per loop)."""
         if self.acc is None:
+            L = _lib.lib()
             B, Th, D, A, Z, C, K = self.dims
-            flat = torch.zeros(A * C + C * K + A + 1, device=dev, dtype=torch.float32)
-            o = 0
-            self.acc = {}
-            for name, n in (("dW_att", A * C), ("dW_conv", C * K), ("dgvec", A), ("dgvec_b", 1)):
-                self.acc[name] = flat[o:o + n]
-                o += n
-            self.acc["_flat"] = flat
+            self.acc_stride = int(L.re2e_attloc_acc_floats(A, C, K))
+            self.acc_nslots = int(L.re2e_attloc_acc_slots(B))
+            self.acc = torch.zeros(self.acc_nslots, self.acc_stride, device=dev, dtype=torch.float32)
 
 
 class _Precompute(torch.autograd.Function):
@@ -117,10 +115,14 @@ class _Precompute(torch.autograd.Function):
         elif need[3]:
             dW_dec = torch.zeros(A, Z, device=dev, dtype=torch.float32)
         if st.acc is not None:
-            dW_att = st.acc["dW_att"].view(A, C).clone()
-            dW_conv = st.acc["dW_conv"].view(C, 1, 1, K).clone()
-            dgw = st.acc["dgvec"].view(1, A).clone()
-            dgb = st.acc["dgvec_b"].view(1).clone()
+            tot = torch.empty(A * C + C * K + A + 1, device=dev, dtype=torch.float32)
+            with torch.cuda.device(dev):
+                _lib.check(L.re2e_attloc_acc_reduce(_lib.ptr(st.acc), st.acc_nslots, _lib.ptr(tot), A, C, K,
+                                                    _lib.stream_ptr()), "re2e_attloc_acc_reduce")
+            dW_att = tot[:A * C].view(A, C)
+            dW_conv = tot[A * C:A * C + C * K].view(C, 1, 1, K)
+            dgw = tot[A * C + C * K:A * C + C * K + A].view(1, A)
+            dgb = tot[A * C + C * K + A:].view(1)
         st.clear_grads()
         return d_enc, dW_enc, db_enc, dW_dec, dW_att, dW_conv, dgw, dgb, None
 
@@ -174,22 +176,18 @@ class _Step(torch.autograd.Function):
         d_decproj = torch.empty(B, A, device=dev, dtype=torch.float32)
         want_dprev = ctx.needs_input_grad[2] and not ctx.skip_dprev
         d_prev = torch.empty(B, Th, device=dev, dtype=torch.float32) if want_dprev else None
-        acc = st.acc
+        d_dz = (torch.empty(B, Z, device=dev, dtype=torch.float32)
+                if (ctx.has_dz and ctx.needs_input_grad[1]) else None)
         with torch.cuda.device(dev):
             _lib.check(L.re2e_attloc_step_bwd(
                 _lib.ptr(dc), _lib.ptr(dw), _lib.ptr(xsave), _lib.ptr(st.enc), _lib.ptr(ap), _lib.ptr(w),
-                _lib.ptr(conv), _lib.ptr(W_att), _lib.ptr(W_conv), _lib.ptr(gvec),
-                ctx.scaling, _lib.ptr(st.d_pre), 0 if first else 1, _lib.ptr(d_decproj), _lib.ptr(d_prev),
-                _lib.ptr(acc["dW_att"]), _lib.ptr(acc["dW_conv"]), _lib.ptr(acc["dgvec"]),
-                _lib.ptr(acc["dgvec_b"]), B, Th, D, A, C, K, _lib.stream_ptr()), "re2e_attloc_step_bwd")
-            d_dz = None
-            if ctx.has_dz:
-                st.bwd_ddp.append(d_decproj)
-                st.bwd_decz.append(dz)
-                if ctx.needs_input_grad[1]:
-                    d_dz = torch.empty(B, Z, device=dev, dtype=torch.float32)
-                    _lib.check(L.re2e_skinny_nn(_lib.ptr(d_decproj), _lib.ptr(W_dec), _lib.ptr(d_dz), B, Z, A, 0,
-                                                _lib.stream_ptr()), "re2e_skinny_nn")
+                _lib.ptr(conv), _lib.ptr(W_dec), _lib.ptr(W_att), _lib.ptr(W_conv), _lib.ptr(gvec),
+                ctx.scaling, _lib.ptr(st.d_pre), 0 if first else 1, _lib.ptr(d_decproj), _lib.ptr(d_dz),
+                _lib.ptr(d_prev), _lib.ptr(st.acc), st.acc_nslots, B, Th, D, A, Z, C, K, _lib.stream_ptr()),
+                "re2e_attloc_step_bwd")
+        if ctx.has_dz:
+            st.bwd_ddp.append(d_decproj)
+            st.bwd_decz.append(dz)
         if dc is not None:
             st.bwd_w.append(w)
             st.bwd_dc.append(dc)

@@ -71,7 +71,8 @@ def test_golden(name):
     ((320, 300, 320, 10, 100), 32, 200, 3, 3),        # config 3 shape (cluster of 4 per utterance)
     ((320, 300, 320, 10, 100), 1, 163, 3, 5),         # decode-like: B=1, odd Th, cluster of 8
     ((64, 40, 128, 7, 3), 5, 19, 4, 6),               # odd sizes: C != 10 path, short filters
-    ((512, 128, 512, 10, 20), 2, 700, 2, 7),          # long Th: ring wraps (stages refilled)
+    ((512, 128, 512, 10, 20), 2, 400, 2, 7),          # wide + long: fwd ring wraps, bwd enc_h ring wraps
+    ((320, 300, 320, 10, 100), 2, 700, 2, 8),         # long Th: backward splits over a cluster of 16
 ])
 def test_oracle_parity(dims, B, Th, steps, seed):
     e, d, a, c, f = dims
