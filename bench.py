@@ -185,7 +185,7 @@ def kernel_specs(hp, db, cfg, dev):
     dz = db.dec_z[0].contiguous()
     dc, dw = torch.randn(B, D).to(dev), torch.randn(B, Th).to(dev)
     d_pre, ddp, dprev = torch.zeros(B, Th, A, **f32), torch.empty(B, A, **f32), torch.empty(B, Th, **f32)
-    nslots = int(L.re2e_attloc_acc_slots(B))
+    nslots = int(L.re2e_attloc_acc_slots(B, Th, D, A, Z, C, K))
     acc = torch.zeros(nslots, int(L.re2e_attloc_acc_floats(A, C, K)), **f32)
     d_dz = torch.empty(B, Z, **f32)
     logits = torch.randn(B, Th, V).to(dev)

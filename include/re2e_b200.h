@@ -102,14 +102,14 @@ int re2e_attloc_step_fwd(const float *pre, const float *enc_h, const float *dec_
  *   d_decproj (B,A)       = dE/d(dec_z @ W_dec^T)        (kept for dW_dec = sum_steps d_decproj^T dec_z)
  *   d_dec_z (B,Z)         = d_decproj @ W_dec            (NULL to skip: first decoder step has no dec_z)
  *   d_att_prev (B,Th)     = dE/d att_prev                (NULL to skip, e.g. first decoder step)
- *   acc_slots             parameter-gradient accumulators, n_slots >= re2e_attloc_acc_slots(B) private slots of
+ *   acc_slots             parameter-gradient accumulators, n_slots >= re2e_attloc_acc_slots(...) private slots of
  *                         re2e_attloc_acc_floats(A,C,K) floats each, layout [dW_att A*C | dW_conv C*K | dgvec A |
  *                         dgvec_b 1]; zero them once per decoder loop, every step ADDS into them without atomics
  *                         (one slot per CTA), re2e_attloc_acc_reduce sums the slots after the loop.
  * d enc_h is NOT produced here: sum_i w_i (x) dc_i is a rank-(#steps) update applied once by
  * re2e_attloc_enc_grad after the loop (no per-step read-modify-write of (B,Th,D)). */
 size_t re2e_attloc_acc_floats(int A, int C, int K);
-int re2e_attloc_acc_slots(int B);
+int re2e_attloc_acc_slots(int B, int Th, int D, int A, int Z, int C, int K);
 int re2e_attloc_step_bwd(const float *dc, const float *dw, const float *xsave, const float *enc_h,
                          const float *att_prev, const float *w, const float *conv, const float *W_dec,
                          const float *W_att, const float *W_conv, const float *gvec, float scaling,

@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
   float *ddp_w = ering;                                     //   kBW*(A/2)  per-warp d dec_proj partials
   float *dgv_w = ddp_w + kBW * (A / 2);                     //   kBW*(A/2)  per-warp d gvec partials
   float *scr = dgv_w + kBW * (A / 2);                       //   kKQ*CP*tloc_max  d att_prev partials
-  float *dzp = scr + kKQ * CP * g.tloc_max;                 //   4*round4(Z)  d dec_z partials
+  float *dzp = scr + kKQ * CP * g.tloc_max;                 //   kBW*round4(ceil(Z/CL))  d dec_z partials
   float *app = ering + (size_t)g.ring_floats;               // App      padded att_prev row
   float *wc_s = app + g.App;                                // CKp
   float *watt_s = wc_s + g.CKp;                             // A*WP
@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
   // d dec_proj / d gvec of this CTA (fixed summation order), d dec_proj partial -> every CTA
   for (int a = tid; a < A; a += NT) {
     const int h = a >= A / 2 ? 1 : 0, ai = a - h * (A / 2);
-    float sd = 0.0f, sg = 0.0f;
+    float sd = 0.0f, sg = slot[A * C + C * K + a];
 #pragma unroll
     for (int pr = 0; pr < kBP; ++pr) {
       sd += ddp_w[(2 * pr + h) * (A / 2) + ai];
@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     }
     for (int r = 0; r < CL; ++r)
       st_async_f32(dsmem_addr(ddp_x + rank * A + a, (uint32_t)r), sd, dsmem_addr(xbar2, (uint32_t)r));
-    if (tloc > 0) slot[A * C + C * K + a] += sg;
+    slot[A * C + C * K + a] = sg;
   }
   if (warp == 0) {   // d gvec.bias = sum_t de[t]  (analytically zero over the utterance; kept for fidelity)
     float s2 = 0.0f;
@@ -790,9 +790,9 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
   }
   // dW_att[a,c] += sum_t d pre[t,a] conv[t,c]   straight from the resident tile (thread <-> a)
   for (int a = tid; a < A; a += NT) {
-    float acc[CP];
+    float acc[CP];    // starts from the slot's running total (loads overlap the frame loop)
 #pragma unroll
-    for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
+    for (int c = 0; c < CP; ++c) acc[c] = c < C ? slot[a * C + c] : 0.0f;
     for (int tl = 0; tl < tloc; ++tl) {
       const float dt = xs[(size_t)tl * A + a];
 #pragma unroll
@@ -804,11 +804,9 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
         if (c4 + 3 < CP) acc[c4 + 3] = fmaf(dt, t4.w, acc[c4 + 3]);
       }
     }
-    if (tloc > 0) {
 #pragma unroll
-      for (int c = 0; c < CP; ++c)
-        if (c < C) slot[a * C + c] += acc[c];
-    }
+    for (int c = 0; c < CP; ++c)
+      if (c < C) slot[a * C + c] = acc[c];
   }
   mbar_wait(xbar2, 0);   // d conv of all Th frames and every rank's d dec_proj partial have landed here
   for (int a = tid; a < A; a += NT) {
@@ -848,22 +846,24 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
       if (nv > 4) o[4] = a4;
     }
   }
-  // ---- d dec_z[z] = sum_a d dec_proj[a] W_dec[a,z]  for this rank's slice of z (thread <-> (z, quarter of A))
+  // ---- d dec_z[z] = sum_a d dec_proj[a] W_dec[a,z]  for this rank's slice of z: warp <-> slice of A/16 rows,
+  //      lane <-> z; the A/16 (<= 32) loads of a pass are independent: one L2 round trip per 32 outputs
   const int zc = (Z + CL - 1) / CL, z_begin = rank * zc, z_n = max(0, min(zc, Z - z_begin));
+  const int rz = round4(zc);
   if (p.d_dec_z) {
-    const int aq = A / 4;
-    for (int item = tid; item < 4 * z_n; item += NT) {
-      const int zi = item % z_n, qa = item / z_n;
-      const float *wcol = p.W_dec + (size_t)(qa * aq) * Z + z_begin + zi;
-      const float *dd = ddp_t + qa * aq;
+    const int aw = A / kBW;                    // rows per warp (A % 64 == 0 -> multiple of 4)
+    const float *dd = ddp_t + warp * aw;
+    for (int zi = lane; zi < z_n; zi += 32) {
+      const float *wcol = p.W_dec + (size_t)(warp * aw) * Z + z_begin + zi;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      for (int a = 0; a < aq; a += 4) {
+#pragma unroll 5
+      for (int a = 0; a < aw; a += 4) {
         s0 = fmaf(dd[a], __ldg(wcol + (size_t)a * Z), s0);
         s1 = fmaf(dd[a + 1], __ldg(wcol + (size_t)(a + 1) * Z), s1);
         s2 = fmaf(dd[a + 2], __ldg(wcol + (size_t)(a + 2) * Z), s2);
         s3 = fmaf(dd[a + 3], __ldg(wcol + (size_t)(a + 3) * Z), s3);
       }
-      dzp[qa * round4(Z) + zi] = (s0 + s1) + (s2 + s3);
+      dzp[warp * rz + zi] = (s0 + s1) + (s2 + s3);
     }
   }
   // ---- dW_conv[c,k] += sum_{t in mine} dconv[t,c] * att_prev[t + k - filts]   (6 taps per thread, one owner each)
@@ -875,9 +875,9 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
       const int kb = kg * KG;
       const float *dr = dcvT + c * g.App + filts;  // dconv[t] at dr[t]
       const float *ar = app + kb;                  // att_prev[t + k - filts] = app[t + k]
-      float acc6[KG];
+      float acc6[KG];   // starts from the slot's running total: the loads overlap the tap loop (no RMW stall after it)
 #pragma unroll
-      for (int i = 0; i < KG; ++i) acc6[i] = 0.0f;
+      for (int i = 0; i < KG; ++i) acc6[i] = kb + i < K ? slot[A * C + c * K + kb + i] : 0.0f;
       float x[KG];
 #pragma unroll
       for (int i = 0; i < KG - 1; ++i) x[i] = ar[t0 + i];
@@ -890,11 +890,9 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
 #pragma unroll
         for (int i = 0; i < KG - 1; ++i) x[i] = x[i + 1];
       }
-      if (tloc > 0) {
 #pragma unroll
-        for (int i = 0; i < KG; ++i)
-          if (kb + i < K) slot[A * C + c * K + kb + i] += acc6[i];
-      }
+      for (int i = 0; i < KG; ++i)
+        if (kb + i < K) slot[A * C + c * K + kb + i] = acc6[i];
     }
   }
   __syncthreads();  // #6
@@ -907,28 +905,39 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
   }
   if (p.d_dec_z) {
     for (int zi = tid; zi < z_n; zi += NT) {
-      const int rz = round4(Z);
-      p.d_dec_z[(size_t)b * Z + z_begin + zi] = (dzp[zi] + dzp[rz + zi]) + (dzp[2 * rz + zi] + dzp[3 * rz + zi]);
+      float sum = 0.0f;
+#pragma unroll
+      for (int w2 = 0; w2 < kBW; ++w2) sum += dzp[w2 * rz + zi];
+      p.d_dec_z[(size_t)b * Z + z_begin + zi] = sum;
     }
   }
   if (tid == 0) bulk_wait<0>();  // all d_pre traffic of this CTA has left shared memory / landed
 }
 
-// out[i] (+)= sum_s slots[s*stride + i]   -- once per decoder loop (deterministic order)
+// out[i] = sum_s slots[s*stride + i]   -- once per decoder loop, fixed summation order.
+// block = 32 outputs x 8 slot groups; group g sums slots g, g+8, ...; the 8 partials are combined through smem.
 __global__ void __launch_bounds__(256)
 acc_reduce_kernel(const float *__restrict__ slots, int n_slots, int stride, int n, float *__restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int s = 0;
-  for (; s + 3 < n_slots; s += 4) {
-    s0 += __ldg(slots + (size_t)s * stride + i);
-    s1 += __ldg(slots + (size_t)(s + 1) * stride + i);
-    s2 += __ldg(slots + (size_t)(s + 2) * stride + i);
-    s3 += __ldg(slots + (size_t)(s + 3) * stride + i);
+  __shared__ float part[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f;
+  if (i < n) {
+    int s = grp;
+    for (; s + 8 < n_slots; s += 16) {
+      s0 += __ldg(slots + (size_t)s * stride + i);
+      s1 += __ldg(slots + (size_t)(s + 8) * stride + i);
+    }
+    if (s < n_slots) s0 += __ldg(slots + (size_t)s * stride + i);
   }
-  for (; s < n_slots; ++s) s0 += __ldg(slots + (size_t)s * stride + i);
-  out[i] = (s0 + s1) + (s2 + s3);
+  part[grp][lane] = s0 + s1;
+  __syncthreads();
+  if (grp == 0 && i < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int g2 = 0; g2 < 8; ++g2) t += part[g2][lane];
+    out[i] = t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1104,7 +1113,8 @@ inline bool pick_geom_bwd(int B, int Th, int D, int A, int Z, int C, int K, int 
   for (;;) {
     g.tloc_max = (Th + CL - 1) / CL;
     g.nch = (g.tloc_max + kBW - 1) / kBW;
-    const size_t alias_floats = (size_t)kBW * A + (size_t)kKQ * CP * g.tloc_max + 4 * (size_t)round4(Z);
+    const size_t alias_floats = (size_t)kBW * A + (size_t)kKQ * CP * g.tloc_max +
+                                (size_t)kBW * round4((Z + CL - 1) / CL);
     const size_t fixed = 512 + sizeof(float) * ((size_t)g.tloc_max * A + (size_t)g.App + g.CKp + (size_t)A * (CP + 1) +
                                                 (size_t)g.tloc_max * CPP + 3 * (size_t)round4(g.tloc_max) +
                                                 2 * (size_t)g.tloc_max * 16 + (size_t)CP * g.App + (size_t)(CL + 1) * A + 16);
@@ -1244,7 +1254,16 @@ extern "C" int re2e_attloc_step_fwd(const float *pre, const float *enc_h, const 
 extern "C" size_t re2e_attloc_acc_floats(int A, int C, int K) {
   return (size_t)round4(A * C + C * K + A + 1);
 }
-extern "C" int re2e_attloc_acc_slots(int B) { return B * 16; }  // one slot per CTA, clusters of at most 16
+// one slot per CTA of the backward launch for this shape (B clusters of CL CTAs); < 0 if the shape is unsupported
+extern "C" int re2e_attloc_acc_slots(int B, int Th, int D, int A, int Z, int C, int K) {
+  int rc = check_dims(B, Th, D, A, C, K);
+  if (rc != RE2E_OK) return rc;
+  int CL;
+  size_t smem;
+  AttGeom g;
+  if (!pick_geom_bwd(B, Th, D, A, Z, C, K, C == 10 ? 10 : 16, CL, g, smem)) return RE2E_E_UNSUPPORTED;
+  return B * CL;
+}
 
 extern "C" int re2e_attloc_step_bwd(const float *dc, const float *dw, const float *xsave, const float *enc_h,
                                     const float *att_prev, const float *w, const float *conv, const float *W_dec,
@@ -1279,7 +1298,7 @@ extern "C" int re2e_attloc_acc_reduce(const float *acc_slots, int n_slots, float
                                       void *stream) {
   RE2E_CHECK_ARG(acc_slots && out && n_slots > 0 && A > 0 && C > 0 && K > 0);
   const int n = A * C + C * K + A + 1;
-  acc_reduce_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  acc_reduce_kernel<<<(n + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       acc_slots, n_slots, (int)re2e_attloc_acc_floats(A, C, K), n, out);
   count_launch();
   return launch_status();

@@ -47,7 +47,8 @@ class _State(object):
             L = _lib.lib()
             B, Th, D, A, Z, C, K = self.dims
             self.acc_stride = int(L.re2e_attloc_acc_floats(A, C, K))
-            self.acc_nslots = int(L.re2e_attloc_acc_slots(B))
+            self.acc_nslots = int(L.re2e_attloc_acc_slots(B, Th, D, A, Z, C, K))
+            _lib.check(min(self.acc_nslots, 0), "re2e_attloc_acc_slots")
             self.acc = torch.zeros(self.acc_nslots, self.acc_stride, device=dev, dtype=torch.float32)
 
 

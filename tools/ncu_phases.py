@@ -26,7 +26,7 @@ def main():
     src = open(os.path.join(n.ROOT, "robust_e2e_gan_b200", "csrc", fname)).read().splitlines()
     start = 0
     for i, l in enumerate(src):
-        if re.sub(r"<.*", "", name.split("::")[-1].split("(")[0]) in l and "__global__" in "".join(src[max(0, i - 2):i + 1]):
+        if re.search(r"(\w+_kernel)", name).group(1) + "(" in l and "__global__" in "".join(src[max(0, i - 2):i + 1]):
             start = i
             break
     marks = []
