@@ -499,6 +499,15 @@ int set_smem(K kernel, size_t bytes) {
 }  // namespace
 }  // namespace re2e
 
+namespace re2e {
+// fbank_tc.cu: tcgen05 path; RE2E_E_UNSUPPORTED when the shape does not fit it
+int fbank_tc_fwd(const float *mask, int mask_is_logit, const float *mag, const float *fc, const float *cmvn,
+                 const int32_t *lens, float *Y, float *G, float *enh_out, int B, int T, int F, int M,
+                 cudaStream_t st);
+int fbank_tc_bwd(const float *dY, const float *G, const float *mask, int mask_is_logit, const float *mag,
+                 const float *fc, const int32_t *lens, float *d_in, int B, int T, int F, int M, cudaStream_t st);
+}  // namespace re2e
+
 using namespace re2e;
 
 extern "C" int re2e_fbank_fwd(const float *mask, int mask_is_logit, const float *mag, const float *fc,
@@ -510,7 +519,8 @@ extern "C" int re2e_fbank_fwd(const float *mask, int mask_is_logit, const float 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int vec_ok = aligned16(mag) && (!mask || aligned16(mask)) && (!enh_out || aligned16(enh_out));
   if (((M & 3) == 0) && !(aligned16(Y) && (!G || aligned16(G)))) return RE2E_E_ARG;
-  int rc;
+  int rc = fbank_tc_fwd(mask, mask_is_logit, mag, fc, cmvn, lens, Y, G, enh_out, B, T, F, M, st);
+  if (rc != RE2E_E_UNSUPPORTED) return rc;   // tensor-core path taken (or a real error)
   if (M <= 48) {
     const FbankGeom g = make_geom<2>(F, M);
     size_t smem = sizeof(float) * ((size_t)g.Fp * g.Mp + (size_t)g.R * g.Fp);

@@ -1,0 +1,304 @@
+// Fused differentiable front-end on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
+//
+//   forward : x = act(mask) * valid * mag  ->  x^2  ->  P = x^2 . fc (F x M mel projection, 3xTF32)  ->  clamp, log, CMVN
+//             (model/enhance_model.py:157-164 + model/feat_model.py:118-135)
+//   backward: dP = dY * G ;  d(x^2) = dP . fc^T (3xTF32)  ;  d_in = d(x^2) * 2 x * d x/d in
+//
+// Why tensor cores here: the projection is 2*N*F*M = 0.53 GFLOP per pass at the bench shape; as fp32 FMAs fed from
+// shared memory it costs ~5x the time the HBM stream needs (measured: 127 us vs 9 us), on tcgen05 it disappears
+// behind the stream.  fp32 parity (1e-4) needs the 3xTF32 split: x = hi + lo (hi = the 19 bits the tensor core
+// reads, lo = x - hi), D += hi*hi + lo*hi + hi*lo.
+//
+// Forward structure (one persistent CTA per SM, each owning a contiguous range of frames):
+//   warps 0..15 : converters -- coalesced 128 B row-segment loads of mask / mag (rows are 1028 B: only 4 B aligned, so
+//                 no TMA), register prefetch two k-chunks ahead, sigmoid/mask/square, hi/lo split, store into the
+//                 128B-swizzled K-major A tile (128 frames x 32 bins) of a shared-memory ring
+//   warp 20     : one lane issues tcgen05.mma.kind::tf32 (A = x^2 tile, B = fc^T resident in shared memory as hi/lo,
+//                 N = mel padded to 16) into one of two TMEM accumulators
+//   warps 16..19: epilogue -- tcgen05.ld the finished accumulator (lane <-> frame), clamp/log/CMVN, store Y and G
+// Algorithmic HBM bytes: 4*N*(2F + 2M) masked with G, 4*N*(F + M) plain.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace re2e {
+namespace {
+
+constexpr int kCW = 16;                          // converter warps
+constexpr int kEW = 4;                           // epilogue warps (one per TMEM lane quarter)
+constexpr int kTcThreads = (kCW + kEW + 1) * 32; // + MMA warp
+constexpr int kRows = 128;                       // frames per MMA tile
+constexpr int kKC = 32;                          // bins per k-chunk (one 128 B swizzle row)
+constexpr int kATile = kRows * 128;              // bytes of one A tile (hi or lo)
+constexpr float kClampTc = 1e-7f;
+constexpr int kMaxStagesTc = 4;
+
+struct FbTcParams {
+  const float *mask, *mag, *fc, *cmvn;
+  const int32_t *lens;
+  float *Y, *G, *enh;
+  int mask_is_logit, N, T, F, M;
+  int NB;            // UMMA N: mel channels padded to a multiple of 16
+  int nchunks;       // ceil(F / 32)
+  int ksteps_last;   // 8-bin MMA steps in the last chunk
+  int rows_per_cta;
+  int nstages;
+};
+
+__device__ __forceinline__ float tf32_trunc_lo(float x) {
+  // the tensor core reads the top 19 bits of an fp32 operand; what it drops is re-fed as a second operand
+  return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+template <bool MASKED, int DEPTH>
+__global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smraw_[];
+  unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smraw_) + 1023) & ~(uintptr_t)1023);
+  const int NB = p.NB, NS = p.nstages, F = p.F, M = p.M;
+  const int fc_bytes = p.nchunks * NB * 128;
+  unsigned char *fc_hi = sm;
+  unsigned char *fc_lo = sm + fc_bytes;
+  unsigned char *stage0 = sm + 2 * fc_bytes;
+  uint64_t *full = reinterpret_cast<uint64_t *>(stage0 + (size_t)NS * 2 * kATile);
+  uint64_t *empty = full + kMaxStagesTc;
+  uint64_t *tfull = empty + kMaxStagesTc;
+  uint64_t *tempty = tfull + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  float *c0_s = reinterpret_cast<float *>(tmem_slot + 2);
+  float *c1_s = c0_s + NB;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row_begin = min(p.N, (int)blockIdx.x * p.rows_per_cta);
+  const int row_end = min(p.N, row_begin + p.rows_per_cta);
+  const int ntiles = (row_end - row_begin + kRows - 1) / kRows;
+  const uint32_t tmem_cols = 2 * NB <= 32 ? 32u : 2 * NB <= 64 ? 64u : 2 * NB <= 128 ? 128u : 2 * NB <= 256 ? 256u : 512u;
+
+  // ---- one-time setup: barriers, TMEM, filter bank (hi/lo, K-major, 128B swizzle), CMVN
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], kCW); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEW); }
+    mbar_fence_init();
+  }
+  if (warp == kCW + kEW) tmem_alloc(tmem_slot, tmem_cols);
+  {
+    float4 *z = reinterpret_cast<float4 *>(fc_hi);
+    for (int i = tid; i < 2 * fc_bytes / 16; i += kTcThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < NB; i += kTcThreads) {
+      c0_s[i] = (p.cmvn && i < M) ? __ldg(p.cmvn + i) : 0.0f;
+      c1_s[i] = (p.cmvn && i < M) ? __ldg(p.cmvn + M + i) : 1.0f;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < F * M; i += kTcThreads) {
+    const int k = i / M, m = i - k * M;
+    const float v = __ldg(p.fc + i);
+    const int ch = k >> 5, kk = k & 31;
+    const int off = ch * NB * 128 + (m >> 3) * 1024 + (m & 7) * 128 + ((((kk >> 2) ^ (m & 7))) << 4) + (kk & 3) * 4;
+    *reinterpret_cast<float *>(fc_hi + off) = v;
+    *reinterpret_cast<float *>(fc_lo + off) = tf32_trunc_lo(v);
+  }
+  fence_proxy_async_smem();   // the filter bank is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nitems = ntiles * p.nchunks;
+
+  if (warp < kCW) {
+    // ================= converters =================
+    const int rr = warp & 7;
+    const uint32_t off0 = (uint32_t)((warp >> 3) * 1024 + rr * 128 + (((lane >> 2) ^ rr) << 4) + (lane & 3) * 4);
+    float mg[DEPTH][8], mk[MASKED ? DEPTH : 1][8];
+    // state of the load stream (runs DEPTH items ahead of the convert stream)
+    int l_row0 = row_begin, l_c = 0, l_item = 0;
+    auto load = [&](float (&g)[8], float (&k)[8]) {
+      const int kcol = l_c * kKC + lane;
+      const bool kin = kcol < F;
+      const size_t base = (size_t)(l_row0 + warp) * F + kcol;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = kin && (l_row0 + warp + 16 * j < row_end);
+        g[j] = ok ? ld_stream1(p.mag + base + (size_t)(16 * j) * F) : 0.0f;
+        if (MASKED) k[j] = ok ? ld_stream1(p.mask + base + (size_t)(16 * j) * F) : 0.0f;
+      }
+      ++l_item;
+      if (++l_c == p.nchunks) { l_c = 0; l_row0 += kRows; }
+    };
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d)
+      if (d < nitems) load(mg[d], mk[MASKED ? d : 0]);
+
+    int c_row0 = row_begin, c_c = 0;
+    uint32_t vmask = 0;
+    int st = 0;
+    uint32_t ph = 0;
+    for (int q0 = 0; q0 < nitems; q0 += DEPTH) {
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d) {
+        const int q = q0 + d;
+        if (q < nitems) {
+          if (c_c == 0) {   // new tile: which of this thread's 8 frames are inside their utterance
+            vmask = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int row = c_row0 + warp + 16 * j;
+              bool v = row < row_end;
+              if (MASKED && v && p.lens) {
+                const int b = row / p.T;
+                v = (row - b * p.T) < __ldg(p.lens + b);
+              }
+              vmask |= (v ? 1u : 0u) << j;
+            }
+          }
+          if (q >= NS) mbar_wait(&empty[st], ph ^ 1u);
+          unsigned char *sa = stage0 + (size_t)st * 2 * kATile + off0;
+          const int kcol = c_c * kKC + lane;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float x = mg[d][j];
+            if (MASKED) {
+              const float s = p.mask_is_logit ? sigmoid_fast(mk[MASKED ? d : 0][j]) : mk[MASKED ? d : 0][j];
+              x = (vmask >> j) & 1u ? s * x : 0.0f;
+              if (p.enh && kcol < F && c_row0 + warp + 16 * j < row_end)
+                p.enh[(size_t)(c_row0 + warp + 16 * j) * F + kcol] = x;
+            }
+            const float x2 = x * x;
+            *reinterpret_cast<float *>(sa + j * 2048) = x2;
+            *reinterpret_cast<float *>(sa + kATile + j * 2048) = tf32_trunc_lo(x2);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[st]);
+          if (++st == NS) { st = 0; ph ^= 1u; }
+          if (++c_c == p.nchunks) { c_c = 0; c_row0 += kRows; }
+          if (l_item < nitems) load(mg[d], mk[MASKED ? d : 0]);
+        }
+      }
+    }
+  } else if (warp == kCW + kEW) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(kRows, NB, false, false);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        if (t >= 2) mbar_wait(&tempty[buf], (uint32_t)(((t >> 1) - 1) & 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NB);
+        for (int c = 0; c < p.nchunks; ++c) {
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(stage0 + (size_t)st * 2 * kATile);
+          const uint32_t a_lo = a_hi + kATile;
+          const uint32_t b_hi = smem_u32(fc_hi + (size_t)c * NB * 128);
+          const uint32_t b_lo = smem_u32(fc_lo + (size_t)c * NB * 128);
+          const int ks = c == p.nchunks - 1 ? p.ksteps_last : 4;
+          for (int k = 0; k < ks; ++k) {
+            const uint64_t dah = umma_desc(a_hi + k * 32, 16, 1024, 2), dal = umma_desc(a_lo + k * 32, 16, 1024, 2);
+            const uint64_t dbh = umma_desc(b_hi + k * 32, 16, 1024, 2), dbl = umma_desc(b_lo + k * 32, 16, 1024, 2);
+            umma_tf32(d_tmem, dah, dbh, idesc, (c | k) ? 1u : 0u);
+            umma_tf32(d_tmem, dal, dbh, idesc, 1u);
+            umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+          }
+          umma_commit(&empty[st]);   // the stage is free once these MMAs have read it
+          if (++st == NS) { st = 0; ph ^= 1u; }
+        }
+        umma_commit(&tfull[buf]);    // accumulator of tile t complete
+      }
+    }
+  } else {
+    // ================= epilogue: TMEM lane <-> frame =================
+    const int e = warp - kCW;        // == warp % 4: the TMEM lane quarter this warp may access
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      mbar_wait(&tfull[buf], (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      const int row = row_begin + t * kRows + 32 * e + lane;
+      const bool rok = row < row_end;
+      for (int c16 = 0; c16 < NB; c16 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)(buf * NB + c16), v);
+        if (c16 >= M) continue;
+        float y[16], gg[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float P = v[i];
+          const bool clamped = P <= kClampTc;
+          const float c1 = c1_s[c16 + i];
+          y[i] = (logf(clamped ? kClampTc : P) + c0_s[c16 + i]) * c1;
+          gg[i] = clamped ? 0.0f : c1 / P;
+        }
+        if (rok) {
+          float *yo = p.Y + (size_t)row * M + c16;
+          float *go = p.G ? p.G + (size_t)row * M + c16 : nullptr;
+          if ((M & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              if (c16 + i < M) {
+                *reinterpret_cast<float4 *>(yo + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+                if (go) *reinterpret_cast<float4 *>(go + i) = make_float4(gg[i], gg[i + 1], gg[i + 2], gg[i + 3]);
+              }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c16 + i < M) {
+                yo[i] = y[i];
+                if (go) go[i] = gg[i];
+              }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kCW + kEW) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+inline size_t fwd_smem_bytes(int nchunks, int NB, int ns) {
+  return 1024 + (size_t)2 * nchunks * NB * 128 + (size_t)ns * 2 * kATile + 512 + (size_t)2 * NB * 4;
+}
+
+}  // namespace
+
+// Returns RE2E_E_UNSUPPORTED when the shape does not fit the tensor-core path (caller falls back to the SIMT kernel).
+int fbank_tc_fwd(const float *mask, int mask_is_logit, const float *mag, const float *fc, const float *cmvn,
+                 const int32_t *lens, float *Y, float *G, float *enh_out, int B, int T, int F, int M,
+                 cudaStream_t st) {
+  FbTcParams p;
+  p.mask = mask; p.mag = mag; p.fc = fc; p.cmvn = cmvn; p.lens = lens; p.Y = Y; p.G = G; p.enh = enh_out;
+  p.mask_is_logit = mask_is_logit; p.N = B * T; p.T = T; p.F = F; p.M = M;
+  p.NB = (M + 15) / 16 * 16;
+  p.nchunks = (F + kKC - 1) / kKC;
+  p.ksteps_last = (F - (p.nchunks - 1) * kKC + 7) / 8;
+  if (p.NB > 256) return RE2E_E_UNSUPPORTED;
+  int ns = kMaxStagesTc;
+  while (ns >= 1 && fwd_smem_bytes(p.nchunks, p.NB, ns) > 226 * 1024) --ns;
+  if (ns < 1) return RE2E_E_UNSUPPORTED;
+  p.nstages = ns;
+  if (((M & 3) == 0) && !(aligned16(Y) && (!G || aligned16(G)))) return RE2E_E_UNSUPPORTED;
+  const int sms = num_sms();
+  int grid = (p.N + 63) / 64;
+  if (grid > sms) grid = sms;
+  p.rows_per_cta = (p.N + grid - 1) / grid;
+  const size_t smem = fwd_smem_bytes(p.nchunks, p.NB, ns);
+  int rc;
+  if (mask) {
+    if ((rc = ensure_smem(reinterpret_cast<const void *>(fbank_tc_fwd_kernel<true, 2>), smem)) != RE2E_OK) return rc;
+    fbank_tc_fwd_kernel<true, 2><<<grid, kTcThreads, smem, st>>>(p);
+  } else {
+    if ((rc = ensure_smem(reinterpret_cast<const void *>(fbank_tc_fwd_kernel<false, 4>), smem)) != RE2E_OK) return rc;
+    fbank_tc_fwd_kernel<false, 4><<<grid, kTcThreads, smem, st>>>(p);
+  }
+  count_launch();
+  return launch_status();
+}
+
+}  // namespace re2e
