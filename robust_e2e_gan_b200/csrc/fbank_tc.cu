@@ -38,11 +38,31 @@ struct FbTcParams {
   float *Y, *G, *enh;
   int mask_is_logit, N, T, F, M;
   int NB;            // UMMA N: mel channels padded to a multiple of 16
-  int nchunks;       // ceil(F / 32)
+  int nchunks;       // 32-bin chunks that go through the tensor core
   int ksteps_last;   // 8-bin MMA steps in the last chunk
+  int ntail;         // trailing bins (<= 4, e.g. the Nyquist bin of F = 257) added by the epilogue as plain FMAs
   int rows_per_cta;
   int nstages;
+  long long *dbg;    // optional per-CTA timing record (RE2E_FB_DEBUG builds only)
 };
+
+#ifdef RE2E_FB_DEBUG
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define DBG_T(var) const long long var = gtime()
+#define DBG_ACC(acc, t0) acc += gtime() - (t0)
+#define DBG_PUT(slot, val)                                        \
+  do {                                                            \
+    if (p.dbg) p.dbg[(size_t)blockIdx.x * 16 + (slot)] = (val);   \
+  } while (0)
+#else
+#define DBG_T(var)
+#define DBG_ACC(acc, t0)
+#define DBG_PUT(slot, val)
+#endif
 
 __device__ __forceinline__ float tf32_trunc_lo(float x) {
   // the tensor core reads the top 19 bits of an fp32 operand; what it drops is re-fed as a second operand
@@ -50,11 +70,13 @@ __device__ __forceinline__ float tf32_trunc_lo(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
-template <bool MASKED, int DEPTH>
+// FC: compile-time number of bins (257) so that the row-strided loads get immediate offsets; 0 = run-time p.F
+template <bool MASKED, int DEPTH, int FC>
 __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcParams p) {
   extern __shared__ __align__(1024) unsigned char smraw_[];
   unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smraw_) + 1023) & ~(uintptr_t)1023);
-  const int NB = p.NB, NS = p.nstages, F = p.F, M = p.M;
+  const int NB = p.NB, NS = p.nstages, F = FC > 0 ? FC : p.F, M = p.M;
+  const int Fmma = p.nchunks * kKC < F ? p.nchunks * kKC : F;   // bins [0, Fmma) on the tensor core, [Fmma, F) in the epilogue
   const int fc_bytes = p.nchunks * NB * 128;
   unsigned char *fc_hi = sm;
   unsigned char *fc_lo = sm + fc_bytes;
@@ -66,8 +88,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
   float *c0_s = reinterpret_cast<float *>(tmem_slot + 2);
   float *c1_s = c0_s + NB;
+  float *fct_s = c1_s + NB;          // [ntail][NB] filter-bank rows of the trailing bins
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  DBG_T(t_start);
+#ifdef RE2E_FB_DEBUG
+  long long w_acc = 0;
+#endif
   const int row_begin = min(p.N, (int)blockIdx.x * p.rows_per_cta);
   const int row_end = min(p.N, row_begin + p.rows_per_cta);
   const int ntiles = (row_end - row_begin + kRows - 1) / kRows;
@@ -87,9 +114,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
       c0_s[i] = (p.cmvn && i < M) ? __ldg(p.cmvn + i) : 0.0f;
       c1_s[i] = (p.cmvn && i < M) ? __ldg(p.cmvn + M + i) : 1.0f;
     }
+    for (int i = tid; i < p.ntail * NB; i += kTcThreads) {
+      const int kt = i / NB, m = i - kt * NB;
+      fct_s[i] = m < M ? __ldg(p.fc + (size_t)(Fmma + kt) * M + m) : 0.0f;
+    }
   }
   __syncthreads();
-  for (int i = tid; i < F * M; i += kTcThreads) {
+  for (int i = tid; i < Fmma * M; i += kTcThreads) {
     const int k = i / M, m = i - k * M;
     const float v = __ldg(p.fc + i);
     const int ch = k >> 5, kk = k & 31;
@@ -103,23 +134,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int nitems = ntiles * p.nchunks;
+  DBG_T(t_setup);
+  if (tid == 0) { DBG_PUT(0, t_start); DBG_PUT(1, t_setup - t_start); }
 
   if (warp < kCW) {
     // ================= converters =================
+    // thread <-> (frames warp + 16 j, bin 32 c + lane).  Frames past the CTA's range are skipped altogether (their
+    // A rows stay uninitialised: a row of A only feeds the same row of D, which is never stored).
     const int rr = warp & 7;
     const uint32_t off0 = (uint32_t)((warp >> 3) * 1024 + rr * 128 + (((lane >> 2) ^ rr) << 4) + (lane & 3) * 4);
     float mg[DEPTH][8], mk[MASKED ? DEPTH : 1][8];
     // state of the load stream (runs DEPTH items ahead of the convert stream)
     int l_row0 = row_begin, l_c = 0, l_item = 0;
     auto load = [&](float (&g)[8], float (&k)[8]) {
+      const int nj = max(0, (min(kRows, row_end - l_row0) - warp + 15) >> 4);
       const int kcol = l_c * kKC + lane;
-      const bool kin = kcol < F;
       const size_t base = (size_t)(l_row0 + warp) * F + kcol;
+      const float *pg = p.mag + base;
+      const float *pk = MASKED ? p.mask + base : nullptr;
+      const bool kin = kcol < Fmma;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const bool ok = kin && (l_row0 + warp + 16 * j < row_end);
-        g[j] = ok ? ld_stream1(p.mag + base + (size_t)(16 * j) * F) : 0.0f;
-        if (MASKED) k[j] = ok ? ld_stream1(p.mask + base + (size_t)(16 * j) * F) : 0.0f;
+        const bool ok = kin && j < nj;
+        g[j] = ok ? ld_stream1(pg + j * 16 * F) : 0.0f;
+        if (MASKED) k[j] = ok ? ld_stream1(pk + j * 16 * F) : 0.0f;
       }
       ++l_item;
       if (++l_c == p.nchunks) { l_c = 0; l_row0 += kRows; }
@@ -128,8 +166,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
     for (int d = 0; d < DEPTH; ++d)
       if (d < nitems) load(mg[d], mk[MASKED ? d : 0]);
 
-    int c_row0 = row_begin, c_c = 0;
-    uint32_t vmask = 0;
+    int c_row0 = row_begin, c_c = 0, nj_c = 0;
+    uint32_t vmask = 0xffu;
     int st = 0;
     uint32_t ph = 0;
     for (int q0 = 0; q0 < nitems; q0 += DEPTH) {
@@ -137,30 +175,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
       for (int d = 0; d < DEPTH; ++d) {
         const int q = q0 + d;
         if (q < nitems) {
-          if (c_c == 0) {   // new tile: which of this thread's 8 frames are inside their utterance
-            vmask = 0;
+          if (c_c == 0) {   // new tile: rows of this warp inside it, and which of them are inside their utterance
+            nj_c = max(0, (min(kRows, row_end - c_row0) - warp + 15) >> 4);
+            if (MASKED && p.lens) {
+              int row = c_row0 + warp;
+              int b = row / p.T, t = row - b * p.T;
+              int len = __ldg(p.lens + min(b, p.N / p.T - 1));
+              vmask = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int row = c_row0 + warp + 16 * j;
-              bool v = row < row_end;
-              if (MASKED && v && p.lens) {
-                const int b = row / p.T;
-                v = (row - b * p.T) < __ldg(p.lens + b);
+              for (int j = 0; j < 8; ++j) {
+                vmask |= (t < len ? 1u : 0u) << j;
+                t += 16;
+                while (t >= p.T) { t -= p.T; ++b; len = __ldg(p.lens + min(b, p.N / p.T - 1)); }
               }
-              vmask |= (v ? 1u : 0u) << j;
             }
           }
-          if (q >= NS) mbar_wait(&empty[st], ph ^ 1u);
+          {
+            DBG_T(tw);
+            if (q >= NS) mbar_wait(&empty[st], ph ^ 1u);
+            DBG_ACC(w_acc, tw);
+          }
           unsigned char *sa = stage0 + (size_t)st * 2 * kATile + off0;
           const int kcol = c_c * kKC + lane;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float x = mg[d][j];
             if (MASKED) {
-              const float s = p.mask_is_logit ? sigmoid_fast(mk[MASKED ? d : 0][j]) : mk[MASKED ? d : 0][j];
-              x = (vmask >> j) & 1u ? s * x : 0.0f;
-              if (p.enh && kcol < F && c_row0 + warp + 16 * j < row_end)
-                p.enh[(size_t)(c_row0 + warp + 16 * j) * F + kcol] = x;
+              const float sg = p.mask_is_logit ? sigmoid_fast(mk[MASKED ? d : 0][j]) : mk[MASKED ? d : 0][j];
+              x = (vmask >> j) & 1u ? sg * x : 0.0f;
+              if (p.enh && kcol < Fmma && j < nj_c) p.enh[(size_t)(c_row0 + warp + 16 * j) * F + kcol] = x;
             }
             const float x2 = x * x;
             *reinterpret_cast<float *>(sa + j * 2048) = x2;
@@ -187,7 +230,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NB);
         for (int c = 0; c < p.nchunks; ++c) {
-          mbar_wait(&full[st], ph);
+          {
+            DBG_T(tw);
+            mbar_wait(&full[st], ph);
+            DBG_ACC(w_acc, tw);
+          }
           tc_fence_after();
           const uint32_t a_hi = smem_u32(stage0 + (size_t)st * 2 * kATile);
           const uint32_t a_lo = a_hi + kATile;
@@ -212,22 +259,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
     const int e = warp - kCW;        // == warp % 4: the TMEM lane quarter this warp may access
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
-      mbar_wait(&tfull[buf], (uint32_t)((t >> 1) & 1));
-      tc_fence_after();
       const int row = row_begin + t * kRows + 32 * e + lane;
       const bool rok = row < row_end;
+      // trailing bins of this frame (issued before the accumulator wait: their latency hides behind the MMAs)
+      float xt2[4] = {0.f, 0.f, 0.f, 0.f};
+      if (rok && p.ntail > 0) {
+        bool valid = true;
+        if (MASKED && p.lens) {
+          const int b = row / p.T;
+          valid = (row - b * p.T) < __ldg(p.lens + b);
+        }
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt)
+          if (kt < p.ntail) {
+            float x = ld_stream1(p.mag + (size_t)row * F + Fmma + kt);
+            if (MASKED) {
+              const float mv = ld_stream1(p.mask + (size_t)row * F + Fmma + kt);
+              const float sg = p.mask_is_logit ? sigmoid_fast(mv) : mv;
+              x = valid ? sg * x : 0.0f;
+              if (p.enh) p.enh[(size_t)row * F + Fmma + kt] = x;
+            }
+            xt2[kt] = x * x;
+          }
+      }
+      {
+        DBG_T(tw);
+        mbar_wait(&tfull[buf], (uint32_t)((t >> 1) & 1));
+        DBG_ACC(w_acc, tw);
+      }
+      tc_fence_after();
       for (int c16 = 0; c16 < NB; c16 += 16) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)(buf * NB + c16), v);
         if (c16 >= M) continue;
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt)
+          if (kt < p.ntail) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(xt2[kt], fct_s[kt * NB + c16 + i], v[i]);
+          }
         float y[16], gg[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float P = v[i];
           const bool clamped = P <= kClampTc;
           const float c1 = c1_s[c16 + i];
-          y[i] = (logf(clamped ? kClampTc : P) + c0_s[c16 + i]) * c1;
-          gg[i] = clamped ? 0.0f : c1 / P;
+          y[i] = (__logf(clamped ? kClampTc : P) + c0_s[c16 + i]) * c1;   // lg2.approx path: <= 3 ulp, far inside 1e-4
+          gg[i] = clamped ? 0.0f : __fdividef(c1, P);
         }
         if (rok) {
           float *yo = p.Y + (size_t)row * M + c16;
@@ -254,8 +332,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
   }
+#ifdef RE2E_FB_DEBUG
+  if (lane == 0 && (warp == 0 || warp == kCW || warp == kCW + kEW)) {
+    const int base = warp == 0 ? 2 : warp == kCW ? 4 : 6;   // converter / epilogue / mma: (end time, wait time)
+    DBG_PUT(base, gtime() - t_start);
+    DBG_PUT(base + 1, w_acc);
+  }
+#endif
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) DBG_PUT(8, gtime() - t_start);
   if (warp == kCW + kEW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -263,10 +349,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
 }
 
 inline size_t fwd_smem_bytes(int nchunks, int NB, int ns) {
-  return 1024 + (size_t)2 * nchunks * NB * 128 + (size_t)ns * 2 * kATile + 512 + (size_t)2 * NB * 4;
+  return 1024 + (size_t)2 * nchunks * NB * 128 + (size_t)ns * 2 * kATile + 512 + (size_t)6 * NB * 4;
 }
 
 }  // namespace
+
+#ifdef RE2E_FB_DEBUG
+long long *g_fb_dbg = nullptr;
+extern "C" int re2e_fb_debug_read(long long *host_out) {   // 16 x 256 values of the last launch
+  if (!g_fb_dbg) return -1;
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpy(host_out, g_fb_dbg, sizeof(long long) * 16 * 256, cudaMemcpyDeviceToHost);
+}
+#endif
 
 // Returns RE2E_E_UNSUPPORTED when the shape does not fit the tensor-core path (caller falls back to the SIMT kernel).
 int fbank_tc_fwd(const float *mask, int mask_is_logit, const float *mag, const float *fc, const float *cmvn,
@@ -275,9 +370,20 @@ int fbank_tc_fwd(const float *mask, int mask_is_logit, const float *mag, const f
   FbTcParams p;
   p.mask = mask; p.mag = mag; p.fc = fc; p.cmvn = cmvn; p.lens = lens; p.Y = Y; p.G = G; p.enh = enh_out;
   p.mask_is_logit = mask_is_logit; p.N = B * T; p.T = T; p.F = F; p.M = M;
+  p.dbg = nullptr;
+#ifdef RE2E_FB_DEBUG
+  {
+    static long long *dbg_buf = nullptr;
+    if (!dbg_buf) cudaMalloc(&dbg_buf, sizeof(long long) * 16 * 256);
+    p.dbg = dbg_buf;
+    extern long long *g_fb_dbg;
+    g_fb_dbg = dbg_buf;
+  }
+#endif
   p.NB = (M + 15) / 16 * 16;
-  p.nchunks = (F + kKC - 1) / kKC;
-  p.ksteps_last = (F - (p.nchunks - 1) * kKC + 7) / 8;
+  p.ntail = (F >= kKC && (F % kKC) >= 1 && (F % kKC) <= 4) ? F % kKC : 0;
+  p.nchunks = (F - p.ntail + kKC - 1) / kKC;
+  p.ksteps_last = (F - p.ntail - (p.nchunks - 1) * kKC + 7) / 8;
   if (p.NB > 256) return RE2E_E_UNSUPPORTED;
   int ns = kMaxStagesTc;
   while (ns >= 1 && fwd_smem_bytes(p.nchunks, p.NB, ns) > 226 * 1024) --ns;
@@ -290,13 +396,20 @@ int fbank_tc_fwd(const float *mask, int mask_is_logit, const float *mag, const f
   p.rows_per_cta = (p.N + grid - 1) / grid;
   const size_t smem = fwd_smem_bytes(p.nchunks, p.NB, ns);
   int rc;
+#define RE2E_FB_LAUNCH(MASKED, DEPTH, FC)                                                                          \
+  do {                                                                                                            \
+    if ((rc = ensure_smem(reinterpret_cast<const void *>(fbank_tc_fwd_kernel<MASKED, DEPTH, FC>), smem)) != RE2E_OK) \
+      return rc;                                                                                                  \
+    fbank_tc_fwd_kernel<MASKED, DEPTH, FC><<<grid, kTcThreads, smem, st>>>(p);                                     \
+  } while (0)
   if (mask) {
-    if ((rc = ensure_smem(reinterpret_cast<const void *>(fbank_tc_fwd_kernel<true, 2>), smem)) != RE2E_OK) return rc;
-    fbank_tc_fwd_kernel<true, 2><<<grid, kTcThreads, smem, st>>>(p);
+    if (F == 257) RE2E_FB_LAUNCH(true, 2, 257);
+    else RE2E_FB_LAUNCH(true, 2, 0);
   } else {
-    if ((rc = ensure_smem(reinterpret_cast<const void *>(fbank_tc_fwd_kernel<false, 4>), smem)) != RE2E_OK) return rc;
-    fbank_tc_fwd_kernel<false, 4><<<grid, kTcThreads, smem, st>>>(p);
+    if (F == 257) RE2E_FB_LAUNCH(false, 4, 257);
+    else RE2E_FB_LAUNCH(false, 4, 0);
   }
+#undef RE2E_FB_LAUNCH
   count_launch();
   return launch_status();
 }
