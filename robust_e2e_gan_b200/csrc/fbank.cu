@@ -551,7 +551,13 @@ extern "C" int re2e_fbank_bwd(const float *dY, const float *G, const float *mask
   const int N = B * T;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
+  bool d_in_done = false;
   if (d_in) {
+    rc = fbank_tc_bwd(dY, G, mask, mask_is_logit, mag, fc, lens, d_in, B, T, F, M, st);
+    if (rc == RE2E_OK) d_in_done = true;
+    else if (rc != RE2E_E_UNSUPPORTED) return rc;
+  }
+  if (d_in && !d_in_done) {
     const FbankGeom g = make_geom<2>(F, M);
     // rows per tile: fill what is left of ~200 KB after the filter bank, multiple of 4
     size_t fixed = sizeof(float) * (size_t)g.Fp * g.Mq;

@@ -348,6 +348,263 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward:  dP = dY * G ;  d(x^2)^T = fc . dP^T  (bins on the MMA M side, frames on the N side) ;
+//            d_in[n,k] = d(x^2)[n,k] * 2 x * dx/d_in
+//
+//   warps 0..15 : epilogue -- TMEM lane <-> BIN, column <-> frame: for a fixed frame the 32 lanes of a warp touch 32
+//                 consecutive bins, so mask / mag loads and d_in stores are coalesced 128 B segments straight from the
+//                 accumulator layout (no shared-memory transpose).  Warp e: lane quarter e%4, M tile (e/4)%2, frame
+//                 half e/8 of the 128-frame tile.
+//   warps 16..19: converters -- thread <-> frame: dP = dY*G (128-bit loads), hi/lo split into the K-major B tile,
+//                 frame validity, and the trailing bins (k >= 256) as plain FMAs
+//   warp 20     : MMA issue: A = fc (resident, hi/lo), 2 M tiles x ceil(M/8) k-steps x 3 MMAs of 128x128x8 per tile
+// TMEM: 2 accumulator buffers x 2 M tiles x 128 columns = all 512 columns.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBwdEpiWarps = 16;
+constexpr int kBwdCvtWarps = 4;
+constexpr int kBwdThreads = (kBwdEpiWarps + kBwdCvtWarps + 1) * 32;
+
+struct FbTcBwdParams {
+  const float *dY, *G, *mask, *mag, *fc;
+  const int32_t *lens;
+  float *d_in;
+  int mask_is_logit, N, T, F, M;
+  int nmt;           // M tiles of 128 bins on the tensor core (1 or 2)
+  int Fmma;          // bins [0, Fmma) on the tensor core, [Fmma, F) as plain FMAs (<= 4)
+  int nkc;           // 32-wide k chunks over the mel axis (1 or 2)
+  int ksteps_last;   // 8-wide MMA steps in the last chunk
+  int rows_per_cta;
+};
+
+template <bool MASKED>
+__global__ void __launch_bounds__(kBwdThreads, 1) fbank_tc_bwd_kernel(const FbTcBwdParams p) {
+  extern __shared__ __align__(1024) unsigned char smraw_[];
+  unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smraw_) + 1023) & ~(uintptr_t)1023);
+  const int F = p.F, M = p.M, nmt = p.nmt, nkc = p.nkc, ntail = F - p.Fmma;
+  const int a_chunk = nmt * 128 * 128;                    // bytes of one k-chunk of A (nmt x 128 bins x 128 B)
+  unsigned char *a_hi = sm;
+  unsigned char *a_lo = sm + (size_t)nkc * a_chunk;
+  unsigned char *b_hi = sm + (size_t)2 * nkc * a_chunk;   // [nkc][128 frames][128 B]
+  unsigned char *b_lo = b_hi + (size_t)nkc * kATile;
+  uint64_t *bfull = reinterpret_cast<uint64_t *>(b_lo + (size_t)nkc * kATile);   // [2]
+  uint64_t *bempty = bfull + 2;                                                   // [1]
+  uint64_t *tfull = bempty + 1;                                                   // [2]
+  uint64_t *tempty = tfull + 2;                                                   // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  float *fct_s = reinterpret_cast<float *>(tmem_slot + 2);   // [4][64] filter-bank rows of the trailing bins
+  float *dtail_s = fct_s + 4 * 64;                           // [2][4][128] d(x^2) of the trailing bins
+  int *vrow_s = reinterpret_cast<int *>(dtail_s + 2 * 4 * 128);   // [2][128] frame inside its utterance?
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row_begin = min(p.N, (int)blockIdx.x * p.rows_per_cta);
+  const int row_end = min(p.N, row_begin + p.rows_per_cta);
+  const int ntiles = (row_end - row_begin + kRows - 1) / kRows;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bfull[i], kBwdCvtWarps);
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], kBwdEpiWarps);
+    }
+    mbar_init(bempty, 1);
+    mbar_fence_init();
+  }
+  if (warp == kBwdEpiWarps + kBwdCvtWarps) tmem_alloc(tmem_slot, 512);
+  {
+    float4 *z = reinterpret_cast<float4 *>(a_hi);
+    for (int i = tid; i < 2 * nkc * a_chunk / 16; i += kBwdThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 4 * 64; i += kBwdThreads) {
+      const int kt = i >> 6, m = i & 63;
+      fct_s[i] = (kt < ntail && m < M) ? __ldg(p.fc + (size_t)(p.Fmma + kt) * M + m) : 0.0f;
+    }
+  }
+  __syncthreads();
+  // A = fc[bin][mel], K-major (mel contiguous), 128B swizzle: chunk c, row k at c*a_chunk + (k>>3)*1024 + (k&7)*128
+  for (int i = tid; i < p.Fmma * M; i += kBwdThreads) {
+    const int k = i / M, m = i - k * M;
+    const float v = __ldg(p.fc + i);
+    const int ch = m >> 5, mm = m & 31;
+    const int off = ch * a_chunk + (k >> 3) * 1024 + (k & 7) * 128 + ((((mm >> 2) ^ (k & 7))) << 4) + (mm & 3) * 4;
+    *reinterpret_cast<float *>(a_hi + off) = v;
+    *reinterpret_cast<float *>(a_lo + off) = tf32_trunc_lo(v);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kBwdEpiWarps) {
+    // ================= epilogue =================
+    const int q = warp & 3, mt = (warp >> 2) & 1, h = warp >> 3;
+    const int k = 128 * mt + 32 * q + lane;               // this lane's bin
+    const bool kok = mt < nmt && k < p.Fmma;
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      const uint32_t par = (uint32_t)((t >> 1) & 1);
+      const int row0 = row_begin + t * kRows;
+      mbar_wait(&bfull[buf], par);      // frame validity / trailing bins of this tile are published
+      mbar_wait(&tfull[buf], par);
+      tc_fence_after();
+      if (mt < nmt) {
+        for (int cb = 0; cb < 64; cb += 16) {
+          const int r0 = 64 * h + cb;                     // first frame (tile-relative) of this batch of 16
+          if (row0 + r0 >= row_end) break;
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 256 + mt * 128 + r0), v);
+          const size_t gbase = (size_t)(row0 + r0) * F + k;
+          float mg[16], mk[MASKED ? 16 : 1];
+          uint32_t vm = 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const bool inr = row0 + r0 + i < row_end;
+            const bool val = inr && (!MASKED || vrow_s[buf * 128 + r0 + i] != 0);
+            vm |= (val ? 1u : 0u) << i;
+            const bool ld = kok && val;
+            mg[i] = ld ? ld_stream1(p.mag + gbase + (size_t)i * F) : 0.0f;
+            if (MASKED) mk[i] = ld ? ld_stream1(p.mask + gbase + (size_t)i * F) : 0.0f;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float fac;
+            if (MASKED) {
+              if (p.mask_is_logit) {
+                const float sg = sigmoid_fast(mk[i]);
+                fac = 2.0f * sg * mg[i] * mg[i] * sg * (1.0f - sg);   // 2 x * mag * s(1-s),  x = s*mag
+              } else {
+                fac = 2.0f * mk[i] * mg[i] * mg[i];                   // 2 x * mag,  x = mask*mag
+              }
+              if (!((vm >> i) & 1u)) fac = 0.0f;
+            } else {
+              fac = 2.0f * mg[i];
+            }
+            if (kok && row0 + r0 + i < row_end) p.d_in[gbase + (size_t)i * F] = v[i] * fac;
+          }
+        }
+      }
+      // trailing bins (k >= Fmma): thread <-> frame, a few strided accesses
+      if (ntail > 0 && q == 0 && mt == 0) {
+#pragma unroll
+        for (int rr = 0; rr < 64; rr += 32) {
+          const int r = 64 * h + rr + lane, row = row0 + r;
+          if (row < row_end) {
+            const bool val = !MASKED || vrow_s[buf * 128 + r] != 0;
+            for (int kt = 0; kt < ntail; ++kt) {
+              const size_t gi = (size_t)row * F + p.Fmma + kt;
+              const float mgv = p.mag[gi];
+              float fac;
+              if (MASKED) {
+                const float mv = p.mask[gi];
+                if (p.mask_is_logit) {
+                  const float sg = sigmoid_fast(mv);
+                  fac = 2.0f * sg * mgv * mgv * sg * (1.0f - sg);
+                } else {
+                  fac = 2.0f * mv * mgv * mgv;
+                }
+                if (!val) fac = 0.0f;
+              } else {
+                fac = 2.0f * mgv;
+              }
+              p.d_in[gi] = dtail_s[(buf * 4 + kt) * 128 + r] * fac;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  } else if (warp < kBwdEpiWarps + kBwdCvtWarps) {
+    // ================= converters: thread <-> frame =================
+    const int r = (warp - kBwdEpiWarps) * 32 + lane;      // tile-relative frame
+    const uint32_t roff = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      const int row = row_begin + t * kRows + r;
+      const bool inr = row < row_end;
+      if (t >= 1) mbar_wait(bempty, (uint32_t)((t - 1) & 1));            // MMAs of tile t-1 have read the B tile
+      if (t >= 2) mbar_wait(&tempty[buf], (uint32_t)(((t >> 1) - 1) & 1));   // epilogue of tile t-2 left this buffer
+      float tail[4] = {0.f, 0.f, 0.f, 0.f};
+      if (inr) {
+        const float *py = p.dY + (size_t)row * M, *pg = p.G + (size_t)row * M;
+        for (int m0 = 0; m0 < M; m0 += 8) {               // one 8-wide k-step at a time (M % 4 == 0)
+          float dp[8];
+#pragma unroll
+          for (int u = 0; u < 8; u += 4) {
+            if (m0 + u < M) {
+              const float4 a = ld_stream4(py + m0 + u), g4 = ld_stream4(pg + m0 + u);
+              dp[u] = a.x * g4.x; dp[u + 1] = a.y * g4.y; dp[u + 2] = a.z * g4.z; dp[u + 3] = a.w * g4.w;
+            } else {
+              dp[u] = dp[u + 1] = dp[u + 2] = dp[u + 3] = 0.0f;
+            }
+          }
+          const int ch = m0 >> 5, mm = m0 & 31;
+#pragma unroll
+          for (int u = 0; u < 8; u += 4) {
+            const uint32_t off = (uint32_t)ch * kATile + roff + (uint32_t)((((mm + u) >> 2) ^ (r & 7)) << 4);
+            *reinterpret_cast<float4 *>(b_hi + off) = make_float4(dp[u], dp[u + 1], dp[u + 2], dp[u + 3]);
+            *reinterpret_cast<float4 *>(b_lo + off) = make_float4(tf32_trunc_lo(dp[u]), tf32_trunc_lo(dp[u + 1]),
+                                                                  tf32_trunc_lo(dp[u + 2]), tf32_trunc_lo(dp[u + 3]));
+          }
+#pragma unroll
+          for (int kt = 0; kt < 4; ++kt)
+            if (kt < ntail) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (m0 + u < M) tail[kt] = fmaf(dp[u], fct_s[kt * 64 + m0 + u], tail[kt]);
+            }
+        }
+      }
+      int valid = inr ? 1 : 0;
+      if (MASKED && inr && p.lens) {
+        const int b = row / p.T;
+        valid = (row - b * p.T) < __ldg(p.lens + b) ? 1 : 0;
+      }
+      vrow_s[buf * 128 + r] = valid;
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) dtail_s[(buf * 4 + kt) * 128 + r] = tail[kt];
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bfull[buf]);
+    }
+  } else {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(128, 128, false, false);
+      for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        mbar_wait(&bfull[buf], (uint32_t)((t >> 1) & 1));
+        tc_fence_after();
+        for (int mt = 0; mt < nmt; ++mt) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256 + mt * 128);
+          for (int c = 0; c < nkc; ++c) {
+            const uint32_t ah = smem_u32(a_hi + (size_t)c * a_chunk + (size_t)mt * kATile);
+            const uint32_t al = smem_u32(a_lo + (size_t)c * a_chunk + (size_t)mt * kATile);
+            const uint32_t bh = smem_u32(b_hi + (size_t)c * kATile), bl = smem_u32(b_lo + (size_t)c * kATile);
+            const int ks = c == nkc - 1 ? p.ksteps_last : 4;
+            for (int kk = 0; kk < ks; ++kk) {
+              const uint64_t dah = umma_desc(ah + kk * 32, 16, 1024, 2), dal = umma_desc(al + kk * 32, 16, 1024, 2);
+              const uint64_t dbh = umma_desc(bh + kk * 32, 16, 1024, 2), dbl = umma_desc(bl + kk * 32, 16, 1024, 2);
+              umma_tf32(d_tmem, dah, dbh, idesc, (c | kk) ? 1u : 0u);
+              umma_tf32(d_tmem, dal, dbh, idesc, 1u);
+              umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+            }
+          }
+        }
+        umma_commit(bempty);         // B tile may be overwritten
+        umma_commit(&tfull[buf]);    // accumulators of tile t complete
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kBwdEpiWarps + kBwdCvtWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 inline size_t fwd_smem_bytes(int nchunks, int NB, int ns) {
   return 1024 + (size_t)2 * nchunks * NB * 128 + (size_t)ns * 2 * kATile + 512 + (size_t)6 * NB * 4;
 }
@@ -410,6 +667,39 @@ int fbank_tc_fwd(const float *mask, int mask_is_logit, const float *mag, const f
     else RE2E_FB_LAUNCH(false, 4, 0);
   }
 #undef RE2E_FB_LAUNCH
+  count_launch();
+  return launch_status();
+}
+
+
+// d_in only (dfc of a trainable bank is handled by the SIMT kernel).  RE2E_E_UNSUPPORTED -> caller falls back.
+int fbank_tc_bwd(const float *dY, const float *G, const float *mask, int mask_is_logit, const float *mag,
+                 const float *fc, const int32_t *lens, float *d_in, int B, int T, int F, int M, cudaStream_t st) {
+  if ((M & 3) || M > 64 || F < 8 || !aligned16(dY) || !aligned16(G)) return RE2E_E_UNSUPPORTED;
+  FbTcBwdParams p;
+  p.dY = dY; p.G = G; p.mask = mask; p.mag = mag; p.fc = fc; p.lens = lens; p.d_in = d_in;
+  p.mask_is_logit = mask_is_logit; p.N = B * T; p.T = T; p.F = F; p.M = M;
+  const int ntail = (F % 128 >= 1 && F % 128 <= 4 && F > 128) ? F % 128 : 0;
+  p.Fmma = F - ntail;
+  p.nmt = (p.Fmma + 127) / 128;
+  if (p.nmt > 2) return RE2E_E_UNSUPPORTED;
+  p.nkc = (M + 31) / 32;
+  p.ksteps_last = (M - (p.nkc - 1) * 32 + 7) / 8;
+  const size_t smem = 1024 + (size_t)2 * p.nkc * p.nmt * 128 * 128 + (size_t)2 * p.nkc * kATile + 256 +
+                      sizeof(float) * (4 * 64 + 2 * 4 * 128) + sizeof(int) * 2 * 128;
+  if (smem > 226 * 1024) return RE2E_E_UNSUPPORTED;
+  const int sms = num_sms();
+  int grid = (p.N + 63) / 64;
+  if (grid > sms) grid = sms;
+  p.rows_per_cta = (p.N + grid - 1) / grid;
+  int rc;
+  if (mask) {
+    if ((rc = ensure_smem(reinterpret_cast<const void *>(fbank_tc_bwd_kernel<true>), smem)) != RE2E_OK) return rc;
+    fbank_tc_bwd_kernel<true><<<grid, kBwdThreads, smem, st>>>(p);
+  } else {
+    if ((rc = ensure_smem(reinterpret_cast<const void *>(fbank_tc_bwd_kernel<false>), smem)) != RE2E_OK) return rc;
+    fbank_tc_bwd_kernel<false><<<grid, kBwdThreads, smem, st>>>(p);
+  }
   count_launch();
   return launch_status();
 }
