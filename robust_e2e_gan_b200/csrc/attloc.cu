@@ -26,6 +26,22 @@
 namespace re2e {
 namespace {
 
+#ifdef RE2E_ATT_DEBUG
+// per-CTA phase timestamps (thread 0), 16 slots per CTA, read back with re2e_att_debug_read
+__device__ long long g_att_dbg[2][16 * 512];
+__device__ __forceinline__ long long att_gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define ATT_MARK(which, slot)                                                          \
+  do {                                                                                 \
+    if (threadIdx.x == 0) g_att_dbg[which][blockIdx.x * 16 + (slot)] = att_gtime();    \
+  } while (0)
+#else
+#define ATT_MARK(which, slot)
+#endif
+
 constexpr int kDplMax = 16;   // D <= 512
 constexpr int kMaxStages = 30;
 constexpr int kTG = 5;        // conv outputs per thread (sliding window)
@@ -163,8 +179,7 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
   const int Dp = round4(D), Dh = (D + 1) / 2;
 
   uint64_t *full = reinterpret_cast<uint64_t *>(smraw);
-  uint64_t *empty = full + kMaxStages;
-  uint64_t *dpbar = empty + kMaxStages;                    // dec_proj row complete (A floats pushed by the cluster)
+  uint64_t *dpbar = full + kMaxStages;                    // dec_proj row complete (A floats pushed by the cluster)
   uint64_t *xbar = dpbar + 1;                              // softmax statistics (+ partial contexts on rank 0) complete
   float *stages = reinterpret_cast<float *>(smraw + 512);
   float *app = stages + (size_t)g.ns * g.stage_floats;     // App   zero padded alignment row, ap[i] at filts+i
@@ -175,12 +190,13 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
   float *convp = dp_s + A;                                 // kKQ*tloc_max*CP  conv partials
   float *conv_s = convp + round4(kKQ * g.tloc_max * CP);   // tloc_max*CPP
   float *e_s = conv_s + g.tloc_max * CPP;                  // round4(tloc_max)  scaled energies
-  float *epart = e_s + round4(g.tloc_max);                 // 2*kFP*2
-  float *wstat = epart + 4 * kFP;                          // kFW*2
+  float *epart = e_s + round4(g.tloc_max);                 // 2*tloc_max  per-frame partial energies of the two halves
+  float *wstat = epart + round4(2 * g.tloc_max);           // kFW*2
   float *cbuf = wstat + 2 * kFW;                           // 8*Dp   partial contexts (used on rank 0)
   float *xch = cbuf + 8 * Dp;                              // 8*2    (max, sum) of every rank
   float *cred = stages;                                    // kFP*Dp, aliases the ring once it is drained
 
+  ATT_MARK(0, 0);
   auto issue = [&](int q) {
     const int st = q % g.ns;
     const int r0 = t0 + kFP * q;
@@ -190,19 +206,6 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
     bulk_g2s(dst, p.pre + ((size_t)b * Th + r0) * A, (uint32_t)rows * A * 4u, &full[st]);
     bulk_g2s(dst + kFP * A, p.enc + ((size_t)b * Th + r0) * D, (uint32_t)rows * D * 4u, &full[st]);
   };
-
-  if (tid == 0) {
-    for (int i = 0; i < g.ns; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kFW); }
-    mbar_init(dpbar, 1);
-    mbar_init(xbar, 1);
-    mbar_fence_init();
-    if (p.dec_z) mbar_expect_tx(dpbar, (uint32_t)A * 4u);
-    mbar_expect_tx(xbar, (uint32_t)CL * 8u + (rank == 0 ? (uint32_t)CL * (uint32_t)D * 4u : 0u));
-    const int first = nch < g.ns ? nch : g.ns;
-    for (int q = 0; q < first; ++q) issue(q);
-  }
-  // "this CTA is running and its barriers exist": peers wait on it before their first remote store
-  cluster_arrive_relaxed();
 
   // ---- every global load of the prologue is issued before the first use: ONE L2 round trip for the small
   //      operands (alignment row, W_conv, W_att, dec_z, gvec) and this warp's W_dec rows
@@ -224,9 +227,13 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
       }
     }
   }
+  float gv[APL];
+#pragma unroll
+  for (int j = 0; j < APL; ++j) gv[j] = __ldg(p.gvec + half * (A / 2) + lane + 32 * j);
+  const float gb = __ldg(p.gvec_b);
+  constexpr int IA = 2, IC = 4, IW = 8;                // first block of every array: loads batched in registers
+  float va[IA], vc[IC], vw[IW], vz;
   {
-    constexpr int IA = 2, IC = 4, IW = 8;              // first block of every array: loads batched in registers
-    float va[IA], vc[IC], vw[IW], vz;
 #pragma unroll
     for (int u = 0; u < IA; ++u) {
       const int i = tid + u * NT, t = i - filts;
@@ -243,6 +250,25 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
       vw[u] = i < A * C ? __ldg(p.W_att + i) : 0.0f;
     }
     vz = (p.dec_z && tid < Z) ? __ldg(p.dec_z + (size_t)b * Z + tid) : 0.0f;
+    }
+  // thread 0: barriers first (peers may push as soon as the cluster handshake completes), then the bulk copies of
+  // the (pre | enc) stages -- issued AFTER this warp's prologue loads are in flight, so the serial issue loop of
+  // one lane does not delay the loads of its warp
+  if (tid == 0) {
+    for (int i = 0; i < g.ns; ++i) mbar_init(&full[i], 1);
+    mbar_init(dpbar, 1);
+    mbar_init(xbar, 1);
+    mbar_fence_init();
+    if (p.dec_z) mbar_expect_tx(dpbar, (uint32_t)A * 4u);
+    mbar_expect_tx(xbar, (uint32_t)CL * 8u + (rank == 0 ? (uint32_t)CL * (uint32_t)D * 4u : 0u));
+  }
+  // "this CTA is running and its barriers exist": peers wait on it before their first remote store
+  cluster_arrive_relaxed();
+  if (tid == 0) {
+    const int first = nch < g.ns ? nch : g.ns;
+    for (int q = 0; q < first; ++q) issue(q);
+  }
+    {
 #pragma unroll
     for (int u = 0; u < IA; ++u)
       if (tid + u * NT < g.App) app[tid + u * NT] = va[u];
@@ -264,11 +290,8 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
     for (int i = tid + IW * NT; i < A * C; i += NT) { const int a = i / C; watt_s[a * WP + (i - a * C)] = __ldg(p.W_att + i); }
     for (int i = tid + NT; i < Z; i += NT) dz_s[i] = p.dec_z ? __ldg(p.dec_z + (size_t)b * Z + i) : 0.0f;
   }
-  float gv[APL];
-#pragma unroll
-  for (int j = 0; j < APL; ++j) gv[j] = __ldg(p.gvec + half * (A / 2) + lane + 32 * j);
-  const float gb = __ldg(p.gvec_b);
   __syncthreads();  // #1
+  ATT_MARK(0, 1);
 
   // ---- mlp_dec slice of this CTA: channels [rank*A/CL, (rank+1)*A/CL), one warp per channel, lane <-> z
   for (int base = 0; base < apc; base += kFW * kCPW) {
@@ -325,6 +348,7 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
     }
   }
 
+  ATT_MARK(0, 2);
   // ---- location convolution: conv[t,c] = sum_k Wc[c,k] * att_prev[t + k - filts]  (zero padded).
   //      item = (k quarter, channel, group of 5 frames): 2 shared loads per 5 FMAs
   {
@@ -354,15 +378,19 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
       if (nv > 4) o[4 * CP] = a4;
     }
   }
-  // W_att rows of this lane's channels -> registers (independent of the conv partials)
-  float Watt[APL][CP];
+  // W_att rows of this lane's channels -> registers (independent of the conv partials), two channels per 64-bit
+  // register pair so that the K=C dot products run as packed FFMA2 (fma.rn.f32x2, sm_100)
+  constexpr int APH = (APL + 1) / 2;
+  float2 WattP[APH][CP];
 #pragma unroll
-  for (int j = 0; j < APL; ++j) {
-    const int a = half * (A / 2) + lane + 32 * j;
+  for (int jp = 0; jp < APH; ++jp) {
+    const int a0 = half * (A / 2) + lane + 32 * (2 * jp), a1 = a0 + 32;
 #pragma unroll
-    for (int c = 0; c < CP; ++c) Watt[j][c] = c < C ? watt_s[a * WP + c] : 0.0f;
+    for (int c = 0; c < CP; ++c)
+      WattP[jp][c] = make_float2(c < C ? watt_s[a0 * WP + c] : 0.0f, (c < C && 2 * jp + 1 < APL) ? watt_s[a1 * WP + c] : 0.0f);
   }
   __syncthreads();  // #2
+  ATT_MARK(0, 3);
   for (int i = tid; i < tloc * CPP; i += NT) {
     const int tl = i / CPP, c = i - tl * CPP;
     float v = 0.0f;
@@ -375,6 +403,7 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
   }
   if (p.dec_z) mbar_wait(dpbar, 0);   // dp_s holds the full dec_proj row (A floats pushed by the CTAs of the cluster)
   __syncthreads();  // #3: conv_s visible
+  ATT_MARK(0, 4);
 
   float m_run = -CUDART_INF_F, s_run = 0.0f;
   float acc[DPL];
@@ -389,67 +418,97 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
     for (int j = 0; j < DPL; ++j)
       if (lane + 32 * j < Dh && half * Dh + lane + 32 * j < D) dmask |= 1u << j;
     const int aoff = half * (A / 2) + lane;
-    const float *tile = stages;
-    const float *cvp = conv_s + pair * CPP;
-    float *xs = p.xsave ? p.xsave + ((size_t)b * Th + t0 + pair) * A + aoff : nullptr;
-    int st = 0;
-    uint32_t ph = 0;
-    for (int q = 0; q < nch; ++q) {
-      if (tid == 0 && q >= 1 && q - 1 + g.ns < nch) {   // ring shorter than the range: refill the stage chunk q-1 used
-        mbar_wait(&empty[(q - 1) % g.ns], (uint32_t)(((q - 1) / g.ns) & 1));
-        issue(q - 1 + g.ns);
+    // The frame range is processed in groups of g.ns chunks (ONE group when the ring holds the whole range, the
+    // common case).  Per group: (1) energies of all its frames back to back -- no barrier inside, so the shuffle
+    // reduction of one frame overlaps the FMAs of the next; (2) one 64-thread barrier inside the pair; (3) local
+    // softmax statistics + context over the group's frames.
+    for (int qg = 0; qg < nch; qg += g.ns) {
+      const int gsz = min(g.ns, nch - qg);
+      const uint32_t ph = (uint32_t)((qg / g.ns) & 1);
+      for (int i = 0; i < gsz; ++i) mbar_wait(&full[i], ph);
+      // (1) partial energies of this warp's half of the channels
+#pragma unroll 2
+      for (int i = 0; i < gsz; ++i) {
+        const int tl = kFP * (qg + i) + pair;
+        if (tl < tloc) {
+          const float *cvp = conv_s + tl * CPP;
+          float cv[CPP];
+#pragma unroll
+          for (int c4 = 0; c4 < CPP; c4 += 4) {
+            const float4 t4 = *reinterpret_cast<const float4 *>(cvp + c4);
+            cv[c4] = t4.x; cv[c4 + 1] = t4.y; cv[c4 + 2] = t4.z; cv[c4 + 3] = t4.w;
+          }
+          const float *row = stages + (size_t)i * g.stage_floats + pair * A + aoff;
+          float *xs = p.xsave ? p.xsave + ((size_t)b * Th + t0 + tl) * A + aoff : nullptr;
+          float part = 0.0f;
+#pragma unroll
+          for (int jp = 0; jp < APH; ++jp) {
+            const bool two = 2 * jp + 1 < APL;
+            float2 u = make_float2(dp[2 * jp] + row[64 * jp], two ? dp[2 * jp + 1] + row[64 * jp + 32] : 0.0f);
+#pragma unroll
+            for (int c = 0; c < CP; ++c) u = __ffma2_rn(WattP[jp][c], make_float2(cv[c], cv[c]), u);
+            const float x0 = tanh_ex2(u.x);
+            if (xs) xs[64 * jp] = x0;  // activation kept for the backward (coalesced 128 B per warp store)
+            part = fmaf(gv[2 * jp], x0, part);
+            if (two) {
+              const float x1 = tanh_ex2(u.y);
+              if (xs) xs[64 * jp + 32] = x1;
+              part = fmaf(gv[2 * jp + 1], x1, part);
+            }
+          }
+          part = warp_sum(part);
+          if (lane == 0) epart[2 * tl + half] = part;
+        }
       }
-      __syncwarp();
-      mbar_wait(&full[st], ph);
-      const int tl = kFP * q + pair;
-      if (tl < tloc) {
-        float cv[CPP];
-#pragma unroll
-        for (int c4 = 0; c4 < CPP; c4 += 4) {
-          const float4 t4 = *reinterpret_cast<const float4 *>(cvp + c4);
-          cv[c4] = t4.x; cv[c4 + 1] = t4.y; cv[c4 + 2] = t4.z; cv[c4 + 3] = t4.w;
+      pair_bar(1 + pair, 64);
+      // (2) scaled energies of the group's frames, running maximum
+      float mg = m_run;
+      for (int i = 0; i < gsz; ++i) {
+        const int tl = kFP * (qg + i) + pair;
+        if (tl < tloc) {
+          const float e = p.scaling * ((epart[2 * tl] + epart[2 * tl + 1]) + gb);
+          if (half == 0 && lane == 0) e_s[tl] = e;
+          mg = fmaxf(mg, e);
         }
-        const float *row = tile + pair * A + aoff;
-        float part = 0.0f;
-#pragma unroll
-        for (int j = 0; j < APL; ++j) {
-          float u = dp[j] + row[32 * j];
-#pragma unroll
-          for (int c = 0; c < CP; ++c) u = fmaf(Watt[j][c], cv[c], u);
-          const float x = tanh_fast(u);
-          if (xs) xs[32 * j] = x;  // activation kept for the backward (coalesced 128 B per warp store)
-          part = fmaf(gv[j], x, part);
-        }
-        part = warp_sum(part);
-        float *ep = epart + (q & 1) * 2 * kFP + pair * 2;
-        if (lane == 0) ep[half] = part;
-        pair_bar(1 + pair, 64);
-        const float e = p.scaling * ((ep[0] + ep[1]) + gb);
-        if (half == 0 && lane == 0) e_s[tl] = e;
-        // online softmax: running max / sum / context of this warp's frames
-        if (e > m_run) {
-          const float sc = __expf(m_run - e);   // exp(-inf) = 0 on the first frame
-          s_run *= sc;
-#pragma unroll
-          for (int j = 0; j < DPL; ++j) acc[j] *= sc;
-          m_run = e;
-        }
-        const float pw = __expf(e - m_run);
-        s_run += pw;
-        const float *er = tile + kFP * A + pair * D + half * Dh + lane;
-#pragma unroll
-        for (int j = 0; j < DPL; ++j)
-          if (dmask & (1u << j)) acc[j] = fmaf(pw, er[32 * j], acc[j]);
       }
-      __syncwarp();
-      if (lane == 0 && g.ns < nch) mbar_arrive1(&empty[st]);
-      cvp += kFP * CPP;
-      if (xs) xs += (size_t)kFP * A;
-      if (++st == g.ns) { st = 0; ph ^= 1u; tile = stages; } else tile += g.stage_floats;
+      if (mg > m_run) {
+        const float sc = __expf(m_run - mg);   // exp(-inf) = 0 for the first group
+        s_run *= sc;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) acc[j] *= sc;
+        m_run = mg;
+      }
+      // (3) un-normalised softmax weights and context
+#pragma unroll 2
+      for (int i = 0; i < gsz; ++i) {
+        const int tl = kFP * (qg + i) + pair;
+        if (tl < tloc) {
+          const float e = p.scaling * ((epart[2 * tl] + epart[2 * tl + 1]) + gb);
+          const float pw = __expf(e - m_run);
+          s_run += pw;
+          const float *er = stages + (size_t)i * g.stage_floats + kFP * A + pair * D + half * Dh + lane;
+          if (dmask == (1u << DPL) - 1u) {   // every lane owns DPL channels (D == 64*DPL): no per-channel predicate
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) acc[j] = fmaf(pw, er[32 * j], acc[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < DPL; ++j)
+              if (dmask & (1u << j)) acc[j] = fmaf(pw, er[32 * j], acc[j]);
+          }
+        }
+      }
+      if (qg + g.ns < nch) {   // ring shorter than the frame range (long utterances): refill behind a CTA barrier
+        __syncthreads();
+        if (tid == 0) {
+          const int nxt = min(g.ns, nch - (qg + g.ns));
+          for (int i = 0; i < nxt; ++i) issue(qg + g.ns + i);
+        }
+      }
     }
     if (lane == 0) { wstat[2 * warp] = m_run; wstat[2 * warp + 1] = s_run; }
   }
   __syncthreads();  // #4: ring drained, per-warp statistics published
+  ATT_MARK(0, 5);
 
   // ---- CTA combine (deterministic order), then push to the cluster
   float Mc = -CUDART_INF_F;
@@ -478,6 +537,7 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
     st_async_f32(dsmem_addr(xch + 2 * rank, (uint32_t)tid), Mc, dsmem_addr(xbar, (uint32_t)tid));
     st_async_f32(dsmem_addr(xch + 2 * rank + 1, (uint32_t)tid), sc, dsmem_addr(xbar, (uint32_t)tid));
   }
+  ATT_MARK(0, 6);
   mbar_wait(xbar, 0);   // every rank's (max, sum) -- and on rank 0 every partial context -- has landed here
   float M = -CUDART_INF_F;
   for (int r = 0; r < CL; ++r) M = fmaxf(M, xch[2 * r]);
@@ -494,6 +554,7 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
       p.c[(size_t)b * D + d] = sum * inv;
     }
   }
+  ATT_MARK(0, 7);
   // no trailing cluster barrier: a CTA leaves only after everything addressed to it has landed (xbar), and it
   // never reads remote shared memory
 }
@@ -537,7 +598,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
   const int nche = (tloc + kBW - 1) / kBW;       // enc_h chunks (16 frames)
 
   uint64_t *full_x = reinterpret_cast<uint64_t *>(smraw);   // [kMaxXChunks]
-  uint64_t *done_x = full_x + kMaxXChunks;                  // [kMaxXChunks]
+  uint64_t *done_x = full_x + kMaxXChunks;                  // [1] every warp finished forming d pre in place
   uint64_t *full_e = done_x + kMaxXChunks;                  // [kMaxEStages]
   uint64_t *xbar1 = full_e + kMaxEStages;                   // sum_t w dwt partials of every rank
   uint64_t *xbar2 = xbar1 + 1;                              // d conv of every frame + d dec_proj partials of every rank
@@ -561,6 +622,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
   float *xch = ddp_t + A;                                   // 16      sum_t w dwt partials of every rank
   float *slot = p.acc_slots + (size_t)blockIdx.x * p.slot_stride;   // [dW_att A*C | dW_conv C*K | dgvec A | dgvec_b 1]
 
+  ATT_MARK(1, 0);
   auto issue_e = [&](int q) {
     const int st = q % g.ns;
     const int r0 = t0 + kBW * q;
@@ -569,21 +631,14 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     bulk_g2s(ering + (size_t)st * g.stage_floats, p.enc + ((size_t)b * Th + r0) * D, (uint32_t)rows * D * 4u, &full_e[st]);
   };
   if (tid == 0) {
-    for (int i = 0; i < nchx; ++i) { mbar_init(&full_x[i], 1); mbar_init(&done_x[i], kBW); }
+    for (int i = 0; i < nchx; ++i) mbar_init(&full_x[i], 1);
+    mbar_init(done_x, kBW);
     for (int i = 0; i < g.ns; ++i) mbar_init(&full_e[i], 1);
     mbar_init(xbar1, 1);
     mbar_init(xbar2, 1);
     mbar_fence_init();
     mbar_expect_tx(xbar1, (uint32_t)CL * 4u);
     mbar_expect_tx(xbar2, (uint32_t)Th * (uint32_t)C * 4u + (uint32_t)CL * (uint32_t)A * 4u);
-    const int first = nche < g.ns ? nche : g.ns;
-    for (int q = 0; q < first; ++q) issue_e(q);
-    for (int q = 0; q < nchx; ++q) {
-      const int r0 = t0 + kBP * q;
-      const int rows = min(kBP, t1 - r0);
-      mbar_expect_tx(&full_x[q], (uint32_t)rows * A * 4u);
-      bulk_g2s(xs + (size_t)kBP * q * A, p.xsave + ((size_t)b * Th + r0) * A, (uint32_t)rows * A * 4u, &full_x[q]);
-    }
   }
   cluster_arrive_relaxed();   // "this CTA is running and its barriers exist"
 
@@ -619,6 +674,18 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     }
     vws = tid < tloc ? __ldg(p.w + (size_t)b * Th + t0 + tid) : 0.0f;
     vdw = (p.dw && tid < tloc) ? __ldg(p.dw + (size_t)b * Th + t0 + tid) : 0.0f;
+    // the bulk copies (enc_h ring first: pass 1 needs it first; then every activation chunk) are issued by one
+    // lane AFTER its warp's prologue loads are in flight
+    if (tid == 0) {
+      const int first = nche < g.ns ? nche : g.ns;
+      for (int q = 0; q < first; ++q) issue_e(q);
+      for (int q = 0; q < nchx; ++q) {
+        const int r0 = t0 + kBP * q;
+        const int rows = min(kBP, t1 - r0);
+        mbar_expect_tx(&full_x[q], (uint32_t)rows * A * 4u);
+        bulk_g2s(xs + (size_t)kBP * q * A, p.xsave + ((size_t)b * Th + r0) * A, (uint32_t)rows * A * 4u, &full_x[q]);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < IA; ++u)
       if (tid + u * NT < g.App) app[tid + u * NT] = va[u];
@@ -660,6 +727,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
       for (int i = tid; i < tloc * (CPP - CP); i += NT) conv_s[(i / (CPP - CP)) * CPP + CP + i % (CPP - CP)] = 0.0f;
   }
   __syncthreads();  // #1
+  ATT_MARK(1, 1);
 
   // ---- pass 1: dwt[t] = dw[t] + enc_h[t,:] . dc   (warp per frame, lane <-> d)
   {
@@ -684,15 +752,18 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
       if (++st == g.ns) { st = 0; ph ^= 1u; }
     }
   }
-  // W_att rows of this lane's channels -> registers
-  float Watt[APL][CP];
+  // W_att rows of this lane's channels -> registers, as pairs along c (packed FFMA2 in pass 2)
+  constexpr int CH2 = (CP + 1) / 2;
+  float2 WattC[APL][CH2];
 #pragma unroll
   for (int j = 0; j < APL; ++j) {
     const int a = half * (A / 2) + lane + 32 * j;
 #pragma unroll
-    for (int c = 0; c < CP; ++c) Watt[j][c] = c < C ? watt_s[a * WP + c] : 0.0f;
+    for (int c2 = 0; c2 < CH2; ++c2)
+      WattC[j][c2] = make_float2(2 * c2 < C ? watt_s[a * WP + 2 * c2] : 0.0f, 2 * c2 + 1 < C ? watt_s[a * WP + 2 * c2 + 1] : 0.0f);
   }
   __syncthreads();  // #2: dwt complete; the enc ring is free
+  ATT_MARK(1, 2);
   cluster_wait();   // peers are resident: remote stores may start
   if (warp == 0) {
     float s1 = 0.0f;
@@ -705,6 +776,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
   for (int r = 0; r < CL; ++r) Stot += xch[r];
   for (int tl = tid; tl < tloc; tl += NT) de_s[tl] = p.scaling * w_s[tl] * (dwt_s[tl] - Stot);
   __syncthreads();  // #3
+  ATT_MARK(1, 3);
 
   // ---- pass 2: through tanh.  pair <-> frame, lane <-> channel
   float dgv[APL], ddp[APL];
@@ -712,25 +784,16 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
   for (int j = 0; j < APL; ++j) { dgv[j] = 0.0f; ddp[j] = 0.0f; }
   {
     const int aoff = half * (A / 2) + lane;
-    auto flush = [&](int q) {   // hand chunk q (d pre, formed in place) to the TMA unit
-      mbar_wait(&done_x[q], 0);
-      const int r0 = kBP * q;
-      const int rows = min(kBP, tloc - r0);
-      float *dst = p.d_pre + ((size_t)b * Th + t0 + r0) * A;
-      if (p.accumulate_pre) bulk_red_add_s2g(dst, xs + (size_t)r0 * A, (uint32_t)rows * A * 4u);
-      else bulk_s2g(dst, xs + (size_t)r0 * A, (uint32_t)rows * A * 4u);
-      bulk_commit();
-    };
+    for (int q = 0; q < nchx; ++q) mbar_wait(&full_x[q], 0);   // landed long ago (issued in the prologue)
+    // no barrier inside the frame loop: the 16-value butterfly of one frame overlaps the FMAs of the next
+#pragma unroll 2
     for (int q = 0; q < nchx; ++q) {
-      if (tid == 0 && q >= 1) flush(q - 1);
-      __syncwarp();
-      mbar_wait(&full_x[q], 0);
       const int tl = kBP * q + pair;
       if (tl < tloc) {
         const float de = de_s[tl];
-        float dcv[16];
+        float2 dcv2[8];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) dcv[c] = 0.0f;
+        for (int c = 0; c < 8; ++c) dcv2[c] = make_float2(0.0f, 0.0f);
         float *row = xs + (size_t)tl * A + aoff;
 #pragma unroll
         for (int j = 0; j < APL; ++j) {
@@ -739,20 +802,34 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
           const float dt = de * gv[j] * (1.0f - x * x);
           ddp[j] += dt;
           row[32 * j] = dt;  // d pre, in place
+          const float2 dt2 = make_float2(dt, dt);
 #pragma unroll
-          for (int c = 0; c < CP; ++c) dcv[c] = fmaf(dt, Watt[j][c], dcv[c]);
+          for (int c2 = 0; c2 < CH2; ++c2) dcv2[c2] = __ffma2_rn(dt2, WattC[j][c2], dcv2[c2]);
         }
+        float dcv[16];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { dcv[2 * c] = dcv2[c].x; dcv[2 * c + 1] = dcv2[c].y; }
         warp_reduce16(dcv, lane);
         if ((lane & 1) == 0) {
           const int ci = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
           dcv_p[(half * g.tloc_max + tl) * 16 + ci] = dcv[0];
         }
       }
-      fence_proxy_async_smem();   // this thread's in-place writes -> visible to the bulk (async proxy) read
-      __syncwarp();
-      if (lane == 0) mbar_arrive1(&done_x[q]);
     }
-    if (tid == 0 && nchx > 0) flush(nchx - 1);
+    fence_proxy_async_smem();   // this thread's in-place writes -> visible to the bulk (async proxy) reads
+    __syncwarp();
+    if (lane == 0) mbar_arrive1(done_x);
+    if (tid == 0) {             // hand the d pre tile (formed in place) to the TMA unit: d_pre[b, t0:t1, :] (+)= tile
+      mbar_wait(done_x, 0);
+      float *dst = p.d_pre + ((size_t)b * Th + t0) * A;
+      const uint32_t total = (uint32_t)tloc * A * 4u;
+      for (uint32_t o = 0; o < total; o += 32768u) {
+        const uint32_t nb = total - o < 32768u ? total - o : 32768u;
+        if (p.accumulate_pre) bulk_red_add_s2g(reinterpret_cast<char *>(dst) + o, reinterpret_cast<char *>(xs) + o, nb);
+        else bulk_s2g(reinterpret_cast<char *>(dst) + o, reinterpret_cast<char *>(xs) + o, nb);
+      }
+      bulk_commit();
+    }
 #pragma unroll
     for (int j = 0; j < APL; ++j) {
       ddp_w[warp * (A / 2) + lane + 32 * j] = ddp[j];
@@ -760,6 +837,24 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     }
   }
   __syncthreads();  // #4: all d pre tiles written, per-warp partials published
+  ATT_MARK(1, 4);
+
+  // d dec_z needs W_dec[this warp's A/16 rows, this rank's slice of z]: issue those loads now (they do not depend on
+  // the cluster exchange below) so that their L2 latency hides behind post pass A
+  constexpr int AW = 4 * APL;                       // = A / 16 rows per warp
+  constexpr int ZP = APL <= 5 ? 3 : 1;              // z passes (of 32 lanes) held in registers
+  const int zc = (Z + CL - 1) / CL, z_begin = rank * zc, z_n = max(0, min(zc, Z - z_begin));
+  const int rz = round4(zc);
+  float wz[ZP][AW];
+  if (p.d_dec_z) {
+#pragma unroll
+    for (int zp = 0; zp < ZP; ++zp) {
+      const int zi = lane + 32 * zp;
+      const float *wcol = p.W_dec + (size_t)(warp * AW) * Z + z_begin + zi;
+#pragma unroll
+      for (int a = 0; a < AW; ++a) wz[zp][a] = zi < z_n ? __ldg(wcol + (size_t)a * Z) : 0.0f;
+    }
+  }
 
   // ---- post pass A
   // d conv of this CTA's frames -> every CTA of the cluster (channel-major, padded)
@@ -808,6 +903,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     for (int c = 0; c < CP; ++c)
       if (c < C) slot[a * C + c] = acc[c];
   }
+  ATT_MARK(1, 5);
   mbar_wait(xbar2, 0);   // d conv of all Th frames and every rank's d dec_proj partial have landed here
   for (int a = tid; a < A; a += NT) {
     float sd = 0.0f;
@@ -816,6 +912,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     if (rank == 0) p.d_decproj[(size_t)b * A + a] = sd;
   }
   __syncthreads();  // #5 (also: scr / dzp alias the per-warp partials read above)
+  ATT_MARK(1, 6);
 
   // ---- d att_prev[s] = sum_c sum_k Wc[c,k] * dconv[s - k + filts, c]   (sliding window, 5 outputs/thread)
   if (p.d_att_prev) {
@@ -847,23 +944,32 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     }
   }
   // ---- d dec_z[z] = sum_a d dec_proj[a] W_dec[a,z]  for this rank's slice of z: warp <-> slice of A/16 rows,
-  //      lane <-> z; the A/16 (<= 32) loads of a pass are independent: one L2 round trip per 32 outputs
-  const int zc = (Z + CL - 1) / CL, z_begin = rank * zc, z_n = max(0, min(zc, Z - z_begin));
-  const int rz = round4(zc);
+  //      lane <-> z (W_dec values prefetched above; further z blocks, if any, are loaded here)
   if (p.d_dec_z) {
-    const int aw = A / kBW;                    // rows per warp (A % 64 == 0 -> multiple of 4)
-    const float *dd = ddp_t + warp * aw;
-    for (int zi = lane; zi < z_n; zi += 32) {
-      const float *wcol = p.W_dec + (size_t)(warp * aw) * Z + z_begin + zi;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 5
-      for (int a = 0; a < aw; a += 4) {
-        s0 = fmaf(dd[a], __ldg(wcol + (size_t)a * Z), s0);
-        s1 = fmaf(dd[a + 1], __ldg(wcol + (size_t)(a + 1) * Z), s1);
-        s2 = fmaf(dd[a + 2], __ldg(wcol + (size_t)(a + 2) * Z), s2);
-        s3 = fmaf(dd[a + 3], __ldg(wcol + (size_t)(a + 3) * Z), s3);
+    const float *dd = ddp_t + warp * AW;
+    for (int zb = 0; zb < z_n; zb += 32 * ZP) {
+      if (zb > 0) {
+#pragma unroll
+        for (int zp = 0; zp < ZP; ++zp) {
+          const int zi = zb + lane + 32 * zp;
+          const float *wcol = p.W_dec + (size_t)(warp * AW) * Z + z_begin + zi;
+#pragma unroll
+          for (int a = 0; a < AW; ++a) wz[zp][a] = zi < z_n ? __ldg(wcol + (size_t)a * Z) : 0.0f;
+        }
       }
-      dzp[warp * rz + zi] = (s0 + s1) + (s2 + s3);
+#pragma unroll
+      for (int zp = 0; zp < ZP; ++zp) {
+        const int zi = zb + lane + 32 * zp;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int a = 0; a < AW; a += 4) {
+          s0 = fmaf(dd[a], wz[zp][a], s0);
+          s1 = fmaf(dd[a + 1], wz[zp][a + 1], s1);
+          s2 = fmaf(dd[a + 2], wz[zp][a + 2], s2);
+          s3 = fmaf(dd[a + 3], wz[zp][a + 3], s3);
+        }
+        if (zi < z_n) dzp[warp * rz + zi] = (s0 + s1) + (s2 + s3);
+      }
     }
   }
   // ---- dW_conv[c,k] += sum_{t in mine} dconv[t,c] * att_prev[t + k - filts]   (6 taps per thread, one owner each)
@@ -896,6 +1002,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     }
   }
   __syncthreads();  // #6
+  ATT_MARK(1, 7);
   if (p.d_att_prev) {
     for (int tl = tid; tl < tloc; tl += NT) {
       float sum = 0.0f;
@@ -911,7 +1018,9 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
       p.d_dec_z[(size_t)b * Z + z_begin + zi] = sum;
     }
   }
+  ATT_MARK(1, 8);
   if (tid == 0) bulk_wait<0>();  // all d_pre traffic of this CTA has left shared memory / landed
+  ATT_MARK(1, 9);
 }
 
 // out[i] = sum_s slots[s*stride + i]   -- once per decoder loop, fixed summation order.
@@ -1083,7 +1192,7 @@ inline bool pick_geom_fwd(int B, int Th, int D, int A, int Z, int C, int K, int 
   g.nch = (g.tloc_max + kFP - 1) / kFP;
   const size_t fixed = 512 + sizeof(float) * ((size_t)g.App + g.CKp + (size_t)A * (CP + 1) + round4(Z) + A +
                                               (size_t)round4(kKQ * g.tloc_max * CP) + (size_t)g.tloc_max * round4(CP) +
-                                              round4(g.tloc_max) + 4 * kFP +
+                                              round4(g.tloc_max) + round4(2 * g.tloc_max) +
                                               2 * kFW + 8 * (size_t)round4(D) + 16);
   const size_t budget = 224 * 1024;
   const size_t stage_bytes = sizeof(float) * (size_t)g.stage_floats;
@@ -1219,6 +1328,13 @@ int skinny(bool nn, const float *X, const float *W, float *out, int M, int N, in
 }  // namespace re2e
 
 using namespace re2e;
+
+#ifdef RE2E_ATT_DEBUG
+extern "C" int re2e_att_debug_read(long long *host_out, int which) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host_out, g_att_dbg, sizeof(long long) * 16 * 512, sizeof(long long) * 16 * 512 * which);
+}
+#endif
 
 extern "C" int re2e_attloc_init_att(const int32_t *hlens, float *att_prev, int B, int Th, void *stream) {
   RE2E_CHECK_ARG(hlens && att_prev && B > 0 && Th > 0);

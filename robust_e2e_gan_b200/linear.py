@@ -30,32 +30,63 @@ def _pad4(n):
     return (n + 3) // 4 * 4
 
 
+def _padded_view(out2, lead, N):
+    """(M, ld) row-padded 2-D buffer -> (*lead, N) view with the padded pitch (no copy)."""
+    ld = out2.stride(0)
+    strides, acc = [], ld
+    for n in reversed(lead):
+        strides.append(acc)
+        acc *= n
+    return out2.as_strided(tuple(lead) + (N,), tuple(reversed(strides)) + (1,))
+
+
+def _as_rows(g, M, N):
+    """View an incoming gradient (*lead, N) as TMA-addressable rows (M, N) with a uniform pitch; copies only
+    when the layout really is not row-regular (never on the hot path: the CTC backward writes its gradient in
+    the padded layout of the logits)."""
+    if g.dim() >= 2 and g.stride(-1) == 1:
+        ld = g.stride(-2) if g.shape[-2] > 1 else max(g.stride(-2), N)
+        ok = ld % 4 == 0 and g.data_ptr() % 16 == 0
+        acc = ld * g.shape[-2]
+        for d in range(g.dim() - 3, -1, -1):            # outer dims must continue the same row pitch
+            ok = ok and (g.shape[d] == 1 or g.stride(d) == acc)
+            acc *= g.shape[d]
+        if ok:
+            return g.as_strided((M, N), (ld, 1))
+    gp = torch.empty(M, _pad4(N), device=g.device, dtype=torch.float32)[:, :N]
+    gp.copy_(g.reshape(M, N))
+    return gp
+
+
 class _LinearTC(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x2, weight, bias):
-        M, K = x2.shape
+    def forward(ctx, x, weight, bias):
+        lead = tuple(x.shape[:-1])
+        K = x.shape[-1]
         N = weight.shape[0]
-        x2 = _lib.f32c(x2)
+        x2 = _lib.f32c(x.detach()).reshape(-1, K)
+        M = x2.shape[0]
         w = _lib.f32c(weight.detach())
         out = torch.empty(M, _pad4(N), device=x2.device, dtype=torch.float32)[:, :N]
         gemm_tf32x3(x2, False, w, False, out, M, N, K, bias=_lib.f32c(bias.detach()) if bias is not None else None)
         ctx.save_for_backward(x2, w)
         ctx.has_bias = bias is not None
-        return out
+        ctx.lead = lead
+        # the (possibly row-padded) N-D view is created HERE: an as_strided outside the Function would make autograd
+        # materialise a zero-filled copy of the whole gradient (108 MB for the CTC logits) in its backward
+        return out if (len(lead) == 1 and out.is_contiguous()) else _padded_view(out, lead, N)
 
     @staticmethod
     def backward(ctx, g):
         x2, w = ctx.saved_tensors
         M, K = x2.shape
         N = w.shape[0]
-        if g.stride(1) != 1 or g.stride(0) % 4 != 0 or g.data_ptr() % 16 != 0:
-            gp = torch.empty(M, _pad4(N), device=g.device, dtype=torch.float32)[:, :N]
-            gp.copy_(g)
-            g = gp
+        g = _as_rows(g, M, N)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, device=g.device, dtype=torch.float32)
             gemm_tf32x3(g, False, w, True, dx, M, K, N)               # dX = g W      (B = W stored [N][K]: MN-major)
+            dx = dx.view(*ctx.lead, K)
         if ctx.needs_input_grad[1]:
             dw = torch.empty(N, K, device=g.device, dtype=torch.float32)
             gemm_tf32x3(g, True, x2, True, dw, N, K, M)               # dW = g^T X    (both MN-major)
@@ -65,17 +96,6 @@ class _LinearTC(torch.autograd.Function):
 
 
 def linear(x, weight, bias=None):
-    """F.linear on the tcgen05 path; x (..., K) fp32 CUDA, weight (N, K), K % 4 == 0."""
-    K = x.shape[-1]
-    N = weight.shape[0]
-    y = _LinearTC.apply(x.reshape(-1, K), weight, bias)
-    lead = tuple(x.shape[:-1])
-    if y.is_contiguous():
-        return y.view(*lead, N)
-    # row-padded output: expose (..., N) with the padded pitch, no copy
-    ld = y.stride(0)
-    strides, acc = [], ld
-    for n in reversed(lead):
-        strides.append(acc)
-        acc *= n
-    return y.as_strided(lead + (N,), tuple(reversed(strides)) + (1,))
+    """F.linear on the tcgen05 path; x (..., K) fp32 CUDA, weight (N, K), K % 4 == 0.  The result may be a view with
+    a row pitch padded to a multiple of 4 floats (TMA-addressable rows); values are exactly (..., N)."""
+    return _LinearTC.apply(x, weight, bias)
