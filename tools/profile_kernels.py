@@ -1,4 +1,6 @@
-"""Run each hot-path kernel a few times on the bench tensors (for `ncu -k regex:... --set full`)."""
+"""Run each hot-path kernel once inside a cudaProfilerStart/Stop range on the bench tensors, for
+    ncu --set full --profile-from-start off --import-source on -o REP python tools/profile_kernels.py [name substrings]
+(two untimed warm-up launches of every kernel happen outside the range)."""
 import os
 import sys
 
@@ -13,11 +15,15 @@ dev = torch.device("cuda:0")
 cfg = dict(DEFAULT_CFG)
 hp = HotPath(cfg, seed=4000).to(dev)
 db = make_batch(cfg, seed=4000).to(dev)
-only = sys.argv[1:] 
-for name, fn, nbytes, reps in bench.kernel_specs(hp, db, cfg, dev):
-    if only and not any(o in name for o in only):
-        continue
+only = sys.argv[1:]
+specs = [s for s in bench.kernel_specs(hp, db, cfg, dev) if not only or any(o in s[0] for o in only)]
+for name, fn, nbytes, reps in specs:
     for _ in range(2):
         fn()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+for name, fn, nbytes, reps in specs:
+    fn()
     torch.cuda.synchronize()
     print("ran", name, flush=True)
+torch.cuda.cudart().cudaProfilerStop()
