@@ -282,6 +282,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run the three branches of the step on ONE stream (A/B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -302,7 +303,7 @@ def main():
     peak, peak_src = load_peaks()
 
     from robust_e2e_gan_b200.hotpath import StepRunner
-    hp = HotPath(cfg, seed=4000).to(dev)                 # identical init on every rank
+    hp = HotPath(cfg, seed=4000, overlap=not args.no_overlap).to(dev)   # identical init on every rank
     hb = make_batch(cfg, seed=4000 + rank).pin()         # distinct utterances per rank
     db = hb.to(dev)
     torch.cuda.synchronize()
@@ -326,7 +327,7 @@ def main():
 
     # ---- the step as a user runs it: StepRunner = CUDA-graph replay over static buffers, H2D on a copy stream
     runner = StepRunner(hp, hb, slots=2)
-    mode = "cuda_graph"
+    mode = "cuda_graph" + ("" if args.no_overlap else " (front-end | CTC | decoder-loop branches on 3 streams)")
     grad_keys = ["d_" + k for k, p in hp.named_parameters() if p.requires_grad]
     if world > 1:
         def allreduce_grads(out):

@@ -21,6 +21,8 @@
 // backward are register-blocked sliding-window FMAs (5 outputs per thread, K split 4 ways).
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace re2e {
@@ -158,6 +160,15 @@ __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint
                "r"(__float_as_uint(v)), "r"(remote_bar)
                : "memory");
 }
+// Programmatic dependent launch (PDL).  The step kernels are launched with programmatic stream serialisation, so
+// a grid may become resident while its predecessor in the stream (normally the previous decoder step) is still
+// running.  Everything before pdl_wait() touches only memory that was final before the predecessor STARTED:
+// parameters, the per-utterance encoder tensors (pre, enc_h) and -- in the backward -- tensors saved by the
+// forward pass.  griddepcontrol.wait returns once the predecessor grid has completed and flushed; all global
+// writes and all reads of per-step inputs (att_prev / dec_z, dc / dw, accumulators) come after it.  A predecessor
+// that never executes launch_dependents (any foreign kernel) degrades to ordinary stream order.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void cluster_arrive_relaxed() {
   asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 }
@@ -235,11 +246,6 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
   float va[IA], vc[IC], vw[IW], vz;
   {
 #pragma unroll
-    for (int u = 0; u < IA; ++u) {
-      const int i = tid + u * NT, t = i - filts;
-      va[u] = (i < g.App && t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
-    }
-#pragma unroll
     for (int u = 0; u < IC; ++u) {
       const int i = tid + u * NT;
       vc[u] = i < C * K ? __ldg(p.W_conv + i) : 0.0f;
@@ -249,8 +255,7 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
       const int i = tid + u * NT;
       vw[u] = i < A * C ? __ldg(p.W_att + i) : 0.0f;
     }
-    vz = (p.dec_z && tid < Z) ? __ldg(p.dec_z + (size_t)b * Z + tid) : 0.0f;
-    }
+  }
   // thread 0: barriers first (peers may push as soon as the cluster handshake completes), then the bulk copies of
   // the (pre | enc) stages -- issued AFTER this warp's prologue loads are in flight, so the serial issue loop of
   // one lane does not delay the loads of its warp
@@ -268,10 +273,7 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
     const int first = nch < g.ns ? nch : g.ns;
     for (int q = 0; q < first; ++q) issue(q);
   }
-    {
-#pragma unroll
-    for (int u = 0; u < IA; ++u)
-      if (tid + u * NT < g.App) app[tid + u * NT] = va[u];
+  {
 #pragma unroll
     for (int u = 0; u < IC; ++u)
       if (tid + u * NT < C * K) wc_s[tid + u * NT] = vc[u];
@@ -280,14 +282,29 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
       const int i = tid + u * NT;
       if (i < A * C) { const int a = i / C; watt_s[a * WP + (i - a * C)] = vw[u]; }
     }
+    for (int i = tid + IC * NT; i < C * K; i += NT) wc_s[i] = __ldg(p.W_conv + i);
+    for (int i = tid + IW * NT; i < A * C; i += NT) { const int a = i / C; watt_s[a * WP + (i - a * C)] = __ldg(p.W_att + i); }
+  }
+  // ---- PDL boundary: the per-step inputs (previous alignment, decoder state) exist only once the predecessor
+  //      grid has completed; the next step's grid may start its own prologue from here on
+  pdl_wait();
+  pdl_launch_dependents();
+  {
+#pragma unroll
+    for (int u = 0; u < IA; ++u) {
+      const int i = tid + u * NT, t = i - filts;
+      va[u] = (i < g.App && t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
+    }
+    vz = (p.dec_z && tid < Z) ? __ldg(p.dec_z + (size_t)b * Z + tid) : 0.0f;
+#pragma unroll
+    for (int u = 0; u < IA; ++u)
+      if (tid + u * NT < g.App) app[tid + u * NT] = va[u];
     if (tid < Z) dz_s[tid] = vz;
     // remainders (shapes beyond the first block)
     for (int i = tid + IA * NT; i < g.App; i += NT) {
       const int t = i - filts;
       app[i] = (t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
     }
-    for (int i = tid + IC * NT; i < C * K; i += NT) wc_s[i] = __ldg(p.W_conv + i);
-    for (int i = tid + IW * NT; i < A * C; i += NT) { const int a = i / C; watt_s[a * WP + (i - a * C)] = __ldg(p.W_att + i); }
     for (int i = tid + NT; i < Z; i += NT) dz_s[i] = p.dec_z ? __ldg(p.dec_z + (size_t)b * Z + i) : 0.0f;
   }
   __syncthreads();  // #1
@@ -642,16 +659,14 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
   }
   cluster_arrive_relaxed();   // "this CTA is running and its barriers exist"
 
-  // ---- prologue loads, batched in registers: one L2 round trip
-  float dcr[DPL2];
-#pragma unroll
-  for (int j = 0; j < DPL2; ++j) dcr[j] = (p.dc && lane + 32 * j < D) ? __ldg(p.dc + (size_t)b * D + lane + 32 * j) : 0.0f;
+  // ---- prologue loads, batched in registers: one L2 round trip.  Everything read here was written by the
+  //      FORWARD pass (or is a parameter), so it is issued before the PDL boundary below.
   float gv[APL];
 #pragma unroll
   for (int j = 0; j < APL; ++j) gv[j] = __ldg(p.gvec + half * (A / 2) + lane + 32 * j);
   {
     constexpr int IA = 2, IC = 4, IW = 8, IV = 2;
-    float va[IA], vc[IC], vw[IW], vv[IV], vws, vdw;
+    float va[IA], vc[IC], vw[IW], vv[IV], vws;
 #pragma unroll
     for (int u = 0; u < IA; ++u) {
       const int i = tid + u * NT, t = i - filts;
@@ -673,7 +688,6 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
       vv[u] = i < tloc * C ? __ldg(p.conv + ((size_t)b * Th + t0) * C + i) : 0.0f;
     }
     vws = tid < tloc ? __ldg(p.w + (size_t)b * Th + t0 + tid) : 0.0f;
-    vdw = (p.dw && tid < tloc) ? __ldg(p.dw + (size_t)b * Th + t0 + tid) : 0.0f;
     // the bulk copies (enc_h ring first: pass 1 needs it first; then every activation chunk) are issued by one
     // lane AFTER its warp's prologue loads are in flight
     if (tid == 0) {
@@ -702,7 +716,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
       const int i = tid + u * NT;
       if (i < tloc * C) { const int tl = i / C; conv_s[tl * CPP + (i - tl * C)] = vv[u]; }
     }
-    if (tid < tloc) { w_s[tid] = vws; dwt_s[tid] = vdw; }
+    if (tid < tloc) w_s[tid] = vws;
     for (int i = tid + IA * NT; i < g.App; i += NT) {
       const int t = i - filts;
       app[i] = (t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
@@ -713,10 +727,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
       const int tl = i / C;
       conv_s[tl * CPP + (i - tl * C)] = __ldg(p.conv + ((size_t)b * Th + t0) * C + i);
     }
-    for (int i = tid + NT; i < tloc; i += NT) {
-      w_s[i] = __ldg(p.w + (size_t)b * Th + t0 + i);
-      dwt_s[i] = p.dw ? __ldg(p.dw + (size_t)b * Th + t0 + i) : 0.0f;
-    }
+    for (int i = tid + NT; i < tloc; i += NT) w_s[i] = __ldg(p.w + (size_t)b * Th + t0 + i);
     // zero the pads of the channel-major d conv rows (the frames themselves are pushed by the cluster)
     const int padn = g.App - Th;
     for (int i = tid; i < CP * padn; i += NT) {
@@ -726,6 +737,14 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     if (CPP > CP)
       for (int i = tid; i < tloc * (CPP - CP); i += NT) conv_s[(i / (CPP - CP)) * CPP + CP + i % (CPP - CP)] = 0.0f;
   }
+  // ---- PDL boundary: the incoming gradients (dc, dw = the next step's d att_prev) are produced by the predecessor
+  //      grid(s); every global write of this kernel (d pre reduce-add, accumulator slots, outputs) comes later
+  pdl_wait();
+  pdl_launch_dependents();
+  float dcr[DPL2];
+#pragma unroll
+  for (int j = 0; j < DPL2; ++j) dcr[j] = (p.dc && lane + 32 * j < D) ? __ldg(p.dc + (size_t)b * D + lane + 32 * j) : 0.0f;
+  for (int i = tid; i < tloc; i += NT) dwt_s[i] = p.dw ? __ldg(p.dw + (size_t)b * Th + t0 + i) : 0.0f;
   __syncthreads();  // #1
   ATT_MARK(1, 1);
 
@@ -1249,6 +1268,11 @@ inline bool pick_geom_bwd(int B, int Th, int D, int A, int Z, int C, int K, int 
   }
 }
 
+inline bool pdl_enabled() {
+  static const bool on = [] { const char *e = getenv("RE2E_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
+}
+
 template <typename Kern, typename Params>
 int launch_cluster(Kern kern, const Params &prm, int B, int CL, int threads, size_t smem, cudaStream_t st) {
   int rc0 = ensure_smem(reinterpret_cast<const void *>(kern), smem);
@@ -1263,13 +1287,17 @@ int launch_cluster(Kern kern, const Params &prm, int B, int CL, int threads, siz
   cfg.blockDim = dim3((unsigned)threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // programmatic dependent launch: the grid may start its prologue while the previous kernel of the stream drains
+  // (see pdl_wait()); RE2E_NO_PDL=1 in the environment restores plain stream order (debugging / A-B timing)
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, kern, prm);
   count_launch();
   return e == cudaSuccess ? RE2E_OK : (int)e;

@@ -70,9 +70,15 @@ class _Opt(object):
 class HotPath(torch.nn.Module):
     """FbankModel + CTC + AttLoc with seeded parameters, and ``step(batch)`` = fwd + bwd."""
 
-    def __init__(self, cfg, seed=1234, mtlalpha=0.5):
+    def __init__(self, cfg, seed=1234, mtlalpha=0.5, overlap=True):
         super().__init__()
         self.cfg = dict(cfg)
+        # overlap=True: the three independent branches of the step (front-end, CTC, attention decoder loop) run on
+        # three CUDA streams, fork/join inside step(); autograd replays each branch's backward on its own stream.
+        # The decoder loop is a serial chain of latency-bound cluster kernels that leaves SMs and issue slots idle;
+        # the bandwidth/tensor-bound front-end and CTC kernels fill them.
+        self.overlap = overlap
+        self._side = None
         c = self.cfg
         self.feat = FbankModel(_Opt(idim=c["F"], fbank_dim=c["M"], enhance_type="blstm", fbank_opti_type="frozen",
                                     train_dataset_len=1000, num_utt_cmvn=100))
@@ -91,6 +97,13 @@ class HotPath(torch.nn.Module):
     def state_dict_cpu(self):
         return {k: v.detach().cpu().clone() for k, v in self.state_dict().items()}
 
+    def _branch_streams(self, dev):
+        """(front-end stream, CTC stream): low priority, so the decoder loop's kernels on the caller's stream are
+        scheduled first whenever both have CTAs pending."""
+        if self._side is None or self._side[0].device != dev:
+            self._side = (torch.cuda.Stream(dev, priority=0), torch.cuda.Stream(dev, priority=0))
+        return self._side
+
     def step(self, b, backward=True, hlens_for_att=None):
         """One fwd+bwd of the hot path on a device Batch.  Returns a dict of outputs and gradients."""
         steps = self.cfg["steps"]
@@ -98,13 +111,22 @@ class HotPath(torch.nn.Module):
         hpad = b.hpad.detach().requires_grad_(backward)
         # one leaf per decoder step (as the LSTMCell outputs are separate tensors in Decoder.forward)
         dec_zs = [b.dec_z[i].detach().requires_grad_(backward) for i in range(steps - 1)]
+        main = torch.cuda.current_stream(hpad.device)
+        if self.overlap:
+            s_fe, s_ctc = self._branch_streams(hpad.device)
+            s_fe.wait_stream(main)
+            s_ctc.wait_stream(main)
+        else:
+            s_fe = s_ctc = main
         # -- front-end (joint_train.py:158-161)
-        enhance_feat = self.feat.forward_masked(mask_logits, b.mix, b.lens, b.cmvn)
-        with torch.no_grad():
-            clean_feat = self.feat(b.clean, b.cmvn)
-            mix_feat = self.feat(b.mix, b.cmvn)
+        with torch.cuda.stream(s_fe):
+            enhance_feat = self.feat.forward_masked(mask_logits, b.mix, b.lens, b.cmvn)
+            with torch.no_grad():
+                clean_feat = self.feat(b.clean, b.cmvn)
+                mix_feat = self.feat(b.mix, b.cmvn)
         # -- CTC branch (model/e2e_model.py:192)
-        loss_ctc = self.ctc(hpad, b.hlens, b.targets if b.targets is not None else b.ys)
+        with torch.cuda.stream(s_ctc):
+            loss_ctc = self.ctc(hpad, b.hlens, b.targets if b.targets is not None else b.ys)
         # -- attention decoder loop (model/e2e_decoder.py:114-122)
         self.att.reset()
         att_w = None
@@ -114,6 +136,9 @@ class HotPath(torch.nn.Module):
             z = None if i == 0 else dec_zs[i - 1]
             att_c, att_w = self.att(hpad, hl, z, att_w)
             cs.append(att_c)
+        if self.overlap:
+            main.wait_stream(s_fe)
+            main.wait_stream(s_ctc)
         out = {"enhance_feat": enhance_feat, "clean_feat": clean_feat, "mix_feat": mix_feat, "loss_ctc": loss_ctc,
                "att_c": torch.stack(cs), "att_w": att_w}
         if backward:
@@ -155,7 +180,9 @@ class StepRunner(object):
         self.hp = hp
         self.dev = next(hp.parameters()).device
         self.copy_stream = torch.cuda.Stream(self.dev)
-        self.run_stream = torch.cuda.Stream(self.dev)
+        # high priority: the decoder loop (a serial chain of latency-bound kernels on this stream) gets SMs before the
+        # bulk front-end / CTC kernels that HotPath.step forks onto its (default-priority) branch streams
+        self.run_stream = torch.cuda.Stream(self.dev, priority=-1)
         B = hp.cfg["B"]
         flat, offs, lens = _targets_host(example_host_batch.ys)
         self.umax = int(umax if umax is not None else max(int(lens.max()) if len(lens) else 1, 1))
