@@ -40,6 +40,16 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peak_tf32():
+    """Dense TF32 tensor peak used for the GEMM entries: half the MEASURED bf16 cuBLAS throughput
+    (MEASURED_PEAKS.json; tf32 runs at half the bf16 rate on tcgen05), else half the recipe's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return round(float(json.load(f)["bf16_tflops"]) / 2.0, 1)
+    return 1125.0
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons through NVML while the timed region runs."""
 
@@ -225,6 +235,28 @@ def kernel_specs(hp, db, cfg, dev):
         _lib.check(L.re2e_ctc_loss_bwd(P(logits), Th * V, V, P(tg.labels), P(tg.offs), P(tg.lens), P(hl), 0, P(nll),
                                        None, P(ws), nb, P(grad), B, Th, V, tg.umax, sp()))
 
+    # dense layers on the tcgen05 3xTF32 GEMM (ctc_lo fwd / dX / dW, mlp_enc fwd): (flops, "tensor") entries
+    from robust_e2e_gan_b200.linear import gemm_tf32x3, _pad4
+    Wlo, blo = hp.ctc.ctc_lo.weight.detach().contiguous(), hp.ctc.ctc_lo.bias.detach().contiguous()
+    Wenc, benc = att.mlp_enc.weight.detach().contiguous(), att.mlp_enc.bias.detach().contiguous()
+    R = B * Th
+    x2 = enc.view(R, D)
+    lg = torch.empty(R, _pad4(V), **f32)[:, :V]
+    gl = (torch.randn(R, _pad4(V), **f32) * 1e-3)[:, :V]
+    dx, dWlo, pre2 = torch.empty(R, D, **f32), torch.empty(V, D, **f32), torch.empty(R, A, **f32)
+
+    def k_lo_fwd():
+        gemm_tf32x3(x2, False, Wlo, False, lg, R, V, D, bias=blo)
+
+    def k_lo_dx():
+        gemm_tf32x3(gl, False, Wlo, True, dx, R, D, V)
+
+    def k_lo_dw():
+        gemm_tf32x3(gl, True, x2, True, dWlo, V, D, R)
+
+    def k_enc_fwd():
+        gemm_tf32x3(x2, False, Wenc, False, pre2, R, A, D, bias=benc)
+
     S = 2 * tg.umax + 1
     specs = [
         ("fbank_fwd(mask,mag->Y,G)", k_fb_fwd, 4.0 * N * (2 * F + 2 * M), 4),
@@ -234,6 +266,10 @@ def kernel_specs(hp, db, cfg, dev):
         ("attloc_step_bwd", k_att_bwd, 4.0 * B * Th * (A + D) + 4.0 * B * Th * A + 4.0 * B * Th * (4 + C), 20),
         ("ctc_fwd(lse+alpha/beta)", k_ctc_fwd, 4.0 * valid_frames * V + 4.0 * 3 * valid_frames * S, 4),
         ("ctc_bwd(grad)", k_ctc_bwd, 4.0 * valid_frames * V + 4.0 * B * Th * V, 4),
+        ("gemm ctc_lo fwd (%dx%dx%d)" % (R, V, D), k_lo_fwd, ("flop", 2.0 * R * V * D), 4),
+        ("gemm ctc_lo dX (%dx%dx%d)" % (R, D, V), k_lo_dx, ("flop", 2.0 * R * V * D), 4),
+        ("gemm ctc_lo dW (%dx%dx%d)" % (V, D, R), k_lo_dw, ("flop", 2.0 * R * V * D), 4),
+        ("gemm mlp_enc fwd (%dx%dx%d)" % (R, A, D), k_enc_fwd, ("flop", 2.0 * R * A * D), 8),
     ]
     return specs
 
@@ -268,6 +304,15 @@ def kernel_rooflines(hp, db, cfg, peak, dev):
             ts.append(e0.elapsed_time(e1) * 1e3 / reps)
         ts.sort()
         us = ts[len(ts) // 2]
+        if isinstance(nbytes, tuple):       # tensor-bound entry: fp32-equivalent flops; 3 TF32 MMAs per product
+            fl = nbytes[1]
+            tf = fl / (us * 1e-6) / 1e12
+            tf32_peak = tensor_peak_tf32()
+            res[name] = {"us_per_launch": round(us, 2), "algorithmic_GFLOP": round(fl / 1e9, 2),
+                         "achieved_TFLOPs_fp32_equiv": round(tf, 1), "executed_TFLOPs_tf32": round(3 * tf, 1),
+                         "frac_of_tf32_peak": round(3 * tf / tf32_peak, 3), "bound": "tensor",
+                         "tf32_peak_TFLOPs": tf32_peak}
+            continue
         ach = nbytes / (us * 1e-6) / 1e9
         res[name] = {"us_per_launch": round(us, 2), "algorithmic_MB": round(nbytes / 1e6, 2),
                      "achieved_GBps": round(ach, 1), "frac_of_hbm_peak": round(ach / peak, 3)}
@@ -394,7 +439,8 @@ def main():
             ks = kernel_rooflines(hp, db, cfg, peak, dev)
             line["kernels"] = ks
             per_step = {"attloc_step_fwd": cfg["steps"], "attloc_step_bwd": cfg["steps"], "fbank_fwd(mag->Y)": 2}
-            dom = max(ks, key=lambda k: ks[k]["us_per_launch"] * per_step.get(k, 1))
+            dom = max((k for k in ks if "frac_of_hbm_peak" in ks[k]),
+                      key=lambda k: ks[k]["us_per_launch"] * per_step.get(k, 1))
             line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ks[dom]["achieved_GBps"], "peak": peak,
                                 "unit": "GB/s", "frac": ks[dom]["frac_of_hbm_peak"], "peak_source": peak_src,
                                 "launches_per_step": per_step.get(dom, 1), "us_per_launch": ks[dom]["us_per_launch"],

@@ -1151,46 +1151,58 @@ __global__ void init_att_kernel(const int32_t *__restrict__ hlens, float *__rest
   att[i] = (t < l) ? 1.0f / (float)l : 0.0f;
 }
 
-// d_enc_h[b,t,:] (+)= sum_i w_all[i,b,t] * dc_all[i,b,:]   -- 8 frames x (lane <-> d) per warp, steps in smem
-__global__ void __launch_bounds__(256)
+// d_enc_h[b,t,:] (+)= sum_i w_all[i,b,t] * dc_all[i,b,:]   (rank-#steps update, once per decoder loop)
+// CTA <-> (utterance, tile of tt frames); the utterance's dc rows [steps][D] and the tile's weights [steps][tt]
+// are staged in shared memory; thread <-> (d, group of 8 frames): w broadcast, dc conflict free, 8 FMAs per 2 LDS.
+constexpr int kEGThreads = 512;
+__global__ void __launch_bounds__(kEGThreads)
 enc_grad_kernel(const float *__restrict__ w_all, const float *__restrict__ dc_all,
                 float *__restrict__ d_enc, int steps, int B, int Th, int D, int tt, int accumulate) {
   extern __shared__ __align__(16) float smem[];
   float *dc_s = smem;                     // [steps][D]
-  float *w_s = smem + (size_t)steps * D;  // [steps][tt]
+  float *w_s = smem + (size_t)round4(steps * D);  // [steps][tt]   (tt % 8 == 0)
   const int tiles = (Th + tt - 1) / tt;
   const int b = blockIdx.x / tiles, t0 = (blockIdx.x - b * tiles) * tt;
   const int rows = min(tt, Th - t0);
   const int tid = threadIdx.x;
-  for (int i = tid; i < steps * D; i += 256) {
-    const int s = i / D, d = i - s * D;
-    dc_s[i] = __ldg(dc_all + ((size_t)s * B + b) * D + d);
+  if ((D & 3) == 0) {
+    const int D4 = D >> 2;
+    for (int i = tid; i < steps * D4; i += kEGThreads) {
+      const int s = i / D4, d4 = i - s * D4;
+      reinterpret_cast<float4 *>(dc_s)[i] = __ldg(reinterpret_cast<const float4 *>(dc_all + ((size_t)s * B + b) * D) + d4);
+    }
+  } else {
+    for (int i = tid; i < steps * D; i += kEGThreads) {
+      const int s = i / D, d = i - s * D;
+      dc_s[i] = __ldg(dc_all + ((size_t)s * B + b) * D + d);
+    }
   }
-  for (int i = tid; i < steps * tt; i += 256) {
+  for (int i = tid; i < steps * tt; i += kEGThreads) {
     const int s = i / tt, r = i - s * tt;
     w_s[i] = r < rows ? __ldg(w_all + ((size_t)s * B + b) * Th + t0 + r) : 0.0f;
   }
   __syncthreads();
-  // thread <-> (d, group of 8 frames): w broadcast from smem, dc conflict free
-  const int ngr = (tt + 7) / 8;
-  for (int item = tid; item < D * ngr; item += 256) {
+  const int ngr = (rows + 7) / 8;
+  for (int item = tid; item < D * ngr; item += kEGThreads) {
     const int d = item % D, gr = item / D;
     float a[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = 0.0f;
+    for (int i = 0; i < 8; ++i) {
+      const int r = gr * 8 + i;
+      a[i] = (accumulate && r < rows) ? d_enc[((size_t)b * Th + t0 + r) * D + d] : 0.0f;   // in flight during the loop
+    }
+#pragma unroll 4
     for (int s = 0; s < steps; ++s) {
       const float dv = dc_s[s * D + d];
-      const float *wr = w_s + s * tt + gr * 8;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = fmaf(wr[i], dv, a[i]);
+      const float4 w0 = *reinterpret_cast<const float4 *>(w_s + s * tt + gr * 8);
+      const float4 w1 = *reinterpret_cast<const float4 *>(w_s + s * tt + gr * 8 + 4);
+      a[0] = fmaf(w0.x, dv, a[0]); a[1] = fmaf(w0.y, dv, a[1]); a[2] = fmaf(w0.z, dv, a[2]); a[3] = fmaf(w0.w, dv, a[3]);
+      a[4] = fmaf(w1.x, dv, a[4]); a[5] = fmaf(w1.y, dv, a[5]); a[6] = fmaf(w1.z, dv, a[6]); a[7] = fmaf(w1.w, dv, a[7]);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = gr * 8 + i;
-      if (r < rows) {
-        float *o = d_enc + ((size_t)b * Th + t0 + r) * D + d;
-        *o = accumulate ? *o + a[i] : a[i];
-      }
+      if (r < rows) d_enc[((size_t)b * Th + t0 + r) * D + d] = a[i];
     }
   }
 }
@@ -1451,15 +1463,15 @@ extern "C" int re2e_attloc_acc_reduce(const float *acc_slots, int n_slots, float
 extern "C" int re2e_attloc_enc_grad(const float *w_all, const float *dc_all, float *d_enc_h, int steps,
                                     int B, int Th, int D, int accumulate, void *stream) {
   RE2E_CHECK_ARG(w_all && dc_all && d_enc_h && steps > 0 && B > 0 && Th > 0 && D > 0);
-  const int tt = 8;
-  const size_t smem = sizeof(float) * ((size_t)steps * D + (size_t)steps * tt);
+  const int tt = 32;   // frames per CTA: the utterance's dc block (steps x D) is re-read Th/tt times from L2
+  const size_t smem = sizeof(float) * ((size_t)round4(steps * D) + (size_t)steps * tt);
   if (smem > 200 * 1024) return RE2E_E_UNSUPPORTED;
   {
     int rc0 = ensure_smem(reinterpret_cast<const void *>(enc_grad_kernel), smem);
     if (rc0 != RE2E_OK) return rc0;
   }
   const int tiles = (Th + tt - 1) / tt;
-  enc_grad_kernel<<<B * tiles, 256, smem, static_cast<cudaStream_t>(stream)>>>(w_all, dc_all, d_enc_h, steps, B,
+  enc_grad_kernel<<<B * tiles, kEGThreads, smem, static_cast<cudaStream_t>(stream)>>>(w_all, dc_all, d_enc_h, steps, B,
                                                                               Th, D, tt, accumulate);
   count_launch();
   return launch_status();
