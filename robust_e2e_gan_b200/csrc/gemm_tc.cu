@@ -77,8 +77,27 @@ struct GemmParams {
   float *C;
   const float *bias;
   int M, N, K, ldc, accumulate;
+  int tma_c;    // C is 16 B aligned with a 16 B row pitch: the epilogue goes through the TMA store / reduce unit
   int kb_per;   // k-blocks per split (gridDim.z splits); split > 1: partial tiles are added with red.global
 };
+
+// shared -> global 2-D tensor store / fp32 reduce-add of one 32 x 32 box (SWIZZLE_128B staging); partial boxes at
+// the M / N edges are clipped by the TMA unit
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, int c0, int c1, const void *src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(c1), "r"(smem_u32(src))
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *tm, int c0, int c1, const void *src) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(c1), "r"(smem_u32(src))
+               : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __device__ __forceinline__ void red_add4(float *p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
@@ -88,7 +107,7 @@ __device__ __forceinline__ void red_add4(float *p, float4 v) {
 template <bool A_MN, bool B_MN, int BN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const GemmParams p) {
+                   const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smraw[];
   constexpr int A_BYTES = kBM * kBK * 4;         // 16 KB
   constexpr int B_BYTES = BN * kBK * 4;
@@ -104,6 +123,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t *empty = conv + STAGES;
   uint64_t *tmem_full = empty + STAGES;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+  float *bias_s = reinterpret_cast<float *>(smraw + (size_t)STAGES * STAGE_BYTES + 1024);   // [BN] this tile's bias
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
@@ -127,6 +147,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                  "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x >= 64) {   // bias of this tile's columns (zero when absent / not this split's job)
+    const bool use_bias = p.bias != nullptr && blockIdx.z == 0;
+    for (int i = threadIdx.x - 64; i < BN; i += kGemmThreads - 64)
+      bias_s[i] = (use_bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
   }
   tc_fence_before();
   __syncthreads();
@@ -209,7 +234,56 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tc_fence_after();
     const int q = warp & 3;
     const int row = m0 + 32 * q + lane;
-    const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
+    if (p.tma_c) {
+      // coalesced asynchronous epilogue: TMEM -> registers (+bias) -> 128 B-swizzled staging rows in the (now idle)
+      // operand ring -> one TMA box store (or fp32 reduce-add for split-K / accumulate) per 32 x 32 block,
+      // double buffered per warp.  The SM issues 8 conflict-minimal STS.128 per block instead of 8 row-strided
+      // STG.128 (32 sectors each), and never waits for the global writes.
+      unsigned char *ebuf = stage0 + (size_t)q * 8192;
+      const bool add = split || p.accumulate;
+      const bool rows_ok = m0 + 32 * q < p.M;
+      const int n_al = p.N & ~3;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;
+        if (c >= 2) {
+          if (lane == 0) bulk_wait_read<1>();   // the block staged two iterations ago has left shared memory
+          __syncwarp();
+        }
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32), v);
+        const uint32_t base = smem_u32(ebuf + (size_t)(c & 1) * 4096) + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b4 = *reinterpret_cast<const float4 *>(bias_s + c * 32 + 4 * j4);
+          st_shared_v4(base + (uint32_t)((j4 ^ (lane & 7)) << 4), v[4 * j4] + b4.x, v[4 * j4 + 1] + b4.y,
+                       v[4 * j4 + 2] + b4.z, v[4 * j4 + 3] + b4.w);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && rows_ok && col0 < n_al) {
+          if (add) tma_reduce_add_2d(&tmC, col0, m0 + 32 * q, ebuf + (size_t)(c & 1) * 4096);
+          else tma_store_2d(&tmC, col0, m0 + 32 * q, ebuf + (size_t)(c & 1) * 4096);
+          bulk_commit();
+        }
+        // ragged tail (N % 4 != 0): the TMA unit clips in 16 B units, so the tensor map ends at N & ~3 and the last
+        // 1..3 columns are written from registers (one 32-column block of the whole matrix takes this branch)
+        if (n_al < p.N && n_al >= col0 && n_al < col0 + 32 && row < p.M) {
+          float *dst = p.C + (size_t)row * p.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j >= n_al && col0 + j < p.N) {
+              const float val = v[j] + bias_s[c * 32 + j];
+              if (split) atomicAdd(dst + j, val);
+              else dst[j] = p.accumulate ? dst[j] + val : val;
+            }
+        }
+      }
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+    } else {
+    const bool vec = false;   // this path is only taken when C is not 16 B addressable
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
@@ -248,6 +322,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -258,8 +333,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 template <bool A_MN, bool B_MN, int BN, int STAGES>
-int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &prm, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * 2 * (kBM * kBK * 4 + BN * kBK * 4) + 1024;
+int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, const GemmParams &prm,
+                cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * 2 * (kBM * kBK * 4 + BN * kBK * 4) + 1024 + BN * 4;
   auto kern = gemm_tf32x3_kernel<A_MN, B_MN, BN, STAGES>;
   int rc = ensure_smem(reinterpret_cast<const void *>(kern), smem);
   if (rc != RE2E_OK) return rc;
@@ -270,18 +346,18 @@ int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &
                                       (size_t)prm.M, st);
     if (e != cudaSuccess) return (int)e;
   }
-  kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, prm);
+  kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, tc, prm);
   count_launch();
   return launch_status();
 }
 
 template <int BN, int STAGES>
-int dispatch_major(int a_mn, int b_mn, const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &prm,
-                   cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_gemm<false, false, BN, STAGES>(ta, tb, prm, st);
-  if (!a_mn && b_mn) return launch_gemm<false, true, BN, STAGES>(ta, tb, prm, st);
-  if (a_mn && !b_mn) return launch_gemm<true, false, BN, STAGES>(ta, tb, prm, st);
-  return launch_gemm<true, true, BN, STAGES>(ta, tb, prm, st);
+int dispatch_major(int a_mn, int b_mn, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc,
+                   const GemmParams &prm, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_gemm<false, false, BN, STAGES>(ta, tb, tc, prm, st);
+  if (!a_mn && b_mn) return launch_gemm<false, true, BN, STAGES>(ta, tb, tc, prm, st);
+  if (a_mn && !b_mn) return launch_gemm<true, false, BN, STAGES>(ta, tb, tc, prm, st);
+  return launch_gemm<true, true, BN, STAGES>(ta, tb, tc, prm, st);
 }
 
 }  // namespace
@@ -296,7 +372,7 @@ extern "C" int re2e_gemm_tf32x3(const float *A, int lda, int a_mn, const float *
   RE2E_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0 && ldc >= N);
   RE2E_CHECK_ARG((lda & 3) == 0 && (ldb & 3) == 0 && aligned16(A) && aligned16(B));
   RE2E_CHECK_ARG(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K));
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
   int rc;
   const int BN = (N % 256 == 0 || N > 1024) ? 256 : 160;
   if (!a_mn) rc = make_tmap(&ta, A, K, M, lda, kBM, false);
@@ -308,8 +384,28 @@ extern "C" int re2e_gemm_tf32x3(const float *A, int lda, int a_mn, const float *
   GemmParams prm;
   prm.C = C; prm.bias = bias; prm.M = M; prm.N = N; prm.K = K; prm.ldc = ldc; prm.accumulate = accumulate;
   const int nkb = (K + kBK - 1) / kBK;
-  prm.kb_per = nkb > 24 ? 16 : nkb;   // K > 768: slices of 512
+  // K > 768: split-K (bounds the truncating TMEM accumulation chain to <= 640 products).  The slice length is chosen
+  // per shape so that the CTA count fills whole waves of the machine: cost = waves * (k-blocks + fixed per-CTA
+  // overhead of ~4 k-block times for prologue + epilogue).
+  prm.kb_per = nkb;
+  if (nkb > 24) {
+    const int sms = num_sms();
+    const long long tiles = (long long)((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+    long long best = -1;
+    for (int kp = 12; kp <= 20; ++kp) {
+      const long long ctas = tiles * ((nkb + kp - 1) / kp);
+      const long long cost = ((ctas + sms - 1) / sms) * (kp + 4);
+      if (best < 0 || cost < best) { best = cost; prm.kb_per = kp; }
+    }
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (BN == 256) return dispatch_major<256, 2>(a_mn, b_mn, ta, tb, prm, st);
-  return dispatch_major<160, 3>(a_mn, b_mn, ta, tb, prm, st);
+  // epilogue through the TMA store unit when C is TMA-addressable (16 B aligned, 16 B row pitch); 32 x 32 boxes
+  prm.tma_c = ((ldc & 3) == 0 && aligned16(C) && N >= 4) ? 1 : 0;
+  if (prm.tma_c) {
+    if ((rc = make_tmap(&tc, C, N & ~3, M, ldc, 32, false)) != RE2E_OK) return rc;
+  } else {
+    tc = ta;   // unused
+  }
+  if (BN == 256) return dispatch_major<256, 2>(a_mn, b_mn, ta, tb, tc, prm, st);
+  return dispatch_major<160, 3>(a_mn, b_mn, ta, tb, tc, prm, st);
 }
