@@ -181,7 +181,44 @@ def gen_prefix(ns):
     np.savez_compressed(os.path.join(OUT, "prefix.npz"), **out)
 
 
-def main():
+def gen_beam(ns):
+    """Decoder.recognize_beam (model/e2e_decoder.py:170-369) with the reference AttLoc / CTC / CTCPrefixScore on
+    seeded small models (tests/helpers.py:beam_case): expected n-best token sequences and scores."""
+    import importlib
+    import types
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    e2e_decoder = importlib.import_module("model.e2e_decoder")
+    out = {}
+    for name in helpers.BEAM_CASES:
+        c, sd, h, checksum = helpers.beam_case(name)
+        att = ns.AttLoc(c["D"], c["Z"], c["A"], c["C"], c["filts"], "softmax")
+        dec = e2e_decoder.Decoder(c["D"], c["V"], 1, c["Z"], c["sos"], c["eos"], att)
+        ctc = ns.CTC(c["V"], c["D"], 0.0)
+        dec.load_state_dict({k: v for k, v in sd.items() if not k.startswith("ctc_lo")}, strict=True)
+        ctc.load_state_dict({k: v for k, v in sd.items() if k.startswith("ctc_lo")}, strict=True)
+        dec.eval()
+        args = types.SimpleNamespace(beam_size=c["beam"], penalty=c["penalty"], ctc_weight=c["ctc_weight"],
+                                     maxlenratio=c["maxlenratio"], minlenratio=c["minlenratio"], nbest=c["nbest"],
+                                     lm_weight=0.0)
+        with torch.no_grad():
+            lpz = ctc.log_softmax(h.unsqueeze(0)).data[0] if c["ctc_weight"] > 0.0 else None
+            nbest = dec.recognize_beam(h, lpz, args, [str(i) for i in range(c["V"])], None, None)
+            best_path = ctc.log_softmax(h.unsqueeze(0)).data[0].argmax(1)
+        out[name + ".n"] = np.array(len(nbest))
+        out[name + ".checksum"] = np.array(checksum)
+        out[name + ".best_path"] = npy(best_path).astype(np.int32)
+        for i, hyp in enumerate(nbest):
+            out["%s.yseq%d" % (name, i)] = np.array([int(t) for t in hyp["yseq"]], dtype=np.int32)
+            out["%s.score%d" % (name, i)] = np.array(float(hyp["score"]), dtype=np.float64)
+        print(name, [(len(hh["yseq"]), round(float(hh["score"]), 4)) for hh in nbest])
+    np.savez_compressed(os.path.join(OUT, "beam.npz"), **out)
+
+
+def main(only=None):
+    if only == "beam":
+        gen_beam(refshim.load())
+        return
     if not refshim.available():
         raise SystemExit("reference tree not available; fixtures can only be generated in the build container")
     os.makedirs(OUT, exist_ok=True)
@@ -193,9 +230,10 @@ def main():
                steps=3, seed=43, full=False)
     gen_ctc(ns)
     gen_prefix(ns)
+    gen_beam(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

@@ -1,0 +1,244 @@
+"""Attention decoder around ``AttLoc`` (reference: model/e2e_decoder.py:25-369), next-row N1/N2 of SURVEY.md 8f.
+
+Same constructor, submodule names (``embed``, ``decoder`` = ModuleList of LSTMCell, ``output``, ``att``) and
+state_dict keys as the reference's ``Decoder`` for the configuration the scripts use (no LM fusion,
+``model_unit='char'``), so reference ``asr_state_dict`` checkpoints load unchanged.
+
+* ``forward(hpad, hlen, ys, scheduled_sampling_rate)`` -- the training loop of model/e2e_decoder.py:79-167:
+  AttLoc step kernel per output position with the alignment fed back un-detached, teacher forcing or scheduled
+  sampling, cross-entropy rescaled by ``mean(len(ys_in)) - 1``.  The LSTMCell / output layer / cross-entropy are
+  library ops (cuDNN-free small GEMMs; outside the hot path the north star names).
+* ``recognize_beam(h, lpz, recog_args, char_list, rnnlm=None, fstlm=None)`` -- hybrid CTC/attention beam search
+  (model/e2e_decoder.py:170-369) re-designed for the GPU: ALL live hypotheses advance together -- one AttLoc
+  step launch for the whole beam (B = beam instead of beam x (B = 1) launches), one LSTMCell / output GEMM, one
+  log-softmax launch, and ONE batched CTC prefix-score launch (hypotheses x ctc_beam candidates) whose forward
+  variables stay on the device (the reference copies ``lpz`` to the host and loops over T in numpy per
+  hypothesis, model/e2e_ctc.py:143-146).  Per output position a single small device->host copy (beam x beam
+  candidate scores and ids) feeds the reference's own bookkeeping: stable descending sort, <eos> handling,
+  length penalty, ``end_detect``.  Scores accumulate in fp32 exactly as the reference's 0-dim tensors do.
+"""
+import random
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .e2e_common import pad_list
+from .e2e_ctc import ctc_prefix_score_batch, log_softmax_rows
+
+CTC_SCORING_RATIO = 1.5   # model/e2e_decoder.py:20
+
+
+def end_detect(ended_hyps, i, M=3, D_end=np.log(1 * np.exp(-10))):
+    """model/e2e_common.py:226-254 (Eq. 50 of Watanabe et al., hybrid CTC/attention)."""
+    if len(ended_hyps) == 0:
+        return False
+    count = 0
+    best_hyp = sorted(ended_hyps, key=lambda x: x['score'], reverse=True)[0]
+    for m in range(M):
+        hyp_length = i - m
+        same = [x for x in ended_hyps if len(x['yseq']) == hyp_length]
+        if len(same) > 0:
+            best_same = sorted(same, key=lambda x: x['score'], reverse=True)[0]
+            if best_same['score'] - best_hyp['score'] < D_end:
+                count += 1
+    return count == M
+
+
+def mask_by_length(xs, length, fill=0):
+    """model/e2e_common.py:190-195."""
+    assert xs.size(0) == len(length)
+    ret = xs.new_full(xs.size(), fill)
+    for i, l in enumerate(length):
+        ret[i, :l] = xs[i, :l]
+    return ret
+
+
+def th_accuracy(y_all, pad_target, ignore_label):
+    """model/e2e_common.py:198-205."""
+    pad_pred = y_all.detach().view(pad_target.size(0), pad_target.size(1), y_all.size(1)).max(2)[1]
+    mask = pad_target != ignore_label
+    num = torch.sum(pad_pred.masked_select(mask) == pad_target.masked_select(mask))
+    return float(num) / float(torch.sum(mask))
+
+
+class Decoder(torch.nn.Module):
+    def __init__(self, eprojs, odim, dlayers, dunits, sos, eos, att, verbose=0, char_list=None, labeldist=None,
+                 lsm_weight=0., fusion=None, rnnlm=None, model_unit='char', space_loss_weight=0.1):
+        super(Decoder, self).__init__()
+        if fusion is not None and rnnlm is not None:
+            raise NotImplementedError("LM fusion decoders are outside the hot path (SURVEY.md section 8)")
+        self.dunits = dunits
+        self.dlayers = dlayers
+        self.embed = torch.nn.Embedding(odim, dunits)
+        self.decoder = torch.nn.ModuleList()
+        self.fusion = fusion
+        self.rnnlm = rnnlm
+        self.decoder += [torch.nn.LSTMCell(dunits + eprojs, dunits)]
+        for _ in range(1, self.dlayers):
+            self.decoder += [torch.nn.LSTMCell(dunits, dunits)]
+        self.ignore_id = -1
+        self.output = torch.nn.Linear(dunits, odim)
+        self.loss = None
+        self.att = att
+        self.sos = sos
+        self.eos = eos
+        self.verbose = verbose
+        self.char_list = char_list
+        self.space_loss_weight = 0
+        self.labeldist = labeldist
+        self.vlabeldist = None
+        self.lsm_weight = lsm_weight
+
+    def zero_state(self, hpad):
+        return hpad.new_zeros(hpad.size(0), self.dunits)
+
+    # ------------------------------------------------------------------------------------------ training
+    def forward(self, hpad, hlen, ys, scheduled_sampling_rate=0.0):
+        """model/e2e_decoder.py:79-167.  Returns (loss, acc)."""
+        dev = self.embed.weight.device
+        hlen = list(map(int, hlen))
+        hpad = mask_by_length(hpad.to(dev), hlen, 0)
+        self.loss = None
+        ys = [y.to(dev) for y in ys]
+        eos = ys[0].new_tensor([self.eos])
+        sos = ys[0].new_tensor([self.sos])
+        ys_in = [torch.cat([sos, y], dim=0) for y in ys]
+        ys_out = [torch.cat([y, eos], dim=0) for y in ys]
+        pad_ys_in = pad_list(ys_in, self.eos)
+        pad_ys_out = pad_list(ys_out, self.ignore_id)
+        batch, olength = pad_ys_out.size(0), pad_ys_out.size(1)
+        c_list = [self.zero_state(hpad) for _ in range(self.dlayers)]
+        z_list = [self.zero_state(hpad) for _ in range(self.dlayers)]
+        att_w = None
+        y_all = []
+        self.att.reset()
+        eys = self.embed(pad_ys_in)
+        y_i = None
+        for i in range(olength):
+            att_c, att_w = self.att(hpad, hlen, z_list[0], att_w)
+            if random.random() < scheduled_sampling_rate and i > 0:
+                topi = y_i.topk(1)[1].squeeze(1)
+                ey = torch.cat((self.embed(topi), att_c), dim=1)
+            else:
+                ey = torch.cat((eys[:, i, :], att_c), dim=1)
+            z_list[0], c_list[0] = self.decoder[0](ey, (z_list[0], c_list[0]))
+            for l in range(1, self.dlayers):
+                z_list[l], c_list[l] = self.decoder[l](z_list[l - 1], (z_list[l], c_list[l]))
+            y_i = self.output(z_list[-1])
+            y_all.append(y_i)
+        y_all = torch.stack(y_all, dim=0).transpose(0, 1).contiguous().view(batch * olength, -1)
+        self.loss = F.cross_entropy(y_all, pad_ys_out.view(-1), ignore_index=self.ignore_id, reduction='mean')
+        self.loss = self.loss * (np.mean([len(x) for x in ys_in]) - 1)   # quirk 7 of SURVEY.md 8a
+        acc = th_accuracy(y_all, pad_ys_out, ignore_label=self.ignore_id)
+        if self.labeldist is not None:
+            if self.vlabeldist is None:
+                self.vlabeldist = torch.from_numpy(self.labeldist).to(dev)
+            loss_reg = -torch.sum((F.log_softmax(y_all, dim=1) * self.vlabeldist).view(-1), dim=0) / len(ys_in)
+            self.loss = (1. - self.lsm_weight) * self.loss + self.lsm_weight * loss_reg
+        return self.loss, acc
+
+    # ------------------------------------------------------------------------------------------ beam search
+    @torch.no_grad()
+    def recognize_beam(self, h, lpz, recog_args, char_list=None, rnnlm=None, fstlm=None):
+        """h (Th, D) encoder output of one utterance, lpz (Th, V) CTC log-probs or None.
+        Returns the n-best list of dicts with 'score' (float) and 'yseq' (list of int, <sos> first)."""
+        if rnnlm is not None or fstlm is not None:
+            raise NotImplementedError("LM rescoring is outside the hot path (SURVEY.md section 8)")
+        _lib.lib()
+        dev = self.embed.weight.device
+        h = _lib.f32c(h.detach(), dev)
+        Th = h.size(0)
+        beam = int(recog_args.beam_size)
+        penalty = recog_args.penalty
+        ctc_weight = recog_args.ctc_weight
+        W = beam                                   # hypothesis rows on the device (constant -> one AttLoc cache shape)
+        hb = h.unsqueeze(0).expand(W, Th, h.size(1)).contiguous()
+        hlens = [Th] * W
+        self.att.reset()
+        z = [h.new_zeros(W, self.dunits) for _ in range(self.dlayers)]
+        c = [h.new_zeros(W, self.dunits) for _ in range(self.dlayers)]
+        a_prev = None
+        maxlen = Th if recog_args.maxlenratio == 0 else max(1, int(recog_args.maxlenratio * Th))
+        minlen = int(recog_args.minlenratio * Th)
+
+        use_ctc = lpz is not None
+        if use_ctc:
+            lpz = _lib.f32c(lpz.detach(), dev)
+            V = lpz.size(-1)
+            ctc_beam = min(V, int(beam * CTC_SCORING_RATIO)) if ctc_weight != 1.0 else V
+            # CTCPrefixScore.initial_state (model/e2e_ctc.py:95-107), replicated for every row
+            r0 = torch.full((Th, 2), -10000000000.0, device=dev, dtype=torch.float32)
+            r0[:, 1] = torch.cumsum(lpz[:, 0], dim=0)
+            r_prev = r0.unsqueeze(0).expand(W, Th, 2).contiguous()
+            ctc_prev = torch.zeros(W, device=dev, dtype=torch.float32)
+
+        hyps = [{'score': np.float32(0.0), 'yseq': [self.sos]}]     # hypothesis k lives in device row k
+        score_dev = torch.zeros(W, device=dev, dtype=torch.float32)
+        ended_hyps = []
+        for i in range(maxlen):
+            n = len(hyps)
+            last = [hyps[min(k, n - 1)]['yseq'][i] for k in range(W)]
+            vy = torch.tensor(last, dtype=torch.long, device=dev)
+            ey = self.embed(vy)
+            att_c, att_w = self.att(hb, hlens, z[0], a_prev)
+            ey = torch.cat((ey, att_c), dim=1)
+            z_new, c_new = list(z), list(c)
+            z_new[0], c_new[0] = self.decoder[0](ey, (z[0], c[0]))
+            for l in range(1, self.dlayers):
+                z_new[l], c_new[l] = self.decoder[l](z_new[l - 1], (z[l], c[l]))
+            local_att = log_softmax_rows(self.output(z_new[-1]))                    # (W, V)
+            if use_ctc:
+                _, ids = torch.topk(local_att, ctc_beam, dim=1)                     # attention pre-pruning
+                log_psi, r_new = ctc_prefix_score_batch(
+                    lpz, r_prev, ids.to(torch.int32).contiguous(), vy.to(torch.int32),
+                    torch.full((W,), i, dtype=torch.int32, device=dev), 0, self.eos)
+                local = (1.0 - ctc_weight) * local_att.gather(1, ids) + ctc_weight * (log_psi - ctc_prev.unsqueeze(1))
+                best_scores, joint = torch.topk(local, beam, dim=1)
+                best_ids = ids.gather(1, joint)
+            else:
+                best_scores, best_ids = torch.topk(local_att, beam, dim=1)
+                joint = best_ids
+            cand = score_dev.unsqueeze(1) + best_scores                             # fp32, as hyp['score'] + tensor
+            packed = torch.stack((cand, best_ids.float(), joint.float()), 0)[:, :n].cpu().numpy()
+            cand_h, ids_h, joint_h = packed[0], packed[1].astype(np.int64), packed[2].astype(np.int64)
+            # the reference merges hypothesis by hypothesis with a stable descending sort truncated to `beam`
+            # (model/e2e_decoder.py:296-314) == one stable descending sort over (hypothesis, rank) order
+            flat = [(float(cand_h[r, j]), r, j) for r in range(n) for j in range(beam)]
+            order = sorted(range(len(flat)), key=lambda k: flat[k][0], reverse=True)[:beam]
+            new_hyps = []
+            for k in order:
+                _, r, j = flat[k]
+                new_hyps.append({'score': np.float32(cand_h[r, j]), 'yseq': hyps[r]['yseq'] + [int(ids_h[r, j])],
+                                 '_parent': r, '_j': int(joint_h[r, j]) if use_ctc else j})
+            if i == maxlen - 1:
+                for hyp in new_hyps:
+                    hyp['yseq'].append(self.eos)
+            remained = []
+            for hyp in new_hyps:
+                if hyp['yseq'][-1] == self.eos:
+                    if len(hyp['yseq']) > minlen:
+                        hyp['score'] = np.float32(hyp['score'] + np.float32((i + 1) * penalty))
+                        ended_hyps.append(hyp)
+                else:
+                    remained.append(hyp)
+            if end_detect(ended_hyps, i) and recog_args.maxlenratio == 0.0:
+                break
+            hyps = remained
+            if len(hyps) == 0:
+                break
+            # device state of the surviving hypotheses: one gather per tensor (spare rows repeat the last hypothesis)
+            par = [hyps[min(k, len(hyps) - 1)]['_parent'] for k in range(W)]
+            P = torch.tensor(par, dtype=torch.long, device=dev)
+            z = [t.index_select(0, P) for t in z_new]
+            c = [t.index_select(0, P) for t in c_new]
+            a_prev = att_w.index_select(0, P)
+            score_dev = torch.tensor([float(hyps[min(k, len(hyps) - 1)]['score']) for k in range(W)],
+                                     dtype=torch.float32, device=dev)
+            if use_ctc:
+                J = torch.tensor([hyps[min(k, len(hyps) - 1)]['_j'] for k in range(W)], dtype=torch.long, device=dev)
+                r_prev = r_new[P, J].contiguous()
+                ctc_prev = log_psi[P, J].contiguous()
+        nbest = sorted(ended_hyps, key=lambda x: x['score'], reverse=True)[:min(len(ended_hyps), recog_args.nbest)]
+        return [{'score': float(x['score']), 'yseq': [int(t) for t in x['yseq']]} for x in nbest]

@@ -1,0 +1,100 @@
+"""GPU: the decoder around AttLoc -- batched hybrid CTC/attention beam search (BASELINE config 5) and the training
+loop -- against (a) tests/golden/beam.npz, produced by the UNMODIFIED reference Decoder.recognize_beam, and (b) the
+CPU oracle (oracle/beam.py).  Token sequences must be IDENTICAL; scores within 1e-4 relative."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import beam as obeam
+from robust_e2e_gan_b200 import CTC, AttLoc, Decoder
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "beam.npz"))
+
+
+def build(c, sd):
+    att = AttLoc(c["D"], c["Z"], c["A"], c["C"], c["filts"], "softmax")
+    dec = Decoder(c["D"], c["V"], 1, c["Z"], c["sos"], c["eos"], att)
+    ctc = CTC(c["V"], c["D"], 0.0)
+    dec.load_state_dict({k: v for k, v in sd.items() if not k.startswith("ctc_lo")}, strict=True)
+    ctc.load_state_dict({k: v for k, v in sd.items() if k.startswith("ctc_lo")}, strict=True)
+    return dec.to(DEV).eval(), ctc.to(DEV).eval()
+
+
+def recog_args(c):
+    return types.SimpleNamespace(beam_size=c["beam"], penalty=c["penalty"], ctc_weight=c["ctc_weight"],
+                                 maxlenratio=c["maxlenratio"], minlenratio=c["minlenratio"], nbest=c["nbest"],
+                                 lm_weight=0.0)
+
+
+def run_gpu(c, sd, h):
+    dec, ctc = build(c, sd)
+    hd = h.to(DEV)
+    lpz = ctc.log_softmax(hd.unsqueeze(0))[0] if c["ctc_weight"] > 0.0 else None
+    return dec.recognize_beam(hd, lpz, recog_args(c), [str(i) for i in range(c["V"])]), ctc, hd
+
+
+@pytest.mark.parametrize("name", list(helpers.BEAM_CASES))
+def test_beam_search_matches_reference_golden(name):
+    c, sd, h, checksum = helpers.beam_case(name)
+    assert abs(checksum - float(GOLD[name + ".checksum"])) <= 1e-9 * checksum, "fixture weights not reproduced"
+    nbest, ctc, hd = run_gpu(c, sd, h)
+    n = int(GOLD[name + ".n"])
+    assert len(nbest) == n
+    for i in range(n):
+        assert nbest[i]["yseq"] == [int(t) for t in GOLD["%s.yseq%d" % (name, i)]], "hypothesis %d differs" % i
+        ref = float(GOLD["%s.score%d" % (name, i)])
+        assert abs(nbest[i]["score"] - ref) <= 1e-4 * abs(ref)
+    # CTC best path ("CTC alignment" of the north star) identical
+    assert ctc.best_path(hd.unsqueeze(0))[0].cpu().tolist() == [int(t) for t in GOLD[name + ".best_path"]]
+
+
+@pytest.mark.parametrize("seed,beam,ctc_weight", [(7, 1, 0.0), (8, 6, 0.3), (9, 4, 1.0)])
+def test_beam_search_matches_oracle(seed, beam, ctc_weight):
+    """greedy (beam 1), hybrid and CTC-only scoring on fresh seeds: GPU tokens == oracle tokens."""
+    helpers.BEAM_CASES["_tmp"] = dict(helpers.BEAM_CASES["beam_eos"], seed=seed, beam=beam, ctc_weight=ctc_weight,
+                                      nbest=min(beam, 3), Th=22)
+    try:
+        c, sd, h, _ = helpers.beam_case("_tmp")
+    finally:
+        del helpers.BEAM_CASES["_tmp"]
+    with torch.no_grad():
+        ref = obeam.recognize_beam(sd, h, c)
+    nbest, _, _ = run_gpu(c, sd, h)
+    assert [x["yseq"] for x in nbest] == [x["yseq"] for x in ref]
+    for a, b in zip(nbest, ref):
+        assert abs(a["score"] - b["score"]) <= 1e-4 * abs(b["score"])
+
+
+def test_decoder_training_loop_matches_oracle():
+    """Decoder.forward (teacher forcing): loss, accuracy and gradients w.r.t. the encoder output, the attention
+    parameters and the decoder's own layers."""
+    c, sd, _, _ = helpers.beam_case("beam_small")
+    B, Th = 3, 19
+    g = torch.Generator().manual_seed(5)
+    hpad = torch.tanh(torch.randn(B, Th, c["D"], generator=g))
+    hlen = [19, 15, 11]
+    ys = [torch.randint(1, c["V"] - 1, (n,), generator=g) for n in (6, 4, 5)]
+    # oracle (CPU autograd)
+    sd_o = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    h_o = hpad.clone().requires_grad_(True)
+    loss_o, acc_o = obeam.decoder_forward(sd_o, h_o, hlen, ys, c["sos"], c["eos"])
+    loss_o.backward()
+    # product
+    dec, _ = build(c, sd)
+    dec.train()
+    h_d = hpad.to(DEV).requires_grad_(True)
+    loss, acc = dec(h_d, hlen, [y.to(DEV) for y in ys], 0.0)
+    loss.backward()
+    helpers.assert_close(loss, loss_o, what="loss")
+    assert acc == pytest.approx(acc_o)
+    helpers.assert_close(h_d.grad, h_o.grad, what="d hpad")
+    for k, p in dec.named_parameters():
+        if k == "att.gvec.bias":          # analytically zero gradient (softmax shift invariance)
+            continue
+        helpers.assert_close(p.grad, sd_o[k].grad, what="d " + k, tol=2e-4)
