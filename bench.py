@@ -186,6 +186,7 @@ def kernel_specs(hp, db, cfg, dev):
     att = hp.att
     W_dec, W_att = att.mlp_dec.weight.detach().contiguous(), att.mlp_att.weight.detach().contiguous()
     W_conv = att.loc_conv.weight.detach().view(C, K).contiguous()
+    W_decT = W_dec.t().contiguous()
     gv, gb = att.gvec.weight.detach().view(A).contiguous(), att.gvec.bias.detach().contiguous()
     enc = db.hpad.contiguous()
     pre = torch.addmm(att.mlp_enc.bias.detach(), enc.view(B * Th, D), att.mlp_enc.weight.detach().t()).view(B, Th, A)
@@ -223,8 +224,8 @@ def kernel_specs(hp, db, cfg, dev):
                                           2.0, P(c), P(w), P(dproj), P(conv), P(xsave), B, Th, D, A, Z, C, K, sp()))
 
     def k_att_bwd():
-        _lib.check(L.re2e_attloc_step_bwd(P(dc), P(dw), P(xsave), P(enc), P(ap), P(w), P(conv), P(W_dec), P(W_att),
-                                          P(W_conv), P(gv), 2.0, P(d_pre), 1, P(ddp), P(d_dz), P(dprev), P(acc),
+        _lib.check(L.re2e_attloc_step_bwd(P(dc), P(dw), P(xsave), P(enc), P(ap), P(w), P(conv), P(W_dec), P(W_decT),
+                                          P(W_att), P(W_conv), P(gv), 2.0, P(d_pre), 1, P(ddp), P(d_dz), P(dprev), P(acc),
                                           nslots, B, Th, D, A, Z, C, K, sp()))
 
     def k_ctc_fwd():

@@ -100,7 +100,10 @@ int re2e_attloc_step_fwd(const float *pre, const float *enc_h, const float *dec_
  *   d_pre (B,Th,A)       (+)= dE/dpre   accumulate_pre != 0: TMA reduce-add into d_pre (accumulated
  *                             across steps); == 0: plain store (first backward step, no zero-fill)
  *   d_decproj (B,A)       = dE/d(dec_z @ W_dec^T)        (kept for dW_dec = sum_steps d_decproj^T dec_z)
- *   d_dec_z (B,Z)         = d_decproj @ W_dec            (NULL to skip: first decoder step has no dec_z)
+ *   d_dec_z (B,Z)         = d_decproj @ W_dec            (NULL to skip: first decoder step has no dec_z).  Read from
+ *                           W_decT (Z,A) = W_dec^T, a 16 B aligned copy the caller builds once per decoder loop:
+ *                           each cluster re-reads the whole matrix every step, the transposed rows make that
+ *                           read fully coalesced (required when d_dec_z != NULL)
  *   d_att_prev (B,Th)     = dE/d att_prev                (NULL to skip, e.g. first decoder step)
  *   acc_slots             parameter-gradient accumulators, n_slots >= re2e_attloc_acc_slots(...) private slots of
  *                         re2e_attloc_acc_floats(A,C,K) floats each, layout [dW_att A*C | dW_conv C*K | dgvec A |
@@ -112,7 +115,8 @@ size_t re2e_attloc_acc_floats(int A, int C, int K);
 int re2e_attloc_acc_slots(int B, int Th, int D, int A, int Z, int C, int K);
 int re2e_attloc_step_bwd(const float *dc, const float *dw, const float *xsave, const float *enc_h,
                          const float *att_prev, const float *w, const float *conv, const float *W_dec,
-                         const float *W_att, const float *W_conv, const float *gvec, float scaling,
+                         const float *W_decT, const float *W_att, const float *W_conv, const float *gvec,
+                         float scaling,
                          float *d_pre, int accumulate_pre, float *d_decproj, float *d_dec_z,
                          float *d_att_prev, float *acc_slots, int n_slots, int B, int Th, int D, int A,
                          int Z, int C, int K, void *stream);

@@ -38,7 +38,7 @@ SIGNATURES = {
     "re2e_attloc_step_fwd": (_I, [_P] * 9 + [_F] + [_P] * 5 + [_I] * 7 + [_P]),
     "re2e_attloc_acc_floats": (_SZ, [_I, _I, _I]),
     "re2e_attloc_acc_slots": (_I, [_I] * 7),
-    "re2e_attloc_step_bwd": (_I, [_P] * 11 + [_F, _P, _I] + [_P] * 4 + [_I] * 8 + [_P]),
+    "re2e_attloc_step_bwd": (_I, [_P] * 12 + [_F, _P, _I] + [_P] * 4 + [_I] * 8 + [_P]),
     "re2e_attloc_acc_reduce": (_I, [_P, _I, _P, _I, _I, _I, _P]),
     "re2e_attloc_enc_grad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "re2e_skinny_nt": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

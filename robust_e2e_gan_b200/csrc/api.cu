@@ -24,7 +24,7 @@ int ensure_smem(const void *func, size_t bytes) {
 }
 }  // namespace re2e
 
-extern "C" int re2e_abi_version(void) { return 4; }
+extern "C" int re2e_abi_version(void) { return 5; }
 
 extern "C" const char *re2e_build_info(void) {
   return "re2e_b200 sm_100a nvcc " __DATE__ " " __TIME__

@@ -40,14 +40,19 @@ __device__ __forceinline__ long long att_gtime() {
   do {                                                                                 \
     if (threadIdx.x == 0) g_att_dbg[which][blockIdx.x * 16 + (slot)] = att_gtime();    \
   } while (0)
+#define ATT_MARK_T(which, slot, t)                                                       \
+  do {                                                                                 \
+    if (threadIdx.x == (t)) g_att_dbg[which][blockIdx.x * 16 + (slot)] = att_gtime();  \
+  } while (0)
 #else
 #define ATT_MARK(which, slot)
+#define ATT_MARK_T(which, slot, t)
 #endif
 
 constexpr int kDplMax = 16;   // D <= 512
 constexpr int kMaxStages = 30;
 constexpr int kTG = 5;        // conv outputs per thread (sliding window)
-constexpr int kKQ = 4;        // K split
+constexpr int kKQ = 5;        // K split (items = frame groups x C x kKQ = 500 of 512 threads at the default shape)
 
 __host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
 
@@ -65,7 +70,7 @@ struct AttFwdParams {
 };
 
 struct AttBwdParams {
-  const float *dc, *dw, *xsave, *enc, *att_prev, *w, *conv, *W_dec, *W_att, *W_conv, *gvec;
+  const float *dc, *dw, *xsave, *enc, *att_prev, *w, *conv, *W_dec, *W_decT, *W_att, *W_conv, *gvec;
   float scaling;
   float *d_pre, *d_decproj, *d_dec_z, *d_att_prev, *acc_slots;
   int accumulate_pre, slot_stride;
@@ -269,9 +274,21 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
   }
   // "this CTA is running and its barriers exist": peers wait on it before their first remote store
   cluster_arrive_relaxed();
+  // whole == the ring holds the CTA's entire frame range (the common case): pre[b, t0:t1, :] and enc_h[b, t0:t1, :]
+  // are two contiguous spans, fetched by TWO bulk copies on ONE mbarrier, laid out [pre rows | enc rows] -- the
+  // single issuing lane is on the critical path of the prologue (everyone waits for it at barrier #1).
+  const bool whole = g.ns >= nch;
   if (tid == 0) {
-    const int first = nch < g.ns ? nch : g.ns;
-    for (int q = 0; q < first; ++q) issue(q);
+    if (whole) {
+      if (tloc > 0) {
+        mbar_expect_tx(&full[0], (uint32_t)tloc * (uint32_t)(A + D) * 4u);
+        bulk_g2s(stages, p.pre + ((size_t)b * Th + t0) * A, (uint32_t)tloc * A * 4u, &full[0]);
+        bulk_g2s(stages + (size_t)g.tloc_max * A, p.enc + ((size_t)b * Th + t0) * D, (uint32_t)tloc * D * 4u, &full[0]);
+      }
+    } else {
+      const int first = nch < g.ns ? nch : g.ns;
+      for (int q = 0; q < first; ++q) issue(q);
+    }
   }
   {
 #pragma unroll
@@ -442,7 +459,9 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
     for (int qg = 0; qg < nch; qg += g.ns) {
       const int gsz = min(g.ns, nch - qg);
       const uint32_t ph = (uint32_t)((qg / g.ns) & 1);
-      for (int i = 0; i < gsz; ++i) mbar_wait(&full[i], ph);
+      if (whole) { if (tloc > 0) mbar_wait(&full[0], 0); }
+      else for (int i = 0; i < gsz; ++i) mbar_wait(&full[i], ph);
+      ATT_MARK(0, 8);
       // (1) partial energies of this warp's half of the channels
 #pragma unroll 2
       for (int i = 0; i < gsz; ++i) {
@@ -455,7 +474,7 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
             const float4 t4 = *reinterpret_cast<const float4 *>(cvp + c4);
             cv[c4] = t4.x; cv[c4 + 1] = t4.y; cv[c4 + 2] = t4.z; cv[c4 + 3] = t4.w;
           }
-          const float *row = stages + (size_t)i * g.stage_floats + pair * A + aoff;
+          const float *row = (whole ? stages + (size_t)tl * A : stages + (size_t)i * g.stage_floats + pair * A) + aoff;
           float *xs = p.xsave ? p.xsave + ((size_t)b * Th + t0 + tl) * A + aoff : nullptr;
           float part = 0.0f;
 #pragma unroll
@@ -477,7 +496,45 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
           if (lane == 0) epart[2 * tl + half] = part;
         }
       }
+      ATT_MARK(0, 9);
       pair_bar(1 + pair, 64);
+      ATT_MARK(0, 10);
+      if (gsz <= 8) {
+        // common case (<= 8 frames per pair and group): everything of steps (2) and (3) for the group's frames is
+        // issued up front -- 16 broadcast LDS, 8 exponentials, 8*DPL independent LDS -- instead of one frame at a
+        // time (the per-frame version is latency bound: LDS -> FADD -> EX2 -> FFMA chains back to back)
+        float ev[8];
+        float mg8 = m_run;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int tl = kFP * (qg + i) + pair;
+          const bool ok = i < gsz && tl < tloc;
+          ev[i] = ok ? p.scaling * ((epart[2 * tl] + epart[2 * tl + 1]) + gb) : -CUDART_INF_F;
+          if (ok && half == 0 && lane == 0) e_s[tl] = ev[i];
+          mg8 = fmaxf(mg8, ev[i]);
+        }
+        if (mg8 > m_run) {
+          const float sc = __expf(m_run - mg8);   // exp(-inf) = 0 for the first group
+          s_run *= sc;
+#pragma unroll
+          for (int j = 0; j < DPL; ++j) acc[j] *= sc;
+          m_run = mg8;
+        }
+        const float *er0 = (whole ? stages + (size_t)g.tloc_max * A + (size_t)(kFP * qg + pair) * D
+                                  : stages + kFP * A + pair * D) + half * Dh + lane;
+        const size_t estride = whole ? (size_t)kFP * D : (size_t)g.stage_floats;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float pw = ev[i] == -CUDART_INF_F ? 0.0f : __expf(ev[i] - m_run);
+          s_run += pw;
+          if (ev[i] != -CUDART_INF_F) {
+            const float *er = er0 + i * estride;
+#pragma unroll
+            for (int j = 0; j < DPL; ++j)
+              if (dmask & (1u << j)) acc[j] = fmaf(pw, er[32 * j], acc[j]);
+          }
+        }
+      } else {
       // (2) scaled energies of the group's frames, running maximum
       float mg = m_run;
       for (int i = 0; i < gsz; ++i) {
@@ -503,7 +560,8 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
           const float e = p.scaling * ((epart[2 * tl] + epart[2 * tl + 1]) + gb);
           const float pw = __expf(e - m_run);
           s_run += pw;
-          const float *er = stages + (size_t)i * g.stage_floats + kFP * A + pair * D + half * Dh + lane;
+          const float *er = (whole ? stages + (size_t)g.tloc_max * A + (size_t)tl * D
+                                   : stages + (size_t)i * g.stage_floats + kFP * A + pair * D) + half * Dh + lane;
           if (dmask == (1u << DPL) - 1u) {   // every lane owns DPL channels (D == 64*DPL): no per-channel predicate
 #pragma unroll
             for (int j = 0; j < DPL; ++j) acc[j] = fmaf(pw, er[32 * j], acc[j]);
@@ -514,6 +572,8 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
           }
         }
       }
+      }
+      ATT_MARK(0, 11);
       if (qg + g.ns < nch) {   // ring shorter than the frame range (long utterances): refill behind a CTA barrier
         __syncthreads();
         if (tid == 0) {
@@ -640,6 +700,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
   float *slot = p.acc_slots + (size_t)blockIdx.x * p.slot_stride;   // [dW_att A*C | dW_conv C*K | dgvec A | dgvec_b 1]
 
   ATT_MARK(1, 0);
+  const bool whole_e = g.ns >= nche;   // the enc_h ring holds the CTA's whole frame range
   auto issue_e = [&](int q) {
     const int st = q % g.ns;
     const int r0 = t0 + kBW * q;
@@ -648,7 +709,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     bulk_g2s(ering + (size_t)st * g.stage_floats, p.enc + ((size_t)b * Th + r0) * D, (uint32_t)rows * D * 4u, &full_e[st]);
   };
   if (tid == 0) {
-    for (int i = 0; i < nchx; ++i) mbar_init(&full_x[i], 1);
+    mbar_init(&full_x[0], 1);
     mbar_init(done_x, kBW);
     for (int i = 0; i < g.ns; ++i) mbar_init(&full_e[i], 1);
     mbar_init(xbar1, 1);
@@ -690,15 +751,18 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     vws = tid < tloc ? __ldg(p.w + (size_t)b * Th + t0 + tid) : 0.0f;
     // the bulk copies (enc_h ring first: pass 1 needs it first; then every activation chunk) are issued by one
     // lane AFTER its warp's prologue loads are in flight
-    if (tid == 0) {
-      const int first = nche < g.ns ? nche : g.ns;
-      for (int q = 0; q < first; ++q) issue_e(q);
-      for (int q = 0; q < nchx; ++q) {
-        const int r0 = t0 + kBP * q;
-        const int rows = min(kBP, t1 - r0);
-        mbar_expect_tx(&full_x[q], (uint32_t)rows * A * 4u);
-        bulk_g2s(xs + (size_t)kBP * q * A, p.xsave + ((size_t)b * Th + r0) * A, (uint32_t)rows * A * 4u, &full_x[q]);
+    if (tid == 0 && tloc > 0) {
+      // one bulk copy for the enc_h range (when the ring holds it all) and ONE for the activations: the issuing lane
+      // is on the prologue's critical path (everyone waits for it at barrier #1)
+      if (whole_e) {
+        mbar_expect_tx(&full_e[0], (uint32_t)tloc * D * 4u);
+        bulk_g2s(ering, p.enc + ((size_t)b * Th + t0) * D, (uint32_t)tloc * D * 4u, &full_e[0]);
+      } else {
+        const int first = nche < g.ns ? nche : g.ns;
+        for (int q = 0; q < first; ++q) issue_e(q);
       }
+      mbar_expect_tx(&full_x[0], (uint32_t)tloc * A * 4u);
+      bulk_g2s(xs, p.xsave + ((size_t)b * Th + t0) * A, (uint32_t)tloc * A * 4u, &full_x[0]);
     }
 #pragma unroll
     for (int u = 0; u < IA; ++u)
@@ -753,7 +817,8 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     int st = 0;
     uint32_t ph = 0;
     for (int q = 0; q < nche; ++q) {
-      mbar_wait(&full_e[st], ph);
+      if (!whole_e) mbar_wait(&full_e[st], ph);
+      else if (q == 0) mbar_wait(&full_e[0], 0);
       const int tl = kBW * q + warp;
       if (tl < tloc) {
         const float *row = ering + (size_t)st * g.stage_floats + warp * D + lane;
@@ -803,7 +868,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
   for (int j = 0; j < APL; ++j) { dgv[j] = 0.0f; ddp[j] = 0.0f; }
   {
     const int aoff = half * (A / 2) + lane;
-    for (int q = 0; q < nchx; ++q) mbar_wait(&full_x[q], 0);   // landed long ago (issued in the prologue)
+    if (tloc > 0) mbar_wait(&full_x[0], 0);   // landed long ago (issued in the prologue)
     // no barrier inside the frame loop: the 16-value butterfly of one frame overlaps the FMAs of the next
 #pragma unroll 2
     for (int q = 0; q < nchx; ++q) {
@@ -858,24 +923,32 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
   __syncthreads();  // #4: all d pre tiles written, per-warp partials published
   ATT_MARK(1, 4);
 
-  // d dec_z needs W_dec[this warp's A/16 rows, this rank's slice of z]: issue those loads now (they do not depend on
-  // the cluster exchange below) so that their L2 latency hides behind post pass A
-  constexpr int AW = 4 * APL;                       // = A / 16 rows per warp
-  constexpr int ZP = APL <= 5 ? 3 : 1;              // z passes (of 32 lanes) held in registers
+  // ---- d dec_z[z] = sum_a d dec_proj[a] W_dec[a,z] for this rank's slice of z, from the TRANSPOSED weight
+  //      W_decT (Z x A, built once per decoder loop): row z is one contiguous, 16 B aligned run of A floats, so the
+  //      slice is read with fully coalesced 128-bit loads (15 per thread at the default shape instead of 60 scalar
+  //      ones), warp <-> z rows, lane <-> quad of a.  The loads are issued HERE -- they do not depend on the cluster
+  //      exchange -- and consumed after it (post pass B), so their L2 latency hides behind post pass A.
+  constexpr int AQ = 16 * APL;                      // float4 per W_decT row (A / 4)
+  constexpr int MQ = (AQ + 31) / 32;                // quads per lane
+  constexpr int ZR = APL <= 5 ? 5 : 3;              // z rows per warp held in registers per pass
   const int zc = (Z + CL - 1) / CL, z_begin = rank * zc, z_n = max(0, min(zc, Z - z_begin));
-  const int rz = round4(zc);
-  float wz[ZP][AW];
-  if (p.d_dec_z) {
+  float4 wz[ZR][MQ];
+  auto load_wz = [&](int zb) {
 #pragma unroll
-    for (int zp = 0; zp < ZP; ++zp) {
-      const int zi = lane + 32 * zp;
-      const float *wcol = p.W_dec + (size_t)(warp * AW) * Z + z_begin + zi;
+    for (int r = 0; r < ZR; ++r) {
+      const int zi = zb + warp + kBW * r;
+      const float4 *wr = reinterpret_cast<const float4 *>(p.W_decT + (size_t)(z_begin + min(zi, max(z_n - 1, 0))) * A);
 #pragma unroll
-      for (int a = 0; a < AW; ++a) wz[zp][a] = zi < z_n ? __ldg(wcol + (size_t)a * Z) : 0.0f;
+      for (int m = 0; m < MQ; ++m) {
+        const int j = lane + 32 * m;
+        wz[r][m] = (zi < z_n && j < AQ) ? __ldg(wr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-  }
+  };
+  if (p.d_dec_z) load_wz(0);
+  ATT_MARK(1, 10);
 
-  // ---- post pass A
+  // ---- post pass A (needs nothing from the other CTAs)
   // d conv of this CTA's frames -> every CTA of the cluster (channel-major, padded)
   for (int item = tid; item < tloc * C; item += NT) {
     const int c = item / tloc, tl = item - c * tloc;
@@ -886,7 +959,8 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
   // d dec_proj / d gvec of this CTA (fixed summation order), d dec_proj partial -> every CTA
   for (int a = tid; a < A; a += NT) {
     const int h = a >= A / 2 ? 1 : 0, ai = a - h * (A / 2);
-    float sd = 0.0f, sg = slot[A * C + C * K + a];
+    const float sg0 = slot[A * C + C * K + a];   // consumed only after the pushes: its L2 latency is off the exchange path
+    float sd = 0.0f, sg = 0.0f;
 #pragma unroll
     for (int pr = 0; pr < kBP; ++pr) {
       sd += ddp_w[(2 * pr + h) * (A / 2) + ai];
@@ -894,16 +968,21 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     }
     for (int r = 0; r < CL; ++r)
       st_async_f32(dsmem_addr(ddp_x + rank * A + a, (uint32_t)r), sd, dsmem_addr(xbar2, (uint32_t)r));
-    slot[A * C + C * K + a] = sg;
+    slot[A * C + C * K + a] = sg0 + sg;
   }
-  if (warp == 0) {   // d gvec.bias = sum_t de[t]  (analytically zero over the utterance; kept for fidelity)
+  ATT_MARK(1, 11);
+  if (warp == kBW - 1) {   // d gvec.bias = sum_t de[t]  (analytically zero over the utterance; kept for fidelity)
     float s2 = 0.0f;
     for (int tl = lane; tl < tloc; tl += 32) s2 += de_s[tl];
     s2 = warp_sum(s2);
     if (lane == 0 && tloc > 0) slot[A * C + C * K + A] += s2;
   }
-  // dW_att[a,c] += sum_t d pre[t,a] conv[t,c]   straight from the resident tile (thread <-> a)
-  for (int a = tid; a < A; a += NT) {
+  ATT_MARK_T(1, 12, NT - 1);
+  // The two parameter gradients that only need THIS CTA's frames run side by side on disjoint sets of warps:
+  //   threads [0, A)       : dW_att[a,c] += sum_t d pre[t,a] conv[t,c]   straight from the resident tile (thread <-> a)
+  //   threads [A, NT)      : dW_conv[c,k] += sum_{t in mine} dconv[t,c] att_prev[t + k - filts]  (6 taps per item)
+  if (tid < A) {
+    const int a = tid;
     float acc[CP];    // starts from the slot's running total (loads overlap the frame loop)
 #pragma unroll
     for (int c = 0; c < CP; ++c) acc[c] = c < C ? slot[a * C + c] : 0.0f;
@@ -922,18 +1001,72 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     for (int c = 0; c < CP; ++c)
       if (c < C) slot[a * C + c] = acc[c];
   }
+  {
+    constexpr int KG = 12;   // taps per item: C * ceil(K / 12) = 170 items <= the 192 threads left beside dW_att
+    const int nkg = (K + KG - 1) / KG;
+    const int first = A < NT ? A : 0, nthr = A < NT ? NT - A : NT;   // A >= NT (A = 512): everyone, after dW_att
+    if (tid >= first) {
+      for (int item = tid - first; item < C * nkg; item += nthr) {
+        const int kg = item % nkg, c = item / nkg;
+        const int kb = kg * KG;
+        const float *ar = app + kb;                  // att_prev[t + k - filts] = app[t + k]
+        float acc6[KG];   // starts from the slot's running total: the loads overlap the tap loop
+#pragma unroll
+        for (int i = 0; i < KG; ++i) acc6[i] = kb + i < K ? slot[A * C + c * K + kb + i] : 0.0f;
+        float x[KG];
+#pragma unroll
+        for (int i = 0; i < KG - 1; ++i) x[i] = ar[t0 + i];
+#pragma unroll 4
+        for (int tl = 0; tl < tloc; ++tl) {
+          x[KG - 1] = ar[t0 + tl + KG - 1];
+          const float dv = dcv_p[tl * 16 + c] + dcv_p[(g.tloc_max + tl) * 16 + c];   // d conv of MY frame tl
+#pragma unroll
+          for (int i = 0; i < KG; ++i) acc6[i] = fmaf(dv, x[i], acc6[i]);
+#pragma unroll
+          for (int i = 0; i < KG - 1; ++i) x[i] = x[i + 1];
+        }
+#pragma unroll
+        for (int i = 0; i < KG; ++i)
+          if (kb + i < K) slot[A * C + c * K + kb + i] = acc6[i];
+      }
+    }
+  }
   ATT_MARK(1, 5);
-  mbar_wait(xbar2, 0);   // d conv of all Th frames and every rank's d dec_proj partial have landed here
+  ATT_MARK_T(1, 13, NT - 1);
+  mbar_wait(xbar2, 0);
+  ATT_MARK(1, 14);   // d conv of all Th frames and every rank's d dec_proj partial have landed here
   for (int a = tid; a < A; a += NT) {
     float sd = 0.0f;
     for (int r = 0; r < CL; ++r) sd += ddp_x[r * A + a];
     ddp_t[a] = sd;
     if (rank == 0) p.d_decproj[(size_t)b * A + a] = sd;
   }
-  __syncthreads();  // #5 (also: scr / dzp alias the per-warp partials read above)
+  __syncthreads();  // #5 (also: scr aliases the per-warp partials read above)
   ATT_MARK(1, 6);
 
-  // ---- d att_prev[s] = sum_c sum_k Wc[c,k] * dconv[s - k + filts, c]   (sliding window, 5 outputs/thread)
+  // ---- post pass B
+  // d dec_z from the prefetched W_decT rows: one dot product of length A per z row, reduced inside the warp
+  if (p.d_dec_z) {
+    for (int zb = 0; zb < z_n; zb += kBW * ZR) {
+      if (zb > 0) load_wz(zb);
+#pragma unroll
+      for (int r = 0; r < ZR; ++r) {
+        float s0 = 0.0f;
+#pragma unroll
+        for (int m = 0; m < MQ; ++m) {
+          const int j = lane + 32 * m;
+          if (j < AQ) {
+            const float4 d4 = *reinterpret_cast<const float4 *>(ddp_t + 4 * j);
+            s0 = fmaf(d4.x, wz[r][m].x, fmaf(d4.y, wz[r][m].y, fmaf(d4.z, wz[r][m].z, fmaf(d4.w, wz[r][m].w, s0))));
+          }
+        }
+        s0 = warp_sum(s0);
+        const int zi = zb + warp + kBW * r;
+        if (lane == 0 && zi < z_n) p.d_dec_z[(size_t)b * Z + z_begin + zi] = s0;
+      }
+    }
+  }
+  // d att_prev[s] = sum_c sum_k Wc[c,k] * dconv[s - k + filts, c]   (sliding window, 5 outputs/thread)
   if (p.d_att_prev) {
     const int nsg = (tloc + kTG - 1) / kTG;
     const int Kq = (K + kKQ - 1) / kKQ;
@@ -961,80 +1094,12 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
       if (nv > 3) o[3] = a3;
       if (nv > 4) o[4] = a4;
     }
-  }
-  // ---- d dec_z[z] = sum_a d dec_proj[a] W_dec[a,z]  for this rank's slice of z: warp <-> slice of A/16 rows,
-  //      lane <-> z (W_dec values prefetched above; further z blocks, if any, are loaded here)
-  if (p.d_dec_z) {
-    const float *dd = ddp_t + warp * AW;
-    for (int zb = 0; zb < z_n; zb += 32 * ZP) {
-      if (zb > 0) {
-#pragma unroll
-        for (int zp = 0; zp < ZP; ++zp) {
-          const int zi = zb + lane + 32 * zp;
-          const float *wcol = p.W_dec + (size_t)(warp * AW) * Z + z_begin + zi;
-#pragma unroll
-          for (int a = 0; a < AW; ++a) wz[zp][a] = zi < z_n ? __ldg(wcol + (size_t)a * Z) : 0.0f;
-        }
-      }
-#pragma unroll
-      for (int zp = 0; zp < ZP; ++zp) {
-        const int zi = zb + lane + 32 * zp;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-        for (int a = 0; a < AW; a += 4) {
-          s0 = fmaf(dd[a], wz[zp][a], s0);
-          s1 = fmaf(dd[a + 1], wz[zp][a + 1], s1);
-          s2 = fmaf(dd[a + 2], wz[zp][a + 2], s2);
-          s3 = fmaf(dd[a + 3], wz[zp][a + 3], s3);
-        }
-        if (zi < z_n) dzp[warp * rz + zi] = (s0 + s1) + (s2 + s3);
-      }
-    }
-  }
-  // ---- dW_conv[c,k] += sum_{t in mine} dconv[t,c] * att_prev[t + k - filts]   (6 taps per thread, one owner each)
-  {
-    constexpr int KG = 6;
-    const int nkg = (K + KG - 1) / KG;
-    for (int item = tid; item < C * nkg; item += NT) {
-      const int kg = item % nkg, c = item / nkg;
-      const int kb = kg * KG;
-      const float *dr = dcvT + c * g.App + filts;  // dconv[t] at dr[t]
-      const float *ar = app + kb;                  // att_prev[t + k - filts] = app[t + k]
-      float acc6[KG];   // starts from the slot's running total: the loads overlap the tap loop (no RMW stall after it)
-#pragma unroll
-      for (int i = 0; i < KG; ++i) acc6[i] = kb + i < K ? slot[A * C + c * K + kb + i] : 0.0f;
-      float x[KG];
-#pragma unroll
-      for (int i = 0; i < KG - 1; ++i) x[i] = ar[t0 + i];
-#pragma unroll 4
-      for (int t = t0; t < t1; ++t) {
-        x[KG - 1] = ar[t + KG - 1];
-        const float dv = dr[t];
-#pragma unroll
-        for (int i = 0; i < KG; ++i) acc6[i] = fmaf(dv, x[i], acc6[i]);
-#pragma unroll
-        for (int i = 0; i < KG - 1; ++i) x[i] = x[i + 1];
-      }
-#pragma unroll
-      for (int i = 0; i < KG; ++i)
-        if (kb + i < K) slot[A * C + c * K + kb + i] = acc6[i];
-    }
-  }
-  __syncthreads();  // #6
-  ATT_MARK(1, 7);
-  if (p.d_att_prev) {
+    __syncthreads();  // #6
+    ATT_MARK(1, 7);
     for (int tl = tid; tl < tloc; tl += NT) {
       float sum = 0.0f;
       for (int i = 0; i < kKQ * C; ++i) sum += scr[(size_t)i * g.tloc_max + tl];
       p.d_att_prev[(size_t)b * Th + t0 + tl] = sum;
-    }
-  }
-  if (p.d_dec_z) {
-    for (int zi = tid; zi < z_n; zi += NT) {
-      float sum = 0.0f;
-#pragma unroll
-      for (int w2 = 0; w2 < kBW; ++w2) sum += dzp[w2 * rz + zi];
-      p.d_dec_z[(size_t)b * Z + z_begin + zi] = sum;
     }
   }
   ATT_MARK(1, 8);
@@ -1423,12 +1488,14 @@ extern "C" int re2e_attloc_acc_slots(int B, int Th, int D, int A, int Z, int C, 
 
 extern "C" int re2e_attloc_step_bwd(const float *dc, const float *dw, const float *xsave, const float *enc_h,
                                     const float *att_prev, const float *w, const float *conv, const float *W_dec,
-                                    const float *W_att, const float *W_conv, const float *gvec, float scaling,
+                                    const float *W_decT, const float *W_att, const float *W_conv, const float *gvec,
+                                    float scaling,
                                     float *d_pre, int accumulate_pre, float *d_decproj, float *d_dec_z,
                                     float *d_att_prev, float *acc_slots, int n_slots, int B, int Th, int D, int A,
                                     int Z, int C, int K, void *stream) {
   RE2E_CHECK_ARG(xsave && enc_h && att_prev && w && conv && W_dec && W_att && W_conv && gvec);
   RE2E_CHECK_ARG(d_pre && d_decproj && acc_slots && Z > 0);
+  RE2E_CHECK_ARG(!d_dec_z || (W_decT && aligned16(W_decT)));
   int rc = check_dims(B, Th, D, A, C, K);
   if (rc != RE2E_OK) return rc;
   RE2E_CHECK_ARG(aligned16(xsave) && aligned16(enc_h) && aligned16(d_pre));
@@ -1436,7 +1503,7 @@ extern "C" int re2e_attloc_step_bwd(const float *dc, const float *dw, const floa
   const int CP = C == 10 ? 10 : 16;
   AttBwdParams prm;
   prm.dc = dc; prm.dw = dw; prm.xsave = xsave; prm.enc = enc_h; prm.att_prev = att_prev; prm.w = w;
-  prm.conv = conv; prm.W_dec = W_dec; prm.W_att = W_att; prm.W_conv = W_conv; prm.gvec = gvec;
+  prm.conv = conv; prm.W_dec = W_dec; prm.W_decT = W_decT; prm.W_att = W_att; prm.W_conv = W_conv; prm.gvec = gvec;
   prm.scaling = scaling; prm.d_pre = d_pre; prm.d_decproj = d_decproj; prm.d_dec_z = d_dec_z;
   prm.d_att_prev = d_att_prev; prm.acc_slots = acc_slots; prm.accumulate_pre = accumulate_pre;
   prm.slot_stride = (int)re2e_attloc_acc_floats(A, C, K);

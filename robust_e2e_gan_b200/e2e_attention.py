@@ -33,6 +33,7 @@ class _State(object):
         self.pre = None          # (B,Th,A) detached
         self.hlens_dev = None
         self.weights = None      # detached contiguous views: W_dec, W_att, W_conv(C,K), gvec(A), gvec_b(1)
+        self.W_decT = None       # (Z,A) transposed copy of W_dec for the backward kernel
         self.dims = None         # B,Th,D,A,Z,C,K
         self.clear_grads()
 
@@ -69,6 +70,7 @@ class _Precompute(torch.autograd.Function):
         state.weights = (_lib.f32c(W_dec.detach()), _lib.f32c(W_att.detach()),
                          _lib.f32c(W_conv.detach()).view(C, K), _lib.f32c(gvec_w.detach()).view(A),
                          _lib.f32c(gvec_b.detach()).view(1))
+        state.W_decT = None      # (Z, A) copy for the backward, built by the first backward step of the loop
         state.clear_grads()
         ctx.state = state
         ctx.save_for_backward(W_enc)
@@ -171,6 +173,8 @@ class _Step(torch.autograd.Function):
         dc = _lib.f32c(dc, dev) if dc is not None else None
         dw = _lib.f32c(dw, dev) if dw is not None else None
         st.ensure_acc(dev)
+        if st.W_decT is None:    # d dec_z = d dec_proj @ W_dec reads W_dec^T rows (coalesced); once per decoder loop
+            st.W_decT = W_dec.t().contiguous()
         first = st.d_pre is None
         if first:
             st.d_pre = torch.empty(B, Th, A, device=dev, dtype=torch.float32)
@@ -182,8 +186,8 @@ class _Step(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(L.re2e_attloc_step_bwd(
                 _lib.ptr(dc), _lib.ptr(dw), _lib.ptr(xsave), _lib.ptr(st.enc), _lib.ptr(ap), _lib.ptr(w),
-                _lib.ptr(conv), _lib.ptr(W_dec), _lib.ptr(W_att), _lib.ptr(W_conv), _lib.ptr(gvec),
-                ctx.scaling, _lib.ptr(st.d_pre), 0 if first else 1, _lib.ptr(d_decproj), _lib.ptr(d_dz),
+                _lib.ptr(conv), _lib.ptr(W_dec), _lib.ptr(st.W_decT), _lib.ptr(W_att), _lib.ptr(W_conv),
+                _lib.ptr(gvec), ctx.scaling, _lib.ptr(st.d_pre), 0 if first else 1, _lib.ptr(d_decproj), _lib.ptr(d_dz),
                 _lib.ptr(d_prev), _lib.ptr(st.acc), st.acc_nslots, B, Th, D, A, Z, C, K, _lib.stream_ptr()),
                 "re2e_attloc_step_bwd")
         if ctx.has_dz:

@@ -14,8 +14,10 @@ db = make_batch(cfg, seed=4000).to(dev)
 L = _lib.lib()
 L.re2e_att_debug_read.argtypes = [ctypes.c_void_p, ctypes.c_int]
 buf = (ctypes.c_longlong * (16 * 512))()
-names = {0: ["start", "sync1", "decproj", "sync2", "sync3", "sync4(main)", "pushed", "end"],
-         1: ["start", "sync1", "sync2(p1)", "sync3(de)", "sync4(p2)", "postA", "sync5", "sync6", "fin", "bulkwait"]}
+names = {0: ["start", "sync1", "decproj", "sync2", "sync3", "sync4(main)", "pushed", "end", "m_wait", "m_energy",
+             "m_pairbar", "m_ctx"],
+         1: ["start", "sync1", "sync2(p1)", "sync3(de)", "sync4(p2)", "postA", "sync5", "sync6", "fin", "bulkwait",
+             "A_wzissued", "A_pushed", "A_pushed(T)", "A_dWconv(T)", "A_xbar2"]}
 for name, fn, nbytes, reps in bench.kernel_specs(hp, db, cfg, dev):
     if not name.startswith("attloc"):
         continue
