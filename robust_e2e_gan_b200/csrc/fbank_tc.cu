@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
           const int kcol = c_c * kKC + lane;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            if (j >= nj_c) break;   // warp-uniform: rows past the CTA's range (partial last tile) cost nothing
             float x = mg[d][j];
             if (MASKED) {
               const float sg = p.mask_is_logit ? sigmoid_fast(mk[MASKED ? d : 0][j]) : mk[MASKED ? d : 0][j];
