@@ -25,6 +25,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# NCCL writes its banner / debug lines to stdout by default; stdout carries exactly ONE JSON line (the contract)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import torch  # noqa: E402
 
 METRIC = "utterances/sec (joint step fwd/bwd)"
@@ -446,6 +449,16 @@ def main():
                                 "unit": "GB/s", "frac": ks[dom]["frac_of_hbm_peak"], "peak_source": peak_src,
                                 "launches_per_step": per_step.get(dom, 1), "us_per_launch": ks[dom]["us_per_launch"],
                                 "traffic": None}
+            # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/traffic.json,
+            # written by tools/summarize_profiles.py); null when no capture of this kernel is committed
+            tpath = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    tj = json.load(f)
+                if dom in tj.get("kernels", {}):
+                    line["roofline"]["traffic"] = tj["kernels"][dom]["bytes"]
+                    line["roofline"]["traffic_source"] = tj.get("source")
+            line["roofline"]["algorithmic_bytes"] = int(ks[dom]["algorithmic_MB"] * 1e6)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)

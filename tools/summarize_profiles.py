@@ -1,0 +1,98 @@
+"""Turn one round of gpurun artefacts into the tracked evidence under profiles/.
+
+    python tools/summarize_profiles.py TAG [gpurun_out]
+
+Reads gpurun_out/{bench_final.json, launches.csv, kernels_full_raw.csv} and writes
+profiles/TAG_bench.json, TAG_launches.csv, TAG_kernels_full_raw.csv, TAG_summary.md and profiles/traffic.json
+(DRAM bytes per launch of every hot-path kernel, read by bench.py for roofline.traffic).
+"""
+import collections
+import csv
+import json
+import os
+import re
+import shutil
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]
+src = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+
+KMAP = collections.OrderedDict([   # kernel-name substring -> bench.py `kernels` entry
+    ("fbank_tc_fwd_kernel<1", "fbank_fwd(mask,mag->Y,G)"), ("fbank_tc_fwd_kernel<0", "fbank_fwd(mag->Y)"),
+    ("fbank_tc_bwd", "fbank_bwd(->d mask)"), ("attloc_fwd", "attloc_step_fwd"), ("attloc_bwd", "attloc_step_bwd"),
+    ("ctc_lse", "ctc_fwd(lse+alpha/beta)"), ("ctc_ab", None), ("ctc_grad", "ctc_bwd(grad)"),
+    ("gemm_tf32x3_kernel<0, 0, 256", "gemm ctc_lo fwd"), ("gemm_tf32x3_kernel<0, 1, 160", "gemm ctc_lo dX"),
+    ("gemm_tf32x3_kernel<1, 1, 160", "gemm ctc_lo dW"), ("gemm_tf32x3_kernel<0, 0, 160", "gemm mlp_enc fwd")])
+
+
+def short(n):
+    m = re.search(r'(?:re2e::\(anonymous namespace\)::|re2e::<unnamed>::|re2e::|at::native::<unnamed>::|at::native::'
+                  r'|at::<unnamed>::|at::|unnamed>::)([A-Za-z0-9_]+(?:<[0-9, ()a-z]+>)?)', n)
+    return m.group(1) if m else n[:50]
+
+
+bench = json.load(open(os.path.join(src, "bench_final.json")))
+shutil.copy(os.path.join(src, "bench_final.json"), os.path.join(P, tag + "_bench.json"))
+shutil.copy(os.path.join(src, "launches.csv"), os.path.join(P, tag + "_launches.csv"))
+shutil.copy(os.path.join(src, "kernels_full_raw.csv"), os.path.join(P, tag + "_kernels_full_raw.csv"))
+
+with open(os.path.join(src, "launches.csv")) as f:
+    rows = list(csv.DictReader([l for l in f if not l.startswith("==")]))
+seq = [(short(x["Kernel Name"]), float(x["Metric Value"].replace(",", "")) / 1000) for x in rows]
+idx = [i for i, s in enumerate(seq) if s[0].startswith("fbank_tc_fwd_kernel<1") or "fbank_tc_fwd_kernel<(bool)1" in s[0]]
+first = [i for i in idx]
+last = seq[first[-2]:first[-1]] if len(first) >= 2 else seq
+agg = collections.OrderedDict()
+for n, t in last:
+    a = agg.setdefault(n, [0, 0.0])
+    a[0] += 1
+    a[1] += t
+tot = sum(a[1] for a in agg.values())
+out = ["# %s: where one step goes (ncu launch list; one graph replay = one step)\n" % tag,
+       "`bench.py` (CUDA events, warm, 3 streams): %.3f ms/step -> %.0f utt/s; e2e %.0f utt/s.  Under ncu the kernels are "
+       "serialised and cold-cache: the same step sums to %.0f us -- use the SHARE column, not the absolute.\n"
+       % (bench["ms_per_step"], bench["value"], bench["e2e"]["value"], tot),
+       "| kernel | launches/step | us total (ncu) | share | avg us |", "|---|---|---|---|---|"]
+for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    out.append("| `%s` | %d | %.1f | %.1f%% | %.2f |" % (n, c, t, 100 * t / tot, t / c))
+
+raw = list(csv.reader(open(os.path.join(src, "kernels_full_raw.csv"))))
+hdr = raw[0]
+ix = {h: i for i, h in enumerate(hdr)}
+traffic = {}
+out += ["", "## Per kernel: ncu --set full (one cold launch) next to bench.py's warm CUDA-event timing\n",
+        "| kernel | ncu us | dram read MB | dram write MB | bench entry | algorithmic | bench us | achieved | frac of peak |",
+        "|---|---|---|---|---|---|---|---|---|"]
+for d in raw[2:]:
+    full = d[ix["Kernel Name"]]
+    key = next((k for k in KMAP if k in full.replace("(int)", "").replace("(bool)", "")), None)
+    if key is None:
+        continue
+    ent = KMAP[key]
+    kb = next((v for k, v in bench.get("kernels", {}).items() if ent and k.startswith(ent)), None)
+    rd, wr = float(d[ix["dram__bytes_read.sum"]]), float(d[ix["dram__bytes_write.sum"]])
+    unit_r, unit_w = raw[1][ix["dram__bytes_read.sum"]], raw[1][ix["dram__bytes_write.sum"]]
+    scale = {"Mbyte": 1.0, "Kbyte": 1e-3, "byte": 1e-6, "Gbyte": 1e3}
+    rd, wr = rd * scale.get(unit_r, 1.0), wr * scale.get(unit_w, 1.0)
+    if ent:
+        traffic[ent] = {"dram_read_MB": round(rd, 2), "dram_write_MB": round(wr, 2), "bytes": int((rd + wr) * 1e6)}
+    if kb and "achieved_GBps" in kb:
+        alg, ach, fr = "%.1f MB" % kb["algorithmic_MB"], "%.0f GB/s" % kb["achieved_GBps"], "%.3f (HBM)" % kb["frac_of_hbm_peak"]
+    elif kb:
+        alg, ach, fr = "%.2f GFLOP" % kb["algorithmic_GFLOP"], "%.0f TF/s tf32 executed" % kb["executed_TFLOPs_tf32"], \
+            "%.3f (tf32 tensor)" % kb["frac_of_tf32_peak"]
+    else:
+        alg = ach = fr = "-"
+    out.append("| `%s` | %.1f | %.1f | %.1f | %s | %s | %s | %s | %s |" % (
+        key, float(d[ix["gpu__time_duration.sum"]]), rd, wr, ent or "(part of ctc_fwd)", alg,
+        kb["us_per_launch"] if kb else "-", ach, fr))
+out += ["", "Notes: a single profiled launch undercounts `dram__bytes_write` (dirty lines stay in the 126 MB L2).  AttLoc's",
+        "per-step working set (pre + enc_h, 16.4 MB) is L2 resident across the 41 steps, so its warm launches read ~nothing",
+        "from DRAM; its HBM figure is the algorithmic one (SURVEY 8d caveat).  GEMM rows: executed tf32 flops = 3 x the",
+        "fp32-equivalent product (3xTF32 split) against half the measured bf16 cuBLAS peak."]
+open(os.path.join(P, tag + "_summary.md"), "w").write("\n".join(out) + "\n")
+json.dump({"source": "profiles/%s_kernels_full_raw.csv (ncu --set full, one cold launch per kernel)" % tag,
+           "kernels": traffic}, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+print("\n".join(out))
