@@ -215,9 +215,66 @@ def gen_beam(ns):
     np.savez_compressed(os.path.join(OUT, "beam.npz"), **out)
 
 
+def gen_kaldi(ns):
+    """Archive written / decoded by the reference's data/kaldi_io.py, transform of mix_data_loader.__getitem__ and
+    _collate_fn outputs on seeded samples (inputs: tests/test_kaldi_feats.py helpers)."""
+    import importlib
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_kaldi_feats as tk
+    import types as _types
+    # data/audioparse.py imports audio front-ends that are not installed and not used by _collate_fn / kaldi_io
+    for missing, attrs in (("librosa", ()), ("python_speech_features", ("fbank", "delta")), ("torchaudio", ()),
+                           ("soundfile", ()), ("sox", ()), ("data.extract_fbanks_module", ())):   # last: prebuilt .so for an old numpy ABI
+        if missing not in sys.modules:
+            try:
+                importlib.import_module(missing)
+            except Exception:
+                m = _types.ModuleType(missing)
+                for a in attrs:
+                    setattr(m, a, None)
+                sys.modules[missing] = m
+    kaldi_io = importlib.import_module("data.kaldi_io")
+    loader = importlib.import_module("data.mix_data_loader")
+    rng = np.random.RandomState(7)
+    f32 = rng.randn(9, 257).astype(np.float32)
+    f64 = rng.rand(4, 40)
+    cm_src = (rng.randn(33, 23) * 3).astype(np.float32)
+    ark = os.path.join(OUT, "kaldi_ref.ark")
+    out = {}
+    with open(ark, "wb") as f:
+        for key, m in (("f32", f32), ("f64", f64)):
+            f.write((key + " ").encode())
+            out["off_" + key] = np.array(f.tell())
+            kaldi_io.write_mat(f, m)
+        f.write(b"cm ")
+        out["off_cm"] = np.array(f.tell())
+        f.write(tk.encode_cm(cm_src))
+    ref = {k: m for k, m in kaldi_io.read_mat_ark(ark)}
+    out.update(f32=ref["f32"], f64=ref["f64"], cm_decoded=ref["cm"])
+    # __getitem__ transform (data/mix_data_loader.py:203-207 + audioparse.transform_feat, delta 0, no splice)
+    spect = np.abs(rng.randn(11, 257)).astype(np.float32)
+    spect[2, :5] = 0.0
+    cmvn = np.stack([-rng.rand(257), 0.5 + rng.rand(257)]).astype(np.float32)
+    out["spect"] = spect.copy()
+    sp = spect.copy()
+    sp[sp <= 1e-7] = 1e-7
+    log_spect = 10 * np.log10(sp)
+    log_spect = (log_spect + cmvn[0, :]) * cmvn[1, :]
+    out.update(spect_clamped=sp, cmvn=cmvn, log_spect=log_spect)
+    res = loader._collate_fn(tk.make_samples())
+    out["c_utt_ids"] = np.array(res[0])
+    for i, name in zip(range(2, 7), ("clean", "clean_log", "mix", "mix_log", "cos")):
+        out["c_" + name] = npy(res[i])
+    out.update(c_targets=npy(res[7]), c_input_sizes=npy(res[8]), c_target_sizes=npy(res[9]))
+    np.savez_compressed(os.path.join(OUT, "kaldi.npz"), **out)
+
+
 def main(only=None):
     if only == "beam":
         gen_beam(refshim.load())
+        return
+    if only == "kaldi":
+        gen_kaldi(refshim.load())
         return
     if not refshim.available():
         raise SystemExit("reference tree not available; fixtures can only be generated in the build container")
@@ -231,6 +288,7 @@ def main(only=None):
     gen_ctc(ns)
     gen_prefix(ns)
     gen_beam(ns)
+    gen_kaldi(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
