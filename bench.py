@@ -375,7 +375,7 @@ def main():
     torch.cuda.synchronize()
 
     # ---- the step as a user runs it: StepRunner = CUDA-graph replay over static buffers, H2D on a copy stream
-    runner = StepRunner(hp, hb, slots=2)
+    runner = StepRunner(hp, hb, slots=3)
     mode = "cuda_graph" + ("" if args.no_overlap else " (front-end | CTC | decoder-loop branches on 3 streams)")
     grad_keys = ["d_" + k for k, p in hp.named_parameters() if p.requires_grad]
     if world > 1:
@@ -413,25 +413,36 @@ def main():
     value = cfg["B"] * world / (ms_per_step * 1e-3)
 
     # ---- end to end through StepRunner: every step copies its pinned host batch in and reads the loss back.
-    #      One step of look-ahead: batch i+1 is copied (copy stream) while step i computes.
-    for _ in range(2):
-        float(runner(hb)["loss_ctc"].cpu())
+    #      Two steps of look-ahead over three input slots: while step i computes, batch i+1 is already resident and
+    #      batch i+2 is being copied (copy stream), so neither the PCIe transfer (94 MB, ~1.8 ms at 55 GB/s) nor the
+    #      host-side staging sits on the critical path of the loop.
+    # The loop is timed in steady state: the pipeline is primed first (untimed), then every timed iteration submits one
+    # host batch (its H2D copy happens inside the window) and reads one finished step's loss back (D2H, synchronises).
+    # (t0 is taken right after a result read, with `ahead` steps in flight -- exactly the state the loop is in at t1;
+    # a device synchronize here would let the first `ahead` timed reads return steps finished before the window.)
+    ahead = 2
     barrier()
+    for _ in range(ahead):
+        runner.submit(hb)
+    for _ in range(3):
+        runner.submit(hb)
+        float(runner.result()["loss_ctc"].detach().cpu())
     t0 = time.perf_counter()
     d2h = 0
-    runner.submit(hb)
     for i in range(args.steps):
-        if i + 1 < args.steps:
-            runner.submit(hb)
-        lv = runner.result()["loss_ctc"].cpu()      # D2H read of the step's result (synchronises)
+        runner.submit(hb)
+        lv = runner.result()["loss_ctc"].detach().cpu()      # D2H read of the step's result (synchronises)
         d2h = lv.numel() * 4
+    t1 = time.perf_counter()
+    for _ in range(ahead):                                   # drain (untimed)
+        runner.result()
     barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
+    e2e_s = torch.tensor([(t1 - t0) / args.steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e = {"value": cfg["B"] * world / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes(hb),
            "d2h_bytes_per_step": d2h, "ms_per_step": float(e2e_s.item()) * 1e3,
-           "api": "robust_e2e_gan_b200.hotpath.StepRunner (graph replay, H2D of batch i+1 overlaps step i)"}
+           "api": "robust_e2e_gan_b200.hotpath.StepRunner (graph replay; 3 input slots, H2D of batches i+1 / i+2 overlaps step i)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
