@@ -144,6 +144,12 @@ int re2e_skinny_nn(const float *X, const float *W, float *out, int M, int N, int
 int re2e_gemm_tf32x3(const float *A, int lda, int a_mn, const float *B, int ldb, int b_mn, float *C,
                      int ldc, const float *bias, int M, int N, int K, int accumulate, void *stream);
 
+/* out[c] = sum_r X[r*ld + c]  (rows x cols, row pitch ld): the bias gradient of a dense layer (db = column sums of dY;
+ * ctc_lo, model/e2e_ctc.py:28, and mlp_enc, model/e2e_attention.py:214).  Deterministic two-pass reduction;
+ * partial: scratch of re2e_colsum_blocks(rows) * cols floats. */
+int re2e_colsum_blocks(int rows);
+int re2e_colsum(const float *X, long long ld, int rows, int cols, float *partial, float *out, void *stream);
+
 /* --------------------------------------------------------------------------------------------
  * CTC.  Replaces the warp_ctc.CTCLoss call at model/e2e_ctc.py:30,63 (softmax + alpha/beta +
  * gradient; arithmetic of the un-vendored warpctc_pytorch) and F.log_softmax at :75.

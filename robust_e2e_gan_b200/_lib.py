@@ -44,6 +44,8 @@ SIGNATURES = {
     "re2e_skinny_nt": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "re2e_skinny_nn": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "re2e_gemm_tf32x3": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "re2e_colsum_blocks": (_I, [_I]),
+    "re2e_colsum": (_I, [_P, _LL, _I, _I, _P, _P, _P]),
     "re2e_ctc_ws_bytes": (_SZ, [_I, _I, _I, _I]),
     "re2e_ctc_loss_fwd": (_I, [_P, _LL, _LL, _P, _P, _P, _P, _I, _P, _P, _P, _SZ, _I, _I, _I, _I, _P]),
     "re2e_ctc_loss_bwd": (_I, [_P, _LL, _LL, _P, _P, _P, _P, _I, _P, _P, _P, _SZ, _P, _I, _I, _I, _I, _P]),

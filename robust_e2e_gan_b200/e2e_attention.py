@@ -22,7 +22,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from .linear import gemm_tf32x3
+from .linear import colsum, gemm_tf32x3
 
 
 class _State(object):
@@ -100,7 +100,7 @@ class _Precompute(torch.autograd.Function):
                 dW_enc = torch.empty(A, D, device=dev, dtype=torch.float32)
                 gemm_tf32x3(dp2, True, st.enc.view(B * Th, D), True, dW_enc, A, D, B * Th)  # d_pre^T @ enc
             if need[2]:
-                db_enc = dp2.sum(0)
+                db_enc = colsum(dp2)
         if need[0] and st.bwd_w:
             if d_enc is None:
                 d_enc = torch.zeros(B, Th, D, device=dev, dtype=torch.float32)

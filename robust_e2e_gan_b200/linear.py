@@ -26,6 +26,21 @@ def gemm_tf32x3(A, a_mn, B, b_mn, C, M, N, K, bias=None, accumulate=False):
     return C
 
 
+def colsum(g):
+    """Column sums of a row-major 2-D view (unit inner stride, any row pitch): db of a dense layer, deterministic."""
+    L = _lib.lib()
+    rows, cols = g.shape
+    assert g.stride(1) == 1
+    ld = g.stride(0) if rows > 1 else max(g.stride(0), cols)
+    nrb = int(L.re2e_colsum_blocks(rows))
+    partial = torch.empty(nrb, cols, device=g.device, dtype=torch.float32)
+    out = torch.empty(cols, device=g.device, dtype=torch.float32)
+    with torch.cuda.device(g.device):
+        _lib.check(L.re2e_colsum(_lib.ptr(g), ld, rows, cols, _lib.ptr(partial), _lib.ptr(out), _lib.stream_ptr()),
+                   "re2e_colsum")
+    return out
+
+
 def _pad4(n):
     return (n + 3) // 4 * 4
 
@@ -91,7 +106,7 @@ class _LinearTC(torch.autograd.Function):
             dw = torch.empty(N, K, device=g.device, dtype=torch.float32)
             gemm_tf32x3(g, True, x2, True, dw, N, K, M)               # dW = g^T X    (both MN-major)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = g.sum(0)
+            db = colsum(g)
         return dx, dw, db
 
 

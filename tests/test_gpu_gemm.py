@@ -40,3 +40,13 @@ def test_gemm_matches_fp64(M, N, K, a_mn, b_mn):
     # accumulate
     gemm_tf32x3(As.to(DEV), bool(a_mn), Bs.to(DEV), bool(b_mn), C, M, N, K, accumulate=True)
     assert rel_err(C[:, :N], 2 * ref - bias.double()) < 2e-5
+
+
+@pytest.mark.parametrize("rows,cols,pad", [(6400, 4233, 3), (1, 5, 0), (257, 320, 0), (130, 129, 7)])
+def test_colsum_matches_fp64_and_is_deterministic(rows, cols, pad):
+    from robust_e2e_gan_b200.linear import colsum
+    g = torch.Generator().manual_seed(rows + cols)
+    X = torch.randn(rows, cols + pad, generator=g).to(DEV)
+    out = colsum(X[:, :cols])
+    assert rel_err(out, X[:, :cols].double().sum(0)) < 1e-5
+    assert torch.equal(out, colsum(X[:, :cols]))
