@@ -18,6 +18,8 @@
 // shape and the UMMA descriptors -- no transposed copies.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -374,7 +376,11 @@ extern "C" int re2e_gemm_tf32x3(const float *A, int lda, int a_mn, const float *
   RE2E_CHECK_ARG(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K));
   CUtensorMap ta, tb, tc;
   int rc;
-  const int BN = (N % 256 == 0 || N > 1024) ? 256 : 160;
+  int BN = (N % 256 == 0 || N > 1024) ? 256 : 160;
+  {
+    static const int force_bn = [] { const char *e = getenv("RE2E_GEMM_BN"); return e ? atoi(e) : 0; }();   // A/B timing aid
+    if (force_bn == 160 || force_bn == 256) BN = force_bn;
+  }
   if (!a_mn) rc = make_tmap(&ta, A, K, M, lda, kBM, false);
   else rc = make_tmap(&ta, A, M, K, lda, kBK, true);
   if (rc != RE2E_OK) return rc;

@@ -5,6 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 import bench
 from robust_e2e_gan_b200 import _lib
+_lib.LIB_PATH = os.environ.get("RE2E_DEBUG_LIB", os.path.join(ROOT, "robust_e2e_gan_b200", "libre2e_b200_fbdbg.so"))
 from robust_e2e_gan_b200.hotpath import DEFAULT_CFG, HotPath, make_batch
 dev = torch.device("cuda:0")
 cfg = dict(DEFAULT_CFG)
