@@ -25,8 +25,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# NCCL writes its banner / debug lines to stdout by default; stdout carries exactly ONE JSON line (the contract)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line (the contract).  NCCL prints its version banner / debug lines to the process's
+# stdout from C, so file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to a private
+# duplicate of the original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 
 import torch  # noqa: E402
 
@@ -159,7 +169,7 @@ def run_reference(args, rank, world):
             "config": workload_config(cfg, world),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(cfg, world):
@@ -480,7 +490,7 @@ def main():
                                     "sample": "%d of %d utterances of the same batch, all %d decoder steps; "
                                               "1 warm-up + median of 3" % (nb, cfg["B"], cfg["steps"]),
                                     "ms_per_step": dt * 1e3}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
