@@ -28,7 +28,8 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kBK = 32;                 // fp32 elements per k-block = one 128 B swizzle row
-constexpr int kGemmThreads = 192;
+constexpr int kConvWarps = 8;              // converter warps; the first four double as the epilogue warps
+constexpr int kGemmThreads = 64 + 32 * kConvWarps;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -136,9 +137,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const bool split = gridDim.z > 1;
 
   if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    if (p.tma_c) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&conv[s], 4);
+      mbar_init(&conv[s], kConvWarps);
       mbar_init(&empty[s], 1);
     }
     mbar_init(tmem_full, 1);
@@ -215,7 +219,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else {
     // ===== converters (lo = tf32(x - hi)), then epilogue =====
-    const int ctid = threadIdx.x - 64;  // 0..127
+    const int ctid = threadIdx.x - 64;  // 0 .. 32*kConvWarps-1
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STAGES;
       mbar_wait(&full[s], (uint32_t)((kb / STAGES) & 1));
@@ -223,7 +227,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       float4 *lo = reinterpret_cast<float4 *>(stage0 + (size_t)s * STAGE_BYTES + A_BYTES + B_BYTES);
       constexpr int N4 = (A_BYTES + B_BYTES) / 16;
 #pragma unroll 4
-      for (int i = ctid; i < N4; i += 128) {
+      for (int i = ctid; i < N4; i += 32 * kConvWarps) {
         const float4 x = hi[i];
         lo[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
       }
@@ -231,7 +235,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&conv[s]);
     }
-    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+    // epilogue (warps 2..5): warp w may touch TMEM lanes [32*(w%4), +32)
+    if (warp < 6) {
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int q = warp & 3;
@@ -323,6 +328,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (col0 + j < p.N) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
         }
       }
+    }
     }
     }
   }
