@@ -128,15 +128,202 @@ ctc_lse_kernel(const float *__restrict__ logits, long long stride_b, long long s
   if (lane == 0) lpmax[row] = mx;
 }
 
+__device__ __forceinline__ void cp_async4(float *dst_smem, const float *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // log(e^a + e^b + e^c) with -inf handling
+// The recursion applies this once per frame on the critical path of a 200-step serial chain, so it is built from the
+// raw approximate units (ex2 / lg2: 2^-22 relative / ~1e-7 absolute on [1,3]) instead of the range-reduced libm
+// expf / logf (~150 instructions): the sum is in [1, 3] (the max term contributes exactly 1), no range fix-ups needed.
+// Absolute error per call ~2e-7, i.e. a few 1e-6 over an utterance -- two orders below the 1e-4 parity tolerance.
 __device__ __forceinline__ float lse3(float a, float b, float c) {
-  float m = fmaxf(a, fmaxf(b, c));
-  if (m == -CUDART_INF_F) return m;
-  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+  // branch free (the lattice corners are -inf for many frames: a divergent early return would serialise the warp):
+  // all three -inf -> m0 = 0, the sum is 0, lg2(0) = -inf and the result is -inf
+  const float m = fmaxf(a, fmaxf(b, c));
+  const float m0 = m == -CUDART_INF_F ? 0.0f : m;
+  const float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+  float ea, eb, ec, l;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"((a - m0) * kLog2e));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"((b - m0) * kLog2e));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ec) : "f"((c - m0) * kLog2e));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"((ea + eb) + ec));
+  return fmaf(l, kLn2, m0);
 }
 
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// alpha / beta with ONE WARP per direction (2 warps per utterance): lane l owns the SPL consecutive lattice states
+// [l*SPL, (l+1)*SPL) in registers, the two neighbours a column update needs from the adjacent lane come through warp
+// shuffles, and the SPL independent log-sum-exps per lane overlap in the pipeline.  No shared-memory column, no CTA
+// barrier: the per-frame critical path is shuffle -> lse3 instead of STS -> bar.sync -> LDS -> lse3 (the CTA-wide
+// version below remains for lattices wider than 32*8 states).  Same outputs / renormalisation scheme as below.
+// ---------------------------------------------------------------------------------------------
+template <int SPL>
+__global__ void __launch_bounds__(32)
+ctc_ab_warp_kernel(const float *__restrict__ lpc, const float *__restrict__ lpmax,
+                   const int32_t *__restrict__ labels, const int32_t *__restrict__ label_offs,
+                   const int32_t *__restrict__ label_lens, const int32_t *__restrict__ input_lens, int blank,
+                   float *__restrict__ alpha, float *__restrict__ beta, double *__restrict__ offA,
+                   double *__restrict__ offB, float *__restrict__ nll, double *__restrict__ nll_d,
+                   float *__restrict__ loss, unsigned int *counter, int B, int Th, int Smax) {
+  // grid (B, 2): blockIdx.y is the direction, so every branch on it is block-uniform (a direction per WARP of one
+  // CTA makes the compiler wrap each shuffle in convergence barriers)
+  constexpr int kRing = SPL <= 4 ? 32 : 16, kAhead = kRing - 8, kSlot = 32 * SPL + 1;
+  __shared__ float ring[kRing * kSlot];        // [kRing][32*SPL states | frame max]
+  const int b = blockIdx.x;
+  const int half = blockIdx.y, lane = threadIdx.x;
+  const int T = min(Th, max(0, __ldg(input_lens + b)));
+  const int U = __ldg(label_lens + b), S = 2 * U + 1;
+  const int32_t *lab = labels + __ldg(label_offs + b);
+  const float NEG = -CUDART_INF_F;
+  const unsigned FULL = 0xffffffffu;
+  const int s0 = lane * SPL;
+  bool live[SPL], skip[SPL], start[SPL];
+#pragma unroll
+  for (int k = 0; k < SPL; ++k) {
+    const int s = s0 + k;
+    live[k] = s < S;
+    skip[k] = false;
+    if (live[k] && (s & 1)) {
+      if (half == 0) skip[k] = s >= 3 && __ldg(lab + (s >> 1)) != __ldg(lab + (s >> 1) - 1);
+      else skip[k] = s + 2 < S && __ldg(lab + (s >> 1)) != __ldg(lab + (s >> 1) + 1);
+    }
+    start[k] = live[k] && (half == 0 ? (s < 2) : (s >= S - 2));
+  }
+  const float *lp_b = lpc + (size_t)b * Th * Smax;
+  const float *lpm_b = lpmax + (size_t)b * Th;
+  float *out_b = (half == 0 ? alpha : beta) + (size_t)b * Th * Smax;
+  double *off_b = (half == 0 ? offA : offB) + (size_t)b * Th;
+  const long long dir = half ? -1 : 1;
+  const int t_first = half ? T - 1 : 0;
+  const long long stepS = dir * Smax;
+
+  // Prefetch through shared memory: every lane copies ITS states of frame i + kAhead with 4-byte cp.async (LDGSTS) into a
+  // ring, one commit group per frame; cp.async.wait_group kAhead then guarantees frame i has landed.  Unlike a register
+  // prefetch this costs no scoreboards (a warp has six, so a rolling register prefetch of 8 frames degenerates to one
+  // full memory latency per frame) and no registers, and it runs 24 (wide lattices: 8) frames ahead.
+  const float *src_p = lp_b + (long long)t_first * Smax + s0;     // frame being ISSUED (advances with the loop)
+  const float *srcm_p = lpm_b + t_first;
+  auto issue_frame = [&](int i) {
+    if (i < T) {
+      float *dst = ring + (i & (kRing - 1)) * kSlot;
+#pragma unroll
+      for (int k = 0; k < SPL; ++k)
+        if (live[k]) cp_async4(dst + s0 + k, src_p + k);
+      if (lane == 0) cp_async4(dst + 32 * SPL, srcm_p);
+    }
+    src_p += stepS;
+    srcm_p += dir;
+    cp_async_commit();
+  };
+  // states beyond this utterance's lattice are never copied: they read as -inf from the ring for the whole run, which
+  // keeps their column entries at -inf without a per-frame select
+#pragma unroll
+  for (int k = 0; k < SPL; ++k)
+    if (!live[k])
+      for (int r = 0; r < kRing; ++r) ring[r * kSlot + s0 + k] = NEG;
+  __syncwarp();
+  for (int i = 0; i < kAhead; ++i) issue_frame(i);
+  float *out_p = out_b + (long long)t_first * Smax + s0;
+  double *off_p = off_b + t_first;
+  double off = 0.0;
+  float a[SPL];
+#pragma unroll
+  for (int k = 0; k < SPL; ++k) a[k] = NEG;
+#pragma unroll 2
+  for (int i = 0; i < T; ++i) {
+    issue_frame(i + kAhead);
+    cp_async_wait<kAhead>();
+    __syncwarp();                                   // lane 0's copy of the frame max is visible to the warp
+    const float *fr = ring + (i & (kRing - 1)) * kSlot;
+    const float lpm = fr[32 * SPL];
+    float lpv[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) lpv[k] = fr[s0 + k] - lpm;      // -inf for states outside the lattice
+    if (lane == 0) off += (double)lpm;
+    // neighbours from the adjacent lane: alpha needs states s-1, s-2 (previous lane's last two), beta s+1, s+2
+    float n1, n2;
+    if (half == 0) {
+      n1 = __shfl_up_sync(FULL, a[SPL - 1], 1);
+      n2 = SPL >= 2 ? __shfl_up_sync(FULL, a[SPL >= 2 ? SPL - 2 : 0], 1) : __shfl_up_sync(FULL, a[0], 2);
+      if (lane == 0) { n1 = NEG; n2 = NEG; }
+      if (SPL == 1 && lane == 1) n2 = NEG;
+    } else {
+      n1 = __shfl_down_sync(FULL, a[0], 1);
+      n2 = SPL >= 2 ? __shfl_down_sync(FULL, a[SPL >= 2 ? 1 : 0], 1) : __shfl_down_sync(FULL, a[0], 2);
+      if (lane == 31) { n1 = NEG; n2 = NEG; }
+      if (SPL == 1 && lane == 30) n2 = NEG;
+    }
+    float v[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+      float x1, x2;   // the two neighbours of state k in this direction
+      if (half == 0) {
+        x1 = k >= 1 ? a[k >= 1 ? k - 1 : 0] : n1;
+        x2 = k >= 2 ? a[k >= 2 ? k - 2 : 0] : (k == 1 ? n1 : n2);
+      } else {
+        x1 = k + 1 < SPL ? a[k + 1 < SPL ? k + 1 : 0] : n1;
+        x2 = k + 2 < SPL ? a[k + 2 < SPL ? k + 2 : 0] : (k + 1 < SPL ? n1 : n2);
+      }
+      // frame 0: a = -inf everywhere, the recursion yields -inf and the start states are seeded instead
+      const float r = lse3(a[k], x1, skip[k] ? x2 : NEG) + lpv[k];
+      v[k] = (i == 0 && start[k]) ? lpv[k] : r;
+    }
+    if ((i & (kRenorm - 1)) == kRenorm - 1) {   // exact renormalisation: subtract the column max, remember it in fp64
+      float m = v[0];
+#pragma unroll
+      for (int k = 1; k < SPL; ++k) m = fmaxf(m, v[k]);
+      m = warp_max(m);
+      if (m != NEG) {
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) v[k] -= m;
+        if (lane == 0) off += (double)m;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+      a[k] = v[k];
+      if (live[k]) out_p[k] = v[k];
+    }
+    if (lane == 0) *off_p = off;
+    out_p += stepS;
+    off_p += dir;
+    __syncwarp();   // every lane is done with this ring slot before it is refilled kRing - kAhead frames later
+  }
+  if (half == 0) {
+    float *fin = ring;
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) fin[s0 + k] = a[k];
+    __syncwarp();
+    if (lane == 0) {
+      double r;
+      if (T == 0) r = (U == 0) ? 0.0 : (double)CUDART_INF_F;
+      else {
+        float x = fin[S - 1], y = S > 1 ? fin[S - 2] : NEG;
+        float m = fmaxf(x, y);
+        if (m == NEG) r = (double)CUDART_INF_F;
+        else r = -((double)m + (double)logf(expf(x - m) + expf(y - m)) + off);
+      }
+      nll[b] = (float)r;
+      nll_d[b] = r;
+      __threadfence();
+      unsigned int done = atomicAdd(counter, 1u);
+      if (done == (unsigned)B - 1) {      // last utterance to finish: deterministic ordered sum
+        __threadfence();
+        double acc = 0.0;
+        for (int k = 0; k < B; ++k) acc += *(volatile double *)(nll_d + k);
+        loss[0] = (float)(acc / (double)B);
+        *counter = 0u;
+      }
+    }
+  }
 }
 
 // one CTA per utterance; blockDim = 2*Sp (Sp = Smax rounded to 32): first half alpha, second beta
@@ -183,34 +370,40 @@ ctc_ab_kernel(const float *__restrict__ lpc, const float *__restrict__ lpmax,
   }
   double off = 0.0;
   int cur = 0;
+  // running pointers (one add per frame instead of 64-bit index arithmetic): frame t of this direction, and the frame
+  // kRenorm steps ahead for the prefetch
+  const long long dir = half ? -1 : 1;
+  const int t_first = half ? T - 1 : 0;
+  const float *pf_ptr = lp_b + ((long long)t_first + dir * kRenorm) * Smax + s;
+  const float *pm_ptr = lpm_b + ((long long)t_first + dir * kRenorm);
+  float *out_p = out_b + (long long)t_first * Smax + s;
+  double *off_p = off_b + t_first;
+  const long long stepS = dir * Smax;
+  const int d1 = half == 0 ? -1 : 1;      // neighbour offsets inside the column
+  const bool start = half == 0 ? (s < 2) : (s >= S - 2);
   for (int i0 = 0; i0 < T; i0 += kRenorm) {
 #pragma unroll
     for (int j = 0; j < kRenorm; ++j) {
       const int i = i0 + j;
       if (i >= T) break;
-      const int t = half ? T - 1 - i : i;
       // every frame is shifted by its own max label log-prob (kept in `off`), so a column only drifts
       // by the gap to the best label between the exact renormalisations below
       const float lpm = pm[j];
       const float lpv = pf[j] - lpm;
-      off += (double)lpm;
+      if (s == 0) off += (double)lpm;   // only the thread that stores / uses the offsets pays for the fp64 pipe
       {  // prefetch frame i + kRenorm
-        const int i2 = i + kRenorm;
-        const int t2 = half ? T - 1 - i2 : i2;
-        pf[j] = (live && i2 < T) ? __ldg(lp_b + (size_t)t2 * Smax + s) : NEG;
-        pm[j] = i2 < T ? __ldg(lpm_b + t2) : 0.0f;
+        const bool more = i + kRenorm < T;
+        pf[j] = (live && more) ? __ldg(pf_ptr) : NEG;
+        pm[j] = more ? __ldg(pm_ptr) : 0.0f;
+        pf_ptr += stepS;
+        pm_ptr += dir;
       }
-      float v;
-      if (i == 0) {
-        const bool start = half == 0 ? (s < 2) : (s >= S - 2);
-        v = (live && start) ? lpv : NEG;
-      } else {
-        const float *c = col + cur * pitch + 2;
-        float a0 = c[s];
-        float a1 = half == 0 ? c[s - 1] : c[s + 1];
-        float a2 = skip ? (half == 0 ? c[s - 2] : c[s + 2]) : NEG;
-        v = live ? lse3(a0, a1, a2) + lpv : NEG;
-      }
+      const float *c = col + cur * pitch + 2 + s;
+      const float a0 = c[0], a1 = c[d1];
+      const float a2 = skip ? c[2 * d1] : NEG;
+      float v = lse3(a0, a1, a2) + lpv;                  // -inf columns stay -inf
+      if (i == 0) v = start ? lpv : NEG;
+      if (!live) v = NEG;
       float *n = col + (cur ^ 1) * pitch + 2;
       if (j == kRenorm - 1) {
         // renormalise: subtract the column max, remember it in fp64
@@ -219,11 +412,16 @@ ctc_ab_kernel(const float *__restrict__ lpc, const float *__restrict__ lpmax,
         named_bar(barid, Sp);
         float gm = NEG;
         for (int w = 0; w < nwarps; ++w) gm = fmaxf(gm, wred[w]);
-        if (gm != NEG) { v -= gm; off += (double)gm; }
+        if (gm != NEG) {
+          v -= gm;
+          if (s == 0) off += (double)gm;
+        }
       }
       n[s] = v;
-      if (live) out_b[(size_t)t * Smax + s] = v;
-      if (s == 0) off_b[t] = off;
+      if (live) *out_p = v;
+      if (s == 0) *off_p = off;
+      out_p += stepS;
+      off_p += dir;
       cur ^= 1;
       named_bar(barid, Sp);
     }
@@ -421,9 +619,24 @@ extern "C" int re2e_ctc_loss_fwd(const float *logits, long long stride_b, long l
   count_launch();
   int rc = launch_status();
   if (rc != RE2E_OK) return rc;
-  const size_t smem = sizeof(float) * (4 * (size_t)(Sp + 4) + 64);
-  ctc_ab_kernel<<<B, 2 * Sp, smem, st>>>(w.lpc, w.lpmax, labels, label_offs, label_lens, input_lens, blank, w.alpha,
-                                         w.beta, w.offA, w.offB, nll, w.nll_d, loss, w.counter, B, Th, Smax, Sp);
+  // lattices of up to 256 states: one warp per direction, the column in registers (SPL states per lane)
+  const int spl = (Smax + 31) / 32;
+#define RE2E_AB_WARP(SPLV)                                                                                          \
+  ctc_ab_warp_kernel<SPLV><<<dim3(B, 2), 32, 0, st>>>(w.lpc, w.lpmax, labels, label_offs, label_lens, input_lens, blank,     \
+                                             w.alpha, w.beta, w.offA, w.offB, nll, w.nll_d, loss, w.counter, B, Th, \
+                                             Smax)
+  if (spl <= 1) RE2E_AB_WARP(1);
+  else if (spl == 2) RE2E_AB_WARP(2);
+  else if (spl == 3) RE2E_AB_WARP(3);
+  else if (spl == 4) RE2E_AB_WARP(4);
+  else if (spl <= 6) RE2E_AB_WARP(6);
+  else if (spl <= 8) RE2E_AB_WARP(8);
+  else {
+    const size_t smem = sizeof(float) * (4 * (size_t)(Sp + 4) + 64);
+    ctc_ab_kernel<<<B, 2 * Sp, smem, st>>>(w.lpc, w.lpmax, labels, label_offs, label_lens, input_lens, blank, w.alpha,
+                                           w.beta, w.offA, w.offB, nll, w.nll_d, loss, w.counter, B, Th, Smax, Sp);
+  }
+#undef RE2E_AB_WARP
   count_launch();
   return launch_status();
 }

@@ -52,7 +52,11 @@ def test_golden_logit_gradient():
 
 
 @pytest.mark.parametrize("B,Th,V,umin,umax,seed", [(8, 100, 4233, 8, 24, 1234), (5, 33, 50, 0, 12, 3),
-                                                    (3, 40, 7, 10, 19, 4), (2, 300, 129, 100, 140, 5)])
+                                                    (3, 40, 7, 10, 19, 4), (2, 300, 129, 100, 140, 5),
+                                                    # lattice widths of every register-column instantiation
+                                                    # (states per lane 3, 4, 6, 8) and of the CTA-wide fallback
+                                                    (4, 120, 31, 33, 47, 6), (3, 150, 40, 50, 63, 7),
+                                                    (3, 220, 50, 70, 95, 8), (2, 280, 60, 100, 127, 9)])
 def test_oracle_parity(B, Th, V, umin, umax, seed):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, Th, V, generator=g) * 3
