@@ -986,6 +986,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     float acc[CP];    // starts from the slot's running total (loads overlap the frame loop)
 #pragma unroll
     for (int c = 0; c < CP; ++c) acc[c] = c < C ? slot[a * C + c] : 0.0f;
+#pragma unroll 5
     for (int tl = 0; tl < tloc; ++tl) {
       const float dt = xs[(size_t)tl * A + a];
 #pragma unroll
@@ -1016,7 +1017,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
         float x[KG];
 #pragma unroll
         for (int i = 0; i < KG - 1; ++i) x[i] = ar[t0 + i];
-#pragma unroll 4
+#pragma unroll 12   // = KG: the register window rotates back onto itself, no moves
         for (int tl = 0; tl < tloc; ++tl) {
           x[KG - 1] = ar[t0 + tl + KG - 1];
           const float dv = dcv_p[tl * 16 + c] + dcv_p[(g.tloc_max + tl) * 16 + c];   // d conv of MY frame tl
