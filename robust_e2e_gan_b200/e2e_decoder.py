@@ -13,9 +13,11 @@ state_dict keys as the reference's ``Decoder`` for the configuration the scripts
   step launch for the whole beam (B = beam instead of beam x (B = 1) launches), one LSTMCell / output GEMM, one
   log-softmax launch, and ONE batched CTC prefix-score launch (hypotheses x ctc_beam candidates) whose forward
   variables stay on the device (the reference copies ``lpz`` to the host and loops over T in numpy per
-  hypothesis, model/e2e_ctc.py:143-146).  Per output position a single small device->host copy (beam x beam
-  candidate scores and ids) feeds the reference's own bookkeeping: stable descending sort, <eos> handling,
-  length penalty, ``end_detect``.  Scores accumulate in fp32 exactly as the reference's 0-dim tensors do.
+  hypothesis, model/e2e_ctc.py:143-146).  All per-position device work runs over static buffers, so from the third
+  position on it is one CUDA-graph replay (captured once per utterance); per position the host writes one small
+  pinned control block (parent rows, CTC candidates, tokens, scores) and reads one block of beam x beam candidate
+  scores / ids back for the reference's own bookkeeping: stable descending sort, <eos> handling, length penalty,
+  ``end_detect``.  Scores accumulate in fp32 exactly as the reference's 0-dim tensors do.
 """
 import random
 
@@ -174,42 +176,111 @@ class Decoder(torch.nn.Module):
             r_prev = r0.unsqueeze(0).expand(W, Th, 2).contiguous()
             ctc_prev = torch.zeros(W, device=dev, dtype=torch.float32)
 
-        hyps = [{'score': np.float32(0.0), 'yseq': [self.sos]}]     # hypothesis k lives in device row k
-        score_dev = torch.zeros(W, device=dev, dtype=torch.float32)
-        ended_hyps = []
-        for i in range(maxlen):
-            n = len(hyps)
-            last = [hyps[min(k, n - 1)]['yseq'][i] for k in range(W)]
-            vy = torch.tensor(last, dtype=torch.long, device=dev)
+        # ---- static device buffers: one output position = one fixed sequence of launches over them, so positions >= 2
+        #      are replayed from a CUDA graph (captured once per utterance); the host only exchanges two small packed
+        #      arrays per position (control in, candidates out) through pinned memory
+        L = self.dlayers
+        ctl = torch.zeros(4, W, dtype=torch.long, device=dev)          # rows: parent, ctc candidate, token, position
+        sc = torch.zeros(W, dtype=torch.float32, device=dev)           # accumulated scores of the rows
+        out = torch.empty(3, W, beam, dtype=torch.float32, device=dev)   # candidate scores, token ids, ctc candidate idx
+        pins = getattr(self, "_pinned", None)          # page-locked staging is expensive to allocate: keep it per beam
+        if pins is None or pins[0].shape[1] != W or pins[2].shape[2] != beam:
+            pins = (torch.zeros(4, W, dtype=torch.long).pin_memory(), torch.zeros(W, dtype=torch.float32).pin_memory(),
+                    torch.empty(3, W, beam, dtype=torch.float32).pin_memory())
+            self._pinned = pins
+        ctl_h, sc_h, out_h = pins
+        ctl_h.zero_()
+        sc_h.zero_()
+        ctl_np, sc_np, out_np = ctl_h.numpy(), sc_h.numpy(), out_h.numpy()      # host views (element access is cheap)
+        st_a = torch.empty(W, Th, dtype=torch.float32, device=dev)
+        if use_ctc:
+            st_r = torch.empty(W, ctc_beam, Th, 2, dtype=torch.float32, device=dev)
+            st_psi = torch.empty(W, ctc_beam, dtype=torch.float32, device=dev)
+
+        def dev_step(first):
+            vy = ctl[2]
+            if first:
+                zz, cc, a_prev = z, c, None
+                if use_ctc:
+                    rp, cp = r_prev, ctc_prev
+            else:
+                P = ctl[0]
+                zz = [t.index_select(0, P) for t in z]
+                cc = [t.index_select(0, P) for t in c]
+                a_prev = st_a.index_select(0, P)
+                if use_ctc:
+                    rp = st_r[P, ctl[1]].contiguous()
+                    cp = st_psi[P, ctl[1]].contiguous()
             ey = self.embed(vy)
-            att_c, att_w = self.att(hb, hlens, z[0], a_prev)
+            att_c, att_w = self.att(hb, hlens, zz[0], a_prev)
             ey = torch.cat((ey, att_c), dim=1)
-            z_new, c_new = list(z), list(c)
-            z_new[0], c_new[0] = self.decoder[0](ey, (z[0], c[0]))
-            for l in range(1, self.dlayers):
-                z_new[l], c_new[l] = self.decoder[l](z_new[l - 1], (z[l], c[l]))
+            z_new, c_new = list(zz), list(cc)
+            z_new[0], c_new[0] = self.decoder[0](ey, (zz[0], cc[0]))
+            for l in range(1, L):
+                z_new[l], c_new[l] = self.decoder[l](z_new[l - 1], (zz[l], cc[l]))
             local_att = log_softmax_rows(self.output(z_new[-1]))                    # (W, V)
             if use_ctc:
                 _, ids = torch.topk(local_att, ctc_beam, dim=1)                     # attention pre-pruning
-                log_psi, r_new = ctc_prefix_score_batch(
-                    lpz, r_prev, ids.to(torch.int32).contiguous(), vy.to(torch.int32),
-                    torch.full((W,), i, dtype=torch.int32, device=dev), 0, self.eos)
-                local = (1.0 - ctc_weight) * local_att.gather(1, ids) + ctc_weight * (log_psi - ctc_prev.unsqueeze(1))
+                log_psi, r_new = ctc_prefix_score_batch(lpz, rp, ids.to(torch.int32).contiguous(), vy.to(torch.int32),
+                                                        ctl[3].to(torch.int32), 0, self.eos)
+                local = (1.0 - ctc_weight) * local_att.gather(1, ids) + ctc_weight * (log_psi - cp.unsqueeze(1))
                 best_scores, joint = torch.topk(local, beam, dim=1)
                 best_ids = ids.gather(1, joint)
+                st_r.copy_(r_new)
+                st_psi.copy_(log_psi)
             else:
                 best_scores, best_ids = torch.topk(local_att, beam, dim=1)
                 joint = best_ids
-            cand = score_dev.unsqueeze(1) + best_scores                             # fp32, as hyp['score'] + tensor
-            packed = torch.stack((cand, best_ids.float(), joint.float()), 0)[:, :n].cpu().numpy()
-            cand_h, ids_h, joint_h = packed[0], packed[1].astype(np.int64), packed[2].astype(np.int64)
+            for l in range(L):
+                z[l].copy_(z_new[l])
+                c[l].copy_(c_new[l])
+            st_a.copy_(att_w)
+            cand = sc.unsqueeze(1) + best_scores                                    # fp32, as hyp['score'] + tensor
+            out.copy_(torch.stack((cand, best_ids.float(), joint.float()), 0))
+
+        use_graph = bool(getattr(recog_args, "cuda_graph", True)) and maxlen >= 6
+        graph = None
+        hyps = [{'score': np.float32(0.0), 'yseq': [self.sos]}]     # hypothesis k lives in device row k
+        ended_hyps = []
+        for i in range(maxlen):
+            n = len(hyps)
+            ctl_np[2, :] = [hyps[min(k, n - 1)]['yseq'][i] for k in range(W)]
+            ctl_np[3, :] = i
+            ctl.copy_(ctl_h, non_blocking=True)
+            sc.copy_(sc_h, non_blocking=True)
+            if i == 0:
+                dev_step(True)
+            elif i == 1 or not use_graph:
+                dev_step(False)
+            else:
+                if graph is None:
+                    # raw capture_begin / capture_end on a side stream: the torch.cuda.graph context manager also runs
+                    # gc.collect() and empty_cache(), tens of milliseconds per utterance
+                    cur = torch.cuda.current_stream(dev)
+                    if getattr(self, "_cap_stream", None) is None or self._cap_stream.device != dev:
+                        self._cap_stream = torch.cuda.Stream(dev)
+                        self._graph_pool = torch.cuda.graph_pool_handle()
+                    self._cap_stream.wait_stream(cur)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.stream(self._cap_stream):
+                        graph.capture_begin(pool=self._graph_pool)
+                        dev_step(False)
+                        graph.capture_end()
+                    cur.wait_stream(self._cap_stream)
+                    # the shared pool lives as long as one graph references it: keep this utterance's graph until the
+                    # next one has been captured (then its blocks return to the pool)
+                    self._last_graph = graph
+                graph.replay()
+            out_h.copy_(out, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            cand_h = out_np[0, :n]
+            ids_h, joint_h = out_np[1, :n].astype(np.int64), out_np[2, :n].astype(np.int64)
             # the reference merges hypothesis by hypothesis with a stable descending sort truncated to `beam`
             # (model/e2e_decoder.py:296-314) == one stable descending sort over (hypothesis, rank) order
-            flat = [(float(cand_h[r, j]), r, j) for r in range(n) for j in range(beam)]
-            order = sorted(range(len(flat)), key=lambda k: flat[k][0], reverse=True)[:beam]
+            order = np.argsort(-cand_h.reshape(-1), kind='stable')[:beam]
             new_hyps = []
             for k in order:
-                _, r, j = flat[k]
+                r, j = divmod(int(k), beam)
                 new_hyps.append({'score': np.float32(cand_h[r, j]), 'yseq': hyps[r]['yseq'] + [int(ids_h[r, j])],
                                  '_parent': r, '_j': int(joint_h[r, j]) if use_ctc else j})
             if i == maxlen - 1:
@@ -228,17 +299,11 @@ class Decoder(torch.nn.Module):
             hyps = remained
             if len(hyps) == 0:
                 break
-            # device state of the surviving hypotheses: one gather per tensor (spare rows repeat the last hypothesis)
-            par = [hyps[min(k, len(hyps) - 1)]['_parent'] for k in range(W)]
-            P = torch.tensor(par, dtype=torch.long, device=dev)
-            z = [t.index_select(0, P) for t in z_new]
-            c = [t.index_select(0, P) for t in c_new]
-            a_prev = att_w.index_select(0, P)
-            score_dev = torch.tensor([float(hyps[min(k, len(hyps) - 1)]['score']) for k in range(W)],
-                                     dtype=torch.float32, device=dev)
-            if use_ctc:
-                J = torch.tensor([hyps[min(k, len(hyps) - 1)]['_j'] for k in range(W)], dtype=torch.long, device=dev)
-                r_prev = r_new[P, J].contiguous()
-                ctc_prev = log_psi[P, J].contiguous()
+            # control block of the next position: parent row, ctc candidate and score of every surviving hypothesis
+            # (spare rows repeat the last one)
+            rows = [hyps[min(k, len(hyps) - 1)] for k in range(W)]
+            ctl_np[0, :] = [hk['_parent'] for hk in rows]
+            ctl_np[1, :] = [hk['_j'] if use_ctc else 0 for hk in rows]
+            sc_np[:] = [hk['score'] for hk in rows]
         nbest = sorted(ended_hyps, key=lambda x: x['score'], reverse=True)[:min(len(ended_hyps), recog_args.nbest)]
         return [{'score': float(x['score']), 'yseq': [int(t) for t in x['yseq']]} for x in nbest]
