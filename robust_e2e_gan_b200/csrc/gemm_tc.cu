@@ -361,6 +361,260 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM loops over (m tile, n tile, k slice) work items; the fp32 accumulator is double
+// buffered in TMEM (2 x BN columns), so the epilogue of item i (dedicated warps) and the prologue latency of item
+// i+1 overlap the MMAs -- in the one-CTA-per-tile kernel above ~25-33 % of a CTA's life is setup + first-load latency
+// + epilogue with the tensor pipe idle (profiles/r01_s4d_gemm_phases.txt).
+//   warp 0       TMA producer (one lane)        warp 1        MMA issuer (one lane), TMEM alloc / dealloc
+//   warps 2..9   converters (lo copies)         warps 10..13  epilogue (TMEM lane quarter = warp % 4)
+// The epilogue writes straight from registers (16 B per lane and row; fp32 red.add for split-K / accumulate): it no
+// longer sits on the critical path, and the operand ring keeps all of the shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPersistThreads = 14 * 32;
+
+template <bool A_MN, bool B_MN, int BN, int STAGES>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+gemm_tf32x3_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                           const GemmParams p, int MT, int NT, int n_items) {
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  constexpr int A_BYTES = kBM * kBK * 4;
+  constexpr int B_BYTES = BN * kBK * 4;
+  constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+  constexpr uint32_t TMEM_COLS = 512;            // two BN-column accumulators (BN <= 256)
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+  unsigned char *stage0 = smraw;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smraw + (size_t)STAGES * STAGE_BYTES);
+  uint64_t *conv = full + STAGES;
+  uint64_t *empty = conv + STAGES;
+  uint64_t *tmem_full = empty + STAGES;          // [2]
+  uint64_t *tmem_empty = tmem_full + 2;          // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+  float *bias_s = reinterpret_cast<float *>(smraw + (size_t)STAGES * STAGE_BYTES + 1024);   // [2][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb_total = (p.K + kBK - 1) / kBK;
+  const bool split = nkb_total > p.kb_per;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&conv[s], kConvWarps);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int w, int &m0, int &n0, int &kb_begin, int &nkb) {
+    const int mt = w % MT, r = w / MT, nt = r % NT, ks = r / NT;
+    m0 = mt * kBM;
+    n0 = nt * BN;
+    kb_begin = ks * p.kb_per;
+    nkb = min(nkb_total - kb_begin, p.kb_per);
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        int m0, n0, kb_begin, nkb;
+        decode(w, m0, n0, kb_begin, nkb);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
+          unsigned char *st = stage0 + (size_t)s * STAGE_BYTES;
+          mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+          const int k0 = (kb_begin + kb) * kBK;
+          if (!A_MN) {
+            tma_load_2d(st, &tmA, k0, m0, &full[s]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBM / 32; ++j) tma_load_2d(st + j * 4096, &tmA, m0 + 32 * j, k0, &full[s]);
+          }
+          if (!B_MN) {
+            tma_load_2d(st + A_BYTES, &tmB, k0, n0, &full[s]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) tma_load_2d(st + A_BYTES + j * 4096, &tmB, n0 + 32 * j, k0, &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int it = 0, li = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++li) {
+        int m0, n0, kb_begin, nkb;
+        decode(w, m0, n0, kb_begin, nkb);
+        const int buf = li & 1;
+        mbar_wait(&tmem_empty[buf], (uint32_t)(((li >> 1) & 1) ^ 1));   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&conv[s], (uint32_t)((it / STAGES) & 1));
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(stage0 + (size_t)s * STAGE_BYTES);
+          const uint32_t b_hi = a_hi + A_BYTES;
+          const uint32_t a_lo = b_hi + B_BYTES;
+          const uint32_t b_lo = a_lo + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {
+            const uint32_t ao = A_MN ? k * 1024 : k * 32;
+            const uint32_t bo = B_MN ? k * 1024 : k * 32;
+            const uint64_t dah = A_MN ? umma_desc(a_hi + ao, 4096, 512, 1) : umma_desc(a_hi + ao, 16, 1024, 2);
+            const uint64_t dal = A_MN ? umma_desc(a_lo + ao, 4096, 512, 1) : umma_desc(a_lo + ao, 16, 1024, 2);
+            const uint64_t dbh = B_MN ? umma_desc(b_hi + bo, 4096, 512, 1) : umma_desc(b_hi + bo, 16, 1024, 2);
+            const uint64_t dbl = B_MN ? umma_desc(b_lo + bo, 4096, 512, 1) : umma_desc(b_lo + bo, 16, 1024, 2);
+            umma_tf32(d_tmem, dah, dbh, IDESC, (kb | k) ? 1u : 0u);
+            umma_tf32(d_tmem, dal, dbh, IDESC, 1u);
+            umma_tf32(d_tmem, dah, dbl, IDESC, 1u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else if (warp < 2 + kConvWarps) {
+    // ===== converters =====
+    const int ctid = threadIdx.x - 64;
+    int it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      int m0, n0, kb_begin, nkb;
+      decode(w, m0, n0, kb_begin, nkb);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+        const float4 *hi = reinterpret_cast<const float4 *>(stage0 + (size_t)s * STAGE_BYTES);
+        float4 *lo = reinterpret_cast<float4 *>(stage0 + (size_t)s * STAGE_BYTES + A_BYTES + B_BYTES);
+        constexpr int N4 = (A_BYTES + B_BYTES) / 16;
+#pragma unroll 4
+        for (int i = ctid; i < N4; i += 32 * kConvWarps) {
+          const float4 x = hi[i];
+          lo[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[s]);
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int q = warp & 3;
+    const int etid = threadIdx.x - 32 * (2 + kConvWarps);   // 0..127
+    const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
+    int li = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++li) {
+      int m0, n0, kb_begin, nkb;
+      decode(w, m0, n0, kb_begin, nkb);
+      const int buf = li & 1;
+      float *bs = bias_s + buf * BN;
+      // bias of this item's columns (the buffer was last read two items ago; every epilogue warp has passed the
+      // barrier of the item in between)
+      {
+        const bool use_bias = p.bias != nullptr && kb_begin == 0;
+        for (int i = etid; i < BN; i += 128) bs[i] = (use_bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tmem_full[buf], (uint32_t)((li >> 1) & 1));
+      tc_fence_after();
+      const int row = m0 + 32 * q + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * BN + c * 32), v);
+        if (row < p.M) {
+          float *dst = p.C + (size_t)row * p.ldc + col0;
+          if (vec && col0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4 *>(bs + c * 32 + j);
+              float4 o = make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w);
+              if (split) {
+                red_add4(dst + j, o);
+              } else {
+                if (p.accumulate) {
+                  const float4 old = *reinterpret_cast<const float4 *>(dst + j);
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *reinterpret_cast<float4 *>(dst + j) = o;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) {
+                const float val = v[j] + bs[c * 32 + j];
+                if (split) atomicAdd(dst + j, val);
+                else dst[j] = p.accumulate ? dst[j] + val : val;
+              }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <bool A_MN, bool B_MN, int BN, int STAGES>
+int launch_gemm_persist(const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &prm, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * 2 * (kBM * kBK * 4 + BN * kBK * 4) + 1024 + 2 * BN * 4;
+  auto kern = gemm_tf32x3_persist_kernel<A_MN, B_MN, BN, STAGES>;
+  int rc = ensure_smem(reinterpret_cast<const void *>(kern), smem);
+  if (rc != RE2E_OK) return rc;
+  const int nkb = (prm.K + kBK - 1) / kBK;
+  const int MT = (prm.M + kBM - 1) / kBM, NT = (prm.N + BN - 1) / BN, KS = (nkb + prm.kb_per - 1) / prm.kb_per;
+  const long long items = (long long)MT * NT * KS;
+  if (items > 0x7fffffff) return RE2E_E_UNSUPPORTED;
+  if (KS > 1 && !prm.accumulate) {
+    cudaError_t e = cudaMemset2DAsync(prm.C, sizeof(float) * (size_t)prm.ldc, 0, sizeof(float) * (size_t)prm.N,
+                                      (size_t)prm.M, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int grid = (int)(items < num_sms() ? items : num_sms());
+  kern<<<grid, kPersistThreads, smem, st>>>(ta, tb, prm, MT, NT, (int)items);
+  count_launch();
+  return launch_status();
+}
+
+template <int BN, int STAGES>
+int dispatch_major_persist(int a_mn, int b_mn, const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &prm,
+                           cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_gemm_persist<false, false, BN, STAGES>(ta, tb, prm, st);
+  if (!a_mn && b_mn) return launch_gemm_persist<false, true, BN, STAGES>(ta, tb, prm, st);
+  if (a_mn && !b_mn) return launch_gemm_persist<true, false, BN, STAGES>(ta, tb, prm, st);
+  return launch_gemm_persist<true, true, BN, STAGES>(ta, tb, prm, st);
+}
+
 template <bool A_MN, bool B_MN, int BN, int STAGES>
 int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, const GemmParams &prm,
                 cudaStream_t st) {
@@ -443,6 +697,17 @@ extern "C" int re2e_gemm_tf32x3(const float *A, int lda, int a_mn, const float *
     }
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    // persistent tile loop with a double-buffered TMEM accumulator (RE2E_GEMM_PERSIST=0 selects the one-CTA-per-tile
+    // kernel below, kept as the reference implementation and for A/B timing)
+    static const bool persist = [] { const char *e = getenv("RE2E_GEMM_PERSIST"); return !(e && e[0] == '0'); }();
+    const long long items = (long long)((M + kBM - 1) / kBM) * ((N + BN - 1) / BN) * ((nkb + prm.kb_per - 1) / prm.kb_per);
+    if (persist && items > num_sms()) {   // a single wave gains nothing from the tile loop
+      prm.tma_c = 0;
+      if (BN == 256) return dispatch_major_persist<256, 2>(a_mn, b_mn, ta, tb, prm, st);
+      return dispatch_major_persist<160, 3>(a_mn, b_mn, ta, tb, prm, st);
+    }
+  }
   // epilogue through the TMA store unit when C is TMA-addressable (16 B aligned, 16 B row pitch); 32 x 32 boxes
   prm.tma_c = ((ldc & 3) == 0 && aligned16(C) && N >= 4) ? 1 : 0;
   if (prm.tma_c) {
