@@ -23,8 +23,8 @@ KMAP = collections.OrderedDict([   # kernel-name substring -> bench.py `kernels`
     ("fbank_tc_fwd_kernel<1", "fbank_fwd(mask,mag->Y,G)"), ("fbank_tc_fwd_kernel<0", "fbank_fwd(mag->Y)"),
     ("fbank_tc_bwd", "fbank_bwd(->d mask)"), ("attloc_fwd", "attloc_step_fwd"), ("attloc_bwd", "attloc_step_bwd"),
     ("ctc_lse", "ctc_fwd(lse+alpha/beta)"), ("ctc_ab", None), ("ctc_grad", "ctc_bwd(grad)"),
-    ("gemm_tf32x3_kernel<0, 0, 256", "gemm ctc_lo fwd"), ("gemm_tf32x3_kernel<0, 1, 160", "gemm ctc_lo dX"),
-    ("gemm_tf32x3_kernel<1, 1, 160", "gemm ctc_lo dW"), ("gemm_tf32x3_kernel<0, 0, 160", "gemm mlp_enc fwd")])
+    ("gemm_tf32x3_persist_kernel<0, 0, 256", "gemm ctc_lo fwd"), ("gemm_tf32x3_persist_kernel<0, 1, 160", "gemm ctc_lo dX"),
+    ("gemm_tf32x3_persist_kernel<1, 1, 160", "gemm ctc_lo dW"), ("gemm_tf32x3_kernel<0, 0, 160", "gemm mlp_enc fwd")])
 
 
 def short(n):
