@@ -61,3 +61,42 @@ def test_step_runner_matches_eager_and_oracle():
     again = runner(b1)
     assert torch.equal(again["enhance_feat"].cpu(), outs[1]["enhance_feat"])
     assert torch.equal(again["att_c"].cpu(), outs[1]["att_c"])
+
+
+def test_step_runner_three_slots_two_batches_ahead():
+    """The bench's end-to-end loop: three input slots, two host batches in flight ahead of the compute.  Results come
+    back in submission order and match the single-step results of the same batches."""
+    from robust_e2e_gan_b200.hotpath import StepRunner
+    cfg = dict(B=4, T=64, F=257, M=40, Th=16, D=320, A=320, Z=300, C=10, filts=100, V=97, U=5, steps=4)
+    hp = HotPath(cfg, seed=21).to(DEV)
+    batches = [make_batch(cfg, seed=30 + i).pin() for i in range(3)]
+    runner = StepRunner(hp, batches[0], slots=3)
+    single = []
+    for hb in batches:
+        o = runner(hb)
+        single.append((float(o["loss_ctc"].detach().cpu()), o["att_c"].detach().cpu().clone()))
+    order = [0, 1, 2, 2, 0, 1, 1, 0]
+    runner.submit(batches[order[0]])
+    runner.submit(batches[order[1]])
+    got = []
+    for i in range(len(order)):
+        if i + 2 < len(order):
+            runner.submit(batches[order[i + 2]])
+        o = runner.result()
+        got.append((float(o["loss_ctc"].detach().cpu()), o["att_c"].detach().cpu().clone()))
+    for k, (loss, c) in zip(order, got):
+        assert loss == single[k][0]
+        assert torch.equal(c, single[k][1])
+    with pytest.raises(RuntimeError):          # a fourth outstanding submit would overwrite an unread slot
+        for _ in range(4):
+            runner.submit(batches[0])
+
+
+def test_collate_writes_pinned_batches():
+    from robust_e2e_gan_b200 import kaldi_feats as kf
+    g = torch.Generator().manual_seed(1)
+    samples = [("u%d" % i, "s", *[torch.rand(5 + i, 7, generator=g) for _ in range(5)], torch.tensor([1, 2])) for i in range(3)]
+    out = kf.collate(samples)
+    assert all(out[i].is_pinned() for i in range(2, 7)) and out[8].is_pinned()
+    assert out[0] == ["u2", "u1", "u0"] and out[8].tolist() == [7, 6, 5]
+    assert torch.equal(out[4][0], samples[2][4]) and float(out[4][2, 5:].abs().sum()) == 0.0
