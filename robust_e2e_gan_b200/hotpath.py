@@ -79,6 +79,10 @@ class HotPath(torch.nn.Module):
         # the bandwidth/tensor-bound front-end and CTC kernels fill them.
         self.overlap = overlap
         self._side = None
+        if overlap and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            # the leaves (mask logits, encoder output) are created on the caller's stream while two of the three branches
+            # produce their gradients on side streams: intentional, the engine inserts the needed waits
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         c = self.cfg
         self.feat = FbankModel(_Opt(idim=c["F"], fbank_dim=c["M"], enhance_type="blstm", fbank_opti_type="frozen",
                                     train_dataset_len=1000, num_utt_cmvn=100))
