@@ -354,6 +354,8 @@ def main():
     import torch.distributed as dist
     rank, world = init_distributed()
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    from robust_e2e_gan_b200.parallel import bind_host_to_gpu
+    bound_cpus = bind_host_to_gpu(local)                 # before any pinned allocation (first touch decides the node)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     from robust_e2e_gan_b200 import _lib
@@ -369,9 +371,39 @@ def main():
     flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)   # 256 MiB > 126 MB L2
 
     def barrier():
+        # device first: the replayed graphs carry their own NCCL kernels, and collectives of one job must not be
+        # enqueued eagerly while a replay that contains others is still in flight (their order could differ per rank)
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if world > 1:
+        # Gradient exchange INSIDE the captured step (section 5 of DESIGN.md): a parameter whose gradient is large
+        # (ctc_lo.weight, 5.4 MB) is all-reduced from its post-accumulate-grad hook -- i.e. on the CTC branch's stream as
+        # soon as the dW GEMM has finished, overlapping the decoder loop that is still running on the main stream; the
+        # small ones (AttLoc, biases: 0.83 MB together) become ready with the last kernels of the loop and go out as ONE
+        # flat message at the end.  NCCL averages (ReduceOp.AVG): no separate scaling pass.
+        big = [p for _, p in hp.named_parameters() if p.requires_grad and p.numel() * p.element_size() >= (1 << 20)]
+        small_keys = ["d_" + k for k, p in hp.named_parameters()
+                      if p.requires_grad and p.numel() * p.element_size() < (1 << 20)]
+        inflight = []
+        gg = dist.new_group(list(range(world)))     # own communicator: never interleaves with the eager barrier / MAX
+
+        def reduce_when_ready(p):
+            inflight.append(dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=gg, async_op=True))
+
+        for p in big:
+            p.register_post_accumulate_grad_hook(reduce_when_ready)
+
+        def join_grad_reduce(out):
+            flat = torch.cat([out[k].reshape(-1) for k in small_keys if k in out])
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=gg)
+            out["_small_grads_mean"] = flat
+            while inflight:
+                inflight.pop().wait()
+
+        hp.after_backward = join_grad_reduce
 
     # ---- warm-up (eager public modules), launch count of one step
     n0 = _lib.launch_count()
@@ -387,14 +419,8 @@ def main():
     # ---- the step as a user runs it: StepRunner = CUDA-graph replay over static buffers, H2D on a copy stream
     runner = StepRunner(hp, hb, slots=3)
     mode = "cuda_graph" + ("" if args.no_overlap else " (front-end | CTC | decoder-loop branches on 3 streams)")
-    grad_keys = ["d_" + k for k, p in hp.named_parameters() if p.requires_grad]
     if world > 1:
-        def allreduce_grads(out):
-            flat = torch.cat([out[k].reshape(-1) for k in grad_keys if k in out])
-            dist.all_reduce(flat)
-            flat.div_(world)
-            out["_grads_flat_mean"] = flat
-        runner.post = allreduce_grads
+        mode += "; gradient all-reduce captured in the graph (ctc_lo.weight from its grad hook, the rest as one flat message)"
     if rank == 0:
         sys.stderr.write("[bench] timing mode: %s; launches/step %d\n" % (mode, launches_per_step))
 
@@ -457,7 +483,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": workload_config(cfg, world),
-            "mode": mode, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks}
+            "mode": mode, "host_affinity": ("%d CPUs local to the GPU" % bound_cpus) if bound_cpus else "inherited",
+            "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks}
 
     if rank == 0:
         if not args.no_kernels:
@@ -492,8 +519,18 @@ def main():
                                     "ms_per_step": dt * 1e3}
         emit(line)
     if world > 1:
+        torch.cuda.synchronize()
         dist.barrier()
+        # teardown: graphs first (they hold the captured collectives' communicator), then the process groups; a timer
+        # bounds it -- the result line is already out, a stuck communicator teardown must not hang the launcher
+        import threading
+        killer = threading.Timer(30.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
+        hp.after_backward = None
+        runner.close()
         dist.destroy_process_group()
+        killer.cancel()
 
 
 if __name__ == "__main__":

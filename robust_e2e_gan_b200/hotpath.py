@@ -79,6 +79,9 @@ class HotPath(torch.nn.Module):
         # the bandwidth/tensor-bound front-end and CTC kernels fill them.
         self.overlap = overlap
         self._side = None
+        # optional callable(out) invoked at the end of step() after the backward pass, on the caller's stream -- inside
+        # a CUDA-graph capture of the step when there is one.  A data-parallel job joins its gradient all-reduces here.
+        self.after_backward = None
         if overlap and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
             # the leaves (mask logits, encoder output) are created on the caller's stream while two of the three branches
             # produce their gradients on side streams: intentional, the engine inserts the needed waits
@@ -153,6 +156,8 @@ class HotPath(torch.nn.Module):
             for k, p in self.named_parameters():
                 if p.requires_grad and p.grad is not None:
                     out["d_" + k] = p.grad
+            if self.after_backward is not None:
+                self.after_backward(out)
         return out
 
 
@@ -289,6 +294,18 @@ class StepRunner(object):
             if self.post is not None:
                 self.post(slot["out"])
         return slot["out"]
+
+    def close(self):
+        """Drop the captured graphs and their static buffers.  A job whose step captured NCCL collectives must call
+        this before ``destroy_process_group()``: a communicator cannot be torn down while a live CUDA graph still
+        references its kernels."""
+        torch.cuda.synchronize(self.dev)
+        for slot in self.slots:
+            slot["graph"] = None
+            slot["out"] = None
+        self._pending = []
+        self._drop_refs()
+        torch.cuda.synchronize(self.dev)
 
     def result(self):
         s = self._pending.pop(0)
