@@ -378,12 +378,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    if world > 1:
-        # Gradient exchange INSIDE the captured step (section 5 of DESIGN.md): a parameter whose gradient is large
-        # (ctc_lo.weight, 5.4 MB) is all-reduced from its post-accumulate-grad hook -- i.e. on the CTC branch's stream as
-        # soon as the dW GEMM has finished, overlapping the decoder loop that is still running on the main stream; the
-        # small ones (AttLoc, biases: 0.83 MB together) become ready with the last kernels of the loop and go out as ONE
-        # flat message at the end.  NCCL averages (ReduceOp.AVG): no separate scaling pass.
+    # Gradient exchange of the data-parallel job.  Default: ONE flat NCCL all-reduce (6.2 MB) on the
+    # step's stream right after each replay.  RE2E_GRAD_REDUCE=graph captures the exchange INSIDE the step graph instead:
+    # ctc_lo.weight (5.4 MB) is reduced from its post-accumulate-grad hook on the CTC branch's stream while the decoder
+    # loop is still running, the small gradients (0.83 MB) as one flat message at the end, on their own communicator.
+    # Measured: N=2 1.93 -> 1.84 ms, but N=8 1.87 -> 1.98 ms (the NCCL CTAs then hold SMs the latency-bound decoder chain
+    # is waiting for, and eight ranks reach the hook with more skew) -- hence opt-in.
+    grad_keys = ["d_" + k for k, p in hp.named_parameters() if p.requires_grad]
+    reduce_in_graph = world > 1 and os.environ.get("RE2E_GRAD_REDUCE", "post") == "graph"
+    if reduce_in_graph:
         big = [p for _, p in hp.named_parameters() if p.requires_grad and p.numel() * p.element_size() >= (1 << 20)]
         small_keys = ["d_" + k for k, p in hp.named_parameters()
                       if p.requires_grad and p.numel() * p.element_size() < (1 << 20)]
@@ -419,8 +422,15 @@ def main():
     # ---- the step as a user runs it: StepRunner = CUDA-graph replay over static buffers, H2D on a copy stream
     runner = StepRunner(hp, hb, slots=3)
     mode = "cuda_graph" + ("" if args.no_overlap else " (front-end | CTC | decoder-loop branches on 3 streams)")
-    if world > 1:
+    if reduce_in_graph:
         mode += "; gradient all-reduce captured in the graph (ctc_lo.weight from its grad hook, the rest as one flat message)"
+    elif world > 1:
+        def allreduce_grads(out):
+            flat = torch.cat([out[k].reshape(-1) for k in grad_keys if k in out])
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            out["_grads_flat_mean"] = flat
+        runner.post = allreduce_grads
+        mode += "; one flat gradient all-reduce after each replay"
     if rank == 0:
         sys.stderr.write("[bench] timing mode: %s; launches/step %d\n" % (mode, launches_per_step))
 
