@@ -382,7 +382,7 @@ def main():
     # step's stream right after each replay.  RE2E_GRAD_REDUCE=graph captures the exchange INSIDE the step graph instead:
     # ctc_lo.weight (5.4 MB) is reduced from its post-accumulate-grad hook on the CTC branch's stream while the decoder
     # loop is still running, the small gradients (0.83 MB) as one flat message at the end, on their own communicator.
-    # Measured: N=2 1.93 -> 1.84 ms, but N=8 1.87 -> 1.98 ms (the NCCL CTAs then hold SMs the latency-bound decoder chain
+    # Measured: N=2 1.84 ms (default: 1.83), N=8 1.98 ms (default: 1.87) (the NCCL CTAs then hold SMs the latency-bound decoder chain
     # is waiting for, and eight ranks reach the hook with more skew) -- hence opt-in.
     grad_keys = ["d_" + k for k, p in hp.named_parameters() if p.requires_grad]
     reduce_in_graph = world > 1 and os.environ.get("RE2E_GRAD_REDUCE", "post") == "graph"
