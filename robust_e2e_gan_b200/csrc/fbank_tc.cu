@@ -54,6 +54,8 @@ __device__ __forceinline__ long long gtime() {
 }
 #define DBG_T(var) const long long var = gtime()
 #define DBG_ACC(acc, t0) acc += gtime() - (t0)
+#define DBG_C(var) const long long var = clock64()
+#define DBG_CACC(acc, t0) acc += clock64() - (t0)
 #define DBG_PUT(slot, val)                                        \
   do {                                                            \
     if (p.dbg) p.dbg[(size_t)blockIdx.x * 16 + (slot)] = (val);   \
@@ -61,6 +63,8 @@ __device__ __forceinline__ long long gtime() {
 #else
 #define DBG_T(var)
 #define DBG_ACC(acc, t0)
+#define DBG_C(var)
+#define DBG_CACC(acc, t0)
 #define DBG_PUT(slot, val)
 #endif
 
@@ -94,6 +98,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
   DBG_T(t_start);
 #ifdef RE2E_FB_DEBUG
   long long w_acc = 0;
+  long long c_wait = 0, c_conv = 0, c_fence = 0, c_arrive = 0, c_load = 0;   // converter phases, SM clocks
 #endif
   const int row_begin = min(p.N, (int)blockIdx.x * p.rows_per_cta);
   const int row_end = min(p.N, row_begin + p.rows_per_cta);
@@ -192,9 +197,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
           }
           {
             DBG_T(tw);
+            DBG_C(cw);
             if (q >= NS) mbar_wait(&empty[st], ph ^ 1u);
             DBG_ACC(w_acc, tw);
+            DBG_CACC(c_wait, cw);
           }
+          DBG_C(cc0);
           unsigned char *sa = stage0 + (size_t)st * 2 * kATile + off0;
           const int kcol = c_c * kKC + lane;
 #pragma unroll
@@ -210,12 +218,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
             *reinterpret_cast<float *>(sa + j * 2048) = x2;
             *reinterpret_cast<float *>(sa + kATile + j * 2048) = tf32_trunc_lo(x2);
           }
+          DBG_CACC(c_conv, cc0);   // includes the wait for the item's global loads (first use of its registers)
+          DBG_C(cc1);
           fence_proxy_async_smem();
+          DBG_CACC(c_fence, cc1);
+          DBG_C(cc2);
           __syncwarp();
           if (lane == 0) mbar_arrive(&full[st]);
+          DBG_CACC(c_arrive, cc2);
           if (++st == NS) { st = 0; ph ^= 1u; }
           if (++c_c == p.nchunks) { c_c = 0; c_row0 += kRows; }
+          DBG_C(cc3);
           if (l_item < nitems) load(mg[d], mk[MASKED ? d : 0]);
+          DBG_CACC(c_load, cc3);
         }
       }
     }
@@ -343,6 +358,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
   tc_fence_before();
   __syncthreads();
   if (tid == 0) DBG_PUT(8, gtime() - t_start);
+#ifdef RE2E_FB_DEBUG
+  if (tid == 0) { DBG_PUT(9, c_wait); DBG_PUT(10, c_conv); DBG_PUT(11, c_fence); DBG_PUT(12, c_arrive); DBG_PUT(13, c_load); }
+#endif
   if (warp == kCW + kEW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);

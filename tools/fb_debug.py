@@ -24,5 +24,9 @@ for name, fn, nbytes, reps in bench.kernel_specs(hp, db, cfg, dev):
     t0 = min(buf[i * 16] for i in range(148))
     print(" cta  start  setup | cvt_end cvt_wait | epi_end epi_wait | mma_end mma_wait | total   (ns)")
     for i in list(range(0, 148, 21)) + [147]:
-        r = [buf[i * 16 + k] for k in range(9)]
+        r = [buf[i * 16 + k] for k in range(14)]
         print(" %3d %6d %6d | %7d %8d | %7d %8d | %7d %8d | %6d" % (i, r[0] - t0, r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8]))
+    print(" converter warp 0, SM clocks summed over its items:  wait-empty   convert+STS   fence.proxy   syncwarp+arrive   issue next loads")
+    for i in list(range(0, 148, 21)) + [147]:
+        r = [buf[i * 16 + k] for k in range(9, 14)]
+        print(" %3d %48d %13d %13d %17d %18d" % (i, r[0], r[1], r[2], r[3], r[4]))
