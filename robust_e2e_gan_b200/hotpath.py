@@ -180,7 +180,9 @@ class StepRunner(object):
     device buffers.  ``submit(host_batch)`` copies a (pinned) host batch into the free slot on a copy
     stream -- overlapping the previous step's kernels -- and enqueues the replay; ``result()`` returns
     the oldest outstanding step's output dict (device tensors, valid until that slot is reused two
-    submits later).  ``__call__`` = submit + result.  Shapes are fixed at construction (the reference's
+    submits later).  ``__call__`` = submit + result.  Outputs of EAGER steps taken on the default stream must not be
+    kept alive across the construction: a live autograd graph pins the parameters' gradient accumulators to the stream
+    it ran on, and the capture then fails with cudaErrorStreamCaptureImplicit.  Shapes are fixed at construction (the reference's
     bucketing sampler yields fixed-shape batches, data/mix_data_loader.py:314-346); label sequences may
     vary up to ``umax`` labels each.
     """

@@ -101,3 +101,15 @@ def test_grad_buckets_allreduce_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_bind_host_to_gpu_is_a_no_op_without_topology(monkeypatch):
+    """No NVML / no GPU (this container), or RE2E_NUMA_BIND=0: the process keeps its affinity and 0 is returned."""
+    import os
+    from robust_e2e_gan_b200.parallel import bind_host_to_gpu
+    before = os.sched_getaffinity(0)
+    assert bind_host_to_gpu(0) >= 0
+    monkeypatch.setenv("RE2E_NUMA_BIND", "0")
+    assert bind_host_to_gpu(0) == 0
+    if not __import__("torch").cuda.is_available():
+        assert os.sched_getaffinity(0) == before
