@@ -81,6 +81,11 @@ __device__ __forceinline__ float4 ld_stream4(const float *p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ float2 ld_stream2(const float *p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ float ld_stream1(const float *p) {
   float r;
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));

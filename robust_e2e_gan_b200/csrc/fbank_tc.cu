@@ -10,13 +10,19 @@
 // reads, lo = x - hi), D += hi*hi + lo*hi + hi*lo.
 //
 // Forward structure (one persistent CTA per SM, each owning a contiguous range of frames):
-//   warps 0..15 : converters -- coalesced 128 B row-segment loads of mask / mag (rows are 1028 B: only 4 B aligned, so
-//                 no TMA), register prefetch two k-chunks ahead, sigmoid/mask/square, hi/lo split, store into the
-//                 128B-swizzled K-major A tile (128 frames x 32 bins) of a shared-memory ring
-//   warp 20     : one lane issues tcgen05.mma.kind::tf32 (A = x^2 tile, B = fc^T resident in shared memory as hi/lo,
-//                 N = mel padded to 16) into one of two TMEM accumulators
-//   warps 16..19: epilogue -- tcgen05.ld the finished accumulator (lane <-> frame), clamp/log/CMVN, store Y and G
+//   warps 0..15 : converters -- coalesced row-segment loads of mask / mag (rows are 1028 B: only 4 B aligned, so no
+//                 TMA; 8 B per lane on rows of equal parity when F = 257, else 4 B per lane), register prefetch,
+//                 sigmoid/mask/square, hi/lo split, store into the 128B-swizzled K-major A tiles (128 frames x 32 bins)
+//                 of a shared-memory ring
+//   warp 20     : one lane issues tcgen05.mma.kind::tf32, TWO per 8-bin k-step: A_hi x [B_hi | B_lo] (the filter bank
+//                 is resident per chunk as one tile of hi rows followed by lo rows, N = 2 round8(mel)) and A_lo x B_hi
+//                 into a second column range of one of two TMEM accumulators -- A_hi is fetched once, 12 KB of operands
+//                 per k-step instead of 16.5 KB for three separate products (the MMAs share the shared-memory port with
+//                 the converters' stores: profiles/r01_s5_frontend_phases.txt)
+//   warps 16..19: epilogue -- tcgen05.ld the three column ranges of the finished accumulator (lane <-> frame), sum,
+//                 clamp/log/CMVN, store Y and G
 // Algorithmic HBM bytes: 4*N*(2F + 2M) masked with G, 4*N*(F + M) plain.
+#include <cstdlib>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -38,6 +44,9 @@ struct FbTcParams {
   float *Y, *G, *enh;
   int mask_is_logit, N, T, F, M;
   int NB;            // UMMA N: mel channels padded to a multiple of 16
+  int MB;            // filter-bank rows kept per chunk in shared memory: mel channels padded to a multiple of 8 (one
+                     // swizzle group).  The MMA reads NB rows: rows [MB, NB) alias the next chunk / the A ring -- they
+                     // only reach accumulator columns >= M, which the epilogue never stores
   int nchunks;       // 32-bin chunks that go through the tensor core
   int ksteps_last;   // 8-bin MMA steps in the last chunk
   int ntail;         // trailing bins (<= 4, e.g. the Nyquist bin of F = 257) added by the epilogue as plain FMAs
@@ -75,16 +84,20 @@ __device__ __forceinline__ float tf32_trunc_lo(float x) {
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // FC: compile-time number of bins (257) so that the row-strided loads get immediate offsets; 0 = run-time p.F
-template <bool MASKED, int DEPTH, int FC>
+template <bool MASKED, int DEPTH, int FC, bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcParams p) {
   extern __shared__ __align__(1024) unsigned char smraw_[];
   unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smraw_) + 1023) & ~(uintptr_t)1023);
   const int NB = p.NB, NS = p.nstages, F = FC > 0 ? FC : p.F, M = p.M;
   const int Fmma = p.nchunks * kKC < F ? p.nchunks * kKC : F;   // bins [0, Fmma) on the tensor core, [Fmma, F) in the epilogue
-  const int fc_bytes = p.nchunks * NB * 128;
+  // filter bank, per 32-bin chunk: [hi rows 0..MB | lo rows 0..MB) -- ONE K-major tile of 2 MB rows, so that
+  // A_hi x [B_hi | B_lo] is a single MMA of N = 2 MB; its first NB rows double as the B_hi operand of A_lo x B_hi
+  const int fc_bytes = p.nchunks * p.MB * 128;          // bytes of the hi (or lo) rows of all chunks
+  const int fc_chunk = 2 * p.MB * 128;
   unsigned char *fc_hi = sm;
-  unsigned char *fc_lo = sm + fc_bytes;
+  unsigned char *fc_lo = sm + p.MB * 128;
   unsigned char *stage0 = sm + 2 * fc_bytes;
+  const int WD = 2 * p.MB + NB;                         // accumulator columns per buffer: [hi.hi | hi.lo | lo.hi]
   uint64_t *full = reinterpret_cast<uint64_t *>(stage0 + (size_t)NS * 2 * kATile);
   uint64_t *empty = full + kMaxStagesTc;
   uint64_t *tfull = empty + kMaxStagesTc;
@@ -103,7 +116,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
   const int row_begin = min(p.N, (int)blockIdx.x * p.rows_per_cta);
   const int row_end = min(p.N, row_begin + p.rows_per_cta);
   const int ntiles = (row_end - row_begin + kRows - 1) / kRows;
-  const uint32_t tmem_cols = 2 * NB <= 32 ? 32u : 2 * NB <= 64 ? 64u : 2 * NB <= 128 ? 128u : 2 * NB <= 256 ? 256u : 512u;
+  const uint32_t tmem_cols = 2 * WD <= 32 ? 32u : 2 * WD <= 64 ? 64u : 2 * WD <= 128 ? 128u : 2 * WD <= 256 ? 256u : 512u;
 
   // ---- one-time setup: barriers, TMEM, filter bank (hi/lo, K-major, 128B swizzle), CMVN
   if (tid == 0) {
@@ -129,7 +142,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
     const int k = i / M, m = i - k * M;
     const float v = __ldg(p.fc + i);
     const int ch = k >> 5, kk = k & 31;
-    const int off = ch * NB * 128 + (m >> 3) * 1024 + (m & 7) * 128 + ((((kk >> 2) ^ (m & 7))) << 4) + (kk & 3) * 4;
+    const int off = ch * fc_chunk + (m >> 3) * 1024 + (m & 7) * 128 + ((((kk >> 2) ^ (m & 7))) << 4) + (kk & 3) * 4;
     *reinterpret_cast<float *>(fc_hi + off) = v;
     *reinterpret_cast<float *>(fc_lo + off) = tf32_trunc_lo(v);
   }
@@ -142,8 +155,168 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
   DBG_T(t_setup);
   if (tid == 0) { DBG_PUT(0, t_start); DBG_PUT(1, t_setup - t_start); }
 
-  if (warp < kCW) {
-    // ================= converters =================
+  if (PAIR && FC == 257 && warp < kCW) {
+    // ================= converters, F = 257 (8 B per lane) =================
+    // thread <-> (frames warp + 16 j, bins 64 g + 2 lane, +1): items of 64 bins that fill TWO ring stages, ONE 256 B
+    // request per row and item instead of two of 128 B.  The SM accepts a limited number of load REQUESTS, not bytes
+    // (tools/membench, profiles/r01_s5_membench.txt: 12.1 vs 17.4 us for the matrix from DRAM at equal registers).
+    // A row starts at byte 1028 r, so only even rows are 8 B aligned.  The parity of warp + 16 j depends neither on j
+    // nor on the tile: warps with odd rows load the pairs (2 lane + 1, 2 lane + 2) -- 8 B aligned again -- and store
+    // the two bins to their own slots; lane 31's second bin belongs to the next item (for the last item it is the
+    // Nyquist bin, which the epilogue handles), and bin 0 of every item comes from one extra 8-lane load (lane j <->
+    // row j).  Needs four ring stages (see fbank_tc_fwd) -- with fewer the converters wait for the MMAs after every item.
+    constexpr int PD = DEPTH / 2 > 0 ? DEPTH / 2 : 1;     // items in flight: the same registers as DEPTH 4 B items
+    const int rr = warp & 7;
+    const int hsel = lane >> 4;                           // this lane writes the item's first / second 32-bin chunk
+    const uint32_t offp =
+        (uint32_t)((warp >> 3) * 1024 + rr * 128 + ((((lane & 15) >> 1) ^ rr) << 4) + (lane & 1) * 8);
+    const int par = (row_begin + warp) & 1;
+    float2 mg[PD][8], mk[MASKED ? PD : 1][8];
+    float eg[PD], ek[MASKED ? PD : 1];                    // element 0 of row j in lane j (first item of a tile, odd warps)
+    const int npi = ntiles * 4;
+    int l_row0 = row_begin, l_g = 0, l_item = 0;
+    auto load = [&](float2 (&g)[8], float2 (&k)[8], float &e0g, float &e0k) {
+      const int nj = max(0, (min(kRows, row_end - l_row0) - warp + 15) >> 4);
+      const size_t base = (size_t)(l_row0 + warp) * 257 + 64 * l_g + 2 * lane + par;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = j < nj;
+        g[j] = ok ? ld_stream2(p.mag + base + j * 16 * 257) : make_float2(0.0f, 0.0f);
+        if (MASKED) k[j] = ok ? ld_stream2(p.mask + base + j * 16 * 257) : make_float2(0.0f, 0.0f);
+      }
+      if (par) {
+        const bool ok = lane < nj;
+        const size_t b0 = (size_t)(l_row0 + warp + 16 * (lane & 7)) * 257 + 64 * l_g;
+        e0g = ok ? ld_stream1(p.mag + b0) : 0.0f;
+        if (MASKED) e0k = ok ? ld_stream1(p.mask + b0) : 0.0f;
+      }
+      ++l_item;
+      if (++l_g == 4) { l_g = 0; l_row0 += kRows; }
+    };
+#pragma unroll
+    for (int d = 0; d < PD; ++d) {
+      eg[d] = 0.0f;
+      ek[MASKED ? d : 0] = 0.0f;
+      if (d < npi) load(mg[d], mk[MASKED ? d : 0], eg[d], ek[MASKED ? d : 0]);
+    }
+
+    int c_row0 = row_begin, c_g = 0, nj_c = 0, nchunk = 0;
+    uint32_t vmask = 0xffu;
+    int st = 0;
+    uint32_t ph = 0;
+    for (int q0 = 0; q0 < npi; q0 += PD) {
+#pragma unroll
+      for (int d = 0; d < PD; ++d) {
+        const int q = q0 + d;
+        if (q < npi) {
+          if (c_g == 0) {   // new tile: rows of this warp inside it, and which of them are inside their utterance
+            nj_c = max(0, (min(kRows, row_end - c_row0) - warp + 15) >> 4);
+            if (MASKED && p.lens) {
+              int row = c_row0 + warp;
+              int b = row / p.T, t = row - b * p.T;
+              int len = __ldg(p.lens + min(b, p.N / p.T - 1));
+              vmask = 0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                vmask |= (t < len ? 1u : 0u) << j;
+                t += 16;
+                while (t >= p.T) { t -= p.T; ++b; len = __ldg(p.lens + min(b, p.N / p.T - 1)); }
+              }
+            }
+          }
+          const int s0 = st;
+          const uint32_t ph0 = ph;
+          if (++st == NS) { st = 0; ph ^= 1u; }
+          const int s1 = st;
+          const uint32_t ph1 = ph;
+          if (++st == NS) { st = 0; ph ^= 1u; }
+          {
+            DBG_T(tw);
+            DBG_C(cw);
+            if (nchunk >= NS) mbar_wait(&empty[s0], ph0 ^ 1u);
+            if (nchunk + 1 >= NS) mbar_wait(&empty[s1], ph1 ^ 1u);
+            DBG_ACC(w_acc, tw);
+            DBG_CACC(c_wait, cw);
+          }
+          nchunk += 2;
+          DBG_C(cc0);
+          unsigned char *sa = stage0 + (size_t)(hsel ? s1 : s0) * 2 * kATile + offp;
+          const int kcol = 64 * c_g + 2 * lane;
+          auto masked_x = [&](float g, float k, bool v) {
+            if (!MASKED) return g;
+            const float sg = p.mask_is_logit ? sigmoid_fast(k) : k;
+            return v ? sg * g : 0.0f;
+          };
+          if (!par) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j >= nj_c) break;   // warp-uniform: rows past the CTA's range (partial last tile) cost nothing
+              const float2 g2 = mg[d][j], k2 = mk[MASKED ? d : 0][j];
+              const bool v = (vmask >> j) & 1u;
+              const float xa = masked_x(g2.x, k2.x, v), xb = masked_x(g2.y, k2.y, v);
+              if (MASKED && p.enh) {
+                float *eo = p.enh + (size_t)(c_row0 + warp + 16 * j) * 257 + kcol;
+                eo[0] = xa;
+                eo[1] = xb;
+              }
+              const float2 x2 = make_float2(xa * xa, xb * xb);
+              *reinterpret_cast<float2 *>(sa + j * 2048) = x2;
+              *reinterpret_cast<float2 *>(sa + kATile + j * 2048) = make_float2(tf32_trunc_lo(x2.x), tf32_trunc_lo(x2.y));
+            }
+          } else {
+            // odd rows: the lane holds bins (2 lane + 1, 2 lane + 2) of the item; each goes to its own slot (lane 31's
+            // second one belongs to the NEXT item, which fetches it itself: lane j < 8 holds bin 0 of row j in eg / ek)
+            const int ka = 2 * lane + 1, kb = (2 * lane + 2) & 63;
+            unsigned char *base0 = stage0 + (size_t)s0 * 2 * kATile, *base1 = stage0 + (size_t)s1 * 2 * kATile;
+            const uint32_t rowoff = (uint32_t)((warp >> 3) * 1024 + rr * 128);
+            unsigned char *pa = (ka >> 5 ? base1 : base0) + rowoff + (((((ka & 31) >> 2) ^ rr)) << 4) + (ka & 3) * 4;
+            unsigned char *pb = (kb >> 5 ? base1 : base0) + rowoff + (((((kb & 31) >> 2) ^ rr)) << 4) + (kb & 3) * 4;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j >= nj_c) break;
+              const float2 g2 = mg[d][j], k2 = mk[MASKED ? d : 0][j];
+              const bool v = (vmask >> j) & 1u;
+              const float xa = masked_x(g2.x, k2.x, v), xb = masked_x(g2.y, k2.y, v);
+              if (MASKED && p.enh) {
+                float *eo = p.enh + (size_t)(c_row0 + warp + 16 * j) * 257 + kcol + 1;
+                eo[0] = xa;
+                if (lane < 31) eo[1] = xb;
+              }
+              const float xa2 = xa * xa, xb2 = xb * xb;
+              *reinterpret_cast<float *>(pa + j * 2048) = xa2;
+              *reinterpret_cast<float *>(pa + kATile + j * 2048) = tf32_trunc_lo(xa2);
+              if (lane < 31) {
+                *reinterpret_cast<float *>(pb + j * 2048) = xb2;
+                *reinterpret_cast<float *>(pb + kATile + j * 2048) = tf32_trunc_lo(xb2);
+              }
+            }
+            if (lane < nj_c) {   // bin 0 of the item for row `lane`
+              const bool v = (vmask >> lane) & 1u;
+              const float x0 = masked_x(eg[d], ek[MASKED ? d : 0], v);
+              if (MASKED && p.enh) p.enh[(size_t)(c_row0 + warp + 16 * lane) * 257 + 64 * c_g] = x0;
+              const float x02 = x0 * x0;
+              unsigned char *p0 = base0 + rowoff + ((0 ^ rr) << 4) + lane * 2048;
+              *reinterpret_cast<float *>(p0) = x02;
+              *reinterpret_cast<float *>(p0 + kATile) = tf32_trunc_lo(x02);
+            }
+          }
+          DBG_CACC(c_conv, cc0);
+          DBG_C(cc1);
+          fence_proxy_async_smem();
+          DBG_CACC(c_fence, cc1);
+          DBG_C(cc2);
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(&full[s0]); mbar_arrive(&full[s1]); }
+          DBG_CACC(c_arrive, cc2);
+          if (++c_g == 4) { c_g = 0; c_row0 += kRows; }
+          DBG_C(cc3);
+          if (l_item < npi) load(mg[d], mk[MASKED ? d : 0], eg[d], ek[MASKED ? d : 0]);
+          DBG_CACC(c_load, cc3);
+        }
+      }
+    }
+  } else if (warp < kCW) {
+    // ================= converters (any F) =================
     // thread <-> (frames warp + 16 j, bin 32 c + lane).  Frames past the CTA's range are skipped altogether (their
     // A rows stay uninitialised: a row of A only feeds the same row of D, which is never stored).
     const int rr = warp & 7;
@@ -218,7 +391,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
             *reinterpret_cast<float *>(sa + j * 2048) = x2;
             *reinterpret_cast<float *>(sa + kATile + j * 2048) = tf32_trunc_lo(x2);
           }
-          DBG_CACC(c_conv, cc0);   // includes the wait for the item's global loads (first use of its registers)
+          DBG_CACC(c_conv, cc0);
           DBG_C(cc1);
           fence_proxy_async_smem();
           DBG_CACC(c_fence, cc1);
@@ -237,14 +410,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
   } else if (warp == kCW + kEW) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(kRows, NB, false, false);
+      const uint32_t idesc_cat = umma_idesc_tf32(kRows, 2 * p.MB, false, false);   // A_hi x [B_hi | B_lo]
+      const uint32_t idesc_hi = umma_idesc_tf32(kRows, NB, false, false);          // A_lo x B_hi (rows >= MB: unused columns)
       int st = 0;
       uint32_t ph = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int buf = t & 1;
         if (t >= 2) mbar_wait(&tempty[buf], (uint32_t)(((t >> 1) - 1) & 1));
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NB);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * WD);
         for (int c = 0; c < p.nchunks; ++c) {
           {
             DBG_T(tw);
@@ -254,15 +428,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
           tc_fence_after();
           const uint32_t a_hi = smem_u32(stage0 + (size_t)st * 2 * kATile);
           const uint32_t a_lo = a_hi + kATile;
-          const uint32_t b_hi = smem_u32(fc_hi + (size_t)c * NB * 128);
-          const uint32_t b_lo = smem_u32(fc_lo + (size_t)c * NB * 128);
+          const uint32_t b_cat = smem_u32(fc_hi + (size_t)c * fc_chunk);
           const int ks = c == p.nchunks - 1 ? p.ksteps_last : 4;
           for (int k = 0; k < ks; ++k) {
             const uint64_t dah = umma_desc(a_hi + k * 32, 16, 1024, 2), dal = umma_desc(a_lo + k * 32, 16, 1024, 2);
-            const uint64_t dbh = umma_desc(b_hi + k * 32, 16, 1024, 2), dbl = umma_desc(b_lo + k * 32, 16, 1024, 2);
-            umma_tf32(d_tmem, dah, dbh, idesc, (c | k) ? 1u : 0u);
-            umma_tf32(d_tmem, dal, dbh, idesc, 1u);
-            umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+            const uint64_t db = umma_desc(b_cat + k * 32, 16, 1024, 2);
+            umma_tf32(d_tmem, dah, db, idesc_cat, (c | k) ? 1u : 0u);
+            umma_tf32(d_tmem + (uint32_t)(2 * p.MB), dal, db, idesc_hi, (c | k) ? 1u : 0u);
           }
           umma_commit(&empty[st]);   // the stage is free once these MMAs have read it
           if (++st == NS) { st = 0; ph ^= 1u; }
@@ -305,9 +477,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_fwd_kernel(const FbTcP
       }
       tc_fence_after();
       for (int c16 = 0; c16 < NB; c16 += 16) {
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)(buf * NB + c16), v);
         if (c16 >= M) continue;
+        float v[16];
+        {
+          float v1[16], v2[16];
+          const uint32_t tb = tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)(buf * WD + c16);
+          tmem_ld16(tb, v);                                  // x2_hi . fc_hi
+          tmem_ld16(tb + (uint32_t)p.MB, v1);                // x2_hi . fc_lo
+          tmem_ld16(tb + (uint32_t)(2 * p.MB), v2);          // x2_lo . fc_hi
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += v1[i] + v2[i];
+        }
 #pragma unroll
         for (int kt = 0; kt < 4; ++kt)
           if (kt < p.ntail) {
@@ -624,8 +804,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) fbank_tc_bwd_kernel(const FbTc
   }
 }
 
-inline size_t fwd_smem_bytes(int nchunks, int NB, int ns) {
-  return 1024 + (size_t)2 * nchunks * NB * 128 + (size_t)ns * 2 * kATile + 512 + (size_t)6 * NB * 4;
+inline size_t fwd_smem_bytes(int nchunks, int MB, int NB, int ns) {
+  return 1024 + (size_t)2 * nchunks * MB * 128 + (size_t)ns * 2 * kATile + 512 + (size_t)6 * NB * 4;
 }
 
 }  // namespace
@@ -657,12 +837,13 @@ int fbank_tc_fwd(const float *mask, int mask_is_logit, const float *mag, const f
   }
 #endif
   p.NB = (M + 15) / 16 * 16;
+  p.MB = (M + 7) / 8 * 8;
   p.ntail = (F >= kKC && (F % kKC) >= 1 && (F % kKC) <= 4) ? F % kKC : 0;
   p.nchunks = (F - p.ntail + kKC - 1) / kKC;
   p.ksteps_last = (F - p.ntail - (p.nchunks - 1) * kKC + 7) / 8;
-  if (p.NB > 256) return RE2E_E_UNSUPPORTED;
+  if (2 * (2 * p.MB + p.NB) > 512) return RE2E_E_UNSUPPORTED;   // two accumulator buffers of [hi.hi | hi.lo | lo.hi] columns
   int ns = kMaxStagesTc;
-  while (ns >= 1 && fwd_smem_bytes(p.nchunks, p.NB, ns) > 226 * 1024) --ns;
+  while (ns >= 1 && fwd_smem_bytes(p.nchunks, p.MB, p.NB, ns) > 226 * 1024) --ns;
   if (ns < 1) return RE2E_E_UNSUPPORTED;
   p.nstages = ns;
   if (((M & 3) == 0) && !(aligned16(Y) && (!G || aligned16(G)))) return RE2E_E_UNSUPPORTED;
@@ -670,20 +851,25 @@ int fbank_tc_fwd(const float *mask, int mask_is_logit, const float *mag, const f
   int grid = (p.N + 63) / 64;
   if (grid > sms) grid = sms;
   p.rows_per_cta = (p.N + grid - 1) / grid;
-  const size_t smem = fwd_smem_bytes(p.nchunks, p.NB, ns);
+  const size_t smem = fwd_smem_bytes(p.nchunks, p.MB, p.NB, ns);
   int rc;
-#define RE2E_FB_LAUNCH(MASKED, DEPTH, FC)                                                                          \
-  do {                                                                                                            \
-    if ((rc = ensure_smem(reinterpret_cast<const void *>(fbank_tc_fwd_kernel<MASKED, DEPTH, FC>), smem)) != RE2E_OK) \
-      return rc;                                                                                                  \
-    fbank_tc_fwd_kernel<MASKED, DEPTH, FC><<<grid, kTcThreads, smem, st>>>(p);                                     \
+#define RE2E_FB_LAUNCH(MASKED, DEPTH, FC, PAIR)                                                                          \
+  do {                                                                                                                  \
+    if ((rc = ensure_smem(reinterpret_cast<const void *>(fbank_tc_fwd_kernel<MASKED, DEPTH, FC, PAIR>), smem)) != RE2E_OK) \
+      return rc;                                                                                                        \
+    fbank_tc_fwd_kernel<MASKED, DEPTH, FC, PAIR><<<grid, kTcThreads, smem, st>>>(p);                                     \
   } while (0)
+  static const bool pair_enabled = !(getenv("RE2E_FB_PAIR") && atoi(getenv("RE2E_FB_PAIR")) == 0);   // A/B switch: RE2E_FB_PAIR=0
+  const bool pair = pair_enabled && F == 257 && p.nchunks == 8 && ns >= 4 && (reinterpret_cast<uintptr_t>(mag) & 7u) == 0 &&
+                    (!mask || (reinterpret_cast<uintptr_t>(mask) & 7u) == 0);
   if (mask) {
-    if (F == 257) RE2E_FB_LAUNCH(true, 2, 257);
-    else RE2E_FB_LAUNCH(true, 2, 0);
+    if (pair) RE2E_FB_LAUNCH(true, 2, 257, true);
+    else if (F == 257) RE2E_FB_LAUNCH(true, 2, 257, false);
+    else RE2E_FB_LAUNCH(true, 2, 0, false);
   } else {
-    if (F == 257) RE2E_FB_LAUNCH(false, 4, 257);
-    else RE2E_FB_LAUNCH(false, 4, 0);
+    if (pair) RE2E_FB_LAUNCH(false, 4, 257, true);
+    else if (F == 257) RE2E_FB_LAUNCH(false, 4, 257, false);
+    else RE2E_FB_LAUNCH(false, 4, 0, false);
   }
 #undef RE2E_FB_LAUNCH
   count_launch();
