@@ -62,7 +62,7 @@ def test_golden_masked_fused_and_standalone_tail():
     assert_close(lo2.grad, g["dlogits"], what="d logits (two-stage)")
 
 
-@pytest.mark.parametrize("B,T_,M,seed", [(8, 400, 40, 1234), (3, 101, 80, 5), (2, 7, 23, 6), (1, 1, 40, 8)])
+@pytest.mark.parametrize("B,T_,M,seed", [(8, 400, 40, 1234), (3, 101, 80, 5), (2, 7, 23, 6), (1, 1, 40, 8), (2, 33, 96, 9)])
 def test_oracle_parity_shapes(B, T_, M, seed):
     d = synth.frontend_batch(B=B, T=T_, seed=seed, zeros=min(16, B * T_))
     g = torch.Generator().manual_seed(seed)
