@@ -18,9 +18,9 @@ from .e2e_common import ModelBase
 def kaldi_mel_banks(num_bins=80, nfft=512, samplerate=16000, low_freq=20.0):
     """Kaldi-style triangular bank in the mel domain (mel = 1127 ln(1 + f/700)), (num_bins, nfft/2+1).
 
-    For num_bins == 80 this regenerates the reference's hard-coded table
-    (model/feat_model.py:15-33, weights printed with 6 significant digits) to within 1.4e-5;
-    the reference has no table for any other size (its constructor crashes).
+    Used for every size EXCEPT 80: the reference has a table only for 80 filters (its constructor crashes for any
+    other size), and for 80 ``reference_fbank80`` returns that table's exact constants (this
+    formula lands within 1.4e-5 of them, which is not the same model).
     """
     f32 = np.float32
 
@@ -39,6 +39,19 @@ def kaldi_mel_banks(num_bins=80, nfft=512, samplerate=16000, low_freq=20.0):
             if m > left and m < right:
                 w = (m - left) / (center - left) if m <= center else (right - m) / (right - center)
                 out[b, i] = float('%g' % w)
+    return out
+
+
+def reference_fbank80():
+    """The reference's hard-coded 80-filter bank (model/feat_model.py:15-33) as a dense (80, 257) float64
+    matrix, bit-identical to what its ``get_filterbanks(80)`` builds (constants in fbank80_table.py)."""
+    from . import fbank80_table as tb
+    out = np.zeros((tb.NUM_FILTERS, tb.NUM_BINS), dtype=np.float64)
+    pos = 0
+    for j, (lo, n) in enumerate(zip(tb.FIRST_BIN, tb.RUN)):
+        out[j, lo:lo + n] = tb.WEIGHTS[pos:pos + n]
+        pos += n
+    assert pos == len(tb.WEIGHTS)
     return out
 
 
@@ -191,7 +204,8 @@ class FbankModel(FFTModel):
         self.opt = args
         idim = args.idim
         odim = args.fbank_dim
-        filterbanks = kaldi_mel_banks(num_bins=odim)
+        # 80 filters: the reference's own constants; any other size: Kaldi-style bank by formula (reference: crash)
+        filterbanks = reference_fbank80() if odim == 80 else kaldi_mel_banks(num_bins=odim)
         if args.enhance_type == 'unet_128' or args.enhance_type == 'unet_256':
             idim = 256
             filterbanks = filterbanks[:, :256]

@@ -97,4 +97,4 @@ def test_decoder_training_loop_matches_oracle():
     for k, p in dec.named_parameters():
         if k == "att.gvec.bias":          # analytically zero gradient (softmax shift invariance)
             continue
-        helpers.assert_close(p.grad, sd_o[k].grad, what="d " + k, tol=2e-4)
+        helpers.assert_close(p.grad, sd_o[k].grad, what="d " + k)

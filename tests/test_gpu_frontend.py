@@ -43,6 +43,16 @@ def test_golden_single_input_and_dfc():
     assert_close(m(T(g["mag"]), T(g["cmvn"])), g["y_cmvn"], what="Y from CPU input")
 
 
+def test_fresh_default_model_is_the_reference_model():
+    """No ``fc`` injection: FbankModel(fbank_dim=80) as constructed must already BE the reference's model
+    (bit-identical filter table, model/feat_model.py:15-33) and reproduce the reference's outputs."""
+    g = golden("fbank")
+    m = FbankModel(Args()).to(DEV)
+    assert np.array_equal(m.fc.detach().cpu().numpy(), g["fc"])
+    assert_close(m(T(g["mag"]).to(DEV), T(g["cmvn"])), g["y_cmvn"], what="Y (fresh default model)")
+    assert_close(m(T(g["mag"]).to(DEV)), g["y_plain"], what="Y no cmvn (fresh default model)")
+
+
 def test_golden_masked_fused_and_standalone_tail():
     g = golden("fbank")
     fc = T(g["fc"]).to(DEV)

@@ -35,6 +35,23 @@ def test_mel_banks_shapes_and_support():
     assert synth.mel_fc(257, 40).shape == (257, 40)
 
 
+def test_default_80_filter_bank_is_bit_identical_to_the_reference_table():
+    """A freshly constructed FbankModel(fbank_dim=80) carries the reference's constants (model/feat_model.py:15-33),
+    not a regenerated bank: bit-equal to the ``fc`` of the unmodified reference module held in the golden file."""
+    import types
+    from conftest import golden
+    from robust_e2e_gan_b200.feat_model import FbankModel, reference_fbank80
+    args = types.SimpleNamespace(idim=257, fbank_dim=80, enhance_type="blstm", fbank_opti_type="frozen",
+                                 train_dataset_len=10, num_utt_cmvn=5)
+    m = FbankModel(args)
+    ref_fc = golden("fbank")["fc"]
+    assert m.fc.dtype == torch.float32 and tuple(m.fc.shape) == (257, 80) and not m.fc.requires_grad
+    assert np.array_equal(m.fc.detach().numpy(), ref_fc)
+    assert np.array_equal(reference_fbank80().T.astype(np.float32), ref_fc)
+    args.enhance_type = "unet_256"                                  # model/feat_model.py:102-104: bank cut to 256 bins
+    assert np.array_equal(FbankModel(args).fc.detach().numpy(), ref_fc[:256])
+
+
 def test_shard_range_partitions_exactly():
     for n in (0, 1, 7, 32, 1000):
         for world in (1, 2, 3, 8):
