@@ -3,24 +3,45 @@
 
 #include "common.cuh"
 
+#include <atomic>
 #include <map>
 #include <mutex>
+#include <utility>
 
 namespace re2e {
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
+// the attribute is per (device, function): a process driving several GPUs must set it on each of them
 int ensure_smem(const void *func, size_t bytes) {
   static std::mutex mu;
-  static std::map<const void *, size_t> seen;
+  static std::map<std::pair<int, const void *>, size_t> seen;
   if (bytes > 227 * 1024) return RE2E_E_UNSUPPORTED;
   if (bytes <= 48 * 1024) return RE2E_OK;
-  std::lock_guard<std::mutex> lk(mu);
-  auto it = seen.find(func);
-  if (it != seen.end() && it->second >= bytes) return RE2E_OK;
-  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
-  seen[func] = bytes;
+  std::lock_guard<std::mutex> lk(mu);
+  auto key = std::make_pair(dev, func);
+  auto it = seen.find(key);
+  if (it != seen.end() && it->second >= bytes) return RE2E_OK;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return (int)e;
+  seen[key] = bytes;
   return RE2E_OK;
+}
+
+int num_sms() {
+  static std::mutex mu;
+  static std::map<int, int> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(dev);
+  if (it != cache.end()) return it->second;
+  int sms = 148;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  cache[dev] = sms;
+  return sms;
 }
 }  // namespace re2e
 
@@ -97,4 +118,4 @@ extern "C" const char *re2e_error_string(int code) {
   return "re2e: unknown error";
 }
 
-extern "C" unsigned long long re2e_launch_count(void) { return re2e::g_launches; }
+extern "C" unsigned long long re2e_launch_count(void) { return re2e::g_launches.load(std::memory_order_relaxed); }

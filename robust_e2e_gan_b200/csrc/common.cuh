@@ -3,13 +3,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "re2e_b200.h"
 
 namespace re2e {
 
 // ---- host side ------------------------------------------------------------------------------
-extern unsigned long long g_launches;  // defined in api.cu
-inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
+extern std::atomic<unsigned long long> g_launches;  // defined in api.cu
+inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 #define RE2E_CHECK_ARG(cond) \
   do {                       \
@@ -26,20 +28,14 @@ inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
 // launches (and CUDA-graph capture) issue no attribute calls.  Defined in api.cu.
 int ensure_smem(const void *func, size_t bytes);
 
+// cudaGetLastError (not Peek): a failed launch is reported once, by the call that made it, and does not poison
+// the status of later calls
 inline int launch_status() {
-  cudaError_t e = cudaPeekAtLastError();
+  cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? RE2E_OK : (int)e;
 }
 
-inline int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-  }
-  return sms;
-}
+int num_sms();   // SM count of the CURRENT device (cached per device); defined in api.cu
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

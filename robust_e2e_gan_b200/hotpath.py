@@ -180,7 +180,8 @@ class StepRunner(object):
     device buffers.  ``submit(host_batch)`` copies a (pinned) host batch into the free slot on a copy
     stream -- overlapping the previous step's kernels -- and enqueues the replay; ``result()`` returns
     the oldest outstanding step's output dict (device tensors, valid until that slot is reused two
-    submits later).  ``__call__`` = submit + result.  Outputs of EAGER steps taken on the default stream must not be
+    submits later).  The host batch's own (pinned) tensors are read by asynchronous copies: keep them unchanged until
+    the slot's ``copied`` event has completed (``result()`` of that step implies it).  ``__call__`` = submit + result.  Outputs of EAGER steps taken on the default stream must not be
     kept alive across the construction: a live autograd graph pins the parameters' gradient accumulators to the stream
     it ran on, and the capture then fails with cudaErrorStreamCaptureImplicit.  Shapes are fixed at construction (the reference's
     bucketing sampler yields fixed-shape batches, data/mix_data_loader.py:314-346); label sequences may
@@ -256,6 +257,9 @@ class StepRunner(object):
             raise ValueError("StepRunner: batch has %d utterances / %d labels max, captured for %d / %d"
                              % (len(lens), int(lens.max()) if len(lens) else 0, B, self.umax))
         pin = self._lab_pin[s]
+        # the previous asynchronous H2D copy out of this slot's pinned label block must have finished before the host
+        # rewrites the block (a loop that never reads a result back can run several submits ahead of the device)
+        slot["copied"].synchronize()
         pin.zero_()
         pin[:len(flat)] = torch.from_numpy(flat)
         pin[B * self.umax:B * self.umax + B] = torch.from_numpy(offs)

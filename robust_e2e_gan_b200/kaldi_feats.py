@@ -4,7 +4,8 @@ Host-side Python/numpy, like the reference's own loader (it is I/O, not arithmet
 
 * ``read_mat`` / ``read_mat_scp`` / ``read_mat_ark`` / ``write_mat``: binary Kaldi matrices ('FM ', 'DM ') and the
   one-byte compressed format 'CM ' (data/kaldi_io.py:359-458), ``path:offset`` scp entries (data/kaldi_io.py:36-66).
-  Matrices are returned as float32 C-contiguous arrays; an .ark that is read repeatedly is memory-mapped once.
+  Matrices are returned as writable C-contiguous copies (float32; float64 for 'DM ', as in the reference); an .ark
+  that is read repeatedly is memory-mapped once (at most 64 mappings are kept, least recently used evicted).
 * ``log_spectrum``: the per-utterance transform of MixSequentialDataset.__getitem__
   (data/mix_data_loader.py:198-237): clamp ``<= 1e-7`` -> ``10 log10`` -> input CMVN ``(x + c0) * c1``
   (data/audioparse.py:445-458 with delta_order = 0 and no splicing).
@@ -20,7 +21,8 @@ import struct
 import numpy as np
 import torch
 
-_MAPS = {}
+_MAPS = {}          # path -> (mmap, (size, mtime)); insertion ordered, least recently used first
+_MAX_MAPS = 64      # open archive mappings kept (address space / file handles stay bounded over a large corpus)
 
 
 def _open_at(spec):
@@ -33,12 +35,14 @@ def _open_at(spec):
         offset = int(off)
     key = os.path.abspath(spec)
     st = os.stat(key)
-    ent = _MAPS.get(key)
+    ent = _MAPS.pop(key, None)
     if ent is None or ent[1] != (st.st_size, st.st_mtime_ns):
         with open(key, 'rb') as f:
             buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) if st.st_size else b''
         ent = (buf, (st.st_size, st.st_mtime_ns))
-        _MAPS[key] = ent
+    _MAPS[key] = ent                      # (re)insert as most recently used
+    while len(_MAPS) > _MAX_MAPS:         # evict the least recently used mapping; matrices handed out are copies,
+        _MAPS.pop(next(iter(_MAPS)))      # so dropping the mmap object is safe (it closes once unreferenced)
     return ent[0], offset
 
 
@@ -62,7 +66,9 @@ def _decode_compressed(buf, pos):
 
 
 def _parse_mat(buf, pos):
-    """Binary matrix starting at the '\\0B' marker.  Returns (float32 or float64 array, position after it)."""
+    """Binary matrix starting at the '\\0B' marker.  Returns (C-contiguous WRITABLE array -- a copy, never a view of
+    the read-only mapping; float32 for 'FM ' / 'CM ', float64 for 'DM ' exactly as the reference's reader returns
+    them, data/kaldi_io.py:388-397 -- and the position after the matrix)."""
     if bytes(buf[pos:pos + 2]) != b'\0B':
         raise ValueError("kaldi_feats: only binary Kaldi matrices are supported (missing \\0B marker)")
     header = bytes(buf[pos + 2:pos + 5]).decode()
@@ -82,7 +88,7 @@ def _parse_mat(buf, pos):
     if s1 != 4 or s2 != 4 or rows < 0 or cols < 0:
         raise ValueError("kaldi_feats: corrupt matrix dimensions")
     n = rows * cols
-    mat = np.frombuffer(buf, dtype=dt, count=n, offset=pos).reshape(rows, cols)
+    mat = np.array(np.frombuffer(buf, dtype=dt, count=n, offset=pos).reshape(rows, cols), order='C')
     return mat, pos + n * dt.itemsize
 
 

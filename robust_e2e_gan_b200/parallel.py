@@ -71,6 +71,16 @@ class GradBuckets(object):
         buckets.zero()            # instead of optimizer.zero_grad()
         loss.backward()           # hooks launch all-reduces bucket by bucket
         buckets.finish()          # wait + average; .grad now holds the mean over ranks
+
+    Ordering rules (the same ones DDP keeps):
+      * buckets are reduced in FIXED index order on every rank -- a bucket whose gradients are complete is held back
+        until every lower-index bucket has been launched, and ``finish()`` launches whatever is left (parameters the
+        loss did not touch) in index order, so two ranks with different sets of unused parameters still issue the same
+        sequence of collectives;
+      * on CUDA the collectives run on ONE dedicated communication stream.  Each parameter's hook records an event on
+        the stream its gradient was accumulated on (the three-stream hot path accumulates gradients of one bucket on
+        different streams); the communication stream waits for every event of a bucket before reducing it, and
+        ``finish()`` makes the caller's stream wait for the communication stream.
     """
 
     def __init__(self, params, bucket_mb=25.0, group=None):
@@ -91,8 +101,9 @@ class GradBuckets(object):
             cur_bytes += nbytes
         if cur:
             self.buckets.append(cur)
-        self.flat, self._bucket_of, self._pending, self._handles = [], {}, [], []
+        self.flat, self._bucket_of, self._pending = [], {}, []
         self._hooks = []
+        self._comm = {}                   # device -> communication stream
         for bi, bucket in enumerate(self.buckets):
             total = sum(p.numel() for p in bucket)
             flat = torch.zeros(total, dtype=bucket[0].dtype, device=bucket[0].device)
@@ -104,28 +115,54 @@ class GradBuckets(object):
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(p)))
             self.flat.append(flat)
             self._pending.append(len(bucket))
-        self._launched = [False] * len(self.buckets)
+        self._reset_step()
+
+    def _reset_step(self):
+        self._next = 0                                        # next bucket index to launch (fixed order)
+        self._events = [[] for _ in self.buckets]             # CUDA events of the accumulations, per bucket
+        self._handles = []
+        for bi, bucket in enumerate(self.buckets):
+            self._pending[bi] = len(bucket)
+
+    def _comm_stream(self, dev):
+        if dev not in self._comm:
+            self._comm[dev] = torch.cuda.Stream(dev)
+        return self._comm[dev]
 
     def _make_hook(self, p):
         def hook(param):
             bi = self._bucket_of[p]
+            if param.is_cuda:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(param.device))     # the stream this gradient was accumulated on
+                self._events[bi].append(ev)
             self._pending[bi] -= 1
-            if self._pending[bi] == 0:
-                self._launch(bi)
+            self._launch_ready()
         return hook
 
+    def _launch_ready(self):
+        while self._next < len(self.buckets) and self._pending[self._next] <= 0:
+            self._launch(self._next)
+            self._next += 1
+
     def _launch(self, bi):
+        flat = self.flat[bi]
         if self.world > 1:
-            self._handles.append(dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group,
-                                                 async_op=True))
-        self._launched[bi] = True
+            if flat.is_cuda:
+                cs = self._comm_stream(flat.device)
+                for ev in self._events[bi]:
+                    cs.wait_event(ev)
+                # a bucket launched from finish() (unused parameters): order it after the caller's stream as well
+                cs.wait_stream(torch.cuda.current_stream(flat.device))
+                with torch.cuda.stream(cs):
+                    self._handles.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            else:
+                self._handles.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def zero(self):
-        for bi, flat in enumerate(self.flat):
+        for flat in self.flat:
             flat.zero_()
-            self._pending[bi] = len(self.buckets[bi])
-        self._launched = [False] * len(self.buckets)
-        self._handles = []
+        self._reset_step()
         # re-attach views (an optimizer.zero_grad(set_to_none=True) would have dropped them)
         for bi, bucket in enumerate(self.buckets):
             o = 0
@@ -135,16 +172,23 @@ class GradBuckets(object):
                 o += p.numel()
 
     def finish(self):
-        """Reduce any bucket whose hooks did not all fire (unused parameters), wait, average."""
-        for bi in range(len(self.buckets)):
-            if not self._launched[bi]:
-                self._launch(bi)
+        """Reduce (in index order) every bucket not launched yet -- buckets held back by the fixed order, or whose
+        hooks did not all fire (unused parameters) -- then wait and average."""
+        while self._next < len(self.buckets):
+            self._launch(self._next)
+            self._next += 1
         for h in self._handles:
             h.wait()
         self._handles = []
         if self.world > 1:
             for flat in self.flat:
-                flat.div_(self.world)
+                if flat.is_cuda:
+                    cs = self._comm_stream(flat.device)
+                    with torch.cuda.stream(cs):
+                        flat.div_(self.world)
+                    torch.cuda.current_stream(flat.device).wait_stream(cs)
+                else:
+                    flat.div_(self.world)
 
     def nbytes(self):
         return sum(f.numel() * f.element_size() for f in self.flat)

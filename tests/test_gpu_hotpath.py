@@ -63,6 +63,33 @@ def test_step_runner_matches_eager_and_oracle():
     assert torch.equal(again["att_c"].cpu(), outs[1]["att_c"])
 
 
+def test_bench_shape_step_through_graph_replay_matches_oracle():
+    """The EXACT thing bench.py times: DEFAULT_CFG (B=32, T=800, Th=200, U=40, 41 decoder steps, V=4233), three
+    branch streams, CUDA-graph replay through StepRunner from a pinned host batch -- every output and gradient
+    against the fp32 oracle with the fp64 oracle as tie-breaker, tolerance 1e-4 (max-norm and element-wise)."""
+    from robust_e2e_gan_b200.hotpath import DEFAULT_CFG, StepRunner
+    cfg = dict(DEFAULT_CFG)
+    hp = HotPath(cfg, seed=4000).to(DEV)
+    hb = make_batch(cfg, seed=4001).pin()
+    runner = StepRunner(hp, make_batch(cfg, seed=4000).pin(), slots=2)
+    n0 = _lib.launch_count()
+    out = runner(hb)                                  # a batch the graphs were NOT captured on
+    got = {k: (torch.stack(v) if isinstance(v, (list, tuple)) else v).detach().float().cpu().clone()
+           for k, v in out.items()}
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == n0                  # replay only: no eager launches of ours
+    sd = hp.state_dict_cpu()
+    ref = oracle_step(cfg, hb, sd)
+    ref64 = oracle_step(cfg, hb, sd, dtype=torch.float64)
+    worst = 0.0
+    for k in ref:
+        if k == "d_att.gvec.bias":                    # analytically zero (softmax is shift invariant)
+            continue
+        worst = max(worst, assert_close(got[k], ref[k], truth=ref64[k], what="bench-shape " + k))
+    print("bench-shape step: worst error metric vs oracle %.2e" % worst)
+    runner.close()
+
+
 def test_step_runner_three_slots_two_batches_ahead():
     """The bench's end-to-end loop: three input slots, two host batches in flight ahead of the compute.  Results come
     back in submission order and match the single-step results of the same batches."""
