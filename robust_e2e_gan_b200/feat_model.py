@@ -222,6 +222,8 @@ class FbankModel(FFTModel):
         (B,T,fbank_dim).  fbank_cmvn: (2,fbank_dim) tensor/ndarray, row 0 = -mean, row 1 = 1/std."""
         if fbank_cmvn is not None and not torch.is_tensor(fbank_cmvn):
             fbank_cmvn = torch.from_numpy(np.asarray(fbank_cmvn, dtype=np.float32))
+        if torch.is_tensor(xs) and xs.device != self.fc.device:
+            xs = xs.to(self.fc.device)        # to_cuda (model/feat_model.py:124), differentiable: a CPU leaf gets a CPU grad
         return _FbankFunction.apply(None, xs, self.fc, fbank_cmvn, None, 0, False)[0]
 
     def forward_masked(self, linear_out, mix_inputs, input_sizes, fbank_cmvn=None, return_enhanced=False):
