@@ -17,7 +17,7 @@ import shutil
 SRC_ROOT = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
 DST_ROOT = os.path.join(HERE, "_ref")
-PACKAGES = ("model",)          # everything the hot path, E2E / Decoder and ModelBase.load_model import
+PACKAGES = ("model", "data")   # model/: the hot path, E2E / Decoder, ModelBase.load_model; data/: imported by model/fsrnn.py
 
 
 def _sha(path):

@@ -1,0 +1,76 @@
+// Device helpers shared by the AttLoc kernels (attloc.cu: one step per launch; attloc_loop.cu: the whole decoder
+// loop in one persistent cluster kernel).  sm_100a only.
+#pragma once
+#include "common.cuh"
+
+namespace re2e {
+
+constexpr int kTG = 5;        // conv outputs per thread (sliding window)
+constexpr int kKQ = 5;        // K split (items = frame groups x C x kKQ = 500 of 512 threads at the default shape)
+
+__host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
+
+// sum 16 per-lane values across the warp with recursive halving (16 shuffles instead of 80); on return
+// lane L (L even) holds in v[0] the total of value index  bit4*8 + bit3*4 + bit2*2 + bit1  of L.
+__device__ __forceinline__ void warp_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 16;
+    const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 8;
+    const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+__device__ __forceinline__ void mbar_arrive1(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void pair_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// remote shared-memory store that signals the destination CTA's mbarrier (complete_tx of 4 bytes): the
+// receiver waits on its own barrier -- no cluster-wide barrier, no release fence on the sender
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(__float_as_uint(v)), "r"(remote_bar)
+               : "memory");
+}
+// Programmatic dependent launch (PDL).  The step kernels are launched with programmatic stream serialisation, so
+// a grid may become resident while its predecessor in the stream (normally the previous decoder step) is still
+// running.  Everything before pdl_wait() touches only memory that was final before the predecessor STARTED:
+// parameters, the per-utterance encoder tensors (pre, enc_h) and -- in the backward -- tensors saved by the
+// forward pass.  griddepcontrol.wait returns once the predecessor grid has completed and flushed; all global
+// writes and all reads of per-step inputs (att_prev / dec_z, dc / dw, accumulators) come after it.  A predecessor
+// that never executes launch_dependents (any foreign kernel) degrades to ordinary stream order.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+
+
+}  // namespace re2e

@@ -18,10 +18,23 @@ import torch
 import helpers
 from oracle import refshim
 import robust_e2e_gan_b200 as ours
+from robust_e2e_gan_b200 import synth
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not refshim.available(), reason="reference tree / oracle/_ref not present")]
 DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def strict_fp32_library_math():
+    """The parts of the swapped model that are NOT ours -- the reference's BLSTM encoder and LSTMCell decoder -- run
+    in cuDNN / cuBLAS on the GPU; cuDNN's default TF32 RNN math alone moves every gradient by ~5e-4 against the
+    CPU reference.  Pin the library code to fp32 so the comparison isolates the swapped modules."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def _batch(args, B=3, T=40, seed=0):
@@ -75,10 +88,15 @@ def test_reference_e2e_with_swapped_imports_matches_reference(dims, swap_decoder
     helpers.assert_close(np.float64(g[1]), np.float64(r32[1]), truth=np.float64(r64[1]), what="loss_att")
     assert g[2] == pytest.approx(r32[2])
     assert set(g[3]) == set(r32[3])
+    bad = []
     for k in sorted(r32[3]):
         if k.endswith("att.gvec.bias"):        # analytically zero (softmax shift invariance): no scale to compare to
             continue
-        helpers.assert_close(g[3][k], r32[3][k], truth=r64[3][k], what="d " + k)
+        try:
+            helpers.assert_close(g[3][k], r32[3][k], truth=r64[3][k], what="d " + k)
+        except AssertionError as e:
+            bad.append(str(e))
+    assert not bad, "\n".join(bad)
 
 
 @pytest.mark.parametrize("swap_decoder", [False, True])
@@ -124,7 +142,7 @@ def test_fbank_load_model_from_reference_checkpoint(tmp_path):
     assert mine.fc.is_cuda and torch.equal(mine.fc.detach().cpu(), ref.fc.detach())
     g = torch.Generator().manual_seed(2)
     x = (torch.randn(2, 30, 257, generator=g).abs() * 300).requires_grad_(True)
-    cm = ours.synth.cmvn(80, 4)
+    cm = synth.cmvn(80, 4)
     y_ref = ref(x, cm)
     dY = torch.randn(y_ref.shape, generator=g)
     y_ref.backward(dY)
