@@ -127,6 +127,38 @@ int re2e_attloc_acc_reduce(const float *acc_slots, int n_slots, float *out, int 
 int re2e_attloc_enc_grad(const float *w_all, const float *dc_all, float *d_enc_h, int steps,
                          int B, int Th, int D, int accumulate, void *stream);
 
+/* The attention decoder loop as ONE persistent cluster kernel per direction (csrc/attloc_loop.cu).  Replaces the S
+ * consecutive calls `att_c, att_w = self.att(hpad, hlen, z_list[0], att_w)` of Decoder.forward
+ * (model/e2e_decoder.py:114-122), i.e. S x model/e2e_attention.py:258-299 with the alignment fed back, and the
+ * autograd backward of that chain.  Step-indexed tensors are (S, ...):
+ *   dec_proj (S,B,A)  = dec_z_s @ W_dec^T for every step (row 0 zeros when the first dec_z is None): the caller
+ *                       forms it with ONE dense product, which is possible whenever the decoder states of all steps
+ *                       exist before the loop (the joint-step hot path feeds them; a teacher-forced decoder whose
+ *                       recurrence does not see the context).  When z_s depends on c_{s-1} (LSTMCell fed with the
+ *                       context, Decoder.forward) use the per-step entry points above.
+ *   att_init (B,Th)   the alignment fed to step 0 (re2e_attloc_init_att)
+ *   c_all (S,B,D), w_all (S,B,Th)   outputs of every step;  conv_all (S,B,Th,C) saved for the backward (NULL: skip)
+ * Backward: dc_all (S,B,D) / dw_all (S,B,Th) are the incoming gradients of c_all / w_all (either may be NULL = zeros);
+ * the gradient flowing back through the fed-back alignment is kept inside the kernel.
+ *   d_pre (B,Th,A)      = sum over steps (written, not accumulated into)
+ *   d_decproj (S,B,A)   = dE/d dec_proj           (d dec_z = d_decproj @ W_dec and dW_dec are dense products)
+ *   acc_slots           n_slots >= re2e_attloc_loop_slots(...) slots of re2e_attloc_acc_floats floats, WRITTEN (no
+ *                       zero-fill needed), summed by re2e_attloc_acc_reduce
+ * d enc_h: re2e_attloc_enc_grad(w_all, dc_all, ...) as for the per-step path.
+ * re2e_attloc_loop_supported: 1 when the shape fits (the CTA's frame range of one utterance resident on chip for
+ * the whole loop), else 0 -- callers then use the per-step entry points. */
+int re2e_attloc_loop_supported(int S, int B, int Th, int D, int A, int C, int K);
+int re2e_attloc_loop_slots(int S, int B, int Th, int D, int A, int C, int K);
+int re2e_attloc_loop_fwd(const float *pre, const float *enc_h, const float *dec_proj, const float *att_init,
+                         const float *W_att, const float *W_conv, const float *gvec, const float *gvec_b,
+                         float scaling, float *c_all, float *w_all, float *conv_all, int S, int B, int Th, int D,
+                         int A, int C, int K, void *stream);
+int re2e_attloc_loop_bwd(const float *pre, const float *enc_h, const float *dec_proj, const float *att_init,
+                         const float *w_all, const float *conv_all, const float *dc_all, const float *dw_all,
+                         const float *W_att, const float *W_conv, const float *gvec, float scaling, float *d_pre,
+                         float *d_decproj, float *acc_slots, int n_slots, int S, int B, int Th, int D, int A,
+                         int C, int K, void *stream);
+
 /* Batch-sized ("skinny", M <= a few hundred rows) fp32 products on the per-step path:
  *   out[M,N] (+)= X[M,K] @ W[N,K]^T   (re2e_skinny_nt)   dec_proj = dec_z @ W_dec^T  (mlp_dec, :278)
  *   out[M,N] (+)= X[M,K] @ W[K,N]     (re2e_skinny_nn)   d_dec_z  = d_decproj @ W_dec */

@@ -41,6 +41,10 @@ SIGNATURES = {
     "re2e_attloc_step_bwd": (_I, [_P] * 12 + [_F, _P, _I] + [_P] * 4 + [_I] * 8 + [_P]),
     "re2e_attloc_acc_reduce": (_I, [_P, _I, _P, _I, _I, _I, _P]),
     "re2e_attloc_enc_grad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "re2e_attloc_loop_supported": (_I, [_I] * 7),
+    "re2e_attloc_loop_slots": (_I, [_I] * 7),
+    "re2e_attloc_loop_fwd": (_I, [_P] * 8 + [_F] + [_P] * 3 + [_I] * 7 + [_P]),
+    "re2e_attloc_loop_bwd": (_I, [_P] * 11 + [_F] + [_P] * 3 + [_I] * 8 + [_P]),
     "re2e_skinny_nt": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "re2e_skinny_nn": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "re2e_gemm_tf32x3": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P]),

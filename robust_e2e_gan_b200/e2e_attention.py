@@ -199,6 +199,112 @@ class _Step(torch.autograd.Function):
         return None, d_dz, d_prev, None, None, None
 
 
+class _Loop(torch.autograd.Function):
+    """All S attention steps of one decoder loop in ONE persistent cluster kernel per direction (csrc/attloc_loop.cu).
+
+    inputs : enc_hs_pad (B,Th,D), dec_z_all (S-1,B,Z) [first_none: step 0 has dec_z = None] or (S,B,Z), parameters
+    outputs: c_all (S,B,D), w_all (S,B,Th) -- step i's context / alignment; the alignment is fed back inside the kernel
+    """
+
+    @staticmethod
+    def forward(ctx, enc_hs_pad, dec_z_all, W_enc, b_enc, W_dec, W_att, W_conv, gvec_w, gvec_b, att_init, scaling,
+                first_none):
+        L = _lib.lib()
+        dev = W_enc.device
+        enc = _lib.f32c(enc_hs_pad.detach(), dev)
+        dz = _lib.f32c(dec_z_all.detach(), dev)
+        B, Th, D = enc.shape
+        A, Z, C, K = W_enc.shape[0], W_dec.shape[1], W_att.shape[1], W_conv.shape[-1]
+        off = 1 if first_none else 0
+        S = dz.shape[0] + off
+        We, Wd = _lib.f32c(W_enc.detach()), _lib.f32c(W_dec.detach())
+        Wa, Wc = _lib.f32c(W_att.detach()), _lib.f32c(W_conv.detach()).view(C, K)
+        gw, gb = _lib.f32c(gvec_w.detach()).view(A), _lib.f32c(gvec_b.detach()).view(1)
+        pre = torch.empty(B, Th, A, device=dev, dtype=torch.float32)
+        gemm_tf32x3(enc.view(B * Th, D), False, We, False, pre.view(B * Th, A), B * Th, A, D,
+                    bias=_lib.f32c(b_enc.detach()))
+        # mlp_dec of EVERY step as one dense product (e2e_attention.py:278 x S)
+        dec_proj = torch.empty(S, B, A, device=dev, dtype=torch.float32)
+        if off:
+            dec_proj[0].zero_()
+        if S - off > 0:
+            gemm_tf32x3(dz.view(-1, Z), False, Wd, False, dec_proj[off:].view(-1, A), (S - off) * B, A, Z)
+        att0 = _lib.f32c(att_init.detach(), dev).view(B, Th)
+        need_bwd = any(ctx.needs_input_grad[:9])
+        c_all = torch.empty(S, B, D, device=dev, dtype=torch.float32)
+        w_all = torch.empty(S, B, Th, device=dev, dtype=torch.float32)
+        conv_all = torch.empty(S, B, Th, C, device=dev, dtype=torch.float32) if need_bwd else None
+        with torch.cuda.device(dev):
+            _lib.check(L.re2e_attloc_loop_fwd(_lib.ptr(pre), _lib.ptr(enc), _lib.ptr(dec_proj), _lib.ptr(att0),
+                                              _lib.ptr(Wa), _lib.ptr(Wc), _lib.ptr(gw), _lib.ptr(gb), float(scaling),
+                                              _lib.ptr(c_all), _lib.ptr(w_all), _lib.ptr(conv_all), S, B, Th, D, A, C, K,
+                                              _lib.stream_ptr()), "re2e_attloc_loop_fwd")
+        if need_bwd:
+            ctx.save_for_backward(enc, pre, dec_proj, att0, w_all, conv_all, dz, We, Wd, Wa, Wc, gw)
+            ctx.dims = (S, B, Th, D, A, Z, C, K, off)
+            ctx.scaling = float(scaling)
+            ctx.set_materialize_grads(False)
+        return c_all, w_all
+
+    @staticmethod
+    def backward(ctx, dc_all, dw_all):
+        L = _lib.lib()
+        enc, pre, dec_proj, att0, w_all, conv_all, dz, We, Wd, Wa, Wc, gw = ctx.saved_tensors
+        S, B, Th, D, A, Z, C, K, off = ctx.dims
+        dev = enc.device
+        need = ctx.needs_input_grad
+        if dc_all is None and dw_all is None:
+            return (None,) * 12
+        dc_all = _lib.f32c(dc_all, dev) if dc_all is not None else None
+        dw_all = _lib.f32c(dw_all, dev) if dw_all is not None else None
+        nslots = int(L.re2e_attloc_loop_slots(S, B, Th, D, A, C, K))
+        _lib.check(min(nslots, 0), "re2e_attloc_loop_slots")
+        stride = int(L.re2e_attloc_acc_floats(A, C, K))
+        acc = torch.empty(nslots, stride, device=dev, dtype=torch.float32)
+        d_pre = torch.empty(B, Th, A, device=dev, dtype=torch.float32)
+        d_decproj = torch.empty(S, B, A, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(L.re2e_attloc_loop_bwd(_lib.ptr(pre), _lib.ptr(enc), _lib.ptr(dec_proj), _lib.ptr(att0),
+                                              _lib.ptr(w_all), _lib.ptr(conv_all), _lib.ptr(dc_all), _lib.ptr(dw_all),
+                                              _lib.ptr(Wa), _lib.ptr(Wc), _lib.ptr(gw), ctx.scaling, _lib.ptr(d_pre),
+                                              _lib.ptr(d_decproj), _lib.ptr(acc), nslots, S, B, Th, D, A, C, K,
+                                              _lib.stream_ptr()), "re2e_attloc_loop_bwd")
+        d_enc = d_dz = dW_enc = db_enc = dW_dec = dW_att = dW_conv = dgw = dgb = None
+        dp2 = d_pre.view(B * Th, A)
+        if need[0]:
+            d_enc = torch.empty(B, Th, D, device=dev, dtype=torch.float32)
+            gemm_tf32x3(dp2, False, We, True, d_enc.view(B * Th, D), B * Th, D, A)         # d_pre @ W_enc
+            if dc_all is not None:                                                          # + sum_i w_i (x) dc_i
+                with torch.cuda.device(dev):
+                    _lib.check(L.re2e_attloc_enc_grad(_lib.ptr(w_all), _lib.ptr(dc_all), _lib.ptr(d_enc), S, B, Th, D, 1,
+                                                      _lib.stream_ptr()), "re2e_attloc_enc_grad")
+        if need[2]:
+            dW_enc = torch.empty(A, D, device=dev, dtype=torch.float32)
+            gemm_tf32x3(dp2, True, enc.view(B * Th, D), True, dW_enc, A, D, B * Th)        # d_pre^T @ enc
+        if need[3]:
+            db_enc = colsum(dp2)
+        rows = (S - off) * B
+        ddp2 = d_decproj[off:].view(rows, A)
+        if need[1] and rows > 0:
+            d_dz = torch.empty(S - off, B, Z, device=dev, dtype=torch.float32)
+            gemm_tf32x3(ddp2, False, Wd, True, d_dz.view(rows, Z), rows, Z, A)             # d dec_z = d dec_proj @ W_dec
+        if need[4]:
+            dW_dec = torch.empty(A, Z, device=dev, dtype=torch.float32)
+            if rows > 0:
+                gemm_tf32x3(ddp2, True, dz.view(rows, Z), True, dW_dec, A, Z, rows)        # d dec_proj^T @ dec_z
+            else:
+                dW_dec.zero_()
+        tot = torch.empty(A * C + C * K + A + 1, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(L.re2e_attloc_acc_reduce(_lib.ptr(acc), nslots, _lib.ptr(tot), A, C, K, _lib.stream_ptr()),
+                       "re2e_attloc_acc_reduce")
+        dW_att = tot[:A * C].view(A, C)
+        dW_conv = tot[A * C:A * C + C * K].view(C, 1, 1, K)
+        dgw = tot[A * C + C * K:A * C + C * K + A].view(1, A)
+        dgb = tot[A * C + C * K + A:].view(1)
+        return d_enc, d_dz, dW_enc, db_enc, dW_dec, dW_att, dW_conv, dgw, dgb, None, None, None
+
+
 class AttLoc(torch.nn.Module):
     """location-aware attention (model/e2e_attention.py:199-299).
 
@@ -237,6 +343,53 @@ class AttLoc(torch.nn.Module):
         self.pre_compute_enc_h = None
         self._state = None
         self._anchor = None
+
+    def loop_supported(self, steps, batch, h_length):
+        """True when ``forward_loop`` can run this shape in the persistent loop kernels (the frame range a CTA owns of
+        one utterance must stay resident on chip for the whole loop); otherwise it falls back to ``forward`` per step."""
+        K = self.loc_conv.weight.shape[-1]
+        return bool(_lib.load().re2e_attloc_loop_supported(int(steps), int(batch), int(h_length), self.eprojs,
+                                                           self.att_dim, self.aconv_chans, K))
+
+    def forward_loop(self, enc_hs_pad, enc_hs_len, dec_z_all, first_none=True, att_prev=None, scaling=2.0):
+        """The whole attention loop of Decoder.forward (model/e2e_decoder.py:114-122) for decoder states that are all
+        known up front: step i computes ``att_c_i, att_w_i = forward(enc_hs_pad, enc_hs_len, z_i, att_w_{i-1})``.
+
+        :param dec_z_all: (S-1, B, dunits) with ``first_none`` (step 0 gets dec_z = None, i.e. zeros), else (S, B, dunits)
+        :param att_prev: alignment fed to step 0 (None = uniform over each length, e2e_attention.py:264-268)
+        :return: c_all (S, B, eprojs), w_all (S, B, T_max)
+        One persistent cluster kernel per direction when the shape fits (see csrc/attloc_loop.cu); identical results
+        (to rounding) from the per-step kernels otherwise.
+        """
+        if self.aact_fuc != 'softmax':
+            raise NotImplementedError("AttLoc sm_100a kernels implement aact_fuc='softmax' only")
+        dev = self.mlp_enc.weight.device
+        if dev.type != 'cuda':
+            raise RuntimeError("AttLoc parameters must live on a CUDA device (no CPU fallback)")
+        batch, h_length = enc_hs_pad.size(0), enc_hs_pad.size(1)
+        steps = dec_z_all.size(0) + (1 if first_none else 0)
+        if not self.loop_supported(steps, batch, h_length):
+            self.reset()
+            cs, ws, w = [], [], att_prev
+            for i in range(steps):
+                z = None if (first_none and i == 0) else dec_z_all[i - (1 if first_none else 0)]
+                c, w = self.forward(enc_hs_pad, enc_hs_len, z, w, scaling)
+                cs.append(c)
+                ws.append(w)
+            return torch.stack(cs), torch.stack(ws)
+        if att_prev is None:
+            L = _lib.lib()
+            if torch.is_tensor(enc_hs_len) and enc_hs_len.is_cuda:
+                hl = enc_hs_len.to(torch.int32).contiguous()
+            else:
+                hl = torch.from_numpy(np.fromiter((int(l) for l in enc_hs_len), dtype=np.int32)).to(dev, non_blocking=True)
+            att_prev = torch.empty(batch, h_length, device=dev, dtype=torch.float32)
+            with torch.cuda.device(dev):
+                _lib.check(L.re2e_attloc_init_att(_lib.ptr(hl), _lib.ptr(att_prev), batch, h_length, _lib.stream_ptr()),
+                           "re2e_attloc_init_att")
+        return _Loop.apply(enc_hs_pad, dec_z_all, self.mlp_enc.weight, self.mlp_enc.bias, self.mlp_dec.weight,
+                           self.mlp_att.weight, self.loc_conv.weight, self.gvec.weight, self.gvec.bias, att_prev,
+                           scaling, bool(first_none))
 
     def forward(self, enc_hs_pad, enc_hs_len, dec_z, att_prev, scaling=2.0):
         '''AttLoc forward

@@ -70,9 +70,13 @@ class _Opt(object):
 class HotPath(torch.nn.Module):
     """FbankModel + CTC + AttLoc with seeded parameters, and ``step(batch)`` = fwd + bwd."""
 
-    def __init__(self, cfg, seed=1234, mtlalpha=0.5, overlap=True):
+    def __init__(self, cfg, seed=1234, mtlalpha=0.5, overlap=True, fused_loop=True):
         super().__init__()
         self.cfg = dict(cfg)
+        # fused_loop=True: the attention decoder loop runs as ONE persistent cluster kernel per direction
+        # (AttLoc.forward_loop; the decoder states of all steps are inputs of the step, so mlp_dec of every step is one
+        # dense product).  False: one AttLoc.forward per output position, as Decoder.forward calls it (A/B timing).
+        self.fused_loop = fused_loop
         # overlap=True: the three independent branches of the step (front-end, CTC, attention decoder loop) run on
         # three CUDA streams, fork/join inside step(); autograd replays each branch's backward on its own stream.
         # The decoder loop is a serial chain of latency-bound cluster kernels that leaves SMs and issue slots idle;
@@ -116,8 +120,11 @@ class HotPath(torch.nn.Module):
         steps = self.cfg["steps"]
         mask_logits = b.mask_logits.detach().requires_grad_(backward)
         hpad = b.hpad.detach().requires_grad_(backward)
-        # one leaf per decoder step (as the LSTMCell outputs are separate tensors in Decoder.forward)
-        dec_zs = [b.dec_z[i].detach().requires_grad_(backward) for i in range(steps - 1)]
+        fused = self.fused_loop and steps > 1
+        if fused:
+            dec_z_all = b.dec_z[:steps - 1].detach().requires_grad_(backward)
+        else:   # one leaf per decoder step (as the LSTMCell outputs are separate tensors in Decoder.forward)
+            dec_zs = [b.dec_z[i].detach().requires_grad_(backward) for i in range(steps - 1)]
         main = torch.cuda.current_stream(hpad.device)
         if self.overlap:
             s_fe, s_ctc = self._branch_streams(hpad.device)
@@ -136,23 +143,30 @@ class HotPath(torch.nn.Module):
             loss_ctc = self.ctc(hpad, b.hlens, b.targets if b.targets is not None else b.ys)
         # -- attention decoder loop (model/e2e_decoder.py:114-122)
         self.att.reset()
-        att_w = None
-        cs = []
         hl = hlens_for_att if hlens_for_att is not None else b.hlens_list
-        for i in range(steps):
-            z = None if i == 0 else dec_zs[i - 1]
-            att_c, att_w = self.att(hpad, hl, z, att_w)
-            cs.append(att_c)
+        if fused:
+            c_all, w_all = self.att.forward_loop(hpad, hl, dec_z_all, first_none=True)
+            att_w, cs = w_all[steps - 1], [c_all]
+        else:
+            att_w = None
+            cs = []
+            for i in range(steps):
+                z = None if i == 0 else dec_zs[i - 1]
+                att_c, att_w = self.att(hpad, hl, z, att_w)
+                cs.append(att_c)
+            c_all = torch.stack(cs)
         if self.overlap:
             main.wait_stream(s_fe)
             main.wait_stream(s_ctc)
         out = {"enhance_feat": enhance_feat, "clean_feat": clean_feat, "mix_feat": mix_feat, "loss_ctc": loss_ctc,
-               "att_c": torch.stack(cs), "att_w": att_w}
+               "att_c": c_all, "att_w": att_w}
         if backward:
             outs = [enhance_feat, loss_ctc, att_w] + cs
-            grads = [b.g_feat, torch.full_like(loss_ctc, self.mtlalpha), b.g_w] + [b.g_c[i] for i in range(steps)]
+            grads = [b.g_feat, torch.full_like(loss_ctc, self.mtlalpha), b.g_w] + \
+                ([b.g_c[:steps]] if fused else [b.g_c[i] for i in range(steps)])
             torch.autograd.backward(outs, grads)
-            out.update(d_mask_logits=mask_logits.grad, d_hpad=hpad.grad, d_dec_z=[z.grad for z in dec_zs])
+            out.update(d_mask_logits=mask_logits.grad, d_hpad=hpad.grad,
+                       d_dec_z=dec_z_all.grad if fused else [z.grad for z in dec_zs])
             for k, p in self.named_parameters():
                 if p.requires_grad and p.grad is not None:
                     out["d_" + k] = p.grad

@@ -147,3 +147,88 @@ def test_backward_twice_and_partial_use():
     assert_close(res[0][0], eo.grad, what="d enc (partial use)")
     assert_close(res[0][1]["mlp_dec.weight"], p["mlp_dec.weight"].grad, what="d mlp_dec (partial use)")
     assert_close(res[0][1]["loc_conv.weight"], p["loc_conv.weight"].grad, what="d loc_conv (partial use)")
+
+
+# ---- the whole decoder loop in one persistent kernel per direction (AttLoc.forward_loop, csrc/attloc_loop.cu) -------
+def run_loop(dims, params, enc, hlens, zs, gc, gw_all, scaling=2.0):
+    """gw_all: (steps, B, Th) gradient of EVERY step's alignment (the per-step tests only feed the last one)."""
+    e, d, a, c, f = dims
+    att = AttLoc(e, d, a, c, f, "softmax").to(DEV)
+    att.load_state_dict(params)
+    enc = enc.detach().clone().to(DEV).requires_grad_(True)
+    dz = torch.stack(zs[1:]).detach().clone().to(DEV).requires_grad_(True)
+    c_all, w_all = att.forward_loop(enc, hlens, dz, first_none=True, scaling=scaling)
+    loss = (c_all * torch.stack(gc).to(DEV)).sum() + (w_all * gw_all.to(DEV)).sum()
+    loss.backward()
+    return c_all, w_all, enc.grad, dz.grad, {k: p.grad for k, p in att.named_parameters()}, att
+
+
+def run_oracle_loop(params, enc, hlens, zs, gc, gw_all, dt, scaling=2.0):
+    p = {k: v.detach().clone().to(dt).requires_grad_(True) for k, v in params.items()}
+    enc = enc.detach().clone().to(dt).requires_grad_(True)
+    zs = [None] + [z.detach().clone().to(dt).requires_grad_(True) for z in zs[1:]]
+    cs, ws = o_att.run_steps(p, enc, hlens, zs, scaling)
+    loss = (torch.stack(cs) * torch.stack(gc).to(dt)).sum() + (torch.stack(ws) * gw_all.to(dt)).sum()
+    loss.backward()
+    return torch.stack(cs), torch.stack(ws), enc.grad, torch.stack([z.grad for z in zs[1:]]), {k: v.grad for k, v in p.items()}
+
+
+@pytest.mark.parametrize("dims,B,Th,steps,seed,every_w", [
+    ((320, 300, 320, 10, 100), 32, 200, 41, 3, False),    # the bench shape: clusters of 4, 41 steps
+    ((320, 300, 320, 10, 100), 8, 100, 9, 1234, True),    # BASELINE config 1 shape: clusters of 8
+    ((320, 300, 320, 10, 100), 4, 16, 6, 7, True),        # smoke shape: clusters of 2, 8 frames per CTA
+    ((320, 300, 320, 10, 100), 1, 163, 4, 5, False),      # B = 1, odd Th, clusters of 8 with a short last CTA
+    ((64, 40, 128, 7, 3), 5, 19, 4, 6, True),             # C != 10 instantiation, D != A, short filters
+    ((320, 300, 320, 10, 100), 3, 37, 2, 9, True),        # two steps only
+])
+def test_decoder_loop_kernel_matches_oracle(dims, B, Th, steps, seed, every_w):
+    e, d, a, c, f = dims
+    params, enc, hlens, zs, gc, gw = make_attloc_inputs(e, d, a, c, f, B, Th, steps, seed)
+    g = torch.Generator().manual_seed(seed + 77)
+    gw_all = torch.randn(steps, B, Th, generator=g) / B ** 0.5 if every_w else torch.zeros(steps, B, Th)
+    gw_all[-1] = gw
+    att0 = AttLoc(e, d, a, c, f, "softmax")
+    assert att0.loop_supported(steps, B, Th), "shape expected to run in the persistent loop kernels"
+    from robust_e2e_gan_b200 import _lib
+    n0 = _lib.launch_count()
+    got = run_loop(dims, params, enc, hlens, zs, gc, gw_all)
+    torch.cuda.synchronize()
+    assert _lib.launch_count() - n0 < 30, "the loop must not fall back to one launch per step"
+    r32 = run_oracle_loop(params, enc, hlens, zs, gc, gw_all, torch.float32)
+    r64 = run_oracle_loop(params, enc, hlens, zs, gc, gw_all, torch.float64)
+    for i, what in enumerate(("c_all", "w_all", "d enc", "d dec_z")):
+        assert_close(got[i], r32[i], truth=r64[i], what=what)
+    for k in r32[4]:
+        if k == "gvec.bias":
+            assert float(got[4][k].abs().max()) < 1e-4 * float(r32[4]["gvec.weight"].abs().max())
+            continue
+        assert_close(got[4][k], r32[4][k], truth=r64[4][k], what="d " + k)
+    assert torch.allclose(got[1].sum(-1), torch.ones(steps, B, device=DEV), atol=1e-5)
+
+
+def test_decoder_loop_falls_back_per_step_for_long_utterances():
+    """Th = 700 does not fit on chip for a whole loop: forward_loop must give the same API through the per-step kernels."""
+    dims = (320, 300, 320, 10, 100)
+    params, enc, hlens, zs, gc, gw = make_attloc_inputs(*dims, 2, 700, 3, 8)
+    gw_all = torch.zeros(3, 2, 700)
+    gw_all[-1] = gw
+    assert not AttLoc(*dims, "softmax").loop_supported(3, 2, 700)
+    got = run_loop(dims, params, enc, hlens, zs, gc, gw_all)
+    r32 = run_oracle_loop(params, enc, hlens, zs, gc, gw_all, torch.float32)
+    r64 = run_oracle_loop(params, enc, hlens, zs, gc, gw_all, torch.float64)
+    for i, what in enumerate(("c_all", "w_all", "d enc", "d dec_z")):
+        assert_close(got[i], r32[i], truth=r64[i], what=what + " (fallback)")
+
+
+def test_decoder_loop_replays_identically():
+    """Two runs of the loop kernels on the same inputs are bit-identical (fixed summation orders, no atomics)."""
+    dims = (320, 300, 320, 10, 100)
+    params, enc, hlens, zs, gc, gw = make_attloc_inputs(*dims, 6, 120, 5, 21)
+    gw_all = torch.zeros(5, 6, 120)
+    gw_all[-1] = gw
+    a = run_loop(dims, params, enc, hlens, zs, gc, gw_all)
+    b = run_loop(dims, params, enc, hlens, zs, gc, gw_all)
+    for i in range(4):
+        assert torch.equal(a[i], b[i])
+    for k in a[4]:
+        assert torch.equal(a[4][k], b[4][k]), k
