@@ -26,6 +26,13 @@ DEFAULT_CFG = dict(B=32, T=800, F=257, M=40, Th=200, D=320, A=320, Z=300, C=10, 
 class Batch(object):
     """Host (pinned) or device copy of one synthetic AISHELL-shaped batch."""
     FIELDS = ("mix", "clean", "mask_logits", "cmvn", "hpad", "dec_z", "g_feat", "g_c", "g_w", "lens", "hlens")
+    # What is HOST-resident in the reference flow (the collated batch of data/mix_data_loader.py:264-302: spectra and
+    # lengths; labels are staged separately) ...
+    HOST_FIELDS = ("mix", "clean", "lens", "hlens")
+    # ... and what the networks upstream / downstream of the path produce ON THE DEVICE in the reference flow
+    # (enhancement net output, model/enhance_model.py:131-156; encoder output; LSTMCell states; gradients arriving
+    # from the losses; the CMVN constants of the model): stand-ins here, they never cross PCIe in the real job.
+    UPSTREAM_FIELDS = ("mask_logits", "hpad", "dec_z", "g_feat", "g_c", "g_w", "cmvn")
 
     def __init__(self, **kw):
         self.__dict__.update(kw)
@@ -202,7 +209,14 @@ class StepRunner(object):
     vary up to ``umax`` labels each.
     """
 
-    def __init__(self, hp, example_host_batch, slots=2, umax=None):
+    def __init__(self, hp, example_host_batch, slots=2, umax=None, upstream="host"):
+        """upstream="host": every field of the host batch is copied in per step (the stand-ins included -- what the
+        parity tests feed).  upstream="device": only what is host-resident in the reference flow is copied per step
+        (``Batch.HOST_FIELDS`` + labels); the stand-ins for tensors that upstream networks produce on the device
+        (``Batch.UPSTREAM_FIELDS``) stay resident in each slot as set at construction / by ``set_upstream``."""
+        if upstream not in ("host", "device"):
+            raise ValueError("upstream must be 'host' or 'device'")
+        self.copy_fields = Batch.FIELDS if upstream == "host" else Batch.HOST_FIELDS
         self.hp = hp
         self.dev = next(hp.parameters()).device
         self.copy_stream = torch.cuda.Stream(self.dev)
@@ -280,14 +294,32 @@ class StepRunner(object):
         pin[B * self.umax + B:] = torch.from_numpy(lens)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(slot["done"])           # the slot's previous replay has finished
-            for k in Batch.FIELDS:
+            for k in self.copy_fields:
                 getattr(db, k).copy_(getattr(hb, k), non_blocking=True)
             db._labels_all.copy_(pin, non_blocking=True)
             slot["copied"].record(self.copy_stream)
 
     def h2d_bytes(self, hb):
-        return int(sum(getattr(hb, k).numel() * getattr(hb, k).element_size() for k in Batch.FIELDS)
-                   + self._lab_pin[0].numel() * 4)
+        return int(sum(self.h2d_tensors(hb).values()))
+
+    def h2d_tensors(self, hb):
+        """Bytes per tensor of what ``submit`` copies host -> device for one step."""
+        d = {k: int(getattr(hb, k).numel() * getattr(hb, k).element_size()) for k in self.copy_fields}
+        d["labels+offsets+lengths"] = int(self._lab_pin[0].numel() * 4)
+        return d
+
+    def resident_tensors(self, hb):
+        """Bytes per tensor of the device-resident stand-ins (not copied per step)."""
+        return {k: int(getattr(hb, k).numel() * getattr(hb, k).element_size())
+                for k in Batch.FIELDS if k not in self.copy_fields}
+
+    def set_upstream(self, hb):
+        """(Re)load the device-resident stand-ins of every slot from a host batch (outside the timed loop)."""
+        torch.cuda.synchronize(self.dev)
+        for slot in self.slots:
+            for k in Batch.UPSTREAM_FIELDS:
+                getattr(slot["batch"], k).copy_(getattr(hb, k))
+        torch.cuda.synchronize(self.dev)
 
     def submit(self, host_batch):
         s = self._next
