@@ -57,6 +57,12 @@ __device__ long long g_loop_dbg[2][16 * 512];
 #define LOOP_DBG_FLUSH(which)
 #endif
 
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 constexpr int kLP = 8;            // warp pairs = frames per chunk
 constexpr int kLW = 2 * kLP;      // warps
 constexpr int kLT = kLW * 32;     // threads
@@ -106,6 +112,7 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_fwd_kernel(const LoopFwdPa
 
   uint64_t *full = reinterpret_cast<uint64_t *>(smraw);      // the resident (pre | enc) tile has landed
   uint64_t *xbar = full + 1;                                  // [2] per-step exchange, by step parity
+  uint64_t *tbar = xbar + 2;                                  // partial contexts of the last step (rank 0)
   float *tile = reinterpret_cast<float *>(smraw + 128);       // tloc_max*A pre rows, then tloc_max*D enc rows
   float *app = tile + (size_t)g.tloc_max * (A + D);           // App   zero padded alignment row, a[i] at filts+i
   float *wc_s = app + g.App;                                  // CKp
@@ -113,21 +120,20 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_fwd_kernel(const LoopFwdPa
   float *convp = watt_s + A * WP;                             // round4(kKQ*tloc_max*CP)  conv partials
   float *conv_s = convp + round4(kKQ * g.tloc_max * CP);      // tloc_max*CPP
   float *e_all = conv_s + g.tloc_max * CPP;                   // 2*Thp  scaled energies of ALL frames, by parity
-  float *e_s = e_all + 2 * g.Thp;                             // round4(tloc_max) scaled energies of my frames
-  float *epart = e_s + round4(g.tloc_max);                    // round4(2*tloc_max)
-  float *wstat = epart + round4(2 * g.tloc_max);              // 2*kLW
-  float *cred = wstat + 2 * kLW;                              // kLP*Dp
-  float *cbuf = cred + kLP * Dp;                              // 2*kLMaxCL*Dp  partial contexts (used on rank 0)
-  float *xch = cbuf + 2 * kLMaxCL * Dp;                       // 2*2*kLMaxCL   (max, sum) of every rank
+  float *epart = e_all + 2 * g.Thp;                           // round4(2*tloc_max)  per-half partial energies of my frames
+  float *cred = epart + round4(2 * g.tloc_max);               // kLP*Dp        per-pair partial contexts
+  float *cbuf = cred + kLP * Dp;                              // 2*kLMaxCL*Dp  partial contexts of every rank (used on rank 0)
 
-  const uint32_t xbytes = (uint32_t)CL * 8u + (uint32_t)Th * 4u + (rank == 0 ? (uint32_t)CL * (uint32_t)D * 4u : 0u);
+  const uint32_t xbytes = (uint32_t)Th * 4u + (rank == 0 ? (uint32_t)CL * (uint32_t)D * 4u : 0u);
   if (tid == 0) {
     mbar_init(full, 1);
     mbar_init(&xbar[0], 1);
     mbar_init(&xbar[1], 1);
+    mbar_init(tbar, 1);
     mbar_fence_init();
     mbar_expect_tx(&xbar[0], xbytes);
     mbar_expect_tx(&xbar[1], xbytes);
+    if (rank == 0) mbar_expect_tx(tbar, (uint32_t)CL * (uint32_t)D * 4u);
   }
   cluster_arrive_relaxed();   // "this CTA is running and its barriers exist"
   // parameters (final before any predecessor kernel started)
@@ -173,7 +179,6 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_fwd_kernel(const LoopFwdPa
     const uint32_t par = (uint32_t)s & 1u, ph = ((uint32_t)s >> 1) & 1u;
     float *e_cur = e_all + par * g.Thp;
     float *cb = cbuf + par * kLMaxCL * Dp;
-    float *xc = xch + par * 2 * kLMaxCL;
     // decoder-state projection of this step (consumed after the convolution: its L2 latency is hidden)
     float dp[APL];
 #pragma unroll
@@ -222,116 +227,72 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_fwd_kernel(const LoopFwdPa
     __syncthreads();  // #2: conv_s visible
     LOOP_MARK(2);   // conv reduce
 
-    // ---- energies, online softmax statistics and context over this CTA's frames (pair <-> frame, lane <-> channel)
-    float m_run = -CUDART_INF_F, s_run = 0.0f;
+    // ---- energies of step s and, in the same sweep over the resident frames, the context of step s-1 from the
+    //      normalised alignment that is still in `app` (the context does not feed the recurrence: it is taken off
+    //      the critical path, and no online-softmax bookkeeping is needed).  pair <-> frame, lane <-> channel
     float acc[DPL];
 #pragma unroll
     for (int j = 0; j < DPL; ++j) acc[j] = 0.0f;
-    for (int qg = 0; qg < nch; qg += 8) {
-      const int gsz = min(8, nch - qg);
 #pragma unroll 2
-      for (int i = 0; i < gsz; ++i) {
-        const int tl = kLP * (qg + i) + pair;
-        if (tl < tloc) {
-          const float *cvp = conv_s + tl * CPP;
-          float cv[CPP];
+    for (int q = 0; q < nch; ++q) {
+      const int tl = kLP * q + pair;
+      if (tl < tloc) {
+        const float *cvp = conv_s + tl * CPP;
+        float cv[CPP];
 #pragma unroll
-          for (int c4 = 0; c4 < CPP; c4 += 4) {
-            const float4 t4 = *reinterpret_cast<const float4 *>(cvp + c4);
-            cv[c4] = t4.x; cv[c4 + 1] = t4.y; cv[c4 + 2] = t4.z; cv[c4 + 3] = t4.w;
-          }
-          const float *row = tile + (size_t)tl * A + aoff;
-          float part = 0.0f;
-#pragma unroll
-          for (int jp = 0; jp < APH; ++jp) {
-            const bool two = 2 * jp + 1 < APL;
-            float2 u = make_float2(dp[2 * jp] + row[64 * jp], two ? dp[2 * jp + 1] + row[64 * jp + 32] : 0.0f);
-#pragma unroll
-            for (int c = 0; c < CP; ++c) u = __ffma2_rn(WattP[jp][c], make_float2(cv[c], cv[c]), u);
-            part = fmaf(gv[2 * jp], tanh_ex2(u.x), part);
-            if (two) part = fmaf(gv[2 * jp + 1], tanh_ex2(u.y), part);
-          }
-          part = warp_sum(part);
-          if (lane == 0) epart[2 * tl + half] = part;
+        for (int c4 = 0; c4 < CPP; c4 += 4) {
+          const float4 t4 = *reinterpret_cast<const float4 *>(cvp + c4);
+          cv[c4] = t4.x; cv[c4 + 1] = t4.y; cv[c4 + 2] = t4.z; cv[c4 + 3] = t4.w;
         }
-      }
-      LOOP_MARK(3);   // energies
-      pair_bar(1 + pair, 64);
-      LOOP_MARK(4);   // pair barrier
-      float ev[8];
-      float mg8 = m_run;
+        const float *row = tile + (size_t)tl * A + aoff;
+        const float pw = app[filts + t0 + tl];           // alignment of step s-1 (initial alignment at s = 0: unused)
+        const float *er = tile + (size_t)g.tloc_max * A + (size_t)tl * D + half * Dh + lane;
+        float part = 0.0f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int tl = kLP * (qg + i) + pair;
-        const bool ok = i < gsz && tl < tloc;
-        ev[i] = ok ? p.scaling * ((epart[2 * tl] + epart[2 * tl + 1]) + gb) : -CUDART_INF_F;
-        if (ok && half == 0 && lane == 0) e_s[tl] = ev[i];
-        mg8 = fmaxf(mg8, ev[i]);
-      }
-      if (mg8 > m_run) {
-        const float sc = __expf(m_run - mg8);   // exp(-inf) = 0 for the first group
-        s_run *= sc;
+        for (int jp = 0; jp < APH; ++jp) {
+          const bool two = 2 * jp + 1 < APL;
+          float2 u = make_float2(dp[2 * jp] + row[64 * jp], two ? dp[2 * jp + 1] + row[64 * jp + 32] : 0.0f);
 #pragma unroll
-        for (int j = 0; j < DPL; ++j) acc[j] *= sc;
-        m_run = mg8;
-      }
-      const float *er0 = tile + (size_t)g.tloc_max * A + (size_t)(kLP * qg + pair) * D + half * Dh + lane;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float pw = ev[i] == -CUDART_INF_F ? 0.0f : __expf(ev[i] - m_run);
-        s_run += pw;
-        if (ev[i] != -CUDART_INF_F) {
-          const float *er = er0 + (size_t)i * kLP * D;
-#pragma unroll
-          for (int j = 0; j < DPL; ++j)
-            if (dmask & (1u << j)) acc[j] = fmaf(pw, er[32 * j], acc[j]);
+          for (int c = 0; c < CP; ++c) u = __ffma2_rn(WattP[jp][c], make_float2(cv[c], cv[c]), u);
+          part = fmaf(gv[2 * jp], tanh_ex2(u.x), part);
+          if (two) part = fmaf(gv[2 * jp + 1], tanh_ex2(u.y), part);
         }
+#pragma unroll
+        for (int j = 0; j < DPL; ++j)
+          if (dmask & (1u << j)) acc[j] = fmaf(pw, er[32 * j], acc[j]);
+        part = warp_sum(part);
+        if (lane == 0) epart[2 * tl + half] = part;
       }
     }
-    if (lane == 0) { wstat[2 * warp] = m_run; wstat[2 * warp + 1] = s_run; }
-    LOOP_MARK(5);   // local softmax + context
-    __syncthreads();  // #3: per-warp statistics and e_s published
-    LOOP_MARK(6);   // barrier #3
+#pragma unroll
+    for (int j = 0; j < DPL; ++j)
+      if (dmask & (1u << j)) cred[pair * Dp + half * Dh + lane + 32 * j] = acc[j];
+    LOOP_MARK(3);   // energies + context sweep
+    __syncthreads();  // #3: partial energies and per-pair partial contexts published
+    LOOP_MARK(4);   // barrier #3
 
-    // ---- CTA combine (deterministic order), then ONE push to the cluster
-    float Mc = -CUDART_INF_F;
-#pragma unroll
-    for (int w2 = 0; w2 < kLW; ++w2) Mc = fmaxf(Mc, wstat[2 * w2]);
-    {
-      const float sc = m_run == -CUDART_INF_F ? 0.0f : __expf(m_run - Mc);
-#pragma unroll
-      for (int j = 0; j < DPL; ++j)
-        if (dmask & (1u << j)) cred[pair * Dp + half * Dh + lane + 32 * j] = acc[j] * sc;
-    }
-    __syncthreads();  // #4
+    // ---- ONE push per step: context partial of step s-1 -> rank 0, my frames' scaled energies -> every CTA
     for (int d = tid; d < D; d += NT) {
       float sum = 0.0f;
 #pragma unroll
       for (int pr = 0; pr < kLP; ++pr) sum += cred[pr * Dp + d];
-      st_async_f32(dsmem_addr(cb + rank * Dp + d, 0u), sum, dsmem_addr(&xbar[par], 0u));
+      st_async_f32(dsmem_addr(cb + rank * Dp + d, 0u), s > 0 ? sum : 0.0f, dsmem_addr(&xbar[par], 0u));
     }
-    if (tid < CL) {
-      float sc = 0.0f;
-#pragma unroll
-      for (int pr = 0; pr < kLP; ++pr) {
-        const float mw = wstat[4 * pr];
-        if (mw != -CUDART_INF_F) sc += wstat[4 * pr + 1] * __expf(mw - Mc);
-      }
-      st_async_f32(dsmem_addr(xc + 2 * rank, (uint32_t)tid), Mc, dsmem_addr(&xbar[par], (uint32_t)tid));
-      st_async_f32(dsmem_addr(xc + 2 * rank + 1, (uint32_t)tid), sc, dsmem_addr(&xbar[par], (uint32_t)tid));
-    }
-    for (int i = tid; i < tloc * CL; i += NT) {   // my frames' energies -> every CTA of the cluster (myself included)
+    for (int i = tid; i < tloc * CL; i += NT) {
       const int r = i / tloc, tl = i - r * tloc;
-      st_async_f32(dsmem_addr(e_cur + t0 + tl, (uint32_t)r), e_s[tl], dsmem_addr(&xbar[par], (uint32_t)r));
+      const float e = p.scaling * ((epart[2 * tl] + epart[2 * tl + 1]) + gb);
+      st_async_f32(dsmem_addr(e_cur + t0 + tl, (uint32_t)r), e, dsmem_addr(&xbar[par], (uint32_t)r));
     }
-    LOOP_MARK(7);   // CTA combine + pushes
-    mbar_wait(&xbar[par], ph);   // every rank's (max, sum) and energies -- on rank 0 also the partial contexts -- are here
-    LOOP_MARK(8);   // exchange wait
+    LOOP_MARK(5);   // pushes
+    mbar_wait(&xbar[par], ph);   // the scaled energies of ALL frames (on rank 0 also the partial contexts) are here
+    LOOP_MARK(6);   // exchange wait
+    // softmax statistics of the whole row, redundantly per warp (same order everywhere: bit-identical), no barrier
     float M = -CUDART_INF_F;
-    for (int r = 0; r < CL; ++r) M = fmaxf(M, xc[2 * r]);
+    for (int t = lane; t < Th; t += 32) M = fmaxf(M, e_cur[t]);
+    M = warp_max(M);
     float Ssum = 0.0f;
-    for (int r = 0; r < CL; ++r)
-      if (xc[2 * r] != -CUDART_INF_F) Ssum += xc[2 * r + 1] * __expf(xc[2 * r] - M);
+    for (int t = lane; t < Th; t += 32) Ssum += __expf(e_cur[t] - M);
+    Ssum = warp_sum(Ssum);
     const float inv = 1.0f / Ssum;
     // the normalised alignment of ALL frames: next step's convolution input; this CTA's frames go to HBM
     for (int t = tid; t < Th; t += NT) {
@@ -339,17 +300,51 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_fwd_kernel(const LoopFwdPa
       app[filts + t] = w;
       if (t >= t0 && t < t1) p.w_all[((size_t)s * B + b) * Th + t] = w;
     }
-    if (rank == 0) {
+    if (rank == 0 && s > 0) {
       for (int d = tid; d < D; d += NT) {
         float sum = 0.0f;
-        for (int r = 0; r < CL; ++r)
-          if (xc[2 * r] != -CUDART_INF_F) sum += cb[r * Dp + d] * __expf(xc[2 * r] - M);
-        p.c_all[((size_t)s * B + b) * D + d] = sum * inv;
+        for (int r = 0; r < CL; ++r) sum += cb[r * Dp + d];
+        p.c_all[((size_t)(s - 1) * B + b) * D + d] = sum;
       }
     }
     if (tid == 0) mbar_expect_tx(&xbar[par], xbytes);   // re-arm this parity's barrier for step s+2
     __syncthreads();  // #5: alignment row complete; receive buffers of this parity consumed
-    LOOP_MARK(9);   // normalise + outputs
+    LOOP_MARK(7);   // softmax + outputs
+  }
+  // ---- tail: the context of the last step
+  {
+    float acc[DPL];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) acc[j] = 0.0f;
+    for (int q = 0; q < nch; ++q) {
+      const int tl = kLP * q + pair;
+      if (tl < tloc) {
+        const float pw = app[filts + t0 + tl];
+        const float *er = tile + (size_t)g.tloc_max * A + (size_t)tl * D + half * Dh + lane;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j)
+          if (dmask & (1u << j)) acc[j] = fmaf(pw, er[32 * j], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DPL; ++j)
+      if (dmask & (1u << j)) cred[pair * Dp + half * Dh + lane + 32 * j] = acc[j];
+    __syncthreads();
+    float *cb = cbuf + ((uint32_t)S & 1u) * kLMaxCL * Dp;
+    for (int d = tid; d < D; d += NT) {
+      float sum = 0.0f;
+#pragma unroll
+      for (int pr = 0; pr < kLP; ++pr) sum += cred[pr * Dp + d];
+      st_async_f32(dsmem_addr(cb + rank * Dp + d, 0u), sum, dsmem_addr(tbar, 0u));
+    }
+    if (rank == 0) {
+      mbar_wait(tbar, 0);
+      for (int d = tid; d < D; d += NT) {
+        float sum = 0.0f;
+        for (int r = 0; r < CL; ++r) sum += cb[r * Dp + d];
+        p.c_all[((size_t)(S - 1) * B + b) * D + d] = sum;
+      }
+    }
   }
   LOOP_DBG_FLUSH(0);
   // no trailing cluster barrier: a CTA leaves only after everything addressed to it has landed (its last wait)
@@ -469,13 +464,16 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xbar2 + 2);
   float *xs = reinterpret_cast<float *>(smraw + 128);         // tloc_max*A    d pre tile of the current step
   float *dcvT = xs + (size_t)g.tloc_max * A;                  // 2*CP*App      channel-major zero padded d conv, by parity
-  float *app = dcvT + 2 * CP * g.App;                         // App           padded att_prev of the current step
-  float *wc_s = app + g.App;                                  // CKp
-  float *conv_s = wc_s + g.CKp;                               // tloc_max*CPP
-  float *w_s = conv_s + g.tloc_max * CPP;                     // round4(tloc_max)
-  float *dwt_s = w_s + round4(g.tloc_max);                    // round4(tloc_max)
-  float *de_s = dwt_s + round4(g.tloc_max);                   // round4(tloc_max)
-  float *dwn_s = de_s + round4(g.tloc_max);                   // round4(tloc_max)  chain gradient (d att_prev of my frames)
+  // per-step inputs, double-buffered: the saved tensors of step s-1 are fetched (cp.async) while step s computes
+  float *app2b = dcvT + 2 * CP * g.App;                       // 2*App         padded att_prev (the input of the step)
+  float *conv2b = app2b + 2 * g.App;                          // 2*tloc_max*CPP  saved conv features of my frames
+  float *w2b = conv2b + 2 * g.tloc_max * CPP;                 // 2*round4(tloc_max)  alignment (the output of the step)
+  float *dwx2b = w2b + 2 * round4(g.tloc_max);                // 2*round4(tloc_max)  external gradient of that alignment
+  float *dcr2b = dwx2b + 2 * round4(g.tloc_max);              // 2*Dp          gradient of the step's context
+  float *dp2b = dcr2b + 2 * g.Dp;                             // 2*A           decoder-state projection of the step
+  float *wc_s = dp2b + 2 * A;                                 // CKp
+  float *dwt_s = wc_s + g.CKp;                                // round4(tloc_max)
+  float *dwn_s = dwt_s + round4(g.tloc_max);                  // round4(tloc_max)  chain gradient (d att_prev of my frames)
   float *dcv_p = dwn_s + round4(g.tloc_max);                  // 2*tloc_max*16     per-half d conv partials
   float *ddp_w = dcv_p + 2 * g.tloc_max * 16;                 // kLW*(A/2)         per-warp d dec_proj partials
   float *scr = ddp_w + kLW * (A / 2);                         // max(A*WP, kKQ*CP*tloc_max): W_att staging, then d att_prev partials
@@ -505,9 +503,12 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
       const int c = i / padn, o = i - c * padn;
       dcvT[c * g.App + (o < filts ? o : Th + o)] = 0.0f;
     }
-    // the per-step loads only write the C real channels of a conv row: pads must be (and stay) zero, they meet zero
-    // weights in the recomputation
-    for (int i = tid; i < g.tloc_max * CPP; i += NT) conv_s[i] = 0.0f;
+    // the per-step copies only write the real entries: pads of the conv rows (they meet zero weights in the
+    // recomputation) and of the alignment rows, and absent gradients, must be (and stay) zero
+    for (int i = tid; i < 2 * g.tloc_max * CPP; i += NT) conv2b[i] = 0.0f;
+    for (int i = tid; i < 2 * g.App; i += NT) app2b[i] = 0.0f;
+    for (int i = tid; i < 2 * round4(g.tloc_max); i += NT) dwx2b[i] = 0.0f;
+    for (int i = tid; i < 2 * g.Dp; i += NT) dcr2b[i] = 0.0f;
     for (int i = tid; i < round4(g.tloc_max); i += NT) dwn_s[i] = 0.0f;
   }
   tc_fence_before();
@@ -561,6 +562,30 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
   LOOP_DBG_DECL;
   LOOP_MARK(0);   // prologue
 
+  // asynchronous copy of the saved tensors of iteration `itn` (step S-1-itn) into its buffers
+  auto prefetch = [&](int itn) {
+    const int sn = S - 1 - itn, bn = itn & 1;
+    const size_t sbn = (size_t)sn * B + b;
+    float *wd = w2b + bn * round4(g.tloc_max), *xd = dwx2b + bn * round4(g.tloc_max);
+    for (int i = tid; i < tloc; i += NT) {
+      cp_async4(wd + i, p.w_all + sbn * Th + t0 + i);
+      if (p.dw_all) cp_async4(xd + i, p.dw_all + sbn * Th + t0 + i);
+    }
+    float *cd = conv2b + bn * g.tloc_max * CPP;
+    for (int i = tid; i < tloc * C; i += NT) {
+      const int tl = i / C;
+      cp_async4(cd + tl * CPP + (i - tl * C), p.conv_all + (sbn * Th + t0) * C + i);
+    }
+    const float *prev = sn == 0 ? p.att_init + (size_t)b * Th : p.w_all + (sbn - B) * Th;
+    float *ad = app2b + bn * g.App + filts;
+    for (int t = tid; t < Th; t += NT) cp_async4(ad + t, prev + t);
+    if (p.dc_all)
+      for (int d = tid; d < D; d += NT) cp_async4(dcr2b + bn * g.Dp + d, p.dc_all + sbn * D + d);
+    for (int a = tid; a < A; a += NT) cp_async4(dp2b + bn * A + a, p.dec_proj + sbn * A + a);
+    cp_async_commit();
+  };
+  prefetch(0);
+
   for (int it = 0; it < S; ++it) {
     const int s = S - 1 - it;
     const uint32_t par = (uint32_t)it & 1u, ph = ((uint32_t)it >> 1) & 1u;
@@ -568,61 +593,51 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
     float *ddpx = ddp_x + par * kLMaxCL * A;
     float *xc = xch + par * kLMaxCL;
     const size_t sb = (size_t)s * B + b;
-    // ---- per-step inputs: alignment (output of step s), its conv features, previous alignment (padded), gradients
-    float dcr[DPL2];
-#pragma unroll
-    for (int j = 0; j < DPL2; ++j) dcr[j] = (p.dc_all && lane + 32 * j < D) ? __ldg(p.dc_all + sb * D + lane + 32 * j) : 0.0f;
-    float dp[APL];
-#pragma unroll
-    for (int j = 0; j < APL; ++j) dp[j] = __ldg(p.dec_proj + sb * A + aoff + 32 * j);
-    for (int i = tid; i < tloc; i += NT) {
-      w_s[i] = __ldg(p.w_all + sb * Th + t0 + i);
-      dwt_s[i] = dwn_s[i] + (p.dw_all ? __ldg(p.dw_all + sb * Th + t0 + i) : 0.0f);
-    }
-    for (int i = tid; i < tloc * C; i += NT) {
-      const int tl = i / C;
-      conv_s[tl * CPP + (i - tl * C)] = __ldg(p.conv_all + (sb * Th + t0) * C + i);
-    }
-    {
-      const float *prev = s == 0 ? p.att_init + (size_t)b * Th : p.w_all + (sb - B) * Th;
-      for (int i = tid; i < g.App; i += NT) {
-        const int t = i - filts;
-        app[i] = (t >= 0 && t < Th) ? __ldg(prev + t) : 0.0f;
-      }
-    }
-    __syncthreads();  // #1
+    const int buf = it & 1;
+    float *app = app2b + buf * g.App, *conv_s = conv2b + buf * g.tloc_max * CPP;
+    float *w_s = w2b + buf * round4(g.tloc_max), *dwx_s = dwx2b + buf * round4(g.tloc_max);
+    float *dcr_s = dcr2b + buf * g.Dp, *dp_s = dp2b + buf * A;
+    cp_async_wait_all();
+    __syncthreads();  // #1: this step's inputs (copied during the previous step) are visible; previous step retired
     LOOP_MARK(1);   // per-step loads
+    if (it + 1 < S) prefetch(it + 1);
 
-    // ---- pass 1: dwt[t] += enc_h[t,:] . dc   (warp per frame, lane <-> d, enc_h from TMEM)
-    for (int q = 0; q < nche; ++q) {
-      const int tl = kLW * q + warp;
-      float ev[DPL2];
-      tmem_load<DPL2>(tcol_enc + (uint32_t)(q * DPL2), ev);
-      tmem_wait_ld();
-      float dot = 0.0f;
+    // ---- pass 1: dwt[t] = chain gradient + external gradient + enc_h[t,:] . dc   (warp per frame, lane <-> d, TMEM)
+    {
+      float dcr[DPL2];
 #pragma unroll
-      for (int j = 0; j < DPL2; ++j) dot = fmaf(dcr[j], ev[j], dot);
-      dot = warp_sum(dot);
-      if (lane == 0 && tl < tloc) dwt_s[tl] += dot;
+      for (int j = 0; j < DPL2; ++j) dcr[j] = lane + 32 * j < D ? dcr_s[lane + 32 * j] : 0.0f;
+      for (int q = 0; q < nche; ++q) {
+        const int tl = kLW * q + warp;
+        float ev[DPL2];
+        tmem_load<DPL2>(tcol_enc + (uint32_t)(q * DPL2), ev);
+        tmem_wait_ld();
+        float dot = 0.0f;
+#pragma unroll
+        for (int j = 0; j < DPL2; ++j) dot = fmaf(dcr[j], ev[j], dot);
+        dot = warp_sum(dot);
+        if (lane == 0 && tl < tloc) dwt_s[tl] = dwn_s[tl] + dwx_s[tl] + dot;
+      }
     }
     __syncthreads();  // #2: dwt complete
     LOOP_MARK(2);   // pass 1
-    if (warp == 0) {
+    if (warp == 0) {   // softmax backward needs sum_t w[t] dwt[t] over the whole utterance: partial -> every CTA
       float s1 = 0.0f;
       for (int tl = lane; tl < tloc; tl += 32) s1 = fmaf(w_s[tl], dwt_s[tl], s1);
       s1 = warp_sum(s1);
       if (lane < CL) st_async_f32(dsmem_addr(xc + rank, (uint32_t)lane), s1, dsmem_addr(&xbar1[par], (uint32_t)lane));
     }
-    mbar_wait(&xbar1[par], ph);
+    float dp[APL];
+#pragma unroll
+    for (int j = 0; j < APL; ++j) dp[j] = dp_s[aoff + 32 * j];
+    bool have_S = false;   // the exchange is awaited lazily: the tanh recomputation of the first frame hides it
     float Stot = 0.0f;
-    for (int r = 0; r < CL; ++r) Stot += xc[r];
-    for (int tl = tid; tl < tloc; tl += NT) de_s[tl] = p.scaling * w_s[tl] * (dwt_s[tl] - Stot);
-    if (tid == 0) {
-      mbar_expect_tx(&xbar1[par], x1bytes);
-      if (it > 0) bulk_wait<0>();   // the previous step's d pre tile has left shared memory (and landed)
-    }
-    __syncthreads();  // #3
-    LOOP_MARK(3);   // softmax exchange
+    auto get_S = [&]() {
+      mbar_wait(&xbar1[par], ph);
+      for (int r = 0; r < CL; ++r) Stot += xc[r];
+      if (tid == 0) mbar_expect_tx(&xbar1[par], x1bytes);   // re-arm for step it+2
+      have_S = true;
+    };
 
     // ---- pass 2: recompute x = tanh(W_att conv + pre + dec_proj), through tanh.  pair <-> frame, lane <-> channel
     float ddp[APL];
@@ -635,7 +650,6 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
       tmem_load<APL>(tcol_pre + (uint32_t)(q * APL), pv);
       tmem_wait_ld();
       if (tl < tloc) {
-        const float de = de_s[tl];
         const float *cvp = conv_s + tl * CPP;
         float cv[CPP];
 #pragma unroll
@@ -643,17 +657,24 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
           const float4 t4 = *reinterpret_cast<const float4 *>(cvp + c4);
           cv[c4] = t4.x; cv[c4 + 1] = t4.y; cv[c4 + 2] = t4.z; cv[c4 + 3] = t4.w;
         }
-        float2 dcv2[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) dcv2[c] = make_float2(0.0f, 0.0f);
-        float *row = xs + (size_t)tl * A + aoff;
+        float xv[APL];
 #pragma unroll
         for (int j = 0; j < APL; ++j) {
           float2 u2 = make_float2(pv[j] + dp[j], 0.0f);
 #pragma unroll
           for (int c2 = 0; c2 < CH2; ++c2)
             u2 = __ffma2_rn(WattC[j][c2], make_float2(cv[2 * c2], 2 * c2 + 1 < CPP ? cv[2 * c2 + 1] : 0.0f), u2);
-          const float x = tanh_ex2(u2.x + u2.y);
+          xv[j] = tanh_ex2(u2.x + u2.y);
+        }
+        if (!have_S) get_S();
+        const float de = p.scaling * w_s[tl] * (dwt_s[tl] - Stot);
+        float2 dcv2[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) dcv2[c] = make_float2(0.0f, 0.0f);
+        float *row = xs + (size_t)tl * A + aoff;
+#pragma unroll
+        for (int j = 0; j < APL; ++j) {
+          const float x = xv[j];
           dgv[j] = fmaf(de, x, dgv[j]);
           const float dt = de * gv[j] * (1.0f - x * x);
           ddp[j] += dt;
@@ -672,6 +693,7 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
         }
       }
     }
+    if (!have_S) get_S();       // (a warp without frames of its own)
     LOOP_MARK(4);   // pass 2
     fence_proxy_async_smem();   // this thread's tile writes -> visible to the bulk (async proxy) reads
     __syncwarp();
@@ -708,7 +730,7 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
     }
     if (warp == kLW - 1) {   // d gvec.bias = sum_t de[t]  (analytically zero over the utterance; kept for fidelity)
       float s2 = 0.0f;
-      for (int tl = lane; tl < tloc; tl += 32) s2 += de_s[tl];
+      for (int tl = lane; tl < tloc; tl += 32) s2 += p.scaling * w_s[tl] * (dwt_s[tl] - Stot);
       dgb += warp_sum(s2);
     }
     LOOP_MARK(6);   // pushes
@@ -782,7 +804,14 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
         if (nv > 4) o[4] = a4;
       }
     }
-    if (tid == 0) mbar_expect_tx(&xbar2[par], x2bytes);
+    if (tid == 0) {
+      mbar_expect_tx(&xbar2[par], x2bytes);
+      // the d pre tile must be free before the next step's pass 2 rewrites it: the TMA unit has had the whole post pass
+      // to read it.  The plain store of the first processed step must also have LANDED before the next step's
+      // reduce-add may be issued (stores and reductions to the same addresses are not ordered otherwise).
+      if (it == 0) bulk_wait<0>();
+      else bulk_wait_read<0>();
+    }
     __syncthreads();  // #5
     LOOP_MARK(9);   // d att_prev partials
     if (s > 0) {
@@ -887,8 +916,9 @@ inline bool loop_geom_bwd(int B, int Th, int D, int A, int C, int K, int CP, int
     g.ncols = g.col_enc + 4 * nche_max * dpl2;
     const size_t scr = (size_t)A * (CP + 1) > (size_t)round4(kKQ * CP * g.tloc_max) ? (size_t)A * (CP + 1)
                                                                                    : (size_t)round4(kKQ * CP * g.tloc_max);
-    const size_t floats = (size_t)g.tloc_max * A + 2 * (size_t)CP * g.App + g.App + g.CKp + (size_t)g.tloc_max * CPP +
-                          4 * (size_t)round4(g.tloc_max) + 2 * (size_t)g.tloc_max * 16 + (size_t)kLW * (A / 2) + scr +
+    const size_t floats = (size_t)g.tloc_max * A + 2 * (size_t)CP * g.App + 2 * (size_t)g.App +
+                          2 * (size_t)g.tloc_max * CPP + 4 * (size_t)round4(g.tloc_max) + 2 * (size_t)g.Dp + 2 * (size_t)A +
+                          g.CKp + 2 * (size_t)round4(g.tloc_max) + 2 * (size_t)g.tloc_max * 16 + (size_t)kLW * (A / 2) + scr +
                           2 * (size_t)kLMaxCL * A + 2 * kLMaxCL;
     smem = 128 + sizeof(float) * floats;
     if (smem <= 226 * 1024 && g.ncols <= 512) return true;
