@@ -464,16 +464,13 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xbar2 + 2);
   float *xs = reinterpret_cast<float *>(smraw + 128);         // tloc_max*A    d pre tile of the current step
   float *dcvT = xs + (size_t)g.tloc_max * A;                  // 2*CP*App      channel-major zero padded d conv, by parity
-  // per-step inputs, double-buffered: the saved tensors of step s-1 are fetched (cp.async) while step s computes
-  float *app2b = dcvT + 2 * CP * g.App;                       // 2*App         padded att_prev (the input of the step)
-  float *conv2b = app2b + 2 * g.App;                          // 2*tloc_max*CPP  saved conv features of my frames
-  float *w2b = conv2b + 2 * g.tloc_max * CPP;                 // 2*round4(tloc_max)  alignment (the output of the step)
-  float *dwx2b = w2b + 2 * round4(g.tloc_max);                // 2*round4(tloc_max)  external gradient of that alignment
-  float *dcr2b = dwx2b + 2 * round4(g.tloc_max);              // 2*Dp          gradient of the step's context
-  float *dp2b = dcr2b + 2 * g.Dp;                             // 2*A           decoder-state projection of the step
-  float *wc_s = dp2b + 2 * A;                                 // CKp
-  float *dwt_s = wc_s + g.CKp;                                // round4(tloc_max)
-  float *dwn_s = dwt_s + round4(g.tloc_max);                  // round4(tloc_max)  chain gradient (d att_prev of my frames)
+  float *app = dcvT + 2 * CP * g.App;                         // App           padded att_prev of the current step
+  float *wc_s = app + g.App;                                  // CKp
+  float *conv_s = wc_s + g.CKp;                               // tloc_max*CPP
+  float *w_s = conv_s + g.tloc_max * CPP;                     // round4(tloc_max)
+  float *dwt_s = w_s + round4(g.tloc_max);                    // round4(tloc_max)
+  float *de_s = dwt_s + round4(g.tloc_max);                   // round4(tloc_max)
+  float *dwn_s = de_s + round4(g.tloc_max);                   // round4(tloc_max)  chain gradient (d att_prev of my frames)
   float *dcv_p = dwn_s + round4(g.tloc_max);                  // 2*tloc_max*16     per-half d conv partials
   float *ddp_w = dcv_p + 2 * g.tloc_max * 16;                 // kLW*(A/2)         per-warp d dec_proj partials
   float *scr = ddp_w + kLW * (A / 2);                         // max(A*WP, kKQ*CP*tloc_max): W_att staging, then d att_prev partials
@@ -503,12 +500,9 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
       const int c = i / padn, o = i - c * padn;
       dcvT[c * g.App + (o < filts ? o : Th + o)] = 0.0f;
     }
-    // the per-step copies only write the real entries: pads of the conv rows (they meet zero weights in the
-    // recomputation) and of the alignment rows, and absent gradients, must be (and stay) zero
-    for (int i = tid; i < 2 * g.tloc_max * CPP; i += NT) conv2b[i] = 0.0f;
-    for (int i = tid; i < 2 * g.App; i += NT) app2b[i] = 0.0f;
-    for (int i = tid; i < 2 * round4(g.tloc_max); i += NT) dwx2b[i] = 0.0f;
-    for (int i = tid; i < 2 * g.Dp; i += NT) dcr2b[i] = 0.0f;
+    // the per-step loads only write the C real channels of a conv row: pads must be (and stay) zero, they meet zero
+    // weights in the recomputation
+    for (int i = tid; i < g.tloc_max * CPP; i += NT) conv_s[i] = 0.0f;
     for (int i = tid; i < round4(g.tloc_max); i += NT) dwn_s[i] = 0.0f;
   }
   tc_fence_before();
@@ -562,30 +556,6 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
   LOOP_DBG_DECL;
   LOOP_MARK(0);   // prologue
 
-  // asynchronous copy of the saved tensors of iteration `itn` (step S-1-itn) into its buffers
-  auto prefetch = [&](int itn) {
-    const int sn = S - 1 - itn, bn = itn & 1;
-    const size_t sbn = (size_t)sn * B + b;
-    float *wd = w2b + bn * round4(g.tloc_max), *xd = dwx2b + bn * round4(g.tloc_max);
-    for (int i = tid; i < tloc; i += NT) {
-      cp_async4(wd + i, p.w_all + sbn * Th + t0 + i);
-      if (p.dw_all) cp_async4(xd + i, p.dw_all + sbn * Th + t0 + i);
-    }
-    float *cd = conv2b + bn * g.tloc_max * CPP;
-    for (int i = tid; i < tloc * C; i += NT) {
-      const int tl = i / C;
-      cp_async4(cd + tl * CPP + (i - tl * C), p.conv_all + (sbn * Th + t0) * C + i);
-    }
-    const float *prev = sn == 0 ? p.att_init + (size_t)b * Th : p.w_all + (sbn - B) * Th;
-    float *ad = app2b + bn * g.App + filts;
-    for (int t = tid; t < Th; t += NT) cp_async4(ad + t, prev + t);
-    if (p.dc_all)
-      for (int d = tid; d < D; d += NT) cp_async4(dcr2b + bn * g.Dp + d, p.dc_all + sbn * D + d);
-    for (int a = tid; a < A; a += NT) cp_async4(dp2b + bn * A + a, p.dec_proj + sbn * A + a);
-    cp_async_commit();
-  };
-  prefetch(0);
-
   for (int it = 0; it < S; ++it) {
     const int s = S - 1 - it;
     const uint32_t par = (uint32_t)it & 1u, ph = ((uint32_t)it >> 1) & 1u;
@@ -593,51 +563,61 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
     float *ddpx = ddp_x + par * kLMaxCL * A;
     float *xc = xch + par * kLMaxCL;
     const size_t sb = (size_t)s * B + b;
-    const int buf = it & 1;
-    float *app = app2b + buf * g.App, *conv_s = conv2b + buf * g.tloc_max * CPP;
-    float *w_s = w2b + buf * round4(g.tloc_max), *dwx_s = dwx2b + buf * round4(g.tloc_max);
-    float *dcr_s = dcr2b + buf * g.Dp, *dp_s = dp2b + buf * A;
-    cp_async_wait_all();
-    __syncthreads();  // #1: this step's inputs (copied during the previous step) are visible; previous step retired
-    LOOP_MARK(1);   // per-step loads
-    if (it + 1 < S) prefetch(it + 1);
-
-    // ---- pass 1: dwt[t] = chain gradient + external gradient + enc_h[t,:] . dc   (warp per frame, lane <-> d, TMEM)
+    // ---- per-step inputs: alignment (output of step s), its conv features, previous alignment (padded), gradients
+    float dcr[DPL2];
+#pragma unroll
+    for (int j = 0; j < DPL2; ++j) dcr[j] = (p.dc_all && lane + 32 * j < D) ? __ldg(p.dc_all + sb * D + lane + 32 * j) : 0.0f;
+    float dp[APL];
+#pragma unroll
+    for (int j = 0; j < APL; ++j) dp[j] = __ldg(p.dec_proj + sb * A + aoff + 32 * j);
+    for (int i = tid; i < tloc; i += NT) {
+      w_s[i] = __ldg(p.w_all + sb * Th + t0 + i);
+      dwt_s[i] = dwn_s[i] + (p.dw_all ? __ldg(p.dw_all + sb * Th + t0 + i) : 0.0f);
+    }
+    for (int i = tid; i < tloc * C; i += NT) {
+      const int tl = i / C;
+      conv_s[tl * CPP + (i - tl * C)] = __ldg(p.conv_all + (sb * Th + t0) * C + i);
+    }
     {
-      float dcr[DPL2];
-#pragma unroll
-      for (int j = 0; j < DPL2; ++j) dcr[j] = lane + 32 * j < D ? dcr_s[lane + 32 * j] : 0.0f;
-      for (int q = 0; q < nche; ++q) {
-        const int tl = kLW * q + warp;
-        float ev[DPL2];
-        tmem_load<DPL2>(tcol_enc + (uint32_t)(q * DPL2), ev);
-        tmem_wait_ld();
-        float dot = 0.0f;
-#pragma unroll
-        for (int j = 0; j < DPL2; ++j) dot = fmaf(dcr[j], ev[j], dot);
-        dot = warp_sum(dot);
-        if (lane == 0 && tl < tloc) dwt_s[tl] = dwn_s[tl] + dwx_s[tl] + dot;
+      const float *prev = s == 0 ? p.att_init + (size_t)b * Th : p.w_all + (sb - B) * Th;
+      for (int i = tid; i < g.App; i += NT) {
+        const int t = i - filts;
+        app[i] = (t >= 0 && t < Th) ? __ldg(prev + t) : 0.0f;
       }
+    }
+    __syncthreads();  // #1
+    LOOP_MARK(1);   // per-step loads
+
+    // ---- pass 1: dwt[t] += enc_h[t,:] . dc   (warp per frame, lane <-> d, enc_h from TMEM)
+    for (int q = 0; q < nche; ++q) {
+      const int tl = kLW * q + warp;
+      float ev[DPL2];
+      tmem_load<DPL2>(tcol_enc + (uint32_t)(q * DPL2), ev);
+      tmem_wait_ld();
+      float dot = 0.0f;
+#pragma unroll
+      for (int j = 0; j < DPL2; ++j) dot = fmaf(dcr[j], ev[j], dot);
+      dot = warp_sum(dot);
+      if (lane == 0 && tl < tloc) dwt_s[tl] += dot;
     }
     __syncthreads();  // #2: dwt complete
     LOOP_MARK(2);   // pass 1
-    if (warp == 0) {   // softmax backward needs sum_t w[t] dwt[t] over the whole utterance: partial -> every CTA
+    if (warp == 0) {
       float s1 = 0.0f;
       for (int tl = lane; tl < tloc; tl += 32) s1 = fmaf(w_s[tl], dwt_s[tl], s1);
       s1 = warp_sum(s1);
       if (lane < CL) st_async_f32(dsmem_addr(xc + rank, (uint32_t)lane), s1, dsmem_addr(&xbar1[par], (uint32_t)lane));
     }
-    float dp[APL];
-#pragma unroll
-    for (int j = 0; j < APL; ++j) dp[j] = dp_s[aoff + 32 * j];
-    bool have_S = false;   // the exchange is awaited lazily: the tanh recomputation of the first frame hides it
+    mbar_wait(&xbar1[par], ph);
     float Stot = 0.0f;
-    auto get_S = [&]() {
-      mbar_wait(&xbar1[par], ph);
-      for (int r = 0; r < CL; ++r) Stot += xc[r];
-      if (tid == 0) mbar_expect_tx(&xbar1[par], x1bytes);   // re-arm for step it+2
-      have_S = true;
-    };
+    for (int r = 0; r < CL; ++r) Stot += xc[r];
+    for (int tl = tid; tl < tloc; tl += NT) de_s[tl] = p.scaling * w_s[tl] * (dwt_s[tl] - Stot);
+    if (tid == 0) {
+      mbar_expect_tx(&xbar1[par], x1bytes);
+      if (it > 0) bulk_wait<0>();   // the previous step's d pre tile has left shared memory (and landed)
+    }
+    __syncthreads();  // #3
+    LOOP_MARK(3);   // softmax exchange
 
     // ---- pass 2: recompute x = tanh(W_att conv + pre + dec_proj), through tanh.  pair <-> frame, lane <-> channel
     float ddp[APL];
@@ -650,6 +630,7 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
       tmem_load<APL>(tcol_pre + (uint32_t)(q * APL), pv);
       tmem_wait_ld();
       if (tl < tloc) {
+        const float de = de_s[tl];
         const float *cvp = conv_s + tl * CPP;
         float cv[CPP];
 #pragma unroll
@@ -657,24 +638,17 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
           const float4 t4 = *reinterpret_cast<const float4 *>(cvp + c4);
           cv[c4] = t4.x; cv[c4 + 1] = t4.y; cv[c4 + 2] = t4.z; cv[c4 + 3] = t4.w;
         }
-        float xv[APL];
-#pragma unroll
-        for (int j = 0; j < APL; ++j) {
-          float2 u2 = make_float2(pv[j] + dp[j], 0.0f);
-#pragma unroll
-          for (int c2 = 0; c2 < CH2; ++c2)
-            u2 = __ffma2_rn(WattC[j][c2], make_float2(cv[2 * c2], 2 * c2 + 1 < CPP ? cv[2 * c2 + 1] : 0.0f), u2);
-          xv[j] = tanh_ex2(u2.x + u2.y);
-        }
-        if (!have_S) get_S();
-        const float de = p.scaling * w_s[tl] * (dwt_s[tl] - Stot);
         float2 dcv2[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) dcv2[c] = make_float2(0.0f, 0.0f);
         float *row = xs + (size_t)tl * A + aoff;
 #pragma unroll
         for (int j = 0; j < APL; ++j) {
-          const float x = xv[j];
+          float2 u2 = make_float2(pv[j] + dp[j], 0.0f);
+#pragma unroll
+          for (int c2 = 0; c2 < CH2; ++c2)
+            u2 = __ffma2_rn(WattC[j][c2], make_float2(cv[2 * c2], 2 * c2 + 1 < CPP ? cv[2 * c2 + 1] : 0.0f), u2);
+          const float x = tanh_ex2(u2.x + u2.y);
           dgv[j] = fmaf(de, x, dgv[j]);
           const float dt = de * gv[j] * (1.0f - x * x);
           ddp[j] += dt;
@@ -693,7 +667,6 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
         }
       }
     }
-    if (!have_S) get_S();       // (a warp without frames of its own)
     LOOP_MARK(4);   // pass 2
     fence_proxy_async_smem();   // this thread's tile writes -> visible to the bulk (async proxy) reads
     __syncwarp();
@@ -730,7 +703,7 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
     }
     if (warp == kLW - 1) {   // d gvec.bias = sum_t de[t]  (analytically zero over the utterance; kept for fidelity)
       float s2 = 0.0f;
-      for (int tl = lane; tl < tloc; tl += 32) s2 += p.scaling * w_s[tl] * (dwt_s[tl] - Stot);
+      for (int tl = lane; tl < tloc; tl += 32) s2 += de_s[tl];
       dgb += warp_sum(s2);
     }
     LOOP_MARK(6);   // pushes
@@ -804,14 +777,7 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
         if (nv > 4) o[4] = a4;
       }
     }
-    if (tid == 0) {
-      mbar_expect_tx(&xbar2[par], x2bytes);
-      // the d pre tile must be free before the next step's pass 2 rewrites it: the TMA unit has had the whole post pass
-      // to read it.  The plain store of the first processed step must also have LANDED before the next step's
-      // reduce-add may be issued (stores and reductions to the same addresses are not ordered otherwise).
-      if (it == 0) bulk_wait<0>();
-      else bulk_wait_read<0>();
-    }
+    if (tid == 0) mbar_expect_tx(&xbar2[par], x2bytes);
     __syncthreads();  // #5
     LOOP_MARK(9);   // d att_prev partials
     if (s > 0) {
@@ -916,9 +882,8 @@ inline bool loop_geom_bwd(int B, int Th, int D, int A, int C, int K, int CP, int
     g.ncols = g.col_enc + 4 * nche_max * dpl2;
     const size_t scr = (size_t)A * (CP + 1) > (size_t)round4(kKQ * CP * g.tloc_max) ? (size_t)A * (CP + 1)
                                                                                    : (size_t)round4(kKQ * CP * g.tloc_max);
-    const size_t floats = (size_t)g.tloc_max * A + 2 * (size_t)CP * g.App + 2 * (size_t)g.App +
-                          2 * (size_t)g.tloc_max * CPP + 4 * (size_t)round4(g.tloc_max) + 2 * (size_t)g.Dp + 2 * (size_t)A +
-                          g.CKp + 2 * (size_t)round4(g.tloc_max) + 2 * (size_t)g.tloc_max * 16 + (size_t)kLW * (A / 2) + scr +
+    const size_t floats = (size_t)g.tloc_max * A + 2 * (size_t)CP * g.App + g.App + g.CKp + (size_t)g.tloc_max * CPP +
+                          4 * (size_t)round4(g.tloc_max) + 2 * (size_t)g.tloc_max * 16 + (size_t)kLW * (A / 2) + scr +
                           2 * (size_t)kLMaxCL * A + 2 * kLMaxCL;
     smem = 128 + sizeof(float) * floats;
     if (smem <= 226 * 1024 && g.ncols <= 512) return true;

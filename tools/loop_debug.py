@@ -16,7 +16,7 @@ L = _lib.lib()
 L.re2e_loop_debug_read.argtypes = [ctypes.c_void_p, ctypes.c_int]
 buf = (ctypes.c_longlong * (16 * 512))()
 names = {0: ["prologue", "conv", "conv_red", "sweep(e+ctx)", "bar3", "pushes", "xwait", "softmax+out"],
-         1: ["prologue", "inputs+bar1", "pass1", "-", "pass2", "tma+bar4", "pushes", "param_grads", "xwait2",
+         1: ["prologue", "loads", "pass1", "smx_exch", "pass2", "tma+bar4", "pushes", "param_grads", "xwait2",
              "datt_part", "datt_red"]}
 mhz = 1965.0   # SM clock under load on this pool (clock64 counts SM cycles)
 for spec in bench.kernel_specs(hp, db, cfg, dev):
