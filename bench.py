@@ -356,6 +356,52 @@ def kernel_specs(hp, db, cfg, dev):
     return specs
 
 
+def recog_bench(rank, world, dev, total_utts=1000, per_rank_cap=125):
+    """BASELINE configs[4] (joint_recog.py:143-149, run.sh:199-226): hybrid CTC/attention beam search, beam 10,
+    ctc_weight 0.3, maxlenratio = minlenratio = 0 (end_detect), nbest 1, over a seeded set of 1000 synthetic utterances
+    (encoder outputs Th ~ U(75, 200) = T/4 of 300..800 frames; default AttLoc / decoder / CTC dimensions, V = 4233),
+    utterance-sharded across the ranks with no collective.  Every rank decodes at most ``per_rank_cap`` utterances of
+    its shard (8 ranks x 125 = the full set; fewer ranks = a bounded sample of the same set, stated in the record) so
+    that the default run stays short.  Returns (utterances decoded by this rank, seconds, tokens emitted)."""
+    import types
+    from robust_e2e_gan_b200 import CTC, AttLoc, Decoder, synth
+    from robust_e2e_gan_b200.parallel import shard_range
+    synth.BEAM_CASES["_recog"] = dict(V=4233, D=320, Z=300, A=320, C=10, filts=100, Th=200, beam=10, ctc_weight=0.3,
+                                      nbest=1, penalty=0.0, maxlenratio=0.0, minlenratio=0.0, eos_bias=2.0, seed=5000)
+    c, sd, _, _ = synth.beam_case("_recog")
+    att = AttLoc(c["D"], c["Z"], c["A"], c["C"], c["filts"], "softmax")
+    dec = Decoder(c["D"], c["V"], 1, c["Z"], c["sos"], c["eos"], att)
+    ctc = CTC(c["V"], c["D"], 0.0)
+    dec.load_state_dict({k: v for k, v in sd.items() if not k.startswith("ctc_lo")})
+    ctc.load_state_dict({k: v for k, v in sd.items() if k.startswith("ctc_lo")})
+    dec, ctc = dec.to(dev).eval(), ctc.to(dev).eval()
+    g = torch.Generator().manual_seed(5001)
+    lens = torch.randint(75, 201, (total_utts,), generator=g).tolist()
+    lo, hi = shard_range(total_utts, rank, world)
+    hi = min(hi, lo + per_rank_cap)
+    hs = {}
+    for i in range(total_utts):                    # one generator stream: utterance i is the same at every world size
+        h = torch.tanh(torch.randn(lens[i], c["D"], generator=g))
+        if lo <= i < hi:
+            hs[i] = h.pin_memory()
+    ra = types.SimpleNamespace(beam_size=c["beam"], penalty=c["penalty"], ctc_weight=c["ctc_weight"],
+                               maxlenratio=c["maxlenratio"], minlenratio=c["minlenratio"], nbest=c["nbest"], lm_weight=0.0)
+
+    def decode(i):
+        h = hs[i].to(dev, non_blocking=True)
+        lpz = ctc.log_softmax(h.unsqueeze(0))[0]
+        return dec.recognize_beam(h, lpz, ra, None)
+
+    decode(lo)                                     # warm-up (allocator, shared-memory attributes)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    toks = 0
+    for i in range(lo, hi):
+        toks += len(decode(i)[0]["yseq"]) - 1
+    torch.cuda.synchronize()
+    return hi - lo, time.perf_counter() - t0, toks
+
+
 def kernel_rooflines(hp, db, cfg, peak, dev):
     """Per-kernel CUDA-event timings: each kernel is captured R times into a CUDA graph and replayed, so
     the events see back-to-back launches without Python gaps.  achieved = algorithmic bytes / avg launch."""
@@ -415,6 +461,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run the three branches of the step on ONE stream (A/B)")
+    ap.add_argument("--no-recog", action="store_true", help="skip the beam-search (configs[4]) record")
+    ap.add_argument("--per-step-loop", action="store_true",
+                    help="one AttLoc launch per decoder step instead of the persistent loop kernels (A/B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -437,7 +486,7 @@ def main():
     peak, peak_src = load_peaks()
 
     from robust_e2e_gan_b200.hotpath import StepRunner
-    hp = HotPath(cfg, seed=4000, overlap=not args.no_overlap).to(dev)   # identical init on every rank
+    hp = HotPath(cfg, seed=4000, overlap=not args.no_overlap, fused_loop=not args.per_step_loop).to(dev)   # identical init on every rank
     hb = make_batch(cfg, seed=4000 + rank).pin()         # distinct utterances per rank
     db = hb.to(dev)
     torch.cuda.synchronize()
@@ -578,6 +627,26 @@ def main():
             "mode": mode, "host_affinity": ("%d CPUs local to the GPU" % bound_cpus) if bound_cpus else "inherited",
             "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks}
 
+    # ---- BASELINE configs[4]: beam search, utterance-sharded, no collective (a secondary record on the same line)
+    if not args.no_recog:
+        barrier()
+        n_dec, sec, toks = recog_bench(rank, world, dev)
+        rt = torch.tensor([sec, float(n_dec), float(toks)], device=dev, dtype=torch.float64)
+        if world > 1:
+            mx = rt.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(rt, op=dist.ReduceOp.SUM)
+            sec = float(mx[0].item())
+        total_dec, total_tok = int(rt[1].item()), int(rt[2].item())
+        line["recog"] = {"metric": "utterances/sec (beam search, beam=10, ctc_weight=0.3, maxlenratio=0)",
+                         "value": total_dec / sec, "unit": "utt/s", "n_gpus": world, "utterances": total_dec,
+                         "of_set": 1000, "tokens_per_utt": total_tok / max(1, total_dec),
+                         "ms_per_utt_per_gpu": sec / max(1, total_dec / world) * 1e3,
+                         "sample": "%d of the 1000 seeded utterances (each rank decodes <= 125 of its shard; 8 ranks "
+                                   "cover the set); seeded untrained weights never emit <eos>, so every search runs "
+                                   "to maxlen = Th -- the longest case" % total_dec,
+                         "workload": "BASELINE configs[4]: joint_recog beam search, Th~U(75,200), V=4233, D=A=320, "
+                                     "Z=300, sharded by utterance, no collective"}
     if rank == 0:
         if not args.no_kernels:
             ks = kernel_rooflines(hp, db, cfg, peak, dev)

@@ -140,6 +140,22 @@ def masked_fbank(linear_out, mix_inputs, input_sizes, fc, fbank_cmvn=None, mask_
     return (Y, enh) if return_enhanced else Y
 
 
+def global_mean_var(stats, frames):
+    """(mean, var) per mel bin from running sums ``stats`` = [sum; sum of squares] (2, M) float64 (any device) over
+    ``frames`` frames.  Under utterance-sharded data parallelism (torch.distributed initialised, world > 1) every rank
+    accumulated its own utterances: the statistics of the whole set are the sums over the ranks -- ONE
+    all-reduce of 2M + 1 doubles -- so every rank returns the same CMVN.  Returns float64 numpy arrays."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        packed = torch.cat([stats.reshape(-1), stats.new_tensor([float(frames)])])
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+        stats, frames = packed[:-1].view_as(stats), float(packed[-1].item())
+    s = stats.cpu().numpy()
+    mean = s[0] / frames
+    var = s[1] / frames - np.square(mean)
+    return mean, var
+
+
 # ----------------------------------------------------------------------------------------- module
 class FFTModel(ModelBase):
     """Base of FbankModel in the reference (model/feat_model.py:36-90).  Only ``compute_cmvn`` is
@@ -187,9 +203,7 @@ class FFTModel(ModelBase):
             self.frame_count += int(sizes.clamp(max=T).sum())
             self.cmvn_processed_num += int(sizes.numel())
             return None
-        s = self._dev_sum.cpu().numpy()
-        mean = s[0] / self.frame_count
-        var = s[1] / self.frame_count - np.square(mean)
+        mean, var = global_mean_var(self._dev_sum, self.frame_count)
         self.fbank_cmvn[0, :] = (-mean).astype(np.float32)
         self.fbank_cmvn[1, :] = (1 / np.sqrt(var)).astype(np.float32)
         return self.fbank_cmvn

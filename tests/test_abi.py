@@ -61,3 +61,29 @@ def test_sass_is_sm100a_only_and_uses_tma(built):
     assert "UBLKCP" in sass            # cp.async.bulk (TMA 1-D) in the AttLoc kernels
     assert "UBLKRED" in sass           # cp.reduce.async.bulk: d_pre accumulated by the TMA unit
     assert "UCGABAR" in sass           # cluster barrier
+    assert "UTCHMMA" in sass           # tcgen05.mma (kind::tf32): dense layers and the mel projection
+    assert "LDTM" in sass              # tcgen05.ld: TMEM accumulators read back / resident operands of the loop backward
+    assert "STTM" in sass              # tcgen05.st: pre / enc_h rows parked in TMEM by the decoder-loop backward
+    assert "UTMALDG" in sass           # cp.async.bulk.tensor loads (TMA tiles of the GEMM operands)
+    assert "UTMASTG" in sass           # TMA tensor stores (GEMM epilogue)
+
+
+def test_decoder_loop_kernels_are_cluster_kernels_with_tmem_and_dsmem():
+    """Per-kernel SASS evidence (tools/sass_opcodes.py, committed as profiles/r02_sass_opcodes.txt): the persistent
+    decoder-loop kernels use distributed-shared-memory stores with mbarrier signalling, bulk copies, and (backward)
+    tensor memory + the TMA reduce-add."""
+    import importlib.util
+    if not os.path.exists("/usr/local/cuda/bin/cuobjdump"):
+        pytest.skip("no cuobjdump")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("sass_opcodes", os.path.join(root, "tools", "sass_opcodes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    counts = mod.kernel_opcodes(_lib.LIB_PATH)
+    fwd = [c for n, c in counts.items() if "attloc_loop_fwd_kernel" in n]
+    bwd = [c for n, c in counts.items() if "attloc_loop_bwd_kernel" in n]
+    assert fwd and bwd
+    for c in fwd:
+        assert c["UBLKCP"] >= 2 and c["STAS"] > 0 and c["SYNCS"] > 0 and c["FFMA2"] > 0
+    for c in bwd:
+        assert c["LDTM"] > 0 and c["STTM"] > 0 and c["UBLKRED"] > 0 and c["STAS"] > 0 and c["FFMA2"] > 0

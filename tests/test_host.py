@@ -130,3 +130,32 @@ def test_bind_host_to_gpu_is_a_no_op_without_topology(monkeypatch):
     assert bind_host_to_gpu(0) == 0
     if not __import__("torch").cuda.is_available():
         assert os.sched_getaffinity(0) == before
+
+
+def _cmvn_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from robust_e2e_gan_b200.feat_model import global_mean_var
+    g = torch.Generator().manual_seed(5)
+    y = torch.randn(40, 6, generator=g).double() * 3 + 1.5          # 40 frames of 6 mel bins, the whole set
+    lo, hi = (0, 13) if rank == 0 else (13, 40)                      # unequal shards
+    mine = y[lo:hi]
+    mean, var = global_mean_var(torch.stack([mine.sum(0), (mine * mine).sum(0)]), hi - lo)
+    ok = np.allclose(mean, y.mean(0).numpy()) and np.allclose(var, y.var(0, unbiased=False).numpy())
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_cmvn_statistics_are_reduced_over_ranks_world2_gloo():
+    """compute_cmvn's final step under data parallelism: per-rank (sum, sumsq, count) all-reduced, every
+    rank gets the statistics of the WHOLE set."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cmvn_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

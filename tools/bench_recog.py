@@ -20,7 +20,6 @@ import types
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 import torch  # noqa: E402
 
@@ -31,7 +30,7 @@ def main():
     ap.add_argument("--cpu-utts", type=int, default=2)
     ap.add_argument("--beam", type=int, default=10)
     args = ap.parse_args()
-    import helpers
+    from robust_e2e_gan_b200 import synth as helpers
     from robust_e2e_gan_b200 import CTC, AttLoc, Decoder
     from robust_e2e_gan_b200.parallel import init_distributed, shard_range
     rank, world = init_distributed()
