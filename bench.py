@@ -249,16 +249,37 @@ def kernel_specs(hp, db, cfg, dev):
     nll, loss = torch.empty(B, **f32), torch.empty(1, **f32)
     valid_frames = int(hl.sum())
 
+    # the front-end kernels the step really runs: banded (streaming) for the mel bank, dense tcgen05 otherwise
+    from robust_e2e_gan_b200.feat_model import _band_for
+    band = _band_for(hp.feat.fc, B, T)
+    Y1, Y2 = torch.empty(B, T, M, **f32), torch.empty(B, T, M, **f32)
+
     def k_fb_fwd():
-        _lib.check(L.re2e_fbank_fwd(P(db.mask_logits), 1, P(db.mix), P(fc), P(db.cmvn), P(lens), P(Y), P(G), None,
-                                    B, T, F, M, sp()))
+        if band is not None:
+            _lib.check(L.re2e_fbank_band_fwd(P(db.mask_logits), 1, P(db.mix), None, P(band[0]), P(band[1]), P(db.cmvn),
+                                             P(lens), P(Y), P(G), None, None, B, T, F, M, sp()))
+        else:
+            _lib.check(L.re2e_fbank_fwd(P(db.mask_logits), 1, P(db.mix), P(fc), P(db.cmvn), P(lens), P(Y), P(G), None,
+                                        B, T, F, M, sp()))
 
     def k_fb_fwd_plain():
-        _lib.check(L.re2e_fbank_fwd(None, 0, P(db.clean), P(fc), P(db.cmvn), None, P(Y), None, None, B, T, F, M, sp()))
+        if band is not None:
+            _lib.check(L.re2e_fbank_band_fwd(None, 0, P(db.clean), None, P(band[0]), P(band[1]), P(db.cmvn), None, P(Y),
+                                             None, None, None, B, T, F, M, sp()))
+        else:
+            _lib.check(L.re2e_fbank_fwd(None, 0, P(db.clean), P(fc), P(db.cmvn), None, P(Y), None, None, B, T, F, M, sp()))
+
+    def k_fb_joint():
+        _lib.check(L.re2e_fbank_band_fwd(P(db.mask_logits), 1, P(db.mix), P(db.clean), P(band[0]), P(band[1]), P(db.cmvn),
+                                         P(lens), P(Y), P(G), P(Y1), P(Y2), B, T, F, M, sp()))
 
     def k_fb_bwd():
-        _lib.check(L.re2e_fbank_bwd(P(dY), P(G), P(db.mask_logits), 1, P(db.mix), P(fc), P(lens), P(din), None,
-                                    B, T, F, M, sp()))
+        if band is not None:
+            _lib.check(L.re2e_fbank_band_bwd(P(dY), P(G), P(db.mask_logits), 1, P(db.mix), P(band[2]), P(band[3]), P(lens),
+                                             P(din), B, T, F, M, sp()))
+        else:
+            _lib.check(L.re2e_fbank_bwd(P(dY), P(G), P(db.mask_logits), 1, P(db.mix), P(fc), P(lens), P(din), None,
+                                        B, T, F, M, sp()))
 
     def k_att_fwd():
         _lib.check(L.re2e_attloc_step_fwd(P(pre), P(enc), P(dz), P(ap), P(W_dec), P(W_att), P(W_conv), P(gv), P(gb),
@@ -336,7 +357,7 @@ def kernel_specs(hp, db, cfg, dev):
     loop_bwd_alg = nst * (4.0 * B * Th * (A + D) + 4.0 * B * Th * A + 4.0 * B * Th * (4 + C))
     loop_fwd_res = 4.0 * B * Th * (A + D) + nst * 4.0 * B * (A + D + Th + Th * C)
     loop_bwd_res = 4.0 * B * Th * (A + D) + nst * (4.0 * B * Th * A + 4.0 * B * (2 * A + D + 3 * Th + Th * C))
-    specs = [
+    specs = ([("fbank_joint_fwd(mask,mix,clean->3Y,G)", k_fb_joint, 4.0 * N * (3 * F + 4 * M), 4)] if band is not None else []) + [
         ("fbank_fwd(mask,mag->Y,G)", k_fb_fwd, 4.0 * N * (2 * F + 2 * M), 4),
         ("fbank_fwd(mag->Y)", k_fb_fwd_plain, 4.0 * N * (F + M), 4),
         ("fbank_bwd(->d mask)", k_fb_bwd, 4.0 * N * (2 * M + 3 * F), 4),
@@ -654,8 +675,9 @@ def main():
             # launches of each kernel in ONE step of the timed workload (the per-step AttLoc kernels are only launched
             # when the loop kernels cannot take the shape)
             fused = hp.fused_loop and any(k.startswith("attloc_loop") for k in ks)
+            joint = hp.joint_frontend and any(k.startswith("fbank_joint") for k in ks)
             per_step = {"attloc_step_fwd": 0 if fused else cfg["steps"], "attloc_step_bwd": 0 if fused else cfg["steps"],
-                        "fbank_fwd(mag->Y)": 2}
+                        "fbank_fwd(mag->Y)": 0 if joint else 2, "fbank_fwd(mask,mag->Y,G)": 0 if joint else 1}
             dom = max((k for k in ks if "frac_of_hbm_peak" in ks[k]),
                       key=lambda k: ks[k]["us_per_launch"] * per_step.get(k, 1))
             line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ks[dom]["achieved_GBps"], "peak": peak,

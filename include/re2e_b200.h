@@ -60,6 +60,29 @@ int re2e_fbank_bwd(const float *dY, const float *G, const float *mask, int mask_
                    const float *mag, const float *fc, const int32_t *lens, float *d_in, float *dfc,
                    int B, int T, int F, int M, void *stream);
 
+/* Banded filter bank (csrc/fbank_band.cu).  A triangular mel bank -- the reference's frozen 80-filter table
+ * (model/feat_model.py:15-33: every FFT bin feeds <= 2 filters) or any bank generated like model/e2e_common.py:104-132
+ * -- is banded; for it the front-end is a pure HBM stream (TMA bulk copies of 8-frame spans into a shared-memory ring,
+ * ~450 MACs per frame instead of the dense 257 x M projection).  The caller detects the structure ONCE from fc (F,M)
+ * and passes it as tables:
+ *   flo[M] int32, fw[M*32] : filter m = sum_{k<32} fw[m*32+k] * P[flo[m]+k]   (its support lies in 32 consecutive bins,
+ *                            flo[m] + 32 <= F)
+ *   mlo[F] int32, bw[F*4]  : bin f feeds filters mlo[f] .. mlo[f]+3 with weights bw[f*4+k]   (mlo[f] + 4 <= M)
+ * A bank that does not fit (a trained, dense fc) uses re2e_fbank_fwd / _bwd (tcgen05 dense projection).
+ * Forward, up to three outputs per launch (joint_train.py:158-161 -- `mag` is read once for two of them):
+ *   mask != NULL : Y_enh, G  from act(mask)*[t<lens]*mag   (as re2e_fbank_fwd);  Y_plain (optional) from plain mag
+ *   mask == NULL : Y_enh, G  from plain mag (the single-input form; Y_plain must be NULL)
+ *   mag2, Y2     : optional second plain input and its output (both or neither)
+ * Backward: d_in as re2e_fbank_bwd (no dfc: a frozen bank).  Shapes: (B*T) % 8 == 0, 32 <= F, 4 <= M <= 80
+ * (re2e_fbank_band_supported); inputs 16 B aligned. */
+int re2e_fbank_band_supported(int B, int T, int F, int M);
+int re2e_fbank_band_fwd(const float *mask, int mask_is_logit, const float *mag, const float *mag2,
+                        const int32_t *flo, const float *fw, const float *cmvn, const int32_t *lens, float *Y_enh,
+                        float *G, float *Y_plain, float *Y2, int B, int T, int F, int M, void *stream);
+int re2e_fbank_band_bwd(const float *dY, const float *G, const float *mask, int mask_is_logit, const float *mag,
+                        const int32_t *mlo, const float *bw, const int32_t *lens, float *d_in, int B, int T, int F,
+                        int M, void *stream);
+
 /* Stand-alone mask tail (enhance_model.py:157-164) forward / backward, for callers that
  * need `enhance_out` itself (e.g. the L1 mask loss at :166-172). */
 int re2e_mask_apply_fwd(const float *logits, const float *mag, const int32_t *lens, float *enh,

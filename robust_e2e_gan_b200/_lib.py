@@ -31,6 +31,9 @@ SIGNATURES = {
     "re2e_launch_count": (_c.c_ulonglong, []),
     "re2e_fbank_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "re2e_fbank_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "re2e_fbank_band_supported": (_I, [_I] * 4),
+    "re2e_fbank_band_fwd": (_I, [_P, _I] + [_P] * 10 + [_I] * 4 + [_P]),
+    "re2e_fbank_band_bwd": (_I, [_P, _P, _P, _I] + [_P] * 5 + [_I] * 4 + [_P]),
     "re2e_mask_apply_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "re2e_mask_apply_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "re2e_cmvn_stats": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),

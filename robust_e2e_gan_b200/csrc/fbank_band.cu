@@ -1,0 +1,319 @@
+// Front-end for a BANDED filter bank (sm_100a): mask tail of EnhanceModel.forward (model/enhance_model.py:157-164)
+// + FbankModel.forward (model/feat_model.py:118-135) and its backward, streaming at HBM rate.
+//
+// A triangular mel bank -- the reference's frozen 80-filter table (model/feat_model.py:15-33: 501 non-zeros, every FFT
+// bin feeds at most 2 filters) and the generic 40-filter bank alike -- is banded: filter m only sees a short run of
+// bins, bin f only feeds a couple of neighbouring filters.  The dense 257 x M projection (10 K MACs per frame on the
+// tensor cores, whose operand traffic through shared memory was the measured limiter of the dense kernel) collapses to
+// ~450 MACs per frame: the kernel is a pure stream.  The caller detects the structure once from `fc` and passes it as
+// two small tables (see re2e_fbank_band_fwd in the header); a trained, dense `fc` keeps using the tcgen05 kernels.
+//
+// Rows are F = 257 floats = 1028 B (not 16 B aligned), but a span of 8 rows is 8224 B = 514 x 16 B: every tile of 8
+// frames is ONE contiguous, aligned run per input, fetched by the TMA unit (cp.async.bulk -> UBLKCP) into a ring of
+// shared-memory stages, each signalled on its own mbarrier; 4 stages (up to 25 KB each) are in flight per CTA and two
+// CTAs share an SM, so ~200 KB per SM are outstanding -- enough for the HBM latency-bandwidth product.  Up to THREE
+// outputs per launch (joint_train.py:158-161: enhance_feat from mask x mix, mix_feat from mix, clean_feat from clean):
+// `mix` is read once for two of them.
+//   forward : elementwise x^2 in place in the stage (sigmoid, length mask), then thread <-> (frame, filter) with the
+//             filter's <= 32 weights in registers; Y / G of a tile are 8*M contiguous floats: fully coalesced stores
+//   backward: dP = dY*G per tile in shared memory, thread <-> elements of the (frame, bin) tile with the bin's <= 4
+//             weights from a shared table; the d_in tile is formed in place and handed back to the TMA unit (bulk store)
+// Algorithmic bytes: forward 4N(2F + 2M) masked (+ 4N(F + M) per extra plain output); backward 4N(3F + 2M).
+#include "common.cuh"
+
+namespace re2e {
+namespace {
+
+constexpr int kBR = 8;         // frames per tile (8 * 1028 B = 514 * 16 B)
+constexpr int kBS = 4;         // ring stages
+constexpr int kBandW = 32;     // bins per filter window
+constexpr int kBinW = 4;       // filters per bin window
+
+struct BandFwdParams {
+  const float *mask, *mag, *mag2, *fw, *cmvn;
+  const int32_t *flo, *lens;
+  float *Y_enh, *G, *Y_plain, *Y2;
+  int mask_is_logit, N, T, F, M, ntiles;
+};
+
+struct BandBwdParams {
+  const float *dY, *G, *mask, *mag, *bw;
+  const int32_t *mlo, *lens;
+  float *d_in;
+  int mask_is_logit, N, T, F, M, ntiles;
+};
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// NBUF = inputs per stage: mask (if any), mag, mag2 (if any)
+template <int NBUF>
+__global__ void __launch_bounds__(640, 1) fbank_band_fwd_kernel(const BandFwdParams p) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int F = p.F, M = p.M, T = p.T;
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int tile_f = kBR * F;                       // floats per input tile
+  const bool has_mask = p.mask != nullptr, has2 = p.mag2 != nullptr;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smraw);          // [kBS]
+  float *ring = reinterpret_cast<float *>(smraw + 128);           // kBS * NBUF * tile_f
+  const int my_tiles = p.ntiles > (int)blockIdx.x ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  auto issue = [&](int i) {   // tile #i of this CTA -> stage i % kBS   (one thread)
+    const int st = i % kBS;
+    const size_t row0 = ((size_t)blockIdx.x + (size_t)i * gridDim.x) * kBR;
+    const uint32_t bytes = (uint32_t)tile_f * 4u;
+    float *dst = ring + (size_t)st * NBUF * tile_f;
+    mbar_expect_tx(&full[st], bytes * NBUF);
+    int slot = 0;
+    if (has_mask) bulk_g2s(dst + (slot++) * tile_f, p.mask + row0 * F, bytes, &full[st]);
+    bulk_g2s(dst + (slot++) * tile_f, p.mag + row0 * F, bytes, &full[st]);
+    if (has2) bulk_g2s(dst + (slot++) * tile_f, p.mag2 + row0 * F, bytes, &full[st]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kBS; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+    const int first = my_tiles < kBS ? my_tiles : kBS;
+    for (int i = 0; i < first; ++i) issue(i);
+  }
+  // this thread's (frame, filter): the filter's window of weights lives in registers
+  const int r = tid / M, m = tid - r * M;
+  const bool worker = tid < kBR * M;
+  float w[kBandW];
+  int flo = 0, nw = 0;
+  float c0 = 0.0f, c1 = 1.0f;
+  if (worker) {
+    flo = __ldg(p.flo + m);
+#pragma unroll
+    for (int k = 0; k < kBandW; ++k) {
+      w[k] = __ldg(p.fw + m * kBandW + k);
+      if (w[k] != 0.0f) nw = k + 1;
+    }
+    if (p.cmvn) { c0 = __ldg(p.cmvn + m); c1 = __ldg(p.cmvn + M + m); }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kBandW; ++k) w[k] = 0.0f;
+  }
+  __syncthreads();
+
+  for (int i = 0; i < my_tiles; ++i) {
+    const int st = i % kBS;
+    const size_t row0 = ((size_t)blockIdx.x + (size_t)i * gridDim.x) * kBR;
+    float *buf = ring + (size_t)st * NBUF * tile_f;
+    float *b_mask = buf, *b_mag = has_mask ? buf + tile_f : buf, *b_mag2 = b_mag + tile_f;
+    mbar_wait(&full[st], (uint32_t)(i / kBS) & 1u);
+    // ---- powers in place: mask slot <- (act(mask) * valid * mag)^2, mag slot <- mag^2, mag2 slot <- mag2^2
+    for (int idx = tid; idx < tile_f; idx += NT) {
+      const float x = b_mag[idx];
+      if (has_mask) {
+        const int rr = idx / F;
+        const size_t n = row0 + rr;
+        const int b = (int)(n / T), t = (int)(n - (size_t)b * T);
+        float e = 0.0f;
+        if (!p.lens || t < __ldg(p.lens + b)) {
+          const float mk = b_mask[idx];
+          e = (p.mask_is_logit ? sigmoid_fast(mk) : mk) * x;
+        }
+        b_mask[idx] = e * e;
+      }
+      if (!has_mask || p.Y_plain) b_mag[idx] = x * x;
+      if (has2) { const float y = b_mag2[idx]; b_mag2[idx] = y * y; }
+    }
+    __syncthreads();
+    // ---- banded projection + log + CMVN: thread <-> (frame, filter)
+    if (worker) {
+      const size_t o = row0 * M + tid;                 // the tile's outputs are 8*M contiguous floats
+      const int base = r * F + flo;
+      auto project = [&](const float *P) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int c = 0; c < kBandW / 8; ++c)
+          if (8 * c < nw) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc = fmaf(w[8 * c + k], P[base + 8 * c + k], acc);
+          }
+        return acc;
+      };
+      if (has_mask) {
+        const float P = project(b_mask);
+        const bool ok = P > 1e-7f;
+        p.Y_enh[o] = (__logf(ok ? P : 1e-7f) + c0) * c1;
+        if (p.G) p.G[o] = ok ? __fdividef(c1, P) : 0.0f;
+      }
+      if (!has_mask) {                                 // single-input form: the plain input IS output 0
+        const float P = project(b_mag);
+        const bool ok = P > 1e-7f;
+        p.Y_enh[o] = (__logf(ok ? P : 1e-7f) + c0) * c1;
+        if (p.G) p.G[o] = ok ? __fdividef(c1, P) : 0.0f;
+      } else if (p.Y_plain) {
+        const float P = project(b_mag);
+        p.Y_plain[o] = (__logf(P > 1e-7f ? P : 1e-7f) + c0) * c1;
+      }
+      if (has2) {
+        const float P = project(b_mag2);
+        p.Y2[o] = (__logf(P > 1e-7f ? P : 1e-7f) + c0) * c1;
+      }
+    }
+    __syncthreads();   // stage consumed
+    if (tid == 0 && i + kBS < my_tiles) issue(i + kBS);
+  }
+}
+
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(512, 1) fbank_band_bwd_kernel(const BandBwdParams p) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  constexpr int NBUF = HAS_MASK ? 2 : 1;
+  const int F = p.F, M = p.M, T = p.T;
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int tile_f = kBR * F, tile_m = kBR * M;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smraw);          // [kBS]
+  float *btab = reinterpret_cast<float *>(smraw + 128);           // F * kBinW weights
+  int *mlo_s = reinterpret_cast<int *>(btab + F * kBinW);         // round4(F)
+  float *ring = reinterpret_cast<float *>(mlo_s + ((F + 3) & ~3));   // kBS * (NBUF*tile_f + 2*tile_m)
+  const int stage_f = NBUF * tile_f + 2 * tile_m;
+  const int my_tiles = p.ntiles > (int)blockIdx.x ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  auto issue = [&](int i) {
+    const int st = i % kBS;
+    const size_t row0 = ((size_t)blockIdx.x + (size_t)i * gridDim.x) * kBR;
+    float *dst = ring + (size_t)st * stage_f;
+    const uint32_t bf = (uint32_t)tile_f * 4u, bm = (uint32_t)tile_m * 4u;
+    mbar_expect_tx(&full[st], bf * NBUF + 2u * bm);
+    if (HAS_MASK) bulk_g2s(dst, p.mask + row0 * F, bf, &full[st]);
+    bulk_g2s(dst + (NBUF - 1) * tile_f, p.mag + row0 * F, bf, &full[st]);
+    bulk_g2s(dst + NBUF * tile_f, p.dY + row0 * M, bm, &full[st]);
+    bulk_g2s(dst + NBUF * tile_f + tile_m, p.G + row0 * M, bm, &full[st]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kBS; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+    const int first = my_tiles < kBS ? my_tiles : kBS;
+    for (int i = 0; i < first; ++i) issue(i);
+  }
+  for (int i = tid; i < F * kBinW; i += NT) btab[i] = __ldg(p.bw + i);
+  for (int i = tid; i < F; i += NT) mlo_s[i] = __ldg(p.mlo + i);
+  __syncthreads();
+
+  for (int i = 0; i < my_tiles; ++i) {
+    const int st = i % kBS;
+    const size_t row0 = ((size_t)blockIdx.x + (size_t)i * gridDim.x) * kBR;
+    float *buf = ring + (size_t)st * stage_f;
+    float *b_out = buf;                                   // mask slot (or the mag slot): d_in is formed in place
+    float *b_mag = buf + (NBUF - 1) * tile_f;
+    float *dP = buf + NBUF * tile_f;                      // dY slot <- dY * G
+    const float *Gs = dP + tile_m;
+    mbar_wait(&full[st], (uint32_t)(i / kBS) & 1u);
+    for (int idx = tid; idx < tile_m; idx += NT) dP[idx] *= Gs[idx];
+    __syncthreads();
+    for (int idx = tid; idx < tile_f; idx += NT) {
+      const int rr = idx / F, f = idx - rr * F;
+      const float4 wv = *reinterpret_cast<const float4 *>(btab + f * kBinW);
+      const float *dp = dP + rr * M + mlo_s[f];
+      const float dsq = fmaf(wv.x, dp[0], fmaf(wv.y, dp[1], fmaf(wv.z, dp[2], wv.w * dp[3])));
+      const float mg = b_mag[idx];
+      float out;
+      if (HAS_MASK) {
+        const size_t n = row0 + rr;
+        const int b = (int)(n / T), t = (int)(n - (size_t)b * T);
+        out = 0.0f;
+        if (!p.lens || t < __ldg(p.lens + b)) {
+          const float mk = b_out[idx];
+          if (p.mask_is_logit) {
+            const float s = sigmoid_fast(mk);
+            out = 2.0f * s * mg * dsq * mg * s * (1.0f - s);    // d/d logit of (s*mag)^2 . dsq
+          } else {
+            out = 2.0f * mk * mg * dsq * mg;
+          }
+        }
+      } else {
+        out = 2.0f * mg * dsq;
+      }
+      b_out[idx] = out;
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(p.d_in + row0 * F, b_out, (uint32_t)tile_f * 4u);
+      bulk_commit();
+      // the stage of the PREVIOUS tile is refilled once its store has finished reading shared memory
+      if (i >= 1) {
+        bulk_wait_read<1>();
+        if (i - 1 + kBS < my_tiles) issue(i - 1 + kBS);
+      }
+    }
+  }
+  if (tid == 0) bulk_wait<0>();
+}
+
+inline bool band_shape_ok(int B, int T, int F, int M) {
+  const long long N = (long long)B * T;
+  return N % kBR == 0 && F >= kBandW && M >= kBinW && M <= 80 && N / kBR <= 0x7fffffff;
+}
+
+}  // namespace
+}  // namespace re2e
+
+using namespace re2e;
+
+extern "C" int re2e_fbank_band_supported(int B, int T, int F, int M) { return band_shape_ok(B, T, F, M) ? 1 : 0; }
+
+extern "C" int re2e_fbank_band_fwd(const float *mask, int mask_is_logit, const float *mag, const float *mag2,
+                                   const int32_t *flo, const float *fw, const float *cmvn, const int32_t *lens,
+                                   float *Y_enh, float *G, float *Y_plain, float *Y2, int B, int T, int F, int M,
+                                   void *stream) {
+  RE2E_CHECK_ARG(mag && flo && fw && B > 0 && T > 0 && F > 0 && M > 0);
+  RE2E_CHECK_ARG(Y_enh && (mask || !Y_plain));   // no mask: the plain input is output 0 (Y_enh, G)
+  RE2E_CHECK_ARG((mag2 != nullptr) == (Y2 != nullptr));
+  if (!band_shape_ok(B, T, F, M)) return RE2E_E_UNSUPPORTED;
+  RE2E_CHECK_ARG(aligned16(mag) && (!mask || aligned16(mask)) && (!mag2 || aligned16(mag2)));
+  BandFwdParams prm;
+  prm.mask = mask; prm.mag = mag; prm.mag2 = mag2; prm.fw = fw; prm.cmvn = cmvn; prm.flo = flo; prm.lens = lens;
+  prm.Y_enh = Y_enh; prm.G = G; prm.Y_plain = Y_plain; prm.Y2 = Y2; prm.mask_is_logit = mask_is_logit;
+  prm.N = B * T; prm.T = T; prm.F = F; prm.M = M; prm.ntiles = prm.N / kBR;
+  const int nbuf = (mask ? 1 : 0) + 1 + (mag2 ? 1 : 0);
+  const size_t smem = 128 + sizeof(float) * (size_t)kBS * nbuf * kBR * F;
+  const int threads = (kBR * M + 31) & ~31;
+  const int per_sm = smem * 2 <= 220 * 1024 && threads * 2 <= 2048 ? 2 : 1;
+  int grid = num_sms() * per_sm;
+  if (grid > prm.ntiles) grid = prm.ntiles;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if (nbuf == 1) {
+    if ((rc = ensure_smem(reinterpret_cast<const void *>(fbank_band_fwd_kernel<1>), smem)) != RE2E_OK) return rc;
+    fbank_band_fwd_kernel<1><<<grid, threads, smem, st>>>(prm);
+  } else if (nbuf == 2) {
+    if ((rc = ensure_smem(reinterpret_cast<const void *>(fbank_band_fwd_kernel<2>), smem)) != RE2E_OK) return rc;
+    fbank_band_fwd_kernel<2><<<grid, threads, smem, st>>>(prm);
+  } else {
+    if ((rc = ensure_smem(reinterpret_cast<const void *>(fbank_band_fwd_kernel<3>), smem)) != RE2E_OK) return rc;
+    fbank_band_fwd_kernel<3><<<grid, threads, smem, st>>>(prm);
+  }
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int re2e_fbank_band_bwd(const float *dY, const float *G, const float *mask, int mask_is_logit,
+                                   const float *mag, const int32_t *mlo, const float *bw, const int32_t *lens,
+                                   float *d_in, int B, int T, int F, int M, void *stream) {
+  RE2E_CHECK_ARG(dY && G && mag && mlo && bw && d_in && B > 0 && T > 0 && F > 0 && M > 0);
+  if (!band_shape_ok(B, T, F, M)) return RE2E_E_UNSUPPORTED;
+  RE2E_CHECK_ARG(aligned16(mag) && (!mask || aligned16(mask)) && aligned16(d_in) && aligned16(dY) && aligned16(G));
+  BandBwdParams prm;
+  prm.dY = dY; prm.G = G; prm.mask = mask; prm.mag = mag; prm.bw = bw; prm.mlo = mlo; prm.lens = lens; prm.d_in = d_in;
+  prm.mask_is_logit = mask_is_logit; prm.N = B * T; prm.T = T; prm.F = F; prm.M = M; prm.ntiles = prm.N / kBR;
+  const int nbuf = mask ? 2 : 1;
+  const size_t smem = 128 + sizeof(float) * ((size_t)F * kBinW + ((F + 3) & ~3) +
+                                             (size_t)kBS * ((size_t)nbuf * kBR * F + 2 * (size_t)kBR * M));
+  const int per_sm = smem * 2 <= 220 * 1024 ? 2 : 1;
+  int grid = num_sms() * per_sm;
+  if (grid > prm.ntiles) grid = prm.ntiles;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if (mask) {
+    if ((rc = ensure_smem(reinterpret_cast<const void *>(fbank_band_bwd_kernel<true>), smem)) != RE2E_OK) return rc;
+    fbank_band_bwd_kernel<true><<<grid, 512, smem, st>>>(prm);
+  } else {
+    if ((rc = ensure_smem(reinterpret_cast<const void *>(fbank_band_bwd_kernel<false>), smem)) != RE2E_OK) return rc;
+    fbank_band_bwd_kernel<false><<<grid, 512, smem, st>>>(prm);
+  }
+  count_launch();
+  return launch_status();
+}

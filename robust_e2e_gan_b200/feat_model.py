@@ -72,6 +72,56 @@ def generic_mel_banks(nfilt=40, nfft=512, samplerate=16000, lowfreq=0, highfreq=
     return fbank
 
 
+# ------------------------------------------------------------------------------------ band tables
+BAND_W, BIN_W = 32, 4          # csrc/fbank_band.cu: bins per filter window, filters per bin window
+_BAND_CACHE = {}
+
+
+def band_tables(fc):
+    """Structure tables of a BANDED bank for re2e_fbank_band_* (see include/re2e_b200.h), or None when ``fc`` (F, M)
+    numpy is not banded (some filter's support wider than 32 bins, or some bin feeding filters more than 4 apart --
+    e.g. a trained, dense bank).  Returns (flo int32 (M,), fw float32 (M,32), mlo int32 (F,), bw float32 (F,4))."""
+    F, M = fc.shape
+    if F < BAND_W or M < BIN_W:
+        return None
+    nz = fc != 0
+    flo, fw = np.zeros(M, np.int32), np.zeros((M, BAND_W), np.float32)
+    for m in range(M):
+        idx = np.flatnonzero(nz[:, m])
+        if idx.size:
+            if idx[-1] - idx[0] + 1 > BAND_W:
+                return None
+            flo[m] = min(int(idx[0]), F - BAND_W)
+        fw[m] = fc[flo[m]:flo[m] + BAND_W, m]
+    mlo, bw = np.zeros(F, np.int32), np.zeros((F, BIN_W), np.float32)
+    for f in range(F):
+        idx = np.flatnonzero(nz[f])
+        if idx.size:
+            if idx[-1] - idx[0] + 1 > BIN_W:
+                return None
+            mlo[f] = min(int(idx[0]), M - BIN_W)
+        bw[f] = fc[f, mlo[f]:mlo[f] + BIN_W]
+    return flo, fw, mlo, bw
+
+
+def _band_for(fc, B, T):
+    """Device band tables of ``fc`` when the banded kernels apply to this call, else None.  The structure is detected
+    once per (storage, version) of ``fc`` -- a device-to-host read, so never during a CUDA-graph capture (a capture
+    whose warm-up did not already see this ``fc`` uses the dense kernels)."""
+    F, M = fc.shape
+    if not _lib.load().re2e_fbank_band_supported(B, T, F, M):
+        return None
+    key = (fc.data_ptr(), fc._version, fc.device, F, M)
+    if key not in _BAND_CACHE:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        tabs = band_tables(fc.detach().float().cpu().numpy())
+        if len(_BAND_CACHE) > 16:
+            _BAND_CACHE.clear()
+        _BAND_CACHE[key] = None if tabs is None else tuple(torch.from_numpy(t).to(fc.device) for t in tabs)
+    return _BAND_CACHE[key]
+
+
 # --------------------------------------------------------------------------------------- autograd
 class _FbankFunction(torch.autograd.Function):
     """Y = CMVN(log(clamp((act(mask)*valid*mag)^2 @ fc))) ; mask may be None (single-input form)."""
@@ -92,13 +142,21 @@ class _FbankFunction(torch.autograd.Function):
         Y = torch.empty(B, T, M, device=dev, dtype=torch.float32)
         G = torch.empty(B, T, M, device=dev, dtype=torch.float32) if need_grad else None
         enh = torch.empty(B, T, F, device=dev, dtype=torch.float32) if (want_enh and mask is not None) else None
+        band = _band_for(fc, B, T) if enh is None else None
         with torch.cuda.device(dev):
-            _lib.check(L.re2e_fbank_fwd(_lib.ptr(mask), int(mask_is_logit), _lib.ptr(mag), _lib.ptr(fcc),
-                                        _lib.ptr(cm), _lib.ptr(ln), _lib.ptr(Y), _lib.ptr(G), _lib.ptr(enh),
-                                        B, T, F, M, _lib.stream_ptr()), "re2e_fbank_fwd")
+            if band is not None:      # banded (mel) bank: the streaming kernels
+                _lib.check(L.re2e_fbank_band_fwd(_lib.ptr(mask), int(mask_is_logit), _lib.ptr(mag), None,
+                                                 _lib.ptr(band[0]), _lib.ptr(band[1]), _lib.ptr(cm), _lib.ptr(ln),
+                                                 _lib.ptr(Y), _lib.ptr(G), None, None, B, T, F, M, _lib.stream_ptr()),
+                           "re2e_fbank_band_fwd")
+            else:
+                _lib.check(L.re2e_fbank_fwd(_lib.ptr(mask), int(mask_is_logit), _lib.ptr(mag), _lib.ptr(fcc),
+                                            _lib.ptr(cm), _lib.ptr(ln), _lib.ptr(Y), _lib.ptr(G), _lib.ptr(enh),
+                                            B, T, F, M, _lib.stream_ptr()), "re2e_fbank_fwd")
         if need_grad:
             ctx.save_for_backward(mask, mag, fcc, ln, G)
             ctx.mask_is_logit = int(mask_is_logit)
+            ctx.band = band
         if enh is not None:
             ctx.mark_non_differentiable(enh)
             return Y, enh
@@ -115,13 +173,64 @@ class _FbankFunction(torch.autograd.Function):
         want_in = ctx.needs_input_grad[0] if mask is not None else ctx.needs_input_grad[1]
         d_in = torch.empty(B, T, F, device=dev, dtype=torch.float32) if want_in else None
         dfc = torch.zeros(F, M, device=dev, dtype=torch.float32) if ctx.needs_input_grad[2] else None
+        band = ctx.band
         with torch.cuda.device(dev):
-            _lib.check(L.re2e_fbank_bwd(_lib.ptr(dY), _lib.ptr(G), _lib.ptr(mask), ctx.mask_is_logit,
-                                        _lib.ptr(mag), _lib.ptr(fcc), _lib.ptr(ln), _lib.ptr(d_in),
-                                        _lib.ptr(dfc), B, T, F, M, _lib.stream_ptr()), "re2e_fbank_bwd")
+            if band is not None and d_in is not None:      # banded bank: d_in from the streaming kernel
+                _lib.check(L.re2e_fbank_band_bwd(_lib.ptr(dY), _lib.ptr(G), _lib.ptr(mask), ctx.mask_is_logit,
+                                                 _lib.ptr(mag), _lib.ptr(band[2]), _lib.ptr(band[3]), _lib.ptr(ln),
+                                                 _lib.ptr(d_in), B, T, F, M, _lib.stream_ptr()), "re2e_fbank_band_bwd")
+                if dfc is not None:                        # a trainable bank that is (still) banded: dfc is dense
+                    _lib.check(L.re2e_fbank_bwd(_lib.ptr(dY), _lib.ptr(G), _lib.ptr(mask), ctx.mask_is_logit,
+                                                _lib.ptr(mag), _lib.ptr(fcc), _lib.ptr(ln), None, _lib.ptr(dfc),
+                                                B, T, F, M, _lib.stream_ptr()), "re2e_fbank_bwd")
+            else:
+                _lib.check(L.re2e_fbank_bwd(_lib.ptr(dY), _lib.ptr(G), _lib.ptr(mask), ctx.mask_is_logit,
+                                            _lib.ptr(mag), _lib.ptr(fcc), _lib.ptr(ln), _lib.ptr(d_in),
+                                            _lib.ptr(dfc), B, T, F, M, _lib.stream_ptr()), "re2e_fbank_bwd")
         if mask is not None:
             return d_in, None, dfc, None, None, None, None
         return None, d_in, dfc, None, None, None, None
+
+
+class _FbankJoint(torch.autograd.Function):
+    """The three front-end calls of one joint_train.py iteration (:158-161) in ONE launch when the bank is banded:
+    enhance_feat (mask tail x mix, differentiable w.r.t. the mask), mix_feat and clean_feat (plain, no gradient: the
+    bank is frozen and the inputs are data).  ``mix`` is read once for two outputs."""
+
+    @staticmethod
+    def forward(ctx, mask, mix, clean, fc, cmvn, lens, band):
+        L = _lib.lib()
+        dev = fc.device
+        mix, clean, mask = _lib.f32c(mix, dev), _lib.f32c(clean, dev), _lib.f32c(mask, dev)
+        cm = _lib.f32c(cmvn, dev) if cmvn is not None else None
+        ln = lens.to(dev, torch.int32, non_blocking=True).contiguous() if lens is not None else None
+        B, T, F = mix.shape
+        M = fc.shape[1]
+        need_grad = ctx.needs_input_grad[0]
+        Y, Ym, Yc = (torch.empty(B, T, M, device=dev, dtype=torch.float32) for _ in range(3))
+        G = torch.empty(B, T, M, device=dev, dtype=torch.float32) if need_grad else None
+        with torch.cuda.device(dev):
+            _lib.check(L.re2e_fbank_band_fwd(_lib.ptr(mask), 1, _lib.ptr(mix), _lib.ptr(clean), _lib.ptr(band[0]),
+                                             _lib.ptr(band[1]), _lib.ptr(cm), _lib.ptr(ln), _lib.ptr(Y), _lib.ptr(G),
+                                             _lib.ptr(Ym), _lib.ptr(Yc), B, T, F, M, _lib.stream_ptr()),
+                       "re2e_fbank_band_fwd")
+        if need_grad:
+            ctx.save_for_backward(mask, mix, ln, G, band[2], band[3])
+        ctx.mark_non_differentiable(Ym, Yc)
+        return Y, Ym, Yc
+
+    @staticmethod
+    def backward(ctx, dY, _dYm, _dYc):
+        L = _lib.lib()
+        mask, mix, ln, G, mlo, bw = ctx.saved_tensors
+        B, T, F = mix.shape
+        M = G.shape[2]
+        d_mask = torch.empty(B, T, F, device=mix.device, dtype=torch.float32)
+        with torch.cuda.device(mix.device):
+            _lib.check(L.re2e_fbank_band_bwd(_lib.ptr(_lib.f32c(dY, mix.device)), _lib.ptr(G), _lib.ptr(mask), 1,
+                                             _lib.ptr(mix), _lib.ptr(mlo), _lib.ptr(bw), _lib.ptr(ln), _lib.ptr(d_mask),
+                                             B, T, F, M, _lib.stream_ptr()), "re2e_fbank_band_bwd")
+        return d_mask, None, None, None, None, None, None
 
 
 def fbank(xs, fc, fbank_cmvn=None):
@@ -246,6 +355,28 @@ class FbankModel(FFTModel):
             fbank_cmvn = torch.from_numpy(np.asarray(fbank_cmvn, dtype=np.float32))
         return masked_fbank(linear_out, mix_inputs, input_sizes, self.fc, fbank_cmvn,
                             mask_is_logit=True, return_enhanced=return_enhanced)
+
+
+def _joint_features(self, linear_out, mix_inputs, clean_inputs, input_sizes, fbank_cmvn=None):
+    """enhance_feat, mix_feat, clean_feat of one joint_train.py iteration (:158-161):
+
+        enhance_feat = feat_model(mask-tail(linear_out, mix_inputs, input_sizes), cmvn)     (grad -> linear_out)
+        mix_feat     = feat_model(mix_inputs, cmvn)          clean_feat = feat_model(clean_inputs, cmvn)
+
+    One launch reading mask, mix and clean once when the bank is frozen and banded; three calls otherwise."""
+    if fbank_cmvn is not None and not torch.is_tensor(fbank_cmvn):
+        fbank_cmvn = torch.from_numpy(np.asarray(fbank_cmvn, dtype=np.float32))
+    if not torch.is_tensor(input_sizes):
+        input_sizes = torch.as_tensor(np.asarray(input_sizes))
+    B, T = mix_inputs.shape[0], mix_inputs.shape[1]
+    band = None if self.fc.requires_grad else _band_for(self.fc, B, T)
+    if band is not None and not (mix_inputs.requires_grad or clean_inputs.requires_grad):
+        return _FbankJoint.apply(linear_out, mix_inputs, clean_inputs, self.fc, fbank_cmvn, input_sizes, band)
+    enh = masked_fbank(linear_out, mix_inputs, input_sizes, self.fc, fbank_cmvn)
+    return enh, self.forward(mix_inputs, fbank_cmvn), self.forward(clean_inputs, fbank_cmvn)
+
+
+FbankModel.forward_joint = _joint_features
 
 
 class _MaskApply(torch.autograd.Function):

@@ -84,6 +84,7 @@ class HotPath(torch.nn.Module):
         # (AttLoc.forward_loop; the decoder states of all steps are inputs of the step, so mlp_dec of every step is one
         # dense product).  False: one AttLoc.forward per output position, as Decoder.forward calls it (A/B timing).
         self.fused_loop = fused_loop
+        self.joint_frontend = True     # the three front-end calls of joint_train.py:158-161 as one launch
         # overlap=True: the three independent branches of the step (front-end, CTC, attention decoder loop) run on
         # three CUDA streams, fork/join inside step(); autograd replays each branch's backward on its own stream.
         # The decoder loop is a serial chain of latency-bound cluster kernels that leaves SMs and issue slots idle;
@@ -141,10 +142,13 @@ class HotPath(torch.nn.Module):
             s_fe = s_ctc = main
         # -- front-end (joint_train.py:158-161)
         with torch.cuda.stream(s_fe):
-            enhance_feat = self.feat.forward_masked(mask_logits, b.mix, b.lens, b.cmvn)
-            with torch.no_grad():
-                clean_feat = self.feat(b.clean, b.cmvn)
-                mix_feat = self.feat(b.mix, b.cmvn)
+            if self.joint_frontend:      # one launch: mask, mix and clean each read once
+                enhance_feat, mix_feat, clean_feat = self.feat.forward_joint(mask_logits, b.mix, b.clean, b.lens, b.cmvn)
+            else:
+                enhance_feat = self.feat.forward_masked(mask_logits, b.mix, b.lens, b.cmvn)
+                with torch.no_grad():
+                    clean_feat = self.feat(b.clean, b.cmvn)
+                    mix_feat = self.feat(b.mix, b.cmvn)
         # -- CTC branch (model/e2e_model.py:192)
         with torch.cuda.stream(s_ctc):
             loss_ctc = self.ctc(hpad, b.hlens, b.targets if b.targets is not None else b.ys)

@@ -139,3 +139,72 @@ def test_errors_are_loud():
     fc = synth.mel_fc(257, 40).to(DEV)
     with pytest.raises((RuntimeError, AssertionError)):
         fbank(torch.rand(1, 4, 100, device=DEV), fc)          # wrong idim
+
+
+# ---- banded (mel) bank: the streaming kernels of csrc/fbank_band.cu ------------------------------------------------
+@pytest.mark.parametrize("B,T_,M,seed", [(8, 400, 40, 1234), (32, 800, 40, 2), (4, 200, 80, 3), (2, 12, 40, 4)])
+def test_banded_kernels_match_oracle_and_dense_path(B, T_, M, seed):
+    """The banded kernels are what a frozen mel bank runs on; same results as the oracle AND as the dense tcgen05/SIMT
+    path (forced by perturbing nothing but the dispatch), masked and single-input forms, forward and backward."""
+    from robust_e2e_gan_b200 import feat_model as fm
+    d = synth.frontend_batch(B=B, T=T_, seed=seed, zeros=min(16, B * T_))
+    g = torch.Generator().manual_seed(seed)
+    fc = (synth.mel_fc(257, M) if M == 40 else torch.from_numpy(fm.reference_fbank80().T.astype(np.float32))).to(DEV)
+    assert fm._band_for(fc, B, T_) is not None, "expected the banded path for this bank / shape"
+    cm = synth.cmvn(M, seed)
+    dY = torch.randn(B, T_, M, generator=g)
+    outs = {}
+    for dt in (torch.float32, torch.float64):
+        lo = d["mask_logits"].detach().clone().to(dt).requires_grad_(True)
+        y = o_fe.masked_fbank_forward(lo, d["mix"].to(dt), d["lens"], fc.cpu().to(dt), cm.to(dt))
+        y.backward(dY.to(dt))
+        mg = d["clean"].detach().clone().to(dt).requires_grad_(True)
+        y1 = o_fe.fbank_forward(mg, fc.cpu().to(dt), cm.to(dt))
+        y1.backward(dY.to(dt))
+        outs[dt] = (y.detach(), lo.grad, y1.detach(), mg.grad)
+    n0 = _lib.launch_count()
+    lo = d["mask_logits"].to(DEV).requires_grad_(True)
+    y = masked_fbank(lo, d["mix"].to(DEV), d["lens"], fc, cm.to(DEV))
+    y.backward(dY.to(DEV))
+    mg = d["clean"].to(DEV).requires_grad_(True)
+    y1 = fbank(mg, fc, cm.to(DEV))
+    y1.backward(dY.to(DEV))
+    assert _lib.launch_count() - n0 == 4          # one banded launch per direction and form
+    r32, r64 = outs[torch.float32], outs[torch.float64]
+    for got, i, what in ((y, 0, "Y masked"), (lo.grad, 1, "d logits"), (y1, 2, "Y plain"), (mg.grad, 3, "d mag")):
+        assert_close(got, r32[i], truth=r64[i], what=what + " (banded)")
+    # the dense kernels on the same inputs (a dense-looking copy of the bank: tiny weights everywhere keep it off the band path)
+    fcd = fc.clone()
+    fcd[0, :] += 1e-30
+    assert fm._band_for(fcd, B, T_) is None
+    lo2 = d["mask_logits"].to(DEV).requires_grad_(True)
+    y2 = masked_fbank(lo2, d["mix"].to(DEV), d["lens"], fcd, cm.to(DEV))
+    y2.backward(dY.to(DEV))
+    assert_close(y, y2, what="banded vs dense Y")
+    assert_close(lo.grad, lo2.grad, what="banded vs dense d logits")
+    assert torch.all(lo.grad[B - 1, int(d["lens"][B - 1]):] == 0)      # padded frames: exactly zero gradient
+
+
+def test_joint_three_output_forward_is_one_launch():
+    """FbankModel.forward_joint = the three front-end calls of joint_train.py:158-161 in one launch (mix read once)."""
+    B, T_, M = 8, 400, 40
+    d = synth.frontend_batch(B=B, T=T_, seed=21)
+    m = FbankModel(Args(fbank_dim=M)).to(DEV)
+    m.fc.data.copy_(synth.mel_fc(257, M))
+    cm = synth.cmvn(M, 5).to(DEV)
+    dY = torch.randn(B, T_, M, generator=torch.Generator().manual_seed(3)).to(DEV)
+    lo = d["mask_logits"].to(DEV).requires_grad_(True)
+    m.forward_joint(lo, d["mix"].to(DEV), d["clean"].to(DEV), d["lens"], cm)          # warm-up: band tables
+    n0 = _lib.launch_count()
+    enh, mixf, cleanf = m.forward_joint(lo, d["mix"].to(DEV), d["clean"].to(DEV), d["lens"], cm)
+    assert _lib.launch_count() - n0 == 1
+    enh.backward(dY)
+    assert _lib.launch_count() - n0 == 2
+    lo2 = d["mask_logits"].to(DEV).requires_grad_(True)
+    e2 = m.forward_masked(lo2, d["mix"].to(DEV), d["lens"], cm)
+    e2.backward(dY)
+    assert torch.equal(enh, e2) and torch.equal(lo.grad, lo2.grad)
+    assert torch.equal(mixf, m(d["mix"].to(DEV), cm)) and torch.equal(cleanf, m(d["clean"].to(DEV), cm))
+    ref = o_fe.fbank_forward(d["clean"], m.fc.detach().cpu(), cm.cpu())
+    assert_close(cleanf, ref, what="clean_feat (joint)")
+    assert not mixf.requires_grad and not cleanf.requires_grad
