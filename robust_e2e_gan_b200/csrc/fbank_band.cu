@@ -54,8 +54,15 @@ __global__ void __launch_bounds__(640, 1) fbank_band_fwd_kernel(const BandFwdPar
   const int tile_f = kBR * F;                       // floats per input tile
   const bool has_mask = p.mask != nullptr, has2 = p.mag2 != nullptr;
   uint64_t *full = reinterpret_cast<uint64_t *>(smraw);          // [kBS]
+  int *valid_s = reinterpret_cast<int *>(smraw + 64);             // [2][kBR] frame t < lens[b], for this tile / the next
   float *ring = reinterpret_cast<float *>(smraw + 128);           // kBS * NBUF * tile_f
   const int my_tiles = p.ntiles > (int)blockIdx.x ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // frame validity of tile #i of this CTA (threads 0..7, one frame each): the only place that divides by T
+  auto mark_valid = [&](int i) {
+    const size_t n = ((size_t)blockIdx.x + (size_t)i * gridDim.x) * kBR + tid;
+    const int b = (int)(n / (size_t)T), t = (int)(n - (size_t)b * T);
+    valid_s[(i & 1) * kBR + tid] = (!p.lens || t < __ldg(p.lens + b)) ? 1 : 0;
+  };
 
   auto issue = [&](int i) {   // tile #i of this CTA -> stage i % kBS   (one thread)
     const int st = i % kBS;
@@ -82,16 +89,21 @@ __global__ void __launch_bounds__(640, 1) fbank_band_fwd_kernel(const BandFwdPar
   float c0 = 0.0f, c1 = 1.0f;
   if (worker) {
     flo = __ldg(p.flo + m);
+    const float4 *wr = reinterpret_cast<const float4 *>(p.fw + (size_t)m * kBandW);   // 128 B rows: 8 independent loads
 #pragma unroll
-    for (int k = 0; k < kBandW; ++k) {
-      w[k] = __ldg(p.fw + m * kBandW + k);
-      if (w[k] != 0.0f) nw = k + 1;
+    for (int k4 = 0; k4 < kBandW / 4; ++k4) {
+      const float4 t4 = __ldg(wr + k4);
+      w[4 * k4] = t4.x; w[4 * k4 + 1] = t4.y; w[4 * k4 + 2] = t4.z; w[4 * k4 + 3] = t4.w;
     }
+#pragma unroll
+    for (int k = 0; k < kBandW; ++k)
+      if (w[k] != 0.0f) nw = k + 1;
     if (p.cmvn) { c0 = __ldg(p.cmvn + m); c1 = __ldg(p.cmvn + M + m); }
   } else {
 #pragma unroll
     for (int k = 0; k < kBandW; ++k) w[k] = 0.0f;
   }
+  if (tid < kBR && my_tiles > 0) mark_valid(0);
   __syncthreads();
 
   for (int i = 0; i < my_tiles; ++i) {
@@ -101,23 +113,31 @@ __global__ void __launch_bounds__(640, 1) fbank_band_fwd_kernel(const BandFwdPar
     float *b_mask = buf, *b_mag = has_mask ? buf + tile_f : buf, *b_mag2 = b_mag + tile_f;
     mbar_wait(&full[st], (uint32_t)(i / kBS) & 1u);
     // ---- powers in place: mask slot <- (act(mask) * valid * mag)^2, mag slot <- mag^2, mag2 slot <- mag2^2
-    for (int idx = tid; idx < tile_f; idx += NT) {
-      const float x = b_mag[idx];
+    const bool sq_mag = !has_mask || p.Y_plain != nullptr;
+    const int *vld = valid_s + (i & 1) * kBR;
+    // the tile is one flat, 16 B aligned run of kBR*F floats: 128-bit accesses; a quad may straddle two frames
+    for (int q = tid; q < tile_f / 4; q += NT) {
+      const int e0 = 4 * q;
+      float4 x = *reinterpret_cast<const float4 *>(b_mag + e0);
       if (has_mask) {
-        const int rr = idx / F;
-        const size_t n = row0 + rr;
-        const int b = (int)(n / T), t = (int)(n - (size_t)b * T);
-        float e = 0.0f;
-        if (!p.lens || t < __ldg(p.lens + b)) {
-          const float mk = b_mask[idx];
-          e = (p.mask_is_logit ? sigmoid_fast(mk) : mk) * x;
-        }
-        b_mask[idx] = e * e;
+        const int r0 = e0 / F, nb = (r0 + 1) * F - e0;           // elements of this quad that belong to frame r0
+        const bool ok0 = vld[r0] != 0, ok1 = nb < 4 ? vld[r0 + 1] != 0 : ok0;
+        const float4 mk = *reinterpret_cast<const float4 *>(b_mask + e0);
+        float4 e;
+        e.x = ok0 ? (p.mask_is_logit ? sigmoid_fast(mk.x) : mk.x) * x.x : 0.0f;
+        e.y = (nb > 1 ? ok0 : ok1) ? (p.mask_is_logit ? sigmoid_fast(mk.y) : mk.y) * x.y : 0.0f;
+        e.z = (nb > 2 ? ok0 : ok1) ? (p.mask_is_logit ? sigmoid_fast(mk.z) : mk.z) * x.z : 0.0f;
+        e.w = (nb > 3 ? ok0 : ok1) ? (p.mask_is_logit ? sigmoid_fast(mk.w) : mk.w) * x.w : 0.0f;
+        *reinterpret_cast<float4 *>(b_mask + e0) = make_float4(e.x * e.x, e.y * e.y, e.z * e.z, e.w * e.w);
       }
-      if (!has_mask || p.Y_plain) b_mag[idx] = x * x;
-      if (has2) { const float y = b_mag2[idx]; b_mag2[idx] = y * y; }
+      if (sq_mag) *reinterpret_cast<float4 *>(b_mag + e0) = make_float4(x.x * x.x, x.y * x.y, x.z * x.z, x.w * x.w);
+      if (has2) {
+        const float4 y = *reinterpret_cast<const float4 *>(b_mag2 + e0);
+        *reinterpret_cast<float4 *>(b_mag2 + e0) = make_float4(y.x * y.x, y.y * y.y, y.z * y.z, y.w * y.w);
+      }
     }
     __syncthreads();
+    if (tid < kBR && i + 1 < my_tiles) mark_valid(i + 1);   // ordered before its use by the barrier that ends this tile
     // ---- banded projection + log + CMVN: thread <-> (frame, filter)
     if (worker) {
       const size_t o = row0 * M + tid;                 // the tile's outputs are 8*M contiguous floats
@@ -168,9 +188,15 @@ __global__ void __launch_bounds__(512, 1) fbank_band_bwd_kernel(const BandBwdPar
   float *btab = reinterpret_cast<float *>(smraw + 128);           // F * kBinW weights
   int *mlo_s = reinterpret_cast<int *>(btab + F * kBinW);         // round4(F)
   float *ring = reinterpret_cast<float *>(mlo_s + ((F + 3) & ~3));   // kBS * (NBUF*tile_f + 2*tile_m)
+  int *valid_s = reinterpret_cast<int *>(smraw + 64);             // [2][kBR]
   const int stage_f = NBUF * tile_f + 2 * tile_m;
   const int my_tiles = p.ntiles > (int)blockIdx.x ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
+  auto mark_valid = [&](int i) {
+    const size_t n = ((size_t)blockIdx.x + (size_t)i * gridDim.x) * kBR + tid;
+    const int b = (int)(n / (size_t)T), t = (int)(n - (size_t)b * T);
+    valid_s[(i & 1) * kBR + tid] = (!p.lens || t < __ldg(p.lens + b)) ? 1 : 0;
+  };
   auto issue = [&](int i) {
     const int st = i % kBS;
     const size_t row0 = ((size_t)blockIdx.x + (size_t)i * gridDim.x) * kBR;
@@ -190,6 +216,7 @@ __global__ void __launch_bounds__(512, 1) fbank_band_bwd_kernel(const BandBwdPar
   }
   for (int i = tid; i < F * kBinW; i += NT) btab[i] = __ldg(p.bw + i);
   for (int i = tid; i < F; i += NT) mlo_s[i] = __ldg(p.mlo + i);
+  if (tid < kBR && my_tiles > 0) mark_valid(0);
   __syncthreads();
 
   for (int i = 0; i < my_tiles; ++i) {
@@ -203,30 +230,36 @@ __global__ void __launch_bounds__(512, 1) fbank_band_bwd_kernel(const BandBwdPar
     mbar_wait(&full[st], (uint32_t)(i / kBS) & 1u);
     for (int idx = tid; idx < tile_m; idx += NT) dP[idx] *= Gs[idx];
     __syncthreads();
-    for (int idx = tid; idx < tile_f; idx += NT) {
-      const int rr = idx / F, f = idx - rr * F;
+    if (tid < kBR && i + 1 < my_tiles) mark_valid(i + 1);
+    const int *vld = valid_s + (i & 1) * kBR;
+    // thread <-> bin (two frames' worth of threads): the bin's table entry is read once for the 4 frames it serves
+    for (int f = tid & 255; f < F; f += 256) {
       const float4 wv = *reinterpret_cast<const float4 *>(btab + f * kBinW);
-      const float *dp = dP + rr * M + mlo_s[f];
-      const float dsq = fmaf(wv.x, dp[0], fmaf(wv.y, dp[1], fmaf(wv.z, dp[2], wv.w * dp[3])));
-      const float mg = b_mag[idx];
-      float out;
-      if (HAS_MASK) {
-        const size_t n = row0 + rr;
-        const int b = (int)(n / T), t = (int)(n - (size_t)b * T);
-        out = 0.0f;
-        if (!p.lens || t < __ldg(p.lens + b)) {
-          const float mk = b_out[idx];
-          if (p.mask_is_logit) {
-            const float s = sigmoid_fast(mk);
-            out = 2.0f * s * mg * dsq * mg * s * (1.0f - s);    // d/d logit of (s*mag)^2 . dsq
-          } else {
-            out = 2.0f * mk * mg * dsq * mg;
+      const int ml = mlo_s[f];
+#pragma unroll
+      for (int q = 0; q < kBR / 2; ++q) {
+        const int rr = 2 * q + (tid >> 8);
+        const int idx = rr * F + f;
+        const float *dp = dP + rr * M + ml;
+        const float dsq = fmaf(wv.x, dp[0], fmaf(wv.y, dp[1], fmaf(wv.z, dp[2], wv.w * dp[3])));
+        const float mg = b_mag[idx];
+        float out;
+        if (HAS_MASK) {
+          out = 0.0f;
+          if (vld[rr]) {
+            const float mk = b_out[idx];
+            if (p.mask_is_logit) {
+              const float s = sigmoid_fast(mk);
+              out = 2.0f * s * mg * dsq * mg * s * (1.0f - s);    // d/d logit of (s*mag)^2 . dsq
+            } else {
+              out = 2.0f * mk * mg * dsq * mg;
+            }
           }
+        } else {
+          out = 2.0f * mg * dsq;
         }
-      } else {
-        out = 2.0f * mg * dsq;
+        b_out[idx] = out;
       }
-      b_out[idx] = out;
     }
     fence_proxy_async_smem();
     __syncthreads();
