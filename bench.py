@@ -423,6 +423,41 @@ def recog_bench(rank, world, dev, total_utts=1000, per_rank_cap=125):
     return hi - lo, time.perf_counter() - t0, toks
 
 
+def decoder_forward_bench(cfg, dev, reps=5):
+    """Next-row N1 (model/e2e_decoder.py:79-167): the REAL training loop of the attention decoder -- AttLoc step kernel,
+    LSTMCell (cuBLAS), teacher forcing, output layer batched on the tcgen05 GEMM, cross-entropy -- forward + backward at
+    the bench shape (B=32, Th=200, U=40 labels -> 41 positions, V=4233).  Eager launches (median of `reps`)."""
+    from robust_e2e_gan_b200 import AttLoc, Decoder, synth
+    B, Th, D, A, Z, C, V, U = (cfg[k] for k in ("B", "Th", "D", "A", "Z", "C", "V", "U"))
+    torch.manual_seed(7)
+    att = AttLoc(D, Z, A, C, cfg["filts"], "softmax")
+    dec = Decoder(D, V, 1, Z, V - 1, V - 1, att).to(dev).train()
+    hpad, hl = synth.encoder_batch(B=B, Th=Th, D=D, seed=77)
+    ys = [y.to(dev) for y in synth.targets(B=B, V=V, hlens=hl, seed=77, fixed_U=U)]
+    hpad = hpad.to(dev).requires_grad_(True)
+    from robust_e2e_gan_b200 import _lib
+    ts, launches = [], 0
+    for it in range(reps + 2):
+        dec.zero_grad()
+        hpad.grad = None
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss, acc = dec(hpad, hl, ys, 0.0)
+        loss.backward()
+        e1.record()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - n0
+        if it >= 2:
+            ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    ms = ts[len(ts) // 2]
+    return {"workload": "Decoder.forward + backward (teacher forcing), B=%d Th=%d U=%d V=%d" % (B, Th, U, V),
+            "ms": round(ms, 3), "utt_per_s": round(B / (ms * 1e-3), 1), "our_kernel_launches": int(launches),
+            "mode": "eager launches; AttLoc per-step cluster kernels + cuBLAS LSTMCell + one tcgen05 output-layer GEMM"}
+
+
 def kernel_rooflines(hp, db, cfg, peak, dev):
     """Per-kernel CUDA-event timings: each kernel is captured R times into a CUDA graph and replayed, so
     the events see back-to-back launches without Python gaps.  achieved = algorithmic bytes / avg launch."""
@@ -694,6 +729,8 @@ def main():
                     line["roofline"]["traffic"] = tj["kernels"][dom]["bytes"]
                     line["roofline"]["traffic_source"] = tj.get("source")
             line["roofline"]["algorithmic_bytes"] = int(ks[dom]["algorithmic_MB"] * 1e6)
+        if not args.no_kernels:
+            line["decoder_forward"] = decoder_forward_bench(cfg, dev)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)

@@ -6,8 +6,10 @@ state_dict keys as the reference's ``Decoder`` for the configuration the scripts
 
 * ``forward(hpad, hlen, ys, scheduled_sampling_rate)`` -- the training loop of model/e2e_decoder.py:79-167:
   AttLoc step kernel per output position with the alignment fed back un-detached, teacher forcing or scheduled
-  sampling, cross-entropy rescaled by ``mean(len(ys_in)) - 1``.  The LSTMCell / output layer / cross-entropy are
-  library ops (cuDNN-free small GEMMs; outside the hot path the north star names).
+  sampling, cross-entropy rescaled by ``mean(len(ys_in)) - 1``.  With teacher forcing the output layer of all positions
+  is ONE product on the tcgen05 GEMM after the loop; the LSTMCell and the cross-entropy are library ops.  The decoder
+  state fed to step i depends on the context of step i-1 through the LSTMCell, so this loop calls the per-step AttLoc
+  kernels (``AttLoc.forward_loop``, the persistent loop kernels, needs the states of all steps up front).
 * ``recognize_beam(h, lpz, recog_args, char_list, rnnlm=None, fstlm=None)`` -- hybrid CTC/attention beam search
   (model/e2e_decoder.py:170-369) re-designed for the GPU: ALL live hypotheses advance together -- one AttLoc
   step launch for the whole beam (B = beam instead of beam x (B = 1) launches), one LSTMCell / output GEMM, one
@@ -28,6 +30,7 @@ import torch.nn.functional as F
 from . import _lib
 from .e2e_common import pad_list
 from .e2e_ctc import ctc_prefix_score_batch, log_softmax_rows
+from .linear import linear
 
 CTC_SCORING_RATIO = 1.5   # model/e2e_decoder.py:20
 
@@ -118,6 +121,11 @@ class Decoder(torch.nn.Module):
         self.att.reset()
         eys = self.embed(pad_ys_in)
         y_i = None
+        # Teacher forcing (scheduled_sampling_rate == 0, the scripts' default): no step ever looks at its own output
+        # distribution, so the output layer of ALL positions is one dense product after the loop (tcgen05 3xTF32 GEMM,
+        # (B*olength) x odim x dunits) instead of olength skinny ones inside it -- same values as model/e2e_decoder.py:150.
+        batched_output = scheduled_sampling_rate <= 0.0
+        z_top = []
         for i in range(olength):
             att_c, att_w = self.att(hpad, hlen, z_list[0], att_w)
             if random.random() < scheduled_sampling_rate and i > 0:
@@ -128,9 +136,16 @@ class Decoder(torch.nn.Module):
             z_list[0], c_list[0] = self.decoder[0](ey, (z_list[0], c_list[0]))
             for l in range(1, self.dlayers):
                 z_list[l], c_list[l] = self.decoder[l](z_list[l - 1], (z_list[l], c_list[l]))
-            y_i = self.output(z_list[-1])
-            y_all.append(y_i)
-        y_all = torch.stack(y_all, dim=0).transpose(0, 1).contiguous().view(batch * olength, -1)
+            if batched_output:
+                z_top.append(z_list[-1])
+            else:
+                y_i = self.output(z_list[-1])
+                y_all.append(y_i)
+        if batched_output:
+            z_all = torch.stack(z_top, dim=1)                                   # (B, olength, dunits)
+            y_all = linear(z_all, self.output.weight, self.output.bias).reshape(batch * olength, -1)
+        else:
+            y_all = torch.stack(y_all, dim=0).transpose(0, 1).contiguous().view(batch * olength, -1)
         self.loss = F.cross_entropy(y_all, pad_ys_out.view(-1), ignore_index=self.ignore_id, reduction='mean')
         self.loss = self.loss * (np.mean([len(x) for x in ys_in]) - 1)   # quirk 7 of SURVEY.md 8a
         acc = th_accuracy(y_all, pad_ys_out, ignore_label=self.ignore_id)
