@@ -177,18 +177,25 @@ class GradBuckets(object):
         while self._next < len(self.buckets):
             self._launch(self._next)
             self._next += 1
-        for h in self._handles:
-            h.wait()
-        self._handles = []
         if self.world > 1:
-            for flat in self.flat:
-                if flat.is_cuda:
-                    cs = self._comm_stream(flat.device)
-                    with torch.cuda.stream(cs):
-                        flat.div_(self.world)
-                    torch.cuda.current_stream(flat.device).wait_stream(cs)
-                else:
+            cuda_devs = {flat.device for flat in self.flat if flat.is_cuda}
+            for dev in cuda_devs:
+                # wait + average ON the communication stream (Work.wait() orders the stream that is current when it is
+                # called after the collective -- the division must not run ahead of it), then order the caller after it
+                cs = self._comm_stream(dev)
+                with torch.cuda.stream(cs):
+                    for h in self._handles:
+                        h.wait()
+                    for flat in self.flat:
+                        if flat.device == dev:
+                            flat.div_(self.world)
+                torch.cuda.current_stream(dev).wait_stream(cs)
+            if not cuda_devs:
+                for h in self._handles:
+                    h.wait()
+                for flat in self.flat:
                     flat.div_(self.world)
+        self._handles = []
 
     def nbytes(self):
         return sum(f.numel() * f.element_size() for f in self.flat)

@@ -60,6 +60,7 @@ def test_grad_buckets_nccl_with_three_stream_step(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    import re
+    lines = [json.loads(m) for m in re.findall(r"\{[^{}]*\}", r.stdout)]
     assert len(lines) == 2 and all(l["nbuckets"] > 1 for l in lines)
     assert all(l["worst"] < 1e-5 for l in lines), lines
