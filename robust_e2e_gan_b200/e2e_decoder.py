@@ -52,8 +52,13 @@ def end_detect(ended_hyps, i, M=3, D_end=np.log(1 * np.exp(-10))):
 
 
 def mask_by_length(xs, length, fill=0):
-    """model/e2e_common.py:190-195."""
+    """model/e2e_common.py:190-195.  ``length``: list of ints, or a device tensor (then no host round trip: the
+    whole decoder forward stays CUDA-graph capturable)."""
     assert xs.size(0) == len(length)
+    if torch.is_tensor(length) and length.is_cuda:
+        keep = torch.arange(xs.size(1), device=xs.device)[None, :] < length.to(xs.device)[:, None]
+        keep = keep.view(keep.shape + (1,) * (xs.dim() - 2))
+        return torch.where(keep, xs, xs.new_full((), fill))
     ret = xs.new_full(xs.size(), fill)
     for i, l in enumerate(length):
         ret[i, :l] = xs[i, :l]
@@ -61,11 +66,15 @@ def mask_by_length(xs, length, fill=0):
 
 
 def th_accuracy(y_all, pad_target, ignore_label):
-    """model/e2e_common.py:198-205."""
+    """model/e2e_common.py:198-205.  Returns a Python float like the reference, except while a CUDA graph is being
+    captured (no device-to-host read is possible there): then the 0-dim device tensor."""
     pad_pred = y_all.detach().view(pad_target.size(0), pad_target.size(1), y_all.size(1)).max(2)[1]
     mask = pad_target != ignore_label
-    num = torch.sum(pad_pred.masked_select(mask) == pad_target.masked_select(mask))
-    return float(num) / float(torch.sum(mask))
+    num = torch.sum((pad_pred == pad_target) & mask)
+    den = torch.sum(mask)
+    if y_all.is_cuda and torch.cuda.is_current_stream_capturing():
+        return num.float() / den.float()
+    return float(num) / float(den)
 
 
 class Decoder(torch.nn.Module):
@@ -103,12 +112,13 @@ class Decoder(torch.nn.Module):
     def forward(self, hpad, hlen, ys, scheduled_sampling_rate=0.0):
         """model/e2e_decoder.py:79-167.  Returns (loss, acc)."""
         dev = self.embed.weight.device
-        hlen = list(map(int, hlen))
+        if not (torch.is_tensor(hlen) and hlen.is_cuda):      # a device tensor of lengths stays on the device
+            hlen = list(map(int, hlen))
         hpad = mask_by_length(hpad.to(dev), hlen, 0)
         self.loss = None
         ys = [y.to(dev) for y in ys]
-        eos = ys[0].new_tensor([self.eos])
-        sos = ys[0].new_tensor([self.sos])
+        eos = torch.full((1,), self.eos, dtype=ys[0].dtype, device=ys[0].device)    # (fill kernels: graph capturable)
+        sos = torch.full((1,), self.sos, dtype=ys[0].dtype, device=ys[0].device)
         ys_in = [torch.cat([sos, y], dim=0) for y in ys]
         ys_out = [torch.cat([y, eos], dim=0) for y in ys]
         pad_ys_in = pad_list(ys_in, self.eos)

@@ -98,3 +98,53 @@ def test_decoder_training_loop_matches_oracle():
         if k == "att.gvec.bias":          # analytically zero gradient (softmax shift invariance)
             continue
         helpers.assert_close(p.grad, sd_o[k].grad, what="d " + k)
+
+
+def test_decoder_forward_with_device_lengths_is_capturable_and_identical():
+    """Lengths given as a CUDA tensor keep Decoder.forward free of host round trips (CUDA-graph capturable); results
+    equal the list-of-ints call, and a captured forward + backward replays to the same loss and gradients."""
+    c, sd, _, _ = helpers.beam_case("beam_small")
+    B, Th = 3, 19
+    g = torch.Generator().manual_seed(5)
+    hpad = torch.tanh(torch.randn(B, Th, c["D"], generator=g)).to(DEV)
+    hlen = [19, 15, 11]
+    ys = [torch.randint(1, c["V"] - 1, (n,), generator=g).to(DEV) for n in (6, 4, 5)]
+    dec, _ = build(c, sd)
+    dec.train()
+    # everything -- the eager reference run included -- on ONE side stream: a parameter's gradient accumulator stays tied
+    # to the stream of its first backward, and a capture may not synchronise with the legacy default stream
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        h1 = hpad.clone().requires_grad_(True)
+        loss1, acc1 = dec(h1, hlen, ys, 0.0)
+        loss1.backward()
+        g1 = {k: p.grad.clone() for k, p in dec.named_parameters()}
+        loss1, h1g = loss1.detach().clone(), h1.grad.clone()
+        del h1
+        dec.zero_grad(set_to_none=True)
+        hl_dev = torch.tensor(hlen, device=DEV, dtype=torch.int32)
+        h2 = hpad.clone().requires_grad_(True)
+    import gc
+    gc.collect()
+    with torch.cuda.stream(st):
+        for _ in range(2):                      # warm-up on the capture stream
+            l, a = dec(h2, hl_dev, ys, 0.0)
+            l.backward()
+            dec.zero_grad(set_to_none=True)
+            h2.grad = None
+    torch.cuda.synchronize()
+    del l, a
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=st, capture_error_mode="thread_local"):
+        loss2, acc2 = dec(h2, hl_dev, ys, 0.0)
+        loss2.backward()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.is_tensor(acc2) and float(acc2) == pytest.approx(acc1)
+    helpers.assert_close(loss2, loss1, what="loss (graph replay)")
+    helpers.assert_close(h2.grad, h1g, what="d hpad (graph replay)")
+    for k, p in dec.named_parameters():
+        if k == "att.gvec.bias":
+            continue
+        helpers.assert_close(p.grad, g1[k], what="d %s (graph replay)" % k)

@@ -18,8 +18,9 @@ names = {0: ["start", "sync1", "decproj", "sync2", "sync3", "sync4(main)", "push
              "m_pairbar", "m_ctx"],
          1: ["start", "sync1", "sync2(p1)", "sync3(de)", "sync4(p2)", "postA", "sync5", "sync6", "fin", "bulkwait",
              "A_wzissued", "A_pushed", "A_pushed(T)", "A_dWconv(T)", "A_xbar2"]}
-for name, fn, nbytes, reps in bench.kernel_specs(hp, db, cfg, dev):
-    if not name.startswith("attloc"):
+for spec in bench.kernel_specs(hp, db, cfg, dev):
+    name, fn = spec[0], spec[1]
+    if not name.startswith("attloc_step"):
         continue
     which = 0 if "fwd" in name else 1
     g = torch.cuda.CUDAGraph()

@@ -17,13 +17,13 @@ hp = HotPath(cfg, seed=4000).to(dev)
 db = make_batch(cfg, seed=4000).to(dev)
 only = sys.argv[1:]
 specs = [s for s in bench.kernel_specs(hp, db, cfg, dev) if not only or any(o in s[0] for o in only)]
-for name, fn, nbytes, reps in specs:
+for spec in specs:
     for _ in range(2):
-        fn()
+        spec[1]()
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
-for name, fn, nbytes, reps in specs:
-    fn()
+for spec in specs:
+    spec[1]()
     torch.cuda.synchronize()
-    print("ran", name, flush=True)
+    print("ran", spec[0], flush=True)
 torch.cuda.cudart().cudaProfilerStop()
