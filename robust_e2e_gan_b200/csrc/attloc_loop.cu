@@ -63,6 +63,41 @@ __device__ __forceinline__ void cp_async4(void *dst_smem, const void *src_gmem) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Sum 10 per-lane values across the warp in 12 shuffles (recursive halving on an uneven tree).  On return lane L holds
+// in v[0] the total of value index  5*bit4 + (bit1 ? 2 : (bit2 ? (bit3 ? 4 : 1) : (bit3 ? 3 : 0)))  of L; the lanes with
+// bit1 set hold index 5*bit4 + 2 four times over (any bit3, bit2).
+__device__ __forceinline__ void warp_reduce10(float (&v)[10], int lane) {
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const float send = up ? v[i] : v[i + 5], keep = up ? v[i + 5] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v[i] : v[i + 3], keep = up ? v[i + 3] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    v[2] += __shfl_xor_sync(0xffffffffu, v[2], 8);
+  }
+  {
+    const bool up = lane & 4;
+    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    v[2] += __shfl_xor_sync(0xffffffffu, v[2], 4);
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? v[0] : v[2], keep = up ? v[2] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 constexpr int kLP = 8;            // warp pairs = frames per chunk
 constexpr int kLW = 2 * kLP;      // warps
 constexpr int kLT = kLW * 32;     // threads
@@ -657,13 +692,25 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
 #pragma unroll
           for (int c2 = 0; c2 < CH2; ++c2) dcv2[c2] = __ffma2_rn(dt2, WattC[j][c2], dcv2[c2]);
         }
-        float dcv[16];
+        if constexpr (CP == 10) {     // 10 channels: uneven halving tree, 12 shuffles instead of 31
+          float dcv[10];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { dcv[2 * c] = dcv2[c].x; dcv[2 * c + 1] = dcv2[c].y; }
-        warp_reduce16(dcv, lane);
-        if ((lane & 1) == 0) {
-          const int ci = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          dcv_p[(half * g.tloc_max + tl) * 16 + ci] = dcv[0];
+          for (int c = 0; c < 5; ++c) { dcv[2 * c] = dcv2[c].x; dcv[2 * c + 1] = dcv2[c].y; }
+          warp_reduce10(dcv, lane);
+          if ((lane & 1) == 0 && ((lane & 2) == 0 || (lane & 12) == 0)) {
+            const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1;
+            const int ci = 5 * b4 + ((lane & 2) ? 2 : (b2 ? (b3 ? 4 : 1) : (b3 ? 3 : 0)));
+            dcv_p[(half * g.tloc_max + tl) * 16 + ci] = dcv[0];
+          }
+        } else {
+          float dcv[16];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { dcv[2 * c] = dcv2[c].x; dcv[2 * c + 1] = dcv2[c].y; }
+          warp_reduce16(dcv, lane);
+          if ((lane & 1) == 0) {
+            const int ci = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            dcv_p[(half * g.tloc_max + tl) * 16 + ci] = dcv[0];
+          }
         }
       }
     }

@@ -75,33 +75,59 @@ __global__ void __launch_bounds__(640, 1) fbank_band_fwd_kernel(const BandFwdPar
     bulk_g2s(dst + (slot++) * tile_f, p.mag + row0 * F, bytes, &full[st]);
     if (has2) bulk_g2s(dst + (slot++) * tile_f, p.mag2 + row0 * F, bytes, &full[st]);
   };
+  // The projection reads 16 B-aligned windows that may extend up to 12 B past a frame: past the last frame of a buffer
+  // that is the head of the NEXT buffer (or the slack after the ring).  Those elements meet zero weights, but 0 x NaN is
+  // NaN, so what they can hold before the first bulk copy lands there must be finite: zero the head of every buffer and
+  // the slack once, and order those generic-proxy writes before the first bulk copies.
+  for (int i = tid; i < kBS * NBUF + 1; i += NT)
+    *reinterpret_cast<float4 *>(ring + (size_t)i * tile_f) = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async_smem();
   if (tid == 0) {
     for (int s = 0; s < kBS; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
     const int first = my_tiles < kBS ? my_tiles : kBS;
     for (int i = 0; i < first; ++i) issue(i);
   }
-  // this thread's (frame, filter): the filter's window of weights lives in registers
+  // this thread's (frame, filter): the filter's weights live in registers, laid out on the 16 B-ALIGNED window of the
+  // tile that contains the filter's bins for this frame (rows are 257 floats: the alignment of a filter's first bin
+  // depends on the frame), so the projection reads the tile with 128-bit loads
   const int r = tid / M, m = tid - r * M;
   const bool worker = tid < kBR * M;
-  float w[kBandW];
-  int flo = 0, nw = 0;
+  constexpr int kWQ = kBandW / 4 + 1;              // quads that can hold a shifted window
+  float4 w4[kWQ];
+  int base4 = 0, nq = 0;                           // aligned window start (in quads), quads with a non-zero weight
   float c0 = 0.0f, c1 = 1.0f;
+#pragma unroll
+  for (int q = 0; q < kWQ; ++q) w4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (worker) {
-    flo = __ldg(p.flo + m);
-    const float4 *wr = reinterpret_cast<const float4 *>(p.fw + (size_t)m * kBandW);   // 128 B rows: 8 independent loads
+    const int flo = __ldg(p.flo + m);
+    const int first = r * F + flo, sh = first & 3;
+    base4 = (first - sh) >> 2;
+    const float *wr = p.fw + (size_t)m * kBandW;
 #pragma unroll
-    for (int k4 = 0; k4 < kBandW / 4; ++k4) {
-      const float4 t4 = __ldg(wr + k4);
-      w[4 * k4] = t4.x; w[4 * k4 + 1] = t4.y; w[4 * k4 + 2] = t4.z; w[4 * k4 + 3] = t4.w;
+    for (int q = 0; q < kWQ; ++q) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = 4 * q + j - sh;
+        v[j] = (k >= 0 && k < kBandW) ? __ldg(wr + k) : 0.0f;
+      }
+      w4[q] = make_float4(v[0], v[1], v[2], v[3]);
+      if (v[0] != 0.0f || v[1] != 0.0f || v[2] != 0.0f || v[3] != 0.0f) nq = q + 1;
     }
-#pragma unroll
-    for (int k = 0; k < kBandW; ++k)
-      if (w[k] != 0.0f) nw = k + 1;
     if (p.cmvn) { c0 = __ldg(p.cmvn + m); c1 = __ldg(p.cmvn + M + m); }
-  } else {
+  }
+  // the quads this thread squares in place (same positions in every tile): frame of the quad's first element and how
+  // many of its 4 elements still belong to that frame -- computed once, no division inside the tile loop
+  int qr0[2], qnb[2];
 #pragma unroll
-    for (int k = 0; k < kBandW; ++k) w[k] = 0.0f;
+  for (int k = 0; k < 2; ++k) {
+    const int e0 = 4 * (tid + k * NT);
+    qr0[k] = e0 / F;
+    qnb[k] = (qr0[k] + 1) * F - e0;
   }
   if (tid < kBR && my_tiles > 0) mark_valid(0);
   __syncthreads();
@@ -116,11 +142,10 @@ __global__ void __launch_bounds__(640, 1) fbank_band_fwd_kernel(const BandFwdPar
     const bool sq_mag = !has_mask || p.Y_plain != nullptr;
     const int *vld = valid_s + (i & 1) * kBR;
     // the tile is one flat, 16 B aligned run of kBR*F floats: 128-bit accesses; a quad may straddle two frames
-    for (int q = tid; q < tile_f / 4; q += NT) {
+    auto square_quad = [&](int q, int r0, int nb) {
       const int e0 = 4 * q;
       float4 x = *reinterpret_cast<const float4 *>(b_mag + e0);
       if (has_mask) {
-        const int r0 = e0 / F, nb = (r0 + 1) * F - e0;           // elements of this quad that belong to frame r0
         const bool ok0 = vld[r0] != 0, ok1 = nb < 4 ? vld[r0 + 1] != 0 : ok0;
         const float4 mk = *reinterpret_cast<const float4 *>(b_mask + e0);
         float4 e;
@@ -135,22 +160,30 @@ __global__ void __launch_bounds__(640, 1) fbank_band_fwd_kernel(const BandFwdPar
         const float4 y = *reinterpret_cast<const float4 *>(b_mag2 + e0);
         *reinterpret_cast<float4 *>(b_mag2 + e0) = make_float4(y.x * y.x, y.y * y.y, y.z * y.z, y.w * y.w);
       }
+    };
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (tid + k * NT < tile_f / 4) square_quad(tid + k * NT, qr0[k], qnb[k]);
+    for (int q = tid + 2 * NT; q < tile_f / 4; q += NT) {   // (only for CTAs with fewer than tile_f/8 threads)
+      const int r0 = 4 * q / F;
+      square_quad(q, r0, (r0 + 1) * F - 4 * q);
     }
     __syncthreads();
     if (tid < kBR && i + 1 < my_tiles) mark_valid(i + 1);   // ordered before its use by the barrier that ends this tile
     // ---- banded projection + log + CMVN: thread <-> (frame, filter)
     if (worker) {
       const size_t o = row0 * M + tid;                 // the tile's outputs are 8*M contiguous floats
-      const int base = r * F + flo;
       auto project = [&](const float *P) {
-        float acc = 0.0f;
+        const float4 *P4 = reinterpret_cast<const float4 *>(P) + base4;
+        float a0 = 0.0f, a1 = 0.0f;                    // two chains: the FMA latency overlaps
 #pragma unroll
-        for (int c = 0; c < kBandW / 8; ++c)
-          if (8 * c < nw) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc = fmaf(w[8 * c + k], P[base + 8 * c + k], acc);
+        for (int q = 0; q < kWQ; ++q)
+          if (q < nq) {
+            const float4 x = P4[q];
+            a0 = fmaf(w4[q].x, x.x, a0); a1 = fmaf(w4[q].y, x.y, a1);
+            a0 = fmaf(w4[q].z, x.z, a0); a1 = fmaf(w4[q].w, x.w, a1);
           }
-        return acc;
+        return a0 + a1;
       };
       if (has_mask) {
         const float P = project(b_mask);
@@ -208,9 +241,19 @@ __global__ void __launch_bounds__(512, 1) fbank_band_bwd_kernel(const BandBwdPar
     bulk_g2s(dst + NBUF * tile_f, p.dY + row0 * M, bm, &full[st]);
     bulk_g2s(dst + NBUF * tile_f + tile_m, p.G + row0 * M, bm, &full[st]);
   };
+  // The projection reads 16 B-aligned windows that may extend up to 12 B past a frame: past the last frame of a buffer
+  // that is the head of the NEXT buffer (or the slack after the ring).  Those elements meet zero weights, but 0 x NaN is
+  // NaN, so what they can hold before the first bulk copy lands there must be finite: zero the head of every buffer and
+  // the slack once, and order those generic-proxy writes before the first bulk copies.
+  for (int i = tid; i < kBS * NBUF + 1; i += NT)
+    *reinterpret_cast<float4 *>(ring + (size_t)i * tile_f) = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async_smem();
   if (tid == 0) {
     for (int s = 0; s < kBS; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
     const int first = my_tiles < kBS ? my_tiles : kBS;
     for (int i = 0; i < first; ++i) issue(i);
   }
@@ -302,7 +345,7 @@ extern "C" int re2e_fbank_band_fwd(const float *mask, int mask_is_logit, const f
   prm.Y_enh = Y_enh; prm.G = G; prm.Y_plain = Y_plain; prm.Y2 = Y2; prm.mask_is_logit = mask_is_logit;
   prm.N = B * T; prm.T = T; prm.F = F; prm.M = M; prm.ntiles = prm.N / kBR;
   const int nbuf = (mask ? 1 : 0) + 1 + (mag2 ? 1 : 0);
-  const size_t smem = 128 + sizeof(float) * (size_t)kBS * nbuf * kBR * F;
+  const size_t smem = 128 + sizeof(float) * (size_t)kBS * nbuf * kBR * F + 64;   // + slack: aligned windows may read 12 B past the ring
   const int threads = (kBR * M + 31) & ~31;
   const int per_sm = smem * 2 <= 220 * 1024 && threads * 2 <= 2048 ? 2 : 1;
   int grid = num_sms() * per_sm;
