@@ -425,7 +425,7 @@ def recog_bench(rank, world, dev, total_utts=1000, per_rank_cap=125):
 
 def decoder_forward_bench(cfg, dev, reps=5):
     """Next-row N1 (model/e2e_decoder.py:79-167): the REAL training loop of the attention decoder -- AttLoc step kernel,
-    LSTMCell (cuBLAS), teacher forcing, output layer batched on the tcgen05 GEMM, cross-entropy -- forward + backward at
+    LSTMCell step on the library's kernels, teacher forcing, output layer batched on the tcgen05 GEMM, cross-entropy -- forward + backward at
     the bench shape (B=32, Th=200, U=40 labels -> 41 positions, V=4233).  Eager launches (median of `reps`)."""
     from robust_e2e_gan_b200 import AttLoc, Decoder, synth
     B, Th, D, A, Z, C, V, U = (cfg[k] for k in ("B", "Th", "D", "A", "Z", "C", "V", "U"))
@@ -458,7 +458,8 @@ def decoder_forward_bench(cfg, dev, reps=5):
     ms = ts[len(ts) // 2]
     rec = {"workload": "Decoder.forward + backward (teacher forcing), B=%d Th=%d U=%d V=%d" % (B, Th, U, V),
            "ms_eager": round(ms, 3), "utt_per_s_eager": round(B / (ms * 1e-3), 1), "our_kernel_launches": int(launches),
-           "mode": "AttLoc per-step cluster kernels + cuBLAS LSTMCell + one tcgen05 output-layer GEMM"}
+           "mode": "AttLoc per-step cluster kernels; LSTMCell = embedding-half gates of all positions in one tcgen05 GEMM + "
+                   "two batch-sized products and a fused pointwise kernel per position (lstm.py); one tcgen05 output-layer GEMM"}
     # the same forward + backward captured once into a CUDA graph (lengths as a device tensor: no host round trip
     # inside the loop) and replayed: what the loop costs on the GPU once the Python / launch overhead is gone
     try:

@@ -190,6 +190,19 @@ int re2e_skinny_nt(const float *X, const float *W, float *out, int M, int N, int
 int re2e_skinny_nn(const float *X, const float *W, float *out, int M, int N, int K, int accumulate,
                    void *stream);
 
+/* LSTMCell step of the attention decoder (model/e2e_decoder.py:128, torch.nn.LSTMCell, gate order i,f,g,o), fused
+ * pointwise part (csrc/lstm.cu).  The caller forms the recurrent products with re2e_skinny_nt into `gates` (B,4Z):
+ *   gates = context @ W_ih[:, Z:]^T + h_prev @ W_hh^T ;  egate (B,4Z, optional) = embed(y) @ W_ih[:, :Z]^T + b_ih + b_hh
+ * (the embedding half of every position comes from ONE dense product before the loop).
+ *   fwd: gates <- gate activations (i,f,g,o) in place (saved for the backward); c_out, h_out (B,Z).  c_prev NULL = zeros.
+ *   bwd: dh / dc = gradients arriving at (h_out, c_out), NULL = zero; dgates (B,4Z) w.r.t. the pre-activation gates
+ *        (d context = dgates @ W_ih[:, Z:], d h_prev = dgates @ W_hh via re2e_skinny_nn; weight gradients of all steps are
+ *        two dense products after the loop); dc_prev (B,Z). */
+int re2e_lstm_pointwise_fwd(float *gates, const float *egate, const float *c_prev, float *c_out, float *h_out, int B,
+                            int Z, void *stream);
+int re2e_lstm_pointwise_bwd(const float *act, const float *c_prev, const float *c_new, const float *dh, const float *dc,
+                            float *dgates, float *dc_prev, int B, int Z, void *stream);
+
 /* fp32-accurate dense GEMM on tcgen05 tensor cores (3xTF32 split, fp32 TMEM accumulator; csrc/gemm_tc.cu):
  *   C[M,N] (+)= Aop[M,K] * Bop[N,K]^T (+ bias[N])
  * a_mn = 0: A stored [M][lda] (K contiguous)   a_mn = 1: A stored [K][lda] (M contiguous);  same for B / N.

@@ -31,6 +31,7 @@ from . import _lib
 from .e2e_common import pad_list
 from .e2e_ctc import ctc_prefix_score_batch, log_softmax_rows
 from .linear import linear
+from .lstm import LSTMLoop
 
 CTC_SCORING_RATIO = 1.5   # model/e2e_decoder.py:20
 
@@ -104,6 +105,7 @@ class Decoder(torch.nn.Module):
         self.labeldist = labeldist
         self.vlabeldist = None
         self.lsm_weight = lsm_weight
+        self.fused_lstm = True     # training loop: first LSTMCell on the library's kernels (lstm.py); False = torch.nn.LSTMCell
 
     def zero_state(self, hpad):
         return hpad.new_zeros(hpad.size(0), self.dunits)
@@ -135,15 +137,22 @@ class Decoder(torch.nn.Module):
         # distribution, so the output layer of ALL positions is one dense product after the loop (tcgen05 3xTF32 GEMM,
         # (B*olength) x odim x dunits) instead of olength skinny ones inside it -- same values as model/e2e_decoder.py:150.
         batched_output = scheduled_sampling_rate <= 0.0
+        # ... and the embedding half of the first LSTMCell's input product is one dense product before the loop; per
+        # position only the context / state products (batch-sized) and one fused pointwise kernel remain (lstm.py)
+        lstm0 = LSTMLoop(self.decoder[0], eys) if (batched_output and self.fused_lstm and dev.type == 'cuda') else None
         z_top = []
         for i in range(olength):
             att_c, att_w = self.att(hpad, hlen, z_list[0], att_w)
-            if random.random() < scheduled_sampling_rate and i > 0:
-                topi = y_i.topk(1)[1].squeeze(1)
-                ey = torch.cat((self.embed(topi), att_c), dim=1)
+            if lstm0 is not None:
+                random.random()                                  # (the reference draws one number per position)
+                z_list[0], c_list[0] = lstm0.step(i, att_c, z_list[0], c_list[0])
             else:
-                ey = torch.cat((eys[:, i, :], att_c), dim=1)
-            z_list[0], c_list[0] = self.decoder[0](ey, (z_list[0], c_list[0]))
+                if random.random() < scheduled_sampling_rate and i > 0:
+                    topi = y_i.topk(1)[1].squeeze(1)
+                    ey = torch.cat((self.embed(topi), att_c), dim=1)
+                else:
+                    ey = torch.cat((eys[:, i, :], att_c), dim=1)
+                z_list[0], c_list[0] = self.decoder[0](ey, (z_list[0], c_list[0]))
             for l in range(1, self.dlayers):
                 z_list[l], c_list[l] = self.decoder[l](z_list[l - 1], (z_list[l], c_list[l]))
             if batched_output:
