@@ -148,3 +148,58 @@ def test_decoder_forward_with_device_lengths_is_capturable_and_identical():
         if k == "att.gvec.bias":
             continue
         helpers.assert_close(p.grad, g1[k], what="d %s (graph replay)" % k)
+
+
+@pytest.mark.parametrize("B,Z,D,L", [(32, 300, 320, 5), (3, 48, 64, 4), (10, 300, 320, 3)])
+def test_lstm_loop_matches_torch_lstmcell(B, Z, D, L):
+    """lstm.LSTMLoop (embedding-half gates of all positions in one GEMM + per-position products + fused pointwise
+    kernels; weight gradients in two GEMMs after the loop) against torch.nn.LSTMCell on cat(embedding, context), fp64
+    as tie-breaker: states of every position and all gradients."""
+    from robust_e2e_gan_b200.lstm import LSTMLoop
+    g = torch.Generator().manual_seed(B + Z)
+    cell = torch.nn.LSTMCell(Z + D, Z)
+    with torch.no_grad():
+        for p in cell.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) / (Z + D) ** 0.5)
+    eys = torch.randn(B, L, Z, generator=g)
+    ctxs = torch.randn(L, B, D, generator=g)
+    gz = torch.randn(L, B, Z, generator=g)
+
+    def run_ref(dt, dev):
+        c2 = torch.nn.LSTMCell(Z + D, Z).to(dev, dt)
+        c2.load_state_dict({k: v.to(dt) for k, v in cell.state_dict().items()})
+        e = eys.detach().clone().to(dev, dt).requires_grad_(True)
+        cx = ctxs.detach().clone().to(dev, dt).requires_grad_(True)
+        h, c = torch.zeros(B, Z, dtype=dt, device=dev), torch.zeros(B, Z, dtype=dt, device=dev)
+        hs = []
+        for i in range(L):
+            h, c = c2(torch.cat((e[:, i, :], cx[i]), 1), (h, c))
+            hs.append(h)
+        hs = torch.stack(hs)
+        ((hs * gz.to(dev, dt)).sum() + c.sum()).backward()
+        return [hs.detach(), e.grad, cx.grad] + [p.grad for p in c2.parameters()]
+
+    r32, r64 = run_ref(torch.float32, "cpu"), run_ref(torch.float64, "cpu")
+    cd = torch.nn.LSTMCell(Z + D, Z).to(DEV)
+    cd.load_state_dict(cell.state_dict())
+    e = eys.detach().clone().to(DEV).requires_grad_(True)
+    cx = ctxs.detach().clone().to(DEV).requires_grad_(True)
+    n0 = _lib_count()
+    loop = LSTMLoop(cd, e)
+    h, c = torch.zeros(B, Z, device=DEV), torch.zeros(B, Z, device=DEV)
+    hs = []
+    for i in range(L):
+        h, c = loop.step(i, cx[i], h, c)
+        hs.append(h)
+    hs = torch.stack(hs)
+    ((hs * gz.to(DEV)).sum() + c.sum()).backward()
+    assert _lib_count() - n0 >= 3 * L
+    got = [hs.detach(), e.grad, cx.grad] + [p.grad for p in cd.parameters()]
+    names = ["h of every position", "d embeddings", "d contexts", "d weight_ih", "d weight_hh", "d bias_ih", "d bias_hh"]
+    for a, b32, b64, what in zip(got, r32, r64, names):
+        helpers.assert_close(a, b32, truth=b64, what=what)
+
+
+def _lib_count():
+    from robust_e2e_gan_b200 import _lib
+    return _lib.launch_count()
