@@ -198,6 +198,10 @@ int re2e_skinny_nn(const float *X, const float *W, float *out, int M, int N, int
  *   bwd: dh / dc = gradients arriving at (h_out, c_out), NULL = zero; dgates (B,4Z) w.r.t. the pre-activation gates
  *        (d context = dgates @ W_ih[:, Z:], d h_prev = dgates @ W_hh via re2e_skinny_nn; weight gradients of all steps are
  *        two dense products after the loop); dc_prev (B,Z). */
+/* out[M,N] (+)= X[M,K] @ W[N,K]^T for a batch-sized M and long N / K (the decoder's per-position recurrent products,
+ * N or K = 4Z): one CTA per 8 output columns so that all SMs stream the weight matrix once, reduction staged in chunks
+ * (any K % 4 == 0; X, W 16 B aligned).  The backward uses it on transposed weight copies made once per loop. */
+int re2e_batch_nt(const float *X, const float *W, float *out, int M, int N, int K, int accumulate, void *stream);
 int re2e_lstm_pointwise_fwd(float *gates, const float *egate, const float *c_prev, float *c_out, float *h_out, int B,
                             int Z, void *stream);
 int re2e_lstm_pointwise_bwd(const float *act, const float *c_prev, const float *c_new, const float *dh, const float *dc,

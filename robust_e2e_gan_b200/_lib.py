@@ -50,6 +50,7 @@ SIGNATURES = {
     "re2e_attloc_loop_bwd": (_I, [_P] * 11 + [_F] + [_P] * 3 + [_I] * 8 + [_P]),
     "re2e_skinny_nt": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "re2e_skinny_nn": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "re2e_batch_nt": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "re2e_lstm_pointwise_fwd": (_I, [_P] * 5 + [_I, _I, _P]),
     "re2e_lstm_pointwise_bwd": (_I, [_P] * 7 + [_I, _I, _P]),
     "re2e_gemm_tf32x3": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P]),

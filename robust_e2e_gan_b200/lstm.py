@@ -16,22 +16,19 @@ from . import _lib
 from .linear import gemm_tf32x3, linear
 
 
-def _skinny(nn, X, W, out, M, N, K, accumulate):
+def _batch_nt(X, W, out, M, N, K, accumulate=False):
+    """out[M,N] (+)= X[M,K] @ W[N,K]^T, M = batch rows (re2e_batch_nt: all SMs stream W once)."""
     L = _lib.lib()
-    # the batch-sized kernels stage X (M x K) and 16 rows of W in shared memory; a long reduction (the backward's
-    # K = 4Z) does not fit for M = 32: that product goes to the tcgen05 GEMM (one 128-row tile, split-K)
-    if 4 * (((M * (K | 1)) + 3) // 4 * 4 + 16 * K) > 200 * 1024 and not accumulate:
-        gemm_tf32x3(X, False, W, bool(nn), out, M, N, K)
-        return
-    fn = L.re2e_skinny_nn if nn else L.re2e_skinny_nt
     with torch.cuda.device(out.device):
-        _lib.check(fn(_lib.ptr(X), _lib.ptr(W), _lib.ptr(out), M, N, K, int(accumulate), _lib.stream_ptr()),
-                   "re2e_skinny_nn" if nn else "re2e_skinny_nt")
+        rc = L.re2e_batch_nt(_lib.ptr(X), _lib.ptr(W), _lib.ptr(out), M, N, K, int(accumulate), _lib.stream_ptr())
+        if rc == -2:          # K % 4 != 0 or unaligned operands: the generic batch-sized kernel
+            rc = L.re2e_skinny_nt(_lib.ptr(X), _lib.ptr(W), _lib.ptr(out), M, N, K, int(accumulate), _lib.stream_ptr())
+        _lib.check(rc, "re2e_batch_nt")
 
 
 class _State(object):
     def __init__(self):
-        self.W_c = self.W_hh = self.egates = None
+        self.W_c = self.W_hh = self.W_cT = self.W_hhT = self.egates = None
         self.dg, self.ctx, self.hprev = {}, {}, {}
 
 
@@ -44,6 +41,7 @@ class _Anchor(torch.autograd.Function):
     @staticmethod
     def forward(ctx, W_c, W_hh, egates, state):
         state.W_c, state.W_hh = _lib.f32c(W_c.detach()), _lib.f32c(W_hh.detach())
+        state.W_cT = state.W_hhT = None          # (D,4Z) / (Z,4Z) copies for the backward's products, built on first use
         state.egates = _lib.f32c(egates.detach())
         ctx.state = state
         ctx.set_materialize_grads(False)
@@ -86,8 +84,8 @@ class _Step(torch.autograd.Function):
         B, Z = hp.shape
         D = xc.shape[1]
         gates = torch.empty(B, 4 * Z, device=dev, dtype=torch.float32)
-        _skinny(False, xc, state.W_c, gates, B, 4 * Z, D, 0)                     # context @ W_ih[:, Z:]^T
-        _skinny(False, hp, state.W_hh, gates, B, 4 * Z, Z, 1)                    # + h_prev @ W_hh^T
+        _batch_nt(xc, state.W_c, gates, B, 4 * Z, D)                             # context @ W_ih[:, Z:]^T
+        _batch_nt(hp, state.W_hh, gates, B, 4 * Z, Z, accumulate=True)           # + h_prev @ W_hh^T
         h, c = torch.empty_like(hp), torch.empty_like(hp)
         with torch.cuda.device(dev):
             _lib.check(L.re2e_lstm_pointwise_fwd(_lib.ptr(gates), _lib.ptr(eg), _lib.ptr(cp), _lib.ptr(c), _lib.ptr(h),
@@ -117,8 +115,10 @@ class _Step(torch.autograd.Function):
                        "re2e_lstm_pointwise_bwd")
         d_ctx = torch.empty(B, D, device=dev, dtype=torch.float32)
         d_hp = torch.empty(B, Z, device=dev, dtype=torch.float32)
-        _skinny(True, dg, st.W_c, d_ctx, B, D, 4 * Z, 0)                         # d context = dgates @ W_ih[:, Z:]
-        _skinny(True, dg, st.W_hh, d_hp, B, Z, 4 * Z, 0)                         # d h_prev  = dgates @ W_hh
+        if st.W_cT is None:      # once per loop: transposed copies make the backward's products NT as well
+            st.W_cT, st.W_hhT = st.W_c.t().contiguous(), st.W_hh.t().contiguous()
+        _batch_nt(dg, st.W_cT, d_ctx, B, D, 4 * Z)                               # d context = dgates @ W_ih[:, Z:]
+        _batch_nt(dg, st.W_hhT, d_hp, B, Z, 4 * Z)                               # d h_prev  = dgates @ W_hh
         st.dg[ctx.i], st.ctx[ctx.i], st.hprev[ctx.i] = dg, xc, hp
         return None, d_ctx, d_hp, dcp, None, None
 
