@@ -200,8 +200,19 @@ int re2e_skinny_nn(const float *X, const float *W, float *out, int M, int N, int
  *        two dense products after the loop); dc_prev (B,Z). */
 /* out[M,N] (+)= X[M,K] @ W[N,K]^T for a batch-sized M and long N / K (the decoder's per-position recurrent products,
  * N or K = 4Z): one CTA per 8 output columns so that all SMs stream the weight matrix once, reduction staged in chunks
- * (any K % 4 == 0; X, W 16 B aligned).  The backward uses it on transposed weight copies made once per loop. */
+ * (128-bit staging when K % 4 == 0 and X, W are 16 B aligned, scalar staging otherwise).  The backward uses it on transposed weight copies made once per loop. */
 int re2e_batch_nt(const float *X, const float *W, float *out, int M, int N, int K, int accumulate, void *stream);
+/* One LSTMCell position in one launch (after the embedding half): gates = egate + ctx @ Wcat[:, :D]^T + h_prev @
+ * Wcat[:, D:]^T, then the cell's pointwise arithmetic -> act (B,4Z) gate activations (kept for the backward), c_out, h_out
+ * (B,Z).  Wcat (4Z, D+Z) = [W_ih[:, E:] | W_hh].  Clusters of 4 CTAs split the reduction (deterministic order).
+ * re2e_lstm_step_bwd: d_ctx (B,D) | d_hprev (B,Z) = dgates (B,4Z) @ Wcat, given WcatT (D+Z, 4Z) = Wcat^T (clusters of 8).
+ * Supported: D % 4 == Z % 4 == 0, D, Z <= 640, 16 B aligned operands; else RE2E_E_UNSUPPORTED (callers then compose
+ * re2e_batch_nt + re2e_lstm_pointwise_*). */
+int re2e_lstm_step_supported(int B, int D, int Z);
+int re2e_lstm_step_fwd(const float *ctx, const float *h_prev, const float *c_prev, const float *Wcat, const float *egate,
+                       float *act, float *c_out, float *h_out, int B, int D, int Z, void *stream);
+int re2e_lstm_step_bwd(const float *dgates, const float *WcatT, float *d_ctx, float *d_hprev, int B, int D, int Z,
+                       void *stream);
 int re2e_lstm_pointwise_fwd(float *gates, const float *egate, const float *c_prev, float *c_out, float *h_out, int B,
                             int Z, void *stream);
 int re2e_lstm_pointwise_bwd(const float *act, const float *c_prev, const float *c_new, const float *dh, const float *dc,

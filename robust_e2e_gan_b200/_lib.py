@@ -51,6 +51,9 @@ SIGNATURES = {
     "re2e_skinny_nt": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "re2e_skinny_nn": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "re2e_batch_nt": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "re2e_lstm_step_supported": (_I, [_I, _I, _I]),
+    "re2e_lstm_step_fwd": (_I, [_P] * 8 + [_I, _I, _I, _P]),
+    "re2e_lstm_step_bwd": (_I, [_P] * 4 + [_I, _I, _I, _P]),
     "re2e_lstm_pointwise_fwd": (_I, [_P] * 5 + [_I, _I, _P]),
     "re2e_lstm_pointwise_bwd": (_I, [_P] * 7 + [_I, _I, _P]),
     "re2e_gemm_tf32x3": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P]),

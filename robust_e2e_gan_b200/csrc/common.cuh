@@ -183,5 +183,8 @@ __device__ __forceinline__ float dsmem_ld(uint32_t addr) {
 __device__ __forceinline__ void dsmem_st(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+__device__ __forceinline__ void dsmem_st4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 }  // namespace re2e

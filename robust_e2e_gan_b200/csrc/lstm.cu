@@ -6,6 +6,7 @@
 //     (re2e_skinny_nt, accumulating into one gate buffer) and ONE fused pointwise kernel (this file);
 //   * backward per step: this file's pointwise kernel (gate gradients, d c_prev) + two re2e_skinny_nn products
 //     (d context, d h_prev); the weight gradients of all steps are two dense GEMMs after the loop.
+#include "attloc_common.cuh"
 #include "common.cuh"
 
 namespace re2e {
@@ -64,7 +65,8 @@ constexpr int kBK = 320;       // reduction chunk
 constexpr int kBM = 32;        // rows per pass (lane <-> row)
 
 __global__ void __launch_bounds__(kBMN * 32) batch_nt_kernel(const float *__restrict__ X, const float *__restrict__ W,
-                                                            float *__restrict__ out, int M, int N, int K, int accumulate) {
+                                                            float *__restrict__ out, int M, int N, int K, int accumulate,
+                                                            int vec) {
   extern __shared__ __align__(16) float batch_smem[];
   float *x_s = batch_smem, *w_s = batch_smem + kBM * (kBK + 4);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -73,18 +75,31 @@ __global__ void __launch_bounds__(kBMN * 32) batch_nt_kernel(const float *__rest
     const int rows = min(kBM, M - m0);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     for (int k0 = 0; k0 < K; k0 += kBK) {
-      const int kc = min(kBK, K - k0), kq = kc >> 2;          // K % 4 == 0
+      const int kc = min(kBK, K - k0), kq = (kc + 3) >> 2;
       __syncthreads();                                         // previous chunk consumed
-      for (int i = tid; i < rows * kq; i += kBMN * 32) {
-        const int r = i / kq, q = i - r * kq;
-        *reinterpret_cast<float4 *>(x_s + r * (kBK + 4) + 4 * q) =
-            __ldg(reinterpret_cast<const float4 *>(X + (size_t)(m0 + r) * K + k0) + q);
-      }
-      for (int i = tid; i < kBMN * kq; i += kBMN * 32) {
-        const int r = i / kq, q = i - r * kq;
-        const int nn = blockIdx.x * kBMN + r;
-        *reinterpret_cast<float4 *>(w_s + r * kBK + 4 * q) =
-            nn < N ? __ldg(reinterpret_cast<const float4 *>(W + (size_t)nn * K + k0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vec) {                                               // K % 4 == 0, 16 B aligned operands
+        for (int i = tid; i < rows * kq; i += kBMN * 32) {
+          const int r = i / kq, q = i - r * kq;
+          *reinterpret_cast<float4 *>(x_s + r * (kBK + 4) + 4 * q) =
+              __ldg(reinterpret_cast<const float4 *>(X + (size_t)(m0 + r) * K + k0) + q);
+        }
+        for (int i = tid; i < kBMN * kq; i += kBMN * 32) {
+          const int r = i / kq, q = i - r * kq;
+          const int nn = blockIdx.x * kBMN + r;
+          *reinterpret_cast<float4 *>(w_s + r * kBK + 4 * q) =
+              nn < N ? __ldg(reinterpret_cast<const float4 *>(W + (size_t)nn * K + k0) + q)
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {                                                 // scalar staging, the chunk zero-padded to a quad
+        for (int i = tid; i < rows * 4 * kq; i += kBMN * 32) {
+          const int r = i / (4 * kq), k = i - r * 4 * kq;
+          x_s[r * (kBK + 4) + k] = k < kc ? __ldg(X + (size_t)(m0 + r) * K + k0 + k) : 0.f;
+        }
+        for (int i = tid; i < kBMN * 4 * kq; i += kBMN * 32) {
+          const int r = i / (4 * kq), k = i - r * 4 * kq;
+          const int nn = blockIdx.x * kBMN + r;
+          w_s[r * kBK + k] = (nn < N && k < kc) ? __ldg(W + (size_t)nn * K + k0 + k) : 0.f;
+        }
       }
       __syncthreads();
       if (lane < rows) {
@@ -105,6 +120,214 @@ __global__ void __launch_bounds__(kBMN * 32) batch_nt_kernel(const float *__rest
   }
 }
 
+
+// ---- one LSTMCell position per launch -----------------------------------------------------------------------------
+// Both per-position products have batch-sized M (<= 32 rows per pass) against a 1.5-3 MB weight matrix that stays in
+// L2 between positions, so the step is bound by how many SMs pull the weights and by launch latency, not by FLOPs.
+// Layout: a cluster works on a tile of 32 X rows x 32 W rows and splits the REDUCTION over its CTAs; every CTA fetches
+// its K slice of the 64 rows with one bulk copy per row (one mbarrier), multiplies with a 2-row x 4-column register tile
+// per thread (lanes 0-15 <-> rows r / r + 16, half-warps <-> column quads: 6 128-bit shared loads per 32 FMAs), and
+// stores its partial tile into rank 0's shared memory (st.shared::cluster); after one cluster barrier rank 0 adds the
+// partials in rank order (deterministic) and runs the epilogue:
+//   forward  -- the 32 W rows of cluster t are the four gates of hidden units 8t .. 8t+7, the reduction runs over
+//               [context | h_prev] against [W_ih[:, Z:] | W_hh] (first half of the ranks <-> context, second half <->
+//               h_prev): the epilogue adds the embedding-half gates and applies the cell's pointwise arithmetic, i.e.
+//               the whole position is ONE launch on 38 x 4 = 152 CTAs for Z = 300;
+//   backward -- W rows are 32 consecutive rows of the transposed matrix (D + Z, 4Z), the reduction runs over the 4Z gate
+//               gradients in 8 slices (20 x 8 = 160 CTAs): the epilogue scatters the tile into d context / d h_prev.
+constexpr int kSK = 320;           // longest K slice of one CTA
+constexpr int kST = 32;            // tile edge (X rows, W rows)
+constexpr int kSRP = 40;           // pitch of a partial tile in shared memory
+constexpr int kSThreads = 256;     // warps 0-3: first half of the CTA's K slice, warps 4-7: second half
+
+struct LstmStep {
+  const float *X1, *X2;            // (M,K1), (M,K2); K2 = 0: one source
+  const float *W;                  // rows of K1 + K2 floats
+  int M, K1, K2, NW;               // NW: rows of W (forward 4Z, backward D + Z)
+  int pitch;                       // shared row pitch in floats: longest slice + 4 or + 8 so that pitch / 4 is odd
+                                   // (conflict-free 128-bit reads with lane <-> row)
+  const float *egate, *c_prev;     // forward epilogue
+  float *act, *c_out, *h_out;
+  int Z;
+  float *out1, *out2;              // backward epilogue: columns [0,N1) -> out1 (M,N1), the rest -> out2 (M,NW-N1)
+  int N1;
+};
+
+inline int lstm_step_pitch(int K1, int K2, int cl) {
+  const int parts = K2 > 0 ? cl / 2 : cl;
+  int per = round4((K1 + parts - 1) / parts);
+  if (K2 > 0) per = max(per, round4((K2 + parts - 1) / parts));
+  int pitch = per + 4;
+  if (!((pitch >> 2) & 1)) pitch += 4;
+  return pitch;
+}
+inline size_t lstm_step_smem(int pitch, int cl) { return sizeof(float) * (size_t)(2 * kST * pitch + cl * kST * kSRP); }
+
+template <bool FWD>
+__global__ void __launch_bounds__(kSThreads) lstm_step_kernel(const LstmStep p) {
+  extern __shared__ __align__(16) float step_smem[];
+  const int pitch = p.pitch;
+  float *x_s = step_smem, *w_s = step_smem + kST * pitch, *red = step_smem + 2 * kST * pitch;
+  __shared__ __align__(8) uint64_t bar[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kh = warp >> 2, wq = warp & 3;
+  const int rank = (int)cluster_ctarank(), CL = (int)cluster_nctarank();
+  const int tile = blockIdx.x / CL;
+  const int m0 = blockIdx.y * kST, rows = min(kST, p.M - m0);
+
+  // this rank's slice of the reduction
+  const bool second = p.K2 > 0 && rank >= CL / 2;
+  const int parts = p.K2 > 0 ? CL / 2 : CL, part = second ? rank - CL / 2 : rank;
+  const int Ksrc = second ? p.K2 : p.K1;
+  const float *X = second ? p.X2 : p.X1;
+  const int per = round4((Ksrc + parts - 1) / parts);
+  const int k0 = min(part * per, Ksrc), ks = min(per, Ksrc - k0);
+  const int ldw = p.K1 + p.K2, wofs = (second ? p.K1 : 0) + k0;
+  const int kq = ks >> 2, kq0 = (kq + 1) >> 1;              // quads of the slice; the first kq0 belong to warps 0-3
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  cluster_arrive_relaxed();        // (every CTA of the cluster is running before anyone writes rank 0's shared memory)
+  __syncthreads();
+  if (tid < 128) {                 // one bulk copy per (row, half): threads 0-31 / 64-95 X rows, 32-63 / 96-127 W rows
+    const int half = tid >> 6, r = tid & 31, is_w = (tid >> 5) & 1;
+    const int off = half ? 4 * kq0 : 0, len = half ? 4 * (kq - kq0) : 4 * kq0;
+    const int wrow = FWD ? (r >> 3) * p.Z + tile * 8 + (r & 7) : tile * kST + r;
+    const bool wvalid = FWD ? (tile * 8 + (r & 7) < p.Z) : (wrow < p.NW);
+    if (r == 0 && !is_w && len > 0) {
+      const int nw = FWD ? 4 * min(8, p.Z - tile * 8) : min(kST, p.NW - tile * kST);
+      mbar_expect_tx(&bar[half], (uint32_t)(rows + nw) * (uint32_t)len * 4u);
+    }
+    if (len > 0) {
+      if (!is_w) {
+        if (r < rows) bulk_g2s(x_s + r * pitch + off, X + (size_t)(m0 + r) * Ksrc + k0 + off, (uint32_t)len * 4u, &bar[half]);
+      } else if (wvalid) {
+        bulk_g2s(w_s + r * pitch + off, p.W + (size_t)wrow * ldw + wofs + off, (uint32_t)len * 4u, &bar[half]);
+      }
+    }
+  }
+  // rank 0: this thread's epilogue inputs, fetched while the copies fly
+  float ep[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (FWD && rank == 0) {
+    const int m = tid >> 3, u = tile * 8 + (tid & 7);
+    if (m < rows && u < p.Z) {
+      const size_t row = (size_t)(m0 + m);
+      if (p.egate) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ep[g] = __ldg(p.egate + row * 4 * p.Z + (size_t)g * p.Z + u);
+      }
+      if (p.c_prev) ep[4] = __ldg(p.c_prev + row * p.Z + u);
+    }
+  }
+
+  const int hl = lane & 15, cg = lane >> 4;
+  float acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int qb = kh ? kq0 : 0, qe = kh ? kq : kq0;
+  if (qe > qb) {
+    mbar_wait(&bar[kh], 0);
+    const float4 *xa = reinterpret_cast<const float4 *>(x_s + hl * pitch);
+    const float4 *xb = reinterpret_cast<const float4 *>(x_s + (hl + 16) * pitch);
+    const float4 *wp = reinterpret_cast<const float4 *>(w_s + (8 * wq + 4 * cg) * pitch);
+    const int p4 = pitch >> 2;
+#pragma unroll 2
+    for (int q = qb; q < qe; ++q) {
+      const float4 a = xa[q], b = xb[q];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w = wp[j * p4 + q];
+        acc[0][j] = fmaf(a.x, w.x, acc[0][j]); acc[0][j] = fmaf(a.y, w.y, acc[0][j]);
+        acc[0][j] = fmaf(a.z, w.z, acc[0][j]); acc[0][j] = fmaf(a.w, w.w, acc[0][j]);
+        acc[1][j] = fmaf(b.x, w.x, acc[1][j]); acc[1][j] = fmaf(b.y, w.y, acc[1][j]);
+        acc[1][j] = fmaf(b.z, w.z, acc[1][j]); acc[1][j] = fmaf(b.w, w.w, acc[1][j]);
+      }
+    }
+  }
+
+  // the two K halves meet in this CTA's own slot, then the sum goes to the same slot of rank 0
+  float *mine = red + rank * kST * kSRP;
+  const int col = 8 * wq + 4 * cg;
+  if (kh) {
+    *reinterpret_cast<float4 *>(mine + hl * kSRP + col) = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+    *reinterpret_cast<float4 *>(mine + (hl + 16) * kSRP + col) = make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
+  }
+  __syncthreads();
+  cluster_wait();
+  if (!kh) {
+    const float4 s0 = *reinterpret_cast<const float4 *>(mine + hl * kSRP + col);
+    const float4 s1 = *reinterpret_cast<const float4 *>(mine + (hl + 16) * kSRP + col);
+    const uint32_t dst = dsmem_addr(mine, 0);
+    dsmem_st4(dst + 4u * (uint32_t)(hl * kSRP + col), acc[0][0] + s0.x, acc[0][1] + s0.y, acc[0][2] + s0.z,
+              acc[0][3] + s0.w);
+    dsmem_st4(dst + 4u * (uint32_t)((hl + 16) * kSRP + col), acc[1][0] + s1.x, acc[1][1] + s1.y, acc[1][2] + s1.z,
+              acc[1][3] + s1.w);
+  }
+  cluster_arrive();
+  cluster_wait();
+  if (rank != 0) return;
+
+  if (FWD) {
+    // (row m, hidden unit j of the tile): four gates, partials added in rank order, then the embedding-half gates
+    const int m = tid >> 3, j = tid & 7, u = tile * 8 + j;
+    if (m < rows && u < p.Z) {
+      const size_t row = (size_t)(m0 + m);
+      float pre[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float v = red[m * kSRP + g * 8 + j];
+        for (int c = 1; c < CL; ++c) v += red[(c * kST + m) * kSRP + g * 8 + j];
+        pre[g] = v + ep[g];
+      }
+      const float i = sigmoid_f(pre[0]), f = sigmoid_f(pre[1]), gg = tanhf(pre[2]), o = sigmoid_f(pre[3]);
+      const float c = f * ep[4] + i * gg;
+      float *a = p.act + row * 4 * p.Z + u;
+      a[0] = i; a[p.Z] = f; a[2 * p.Z] = gg; a[3 * p.Z] = o;
+      p.c_out[row * p.Z + u] = c;
+      p.h_out[row * p.Z + u] = o * tanhf(c);
+    }
+  } else {
+    for (int e = tid; e < kST * kST; e += kSThreads) {
+      const int m = e >> 5, j = e & 31, n = tile * kST + j;
+      if (m >= rows || n >= p.NW) continue;
+      float v = red[m * kSRP + j];
+      for (int c = 1; c < CL; ++c) v += red[(c * kST + m) * kSRP + j];
+      if (n < p.N1) p.out1[(size_t)(m0 + m) * p.N1 + n] = v;
+      else p.out2[(size_t)(m0 + m) * (p.NW - p.N1) + (n - p.N1)] = v;
+    }
+  }
+}
+
+template <bool FWD>
+int launch_lstm_step(LstmStep prm, int tiles, int cl, cudaStream_t st) {
+  auto kern = lstm_step_kernel<FWD>;
+  prm.pitch = lstm_step_pitch(prm.K1, prm.K2, cl);
+  const size_t smem = lstm_step_smem(prm.pitch, cl);
+  int rc = ensure_smem(reinterpret_cast<const void *>(kern), smem);
+  if (rc != RE2E_OK) return rc;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(tiles * cl), (unsigned)((prm.M + kST - 1) / kST));
+  cfg.blockDim = dim3((unsigned)kSThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, prm);
+  count_launch();
+  return e == cudaSuccess ? RE2E_OK : (int)e;
+}
+
+constexpr int kFwdCL = 4, kBwdCL = 8;
+
 }  // namespace
 }  // namespace re2e
 
@@ -113,14 +336,41 @@ using namespace re2e;
 extern "C" int re2e_batch_nt(const float *X, const float *W, float *out, int M, int N, int K, int accumulate,
                              void *stream) {
   RE2E_CHECK_ARG(X && W && out && M > 0 && N > 0 && K > 0);
-  if ((K & 3) || !aligned16(X) || !aligned16(W)) return RE2E_E_UNSUPPORTED;
+  const int vec = !(K & 3) && aligned16(X) && aligned16(W);
   const size_t smem = sizeof(float) * (kBM * (kBK + 4) + kBMN * kBK);
   int rc = ensure_smem(reinterpret_cast<const void *>(batch_nt_kernel), smem);
   if (rc != RE2E_OK) return rc;
-  batch_nt_kernel<<<(N + kBMN - 1) / kBMN, kBMN * 32, smem, static_cast<cudaStream_t>(stream)>>>(X, W, out, M, N, K,
-                                                                                               accumulate);
+  batch_nt_kernel<<<(N + kBMN - 1) / kBMN, kBMN * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+      X, W, out, M, N, K, accumulate, vec);
   count_launch();
   return launch_status();
+}
+
+extern "C" int re2e_lstm_step_supported(int B, int D, int Z) {
+  return B > 0 && D > 0 && Z > 0 && !(D & 3) && !(Z & 3) && round4((D + 1) / 2) <= kSK && round4((Z + 1) / 2) <= kSK &&
+         round4((4 * Z + kBwdCL - 1) / kBwdCL) <= kSK;
+}
+
+extern "C" int re2e_lstm_step_fwd(const float *ctx, const float *h_prev, const float *c_prev, const float *Wcat,
+                                  const float *egate, float *act, float *c_out, float *h_out, int B, int D, int Z,
+                                  void *stream) {
+  RE2E_CHECK_ARG(ctx && h_prev && Wcat && act && c_out && h_out && B > 0 && D > 0 && Z > 0);
+  if (!re2e_lstm_step_supported(B, D, Z) || !aligned16(ctx) || !aligned16(h_prev) || !aligned16(Wcat))
+    return RE2E_E_UNSUPPORTED;
+  LstmStep p{};
+  p.X1 = ctx; p.X2 = h_prev; p.W = Wcat; p.M = B; p.K1 = D; p.K2 = Z; p.NW = 4 * Z;
+  p.egate = egate; p.c_prev = c_prev; p.act = act; p.c_out = c_out; p.h_out = h_out; p.Z = Z;
+  return launch_lstm_step<true>(p, (Z + 7) / 8, kFwdCL, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int re2e_lstm_step_bwd(const float *dgates, const float *WcatT, float *d_ctx, float *d_hprev, int B, int D,
+                                  int Z, void *stream) {
+  RE2E_CHECK_ARG(dgates && WcatT && d_ctx && d_hprev && B > 0 && D > 0 && Z > 0);
+  if (!re2e_lstm_step_supported(B, D, Z) || !aligned16(dgates) || !aligned16(WcatT)) return RE2E_E_UNSUPPORTED;
+  LstmStep p{};
+  p.X1 = dgates; p.X2 = nullptr; p.W = WcatT; p.M = B; p.K1 = 4 * Z; p.K2 = 0; p.NW = D + Z;
+  p.out1 = d_ctx; p.out2 = d_hprev; p.N1 = D; p.Z = Z;
+  return launch_lstm_step<false>(p, (D + Z + kST - 1) / kST, kBwdCL, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int re2e_lstm_pointwise_fwd(float *gates, const float *egate, const float *c_prev, float *c_out, float *h_out,

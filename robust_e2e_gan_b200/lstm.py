@@ -5,9 +5,11 @@ Same arithmetic as ``torch.nn.LSTMCell`` (gate order i, f, g, o) split the way t
 
 * ``embed_gates``: the embedding half of the input product plus both biases, for ALL positions, as one dense product
   on the tcgen05 GEMM before the loop (teacher forcing: the tokens are known);
-* ``LSTMLoop.step``: per position only the two batch-sized products that depend on the recurrence (context and previous
-  state; ``re2e_skinny_nt``) and one fused pointwise kernel; its backward is one pointwise kernel plus two
-  ``re2e_skinny_nn`` products;
+* ``LSTMLoop.step``: per position ONE launch (``re2e_lstm_step_fwd``: the two batch-sized products that depend on the
+  recurrence -- context and previous state -- reduced across a 4-CTA cluster, with the pointwise cell arithmetic as the
+  epilogue); its backward is the pointwise kernel plus ONE product launch for d context | d h_prev
+  (``re2e_lstm_step_bwd``, 8-CTA clusters).  Dimensions outside that kernel's range compose ``re2e_batch_nt`` products
+  with the pointwise kernels;
 * the weight gradients of all positions are two dense products after the loop (an anchor node, like AttLoc's).
 """
 import torch
@@ -20,15 +22,13 @@ def _batch_nt(X, W, out, M, N, K, accumulate=False):
     """out[M,N] (+)= X[M,K] @ W[N,K]^T, M = batch rows (re2e_batch_nt: all SMs stream W once)."""
     L = _lib.lib()
     with torch.cuda.device(out.device):
-        rc = L.re2e_batch_nt(_lib.ptr(X), _lib.ptr(W), _lib.ptr(out), M, N, K, int(accumulate), _lib.stream_ptr())
-        if rc == -2:          # K % 4 != 0 or unaligned operands: the generic batch-sized kernel
-            rc = L.re2e_skinny_nt(_lib.ptr(X), _lib.ptr(W), _lib.ptr(out), M, N, K, int(accumulate), _lib.stream_ptr())
-        _lib.check(rc, "re2e_batch_nt")
+        _lib.check(L.re2e_batch_nt(_lib.ptr(X), _lib.ptr(W), _lib.ptr(out), M, N, K, int(accumulate),
+                                   _lib.stream_ptr()), "re2e_batch_nt")
 
 
 class _State(object):
     def __init__(self):
-        self.W_c = self.W_hh = self.W_cT = self.W_hhT = self.egates = None
+        self.W_c = self.W_hh = self.W_cT = self.W_hhT = self.Wcat = self.WcatT = self.egates = None
         self.dg, self.ctx, self.hprev = {}, {}, {}
 
 
@@ -42,6 +42,10 @@ class _Anchor(torch.autograd.Function):
     def forward(ctx, W_c, W_hh, egates, state):
         state.W_c, state.W_hh = _lib.f32c(W_c.detach()), _lib.f32c(W_hh.detach())
         state.W_cT = state.W_hhT = None          # (D,4Z) / (Z,4Z) copies for the backward's products, built on first use
+        D, Z = state.W_c.shape[1], state.W_hh.shape[1]
+        state.Wcat = state.WcatT = None
+        if _lib.lib().re2e_lstm_step_supported(1, D, Z):
+            state.Wcat = torch.cat((state.W_c, state.W_hh), 1)                 # (4Z, D+Z): one launch per position
         state.egates = _lib.f32c(egates.detach())
         ctx.state = state
         ctx.set_materialize_grads(False)
@@ -84,12 +88,17 @@ class _Step(torch.autograd.Function):
         B, Z = hp.shape
         D = xc.shape[1]
         gates = torch.empty(B, 4 * Z, device=dev, dtype=torch.float32)
-        _batch_nt(xc, state.W_c, gates, B, 4 * Z, D)                             # context @ W_ih[:, Z:]^T
-        _batch_nt(hp, state.W_hh, gates, B, 4 * Z, Z, accumulate=True)           # + h_prev @ W_hh^T
         h, c = torch.empty_like(hp), torch.empty_like(hp)
         with torch.cuda.device(dev):
-            _lib.check(L.re2e_lstm_pointwise_fwd(_lib.ptr(gates), _lib.ptr(eg), _lib.ptr(cp), _lib.ptr(c), _lib.ptr(h),
-                                                 B, Z, _lib.stream_ptr()), "re2e_lstm_pointwise_fwd")
+            if state.Wcat is not None:
+                _lib.check(L.re2e_lstm_step_fwd(_lib.ptr(xc), _lib.ptr(hp), _lib.ptr(cp), _lib.ptr(state.Wcat), _lib.ptr(eg),
+                                                _lib.ptr(gates), _lib.ptr(c), _lib.ptr(h), B, D, Z, _lib.stream_ptr()),
+                           "re2e_lstm_step_fwd")
+            else:
+                _batch_nt(xc, state.W_c, gates, B, 4 * Z, D)                     # context @ W_ih[:, Z:]^T
+                _batch_nt(hp, state.W_hh, gates, B, 4 * Z, Z, accumulate=True)   # + h_prev @ W_hh^T
+                _lib.check(L.re2e_lstm_pointwise_fwd(_lib.ptr(gates), _lib.ptr(eg), _lib.ptr(cp), _lib.ptr(c),
+                                                     _lib.ptr(h), B, Z, _lib.stream_ptr()), "re2e_lstm_pointwise_fwd")
         ctx.state, ctx.i = state, i
         ctx.save_for_backward(gates, cp, c, xc, hp)
         ctx.set_materialize_grads(False)
@@ -115,10 +124,17 @@ class _Step(torch.autograd.Function):
                        "re2e_lstm_pointwise_bwd")
         d_ctx = torch.empty(B, D, device=dev, dtype=torch.float32)
         d_hp = torch.empty(B, Z, device=dev, dtype=torch.float32)
-        if st.W_cT is None:      # once per loop: transposed copies make the backward's products NT as well
-            st.W_cT, st.W_hhT = st.W_c.t().contiguous(), st.W_hh.t().contiguous()
-        _batch_nt(dg, st.W_cT, d_ctx, B, D, 4 * Z)                               # d context = dgates @ W_ih[:, Z:]
-        _batch_nt(dg, st.W_hhT, d_hp, B, Z, 4 * Z)                               # d h_prev  = dgates @ W_hh
+        if st.Wcat is not None:
+            if st.WcatT is None:     # once per loop: the transposed copy makes the backward's product row-streamed as well
+                st.WcatT = st.Wcat.t().contiguous()
+            with torch.cuda.device(dev):
+                _lib.check(L.re2e_lstm_step_bwd(_lib.ptr(dg), _lib.ptr(st.WcatT), _lib.ptr(d_ctx), _lib.ptr(d_hp), B, D, Z,
+                                                _lib.stream_ptr()), "re2e_lstm_step_bwd")
+        else:
+            if st.W_cT is None:
+                st.W_cT, st.W_hhT = st.W_c.t().contiguous(), st.W_hh.t().contiguous()
+            _batch_nt(dg, st.W_cT, d_ctx, B, D, 4 * Z)                           # d context = dgates @ W_ih[:, Z:]
+            _batch_nt(dg, st.W_hhT, d_hp, B, Z, 4 * Z)                           # d h_prev  = dgates @ W_hh
         st.dg[ctx.i], st.ctx[ctx.i], st.hprev[ctx.i] = dg, xc, hp
         return None, d_ctx, d_hp, dcp, None, None
 

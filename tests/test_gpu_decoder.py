@@ -150,10 +150,11 @@ def test_decoder_forward_with_device_lengths_is_capturable_and_identical():
         helpers.assert_close(p.grad, g1[k], what="d %s (graph replay)" % k)
 
 
-@pytest.mark.parametrize("B,Z,D,L", [(32, 300, 320, 5), (3, 48, 64, 4), (10, 300, 320, 3), (40, 50, 36, 3), (2, 5, 6, 2)])
+@pytest.mark.parametrize("B,Z,D,L", [(32, 300, 320, 5), (3, 48, 64, 4), (10, 300, 320, 3), (40, 52, 36, 3), (33, 640, 640, 2), (5, 12, 4, 2), (4, 48, 1284, 2)])
 def test_lstm_loop_matches_torch_lstmcell(B, Z, D, L):
-    """lstm.LSTMLoop (embedding-half gates of all positions in one GEMM + per-position products + fused pointwise
-    kernels; weight gradients in two GEMMs after the loop) against torch.nn.LSTMCell on cat(embedding, context), fp64
+    """lstm.LSTMLoop (embedding-half gates of all positions in one GEMM + one cluster kernel per position -- or, for
+    dimensions that kernel does not take (D or Z > 640), batch-sized products + pointwise kernels; weight gradients in
+    two GEMMs after the loop) against torch.nn.LSTMCell on cat(embedding, context), fp64
     as tie-breaker: states of every position and all gradients."""
     from robust_e2e_gan_b200.lstm import LSTMLoop
     g = torch.Generator().manual_seed(B + Z)
@@ -206,11 +207,11 @@ def _lib_count():
 
 
 @pytest.mark.parametrize("M,N,K,acc", [(32, 1200, 320, False), (32, 1200, 300, True), (32, 320, 1200, False),
-                                       (40, 50, 44, True), (1, 8, 4, False), (7, 1201, 644, False)])
+                                       (40, 50, 44, True), (1, 8, 4, False), (7, 1201, 644, False), (33, 75, 50, False), (5, 9, 323, True)])
 def test_batch_nt_product(M, N, K, acc):
     """re2e_batch_nt (the decoder's per-position products, one CTA per 8 output columns) against fp64: rows beyond one
-    32-row pass, column counts that are no multiple of 8, reduction lengths that are no multiple of the staged chunk,
-    and the accumulate form; K % 4 != 0 is reported as unsupported (the caller then takes the generic kernel)."""
+    32-row pass, column counts that are no multiple of 8, reduction lengths that are no multiple of the staged chunk
+    or of 4 (scalar staging), and the accumulate form."""
     from robust_e2e_gan_b200 import _lib
     g = torch.Generator().manual_seed(M * N + K)
     X, W, O = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(M, N, generator=g)
@@ -220,5 +221,3 @@ def test_batch_nt_product(M, N, K, acc):
     L = _lib.lib()
     _lib.check(L.re2e_batch_nt(_lib.ptr(Xd), _lib.ptr(Wd), _lib.ptr(Od), M, N, K, int(acc), _lib.stream_ptr()), "batch_nt")
     helpers.assert_close(Od, want32, truth=want64, what="X @ W^T")
-    bad = torch.zeros(M, K + 1, device=DEV)
-    assert L.re2e_batch_nt(_lib.ptr(bad), _lib.ptr(Wd), _lib.ptr(Od), M, N, K + 1, 0, _lib.stream_ptr()) == -2
