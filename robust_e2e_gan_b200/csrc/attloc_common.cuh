@@ -59,6 +59,12 @@ __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint
                "r"(__float_as_uint(v)), "r"(remote_bar)
                : "memory");
 }
+__device__ __forceinline__ void st_async_f32x4(uint32_t remote_addr, float a, float b, float c, float d, uint32_t remote_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr),
+               "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)),
+               "r"(remote_bar)
+               : "memory");
+}
 // Programmatic dependent launch (PDL).  The step kernels are launched with programmatic stream serialisation, so
 // a grid may become resident while its predecessor in the stream (normally the previous decoder step) is still
 // running.  Everything before pdl_wait() touches only memory that was final before the predecessor STARTED:

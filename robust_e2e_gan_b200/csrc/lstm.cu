@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kSThreads) lstm_step_kernel(const LstmStep p) 
   extern __shared__ __align__(16) float step_smem[];
   const int pitch = p.pitch;
   float *x_s = step_smem, *w_s = step_smem + kST * pitch, *red = step_smem + 2 * kST * pitch;
-  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ __align__(8) uint64_t bar[2], rbar;     // rbar (rank 0): the partial tiles of all ranks have landed
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kh = warp >> 2, wq = warp & 3;
   const int rank = (int)cluster_ctarank(), CL = (int)cluster_nctarank();
   const int tile = blockIdx.x / CL;
@@ -187,9 +187,11 @@ __global__ void __launch_bounds__(kSThreads) lstm_step_kernel(const LstmStep p) 
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    mbar_init(&rbar, 1);
     mbar_fence_init();
+    if (rank == 0) mbar_expect_tx(&rbar, (uint32_t)CL * kST * kST * 4u);
   }
-  cluster_arrive_relaxed();        // (every CTA of the cluster is running before anyone writes rank 0's shared memory)
+  cluster_arrive_relaxed();        // (rank 0's barrier is initialised before anyone signals it)
   __syncthreads();
   if (tid < 128) {                 // one bulk copy per (row, half): threads 0-31 / 64-95 X rows, 32-63 / 96-127 W rows
     const int half = tid >> 6, r = tid & 31, is_w = (tid >> 5) & 1;
@@ -223,11 +225,11 @@ __global__ void __launch_bounds__(kSThreads) lstm_step_kernel(const LstmStep p) 
   }
 
   const int hl = lane & 15, cg = lane >> 4;
-  float acc[2][4];
+  float2 acc[2][4];                // (even-k, odd-k) partial sums: the reduction runs as packed FFMA2
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
   const int qb = kh ? kq0 : 0, qe = kh ? kq : kq0;
   if (qe > qb) {
     mbar_wait(&bar[kh], 0);
@@ -241,35 +243,40 @@ __global__ void __launch_bounds__(kSThreads) lstm_step_kernel(const LstmStep p) 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 w = wp[j * p4 + q];
-        acc[0][j] = fmaf(a.x, w.x, acc[0][j]); acc[0][j] = fmaf(a.y, w.y, acc[0][j]);
-        acc[0][j] = fmaf(a.z, w.z, acc[0][j]); acc[0][j] = fmaf(a.w, w.w, acc[0][j]);
-        acc[1][j] = fmaf(b.x, w.x, acc[1][j]); acc[1][j] = fmaf(b.y, w.y, acc[1][j]);
-        acc[1][j] = fmaf(b.z, w.z, acc[1][j]); acc[1][j] = fmaf(b.w, w.w, acc[1][j]);
+        acc[0][j] = __ffma2_rn(make_float2(a.x, a.y), make_float2(w.x, w.y), acc[0][j]);
+        acc[0][j] = __ffma2_rn(make_float2(a.z, a.w), make_float2(w.z, w.w), acc[0][j]);
+        acc[1][j] = __ffma2_rn(make_float2(b.x, b.y), make_float2(w.x, w.y), acc[1][j]);
+        acc[1][j] = __ffma2_rn(make_float2(b.z, b.w), make_float2(w.z, w.w), acc[1][j]);
       }
     }
   }
+  float s[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[i][j] = acc[i][j].x + acc[i][j].y;
 
-  // the two K halves meet in this CTA's own slot, then the sum goes to the same slot of rank 0
+  // the two K halves meet in this CTA's own slot; the sum goes to the same slot of rank 0 with stores that signal rank 0's
+  // barrier (st.async ... complete_tx): the other ranks are done once the stores are issued, no cluster barrier
   float *mine = red + rank * kST * kSRP;
   const int col = 8 * wq + 4 * cg;
   if (kh) {
-    *reinterpret_cast<float4 *>(mine + hl * kSRP + col) = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
-    *reinterpret_cast<float4 *>(mine + (hl + 16) * kSRP + col) = make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
+    *reinterpret_cast<float4 *>(mine + hl * kSRP + col) = make_float4(s[0][0], s[0][1], s[0][2], s[0][3]);
+    *reinterpret_cast<float4 *>(mine + (hl + 16) * kSRP + col) = make_float4(s[1][0], s[1][1], s[1][2], s[1][3]);
   }
   __syncthreads();
   cluster_wait();
   if (!kh) {
     const float4 s0 = *reinterpret_cast<const float4 *>(mine + hl * kSRP + col);
     const float4 s1 = *reinterpret_cast<const float4 *>(mine + (hl + 16) * kSRP + col);
-    const uint32_t dst = dsmem_addr(mine, 0);
-    dsmem_st4(dst + 4u * (uint32_t)(hl * kSRP + col), acc[0][0] + s0.x, acc[0][1] + s0.y, acc[0][2] + s0.z,
-              acc[0][3] + s0.w);
-    dsmem_st4(dst + 4u * (uint32_t)((hl + 16) * kSRP + col), acc[1][0] + s1.x, acc[1][1] + s1.y, acc[1][2] + s1.z,
-              acc[1][3] + s1.w);
+    const uint32_t dst = dsmem_addr(mine, 0), rb = dsmem_addr(&rbar, 0);
+    st_async_f32x4(dst + 4u * (uint32_t)(hl * kSRP + col), s[0][0] + s0.x, s[0][1] + s0.y, s[0][2] + s0.z, s[0][3] + s0.w,
+                   rb);
+    st_async_f32x4(dst + 4u * (uint32_t)((hl + 16) * kSRP + col), s[1][0] + s1.x, s[1][1] + s1.y, s[1][2] + s1.z,
+                   s[1][3] + s1.w, rb);
   }
-  cluster_arrive();
-  cluster_wait();
   if (rank != 0) return;
+  mbar_wait(&rbar, 0);
 
   if (FWD) {
     // (row m, hidden unit j of the tile): four gates, partials added in rank order, then the embedding-half gates
