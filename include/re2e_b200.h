@@ -201,7 +201,8 @@ int re2e_skinny_nn(const float *X, const float *W, float *out, int M, int N, int
 /* out[M,N] (+)= X[M,K] @ W[N,K]^T for a batch-sized M and long N / K (the decoder's per-position recurrent products,
  * N or K = 4Z): one CTA per 8 output columns so that all SMs stream the weight matrix once, reduction staged in chunks
  * (128-bit staging when K % 4 == 0 and X, W are 16 B aligned, scalar staging otherwise).  The backward uses it on transposed weight copies made once per loop. */
-int re2e_batch_nt(const float *X, const float *W, float *out, int M, int N, int K, int accumulate, void *stream);
+int re2e_batch_nt(const float *X, const float *W, const float *bias /* (N) or NULL */, float *out, int M, int N, int K,
+                  int accumulate, void *stream);
 /* One LSTMCell position in one launch (after the embedding half): gates = egate + ctx @ Wcat[:, :D]^T + h_prev @
  * Wcat[:, D:]^T, then the cell's pointwise arithmetic -> act (B,4Z) gate activations (kept for the backward), c_out, h_out
  * (B,Z).  Wcat (4Z, D+Z) = [W_ih[:, E:] | W_hh].  Clusters of 4 CTAs split the reduction (deterministic order).
@@ -210,7 +211,8 @@ int re2e_batch_nt(const float *X, const float *W, float *out, int M, int N, int 
  * re2e_batch_nt + re2e_lstm_pointwise_*). */
 int re2e_lstm_step_supported(int B, int D, int Z);
 int re2e_lstm_step_fwd(const float *ctx, const float *h_prev, const float *c_prev, const float *Wcat, const float *egate,
-                       float *act, float *c_out, float *h_out, int B, int D, int Z, void *stream);
+                       const int32_t *egate_row /* row of egate per batch row (token lookup), NULL: row m */, float *act,
+                       float *c_out, float *h_out, int B, int D, int Z, void *stream);
 int re2e_lstm_step_bwd(const float *dgates, const float *WcatT, float *d_ctx, float *d_hprev, int B, int D, int Z,
                        void *stream);
 int re2e_lstm_pointwise_fwd(float *gates, const float *egate, const float *c_prev, float *c_out, float *h_out, int B,
@@ -271,6 +273,27 @@ int re2e_ctc_prefix_score(const float *lpz, const float *r_prev, const int32_t *
                           const int32_t *last, const int32_t *out_len, float *log_psi,
                           float *r_new, int T, int V, int H, int Ccand, int blank, int eos,
                           void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Beam search, one output position for all W = beam hypothesis rows (model/e2e_decoder.py:233-314).
+ * The reference advances one hypothesis at a time (beam x B=1 calls) and scores CTC prefixes in a host loop over T;
+ * here a position is gather -> re2e_attloc_step_fwd -> re2e_lstm_step_fwd -> re2e_batch_nt (output layer) ->
+ * re2e_log_softmax_topk -> re2e_ctc_prefix_score -> re2e_beam_joint over static buffers (graph-replayable).
+ *
+ * re2e_beam_gather: for each of nseg state tensors, dst[s][m, :] = src[s][parent[m] (, cand[m]), :] (row_floats[s] floats;
+ *   sub_count[s] > 0: the source has that many candidate sub-rows per parent row, e.g. the CTC states (W, ctc_beam, T, 2)).
+ * re2e_log_softmax_topk: per row log-softmax (optionally written to `full` (rows,V)) and its k largest entries, sorted
+ *   descending, ties to the lower index -- what torch.topk(log_softmax(x), k) returns (model/e2e_decoder.py:262,276).
+ *   V <= 8192, else RE2E_E_UNSUPPORTED.
+ * re2e_beam_joint: local = w_att * att_top + w_ctc * (log_psi - psi_prev[row]) (log_psi NULL: local = att_top), the `beam`
+ *   best of the Cb <= 32 candidates per row; out (3, W, beam) fp32 = {row score + local, token id, candidate index}
+ *   (model/e2e_decoder.py:284-292). */
+int re2e_beam_gather(const int32_t *parent, const int32_t *cand, int W, int nseg, const float *const *src,
+                     float *const *dst, const int *row_floats, const int *sub_count, void *stream);
+int re2e_log_softmax_topk(const float *logits, long long rows, int V, int k, float *full, float *vals, int32_t *ids,
+                          void *stream);
+int re2e_beam_joint(const float *att_top, const int32_t *ids, const float *log_psi, const float *psi_prev, const float *sc,
+                    float w_att, float w_ctc, int W, int Cb, int beam, float *out, void *stream);
 
 #ifdef __cplusplus
 }

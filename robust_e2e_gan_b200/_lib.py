@@ -50,9 +50,12 @@ SIGNATURES = {
     "re2e_attloc_loop_bwd": (_I, [_P] * 11 + [_F] + [_P] * 3 + [_I] * 8 + [_P]),
     "re2e_skinny_nt": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "re2e_skinny_nn": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
-    "re2e_batch_nt": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "re2e_batch_nt": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "re2e_beam_gather": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "re2e_log_softmax_topk": (_I, [_P, _LL, _I, _I, _P, _P, _P, _P]),
+    "re2e_beam_joint": (_I, [_P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P]),
     "re2e_lstm_step_supported": (_I, [_I, _I, _I]),
-    "re2e_lstm_step_fwd": (_I, [_P] * 8 + [_I, _I, _I, _P]),
+    "re2e_lstm_step_fwd": (_I, [_P] * 9 + [_I, _I, _I, _P]),
     "re2e_lstm_step_bwd": (_I, [_P] * 4 + [_I, _I, _I, _P]),
     "re2e_lstm_pointwise_fwd": (_I, [_P] * 5 + [_I, _I, _P]),
     "re2e_lstm_pointwise_bwd": (_I, [_P] * 7 + [_I, _I, _P]),

@@ -1,0 +1,207 @@
+// Device side of ONE output position of the hybrid CTC/attention beam search (model/e2e_decoder.py:233-314, next rows N1
+// and N2 of SURVEY 8f).  All W = beam hypothesis rows are advanced together; the host only merges W x beam candidates
+// per position.  The position is this fixed sequence of launches over static buffers (so it replays from a CUDA graph):
+//   beam_gather       parent rows of every recurrent state -> working copies           (this file)
+//   attloc_step_fwd   attention context / alignment                                    (attloc.cu)
+//   lstm_step_fwd     LSTMCell, embedding half looked up by token                      (lstm.cu)
+//   batch_nt          output layer                                                     (lstm.cu)
+//   log_softmax_topk  log-softmax + the ctc_beam (or beam) best tokens of every row    (this file)
+//   ctc_prefix_score  CTC prefix scores of those candidates                            (ctc.cu)
+//   beam_joint        (1-w) att + w (ctc - ctc_prev), best `beam` per row, + row score (this file)
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace re2e {
+namespace {
+
+constexpr int kMaxSeg = 8;
+struct GatherArgs {
+  const float *src[kMaxSeg];
+  float *dst[kMaxSeg];
+  int row_floats[kMaxSeg];
+  int sub_count[kMaxSeg];          // > 0: source rows are indexed (parent, cand) with this many candidates per parent
+  const int32_t *parent, *cand;
+};
+
+// dst_s[m, :] = src_s[parent[m] (, cand[m]), :] for every state tensor s: grid (W, segments)
+__global__ void __launch_bounds__(128) beam_gather_kernel(const GatherArgs a) {
+  const int m = blockIdx.x, s = blockIdx.y;
+  const int n = a.row_floats[s], sub = a.sub_count[s];
+  const int p = __ldg(a.parent + m);
+  const size_t srow = sub > 0 ? (size_t)p * sub + __ldg(a.cand + m) : (size_t)p;
+  const float *src = a.src[s] + srow * n;
+  float *dst = a.dst[s] + (size_t)m * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// ---- log-softmax of one row + its k largest entries (sorted, ties -> lower index), one CTA per row ------------------
+constexpr int kTkThreads = 1024, kTkVPT = 8;
+
+__device__ __forceinline__ float block_max(float v, float *sh) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[threadIdx.x & 31];
+  r = warp_max(r);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float *sh) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[threadIdx.x & 31];
+  r = warp_sum(r);
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kTkThreads) log_softmax_topk_kernel(const float *__restrict__ x, float *__restrict__ full,
+                                                                      float *__restrict__ vals, int32_t *__restrict__ ids,
+                                                                      int V, int k) {
+  __shared__ float sh[32];
+  __shared__ int shi[32];
+  __shared__ int win;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t row = blockIdx.x;
+  const float *xr = x + row * V;
+  float v[kTkVPT];
+  float m = -CUDART_INF_F;
+#pragma unroll
+  for (int i = 0; i < kTkVPT; ++i) {
+    const int idx = tid + kTkThreads * i;
+    v[i] = idx < V ? __ldg(xr + idx) : -CUDART_INF_F;
+    m = fmaxf(m, v[i]);
+  }
+  m = block_max(m, sh);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kTkVPT; ++i)
+    if (tid + kTkThreads * i < V) s += expf(v[i] - m);
+  s = block_sum(s, sh);
+  const float lse = m + logf(s);
+#pragma unroll
+  for (int i = 0; i < kTkVPT; ++i) {
+    const int idx = tid + kTkThreads * i;
+    if (idx < V) {
+      v[i] -= lse;
+      if (full) full[row * V + idx] = v[i];
+    }
+  }
+  for (int j = 0; j < k; ++j) {
+    float bv = -CUDART_INF_F;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < kTkVPT; ++i) {
+      const int idx = tid + kTkThreads * i;
+      if (idx < V && v[i] > bv) { bv = v[i]; bi = idx; }
+    }
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, bv, of);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, of);
+      if (v2 > bv || (v2 == bv && i2 < bi)) { bv = v2; bi = i2; }
+    }
+    if (lane == 0) { sh[warp] = bv; shi[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      bv = sh[lane];
+      bi = shi[lane];
+#pragma unroll
+      for (int of = 16; of > 0; of >>= 1) {
+        const float v2 = __shfl_xor_sync(0xffffffffu, bv, of);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bi, of);
+        if (v2 > bv || (v2 == bv && i2 < bi)) { bv = v2; bi = i2; }
+      }
+      if (lane == 0) {
+        win = bi;
+        vals[row * k + j] = bv;
+        ids[row * k + j] = bi;
+      }
+    }
+    __syncthreads();
+    const int w = win;
+#pragma unroll
+    for (int i = 0; i < kTkVPT; ++i)
+      if (tid + kTkThreads * i == w) v[i] = -CUDART_INF_F;
+  }
+}
+
+// ---- joint score + per-row top `beam` (one warp per hypothesis row) ------------------------------------------------
+// local = w_att * att_top + w_ctc * (log_psi - psi_prev)   (model/e2e_decoder.py:284-286; separate roundings, as the
+// reference's tensor expression), candidates out[0] = row score + local, out[1] = token id, out[2] = candidate index
+__global__ void __launch_bounds__(128) beam_joint_kernel(const float *__restrict__ att_top, const int32_t *__restrict__ ids,
+                                                         const float *__restrict__ log_psi,
+                                                         const float *__restrict__ psi_prev, const float *__restrict__ sc,
+                                                         float w_att, float w_ctc, int W, int Cb, int beam,
+                                                         float *__restrict__ out) {
+  const int lane = threadIdx.x & 31, h = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (h >= W) return;
+  float val = -CUDART_INF_F;
+  if (lane < Cb) {
+    const float a = att_top[h * Cb + lane];
+    val = log_psi ? __fadd_rn(__fmul_rn(w_att, a), __fmul_rn(w_ctc, __fsub_rn(log_psi[h * Cb + lane], psi_prev[h]))) : a;
+  }
+  const float base = sc[h];
+  for (int b = 0; b < beam; ++b) {
+    float bv = val;
+    int bj = lane;
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, bv, of);
+      const int j2 = __shfl_xor_sync(0xffffffffu, bj, of);
+      if (v2 > bv || (v2 == bv && j2 < bj)) { bv = v2; bj = j2; }
+    }
+    if (lane == 0) {
+      out[(size_t)h * beam + b] = __fadd_rn(base, bv);
+      out[(size_t)(W + h) * beam + b] = (float)ids[h * Cb + bj];
+      out[(size_t)(2 * W + h) * beam + b] = (float)bj;
+    }
+    if (lane == bj) val = -CUDART_INF_F;
+  }
+}
+
+}  // namespace
+}  // namespace re2e
+
+using namespace re2e;
+
+extern "C" int re2e_beam_gather(const int32_t *parent, const int32_t *cand, int W, int nseg, const float *const *src,
+                                float *const *dst, const int *row_floats, const int *sub_count, void *stream) {
+  RE2E_CHECK_ARG(parent && src && dst && row_floats && sub_count && W > 0 && nseg > 0 && nseg <= kMaxSeg);
+  GatherArgs a{};
+  for (int s = 0; s < nseg; ++s) {
+    RE2E_CHECK_ARG(src[s] && dst[s] && row_floats[s] > 0 && (sub_count[s] == 0 || cand));
+    a.src[s] = src[s];
+    a.dst[s] = dst[s];
+    a.row_floats[s] = row_floats[s];
+    a.sub_count[s] = sub_count[s];
+  }
+  a.parent = parent;
+  a.cand = cand;
+  beam_gather_kernel<<<dim3((unsigned)W, (unsigned)nseg), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int re2e_log_softmax_topk(const float *logits, long long rows, int V, int k, float *full, float *vals,
+                                     int32_t *ids, void *stream) {
+  RE2E_CHECK_ARG(logits && vals && ids && rows > 0 && V > 0 && k > 0 && k <= V);
+  if (V > kTkThreads * kTkVPT) return RE2E_E_UNSUPPORTED;
+  log_softmax_topk_kernel<<<(unsigned)rows, kTkThreads, 0, static_cast<cudaStream_t>(stream)>>>(logits, full, vals, ids,
+                                                                                                V, k);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int re2e_beam_joint(const float *att_top, const int32_t *ids, const float *log_psi, const float *psi_prev,
+                               const float *sc, float w_att, float w_ctc, int W, int Cb, int beam, float *out,
+                               void *stream) {
+  RE2E_CHECK_ARG(att_top && ids && sc && out && W > 0 && Cb > 0 && beam > 0 && beam <= Cb && (!log_psi || psi_prev));
+  if (Cb > 32) return RE2E_E_UNSUPPORTED;
+  beam_joint_kernel<<<(W + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(att_top, ids, log_psi, psi_prev, sc, w_att,
+                                                                              w_ctc, W, Cb, beam, out);
+  count_launch();
+  return launch_status();
+}

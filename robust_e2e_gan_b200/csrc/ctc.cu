@@ -545,17 +545,23 @@ log_softmax_kernel(const float *__restrict__ x, float *__restrict__ out, int32_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// Batched prefix scoring: one warp per (hypothesis h, candidate j); sequential over t.
+// Batched prefix scoring (model/e2e_ctc.py:109-155): one WARP per (hypothesis h, candidate j).  Everything that does not
+// depend on the recursion -- phi[t-1] = logaddexp(r_prev[t-1]) (or its blank half for a repeated token), the two columns
+// of lpz -- is fetched 32 frames at a time with lane <-> frame (coalesced); the recursion itself runs uniformly on all
+// lanes over values broadcast by shuffles (three independent logaddexp chains per frame: r^n, r^b, psi), and every lane
+// keeps the pair of its own frame so that r_new is written 32 frames per store.
 __device__ __forceinline__ float logaddexpf_(float a, float b) {
-  float m = fmaxf(a, b), d = fminf(a, b) - m;
-  return m + log1pf(expf(d));
+  const float m = fmaxf(a, b), d = fminf(a, b) - m;
+  return m + __logf(1.0f + __expf(d));
 }
-__global__ void __launch_bounds__(128)
+constexpr int kPrefixWarps = 4;
+__global__ void __launch_bounds__(kPrefixWarps * 32)
 ctc_prefix_kernel(const float *__restrict__ lpz, const float *__restrict__ r_prev,
                   const int32_t *__restrict__ cs, const int32_t *__restrict__ last,
                   const int32_t *__restrict__ out_len, float *__restrict__ log_psi,
                   float *__restrict__ r_new, int T, int V, int H, int Cc, int blank, int eos) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * kPrefixWarps + (threadIdx.x >> 5);
   if (idx >= H * Cc) return;
   const int h = idx / Cc;
   const int c = __ldg(cs + idx);
@@ -565,25 +571,35 @@ ctc_prefix_kernel(const float *__restrict__ lpz, const float *__restrict__ r_pre
   float *rn = r_new + (size_t)idx * T * 2;
   const bool same = ol > 0 && c == __ldg(last + h);
   const int start = ol > 1 ? ol : 1;
-  for (int t = 0; t < start - 1; ++t) { rn[2 * t] = LZ; rn[2 * t + 1] = LZ; }
-  float rn_prev, rb_prev;
-  if (ol == 0) { rn_prev = __ldg(lpz + c); rb_prev = LZ; }
-  else { rn_prev = LZ; rb_prev = LZ; }
-  rn[2 * (start - 1)] = rn_prev;
-  rn[2 * (start - 1) + 1] = rb_prev;
+  for (int t = lane; t < min(start - 1, T); t += 32) *reinterpret_cast<float2 *>(rn + 2 * t) = make_float2(LZ, LZ);
+  float rn_prev = ol == 0 ? __ldg(lpz + c) : LZ, rb_prev = LZ;
+  if (lane == 0 && start - 1 < T) *reinterpret_cast<float2 *>(rn + 2 * (start - 1)) = make_float2(rn_prev, rb_prev);
   float psi = rn_prev;
-  for (int t = start; t < T; ++t) {
-    const float pn = rp[2 * (t - 1)], pb = rp[2 * (t - 1) + 1];
-    const float phi = same ? pb : logaddexpf_(pn, pb);
-    const float xc = __ldg(lpz + (size_t)t * V + c), xb = __ldg(lpz + (size_t)t * V + blank);
-    const float nn = logaddexpf_(rn_prev, phi) + xc;
-    const float nb = logaddexpf_(rn_prev, rb_prev) + xb;
-    psi = logaddexpf_(psi, phi + xc);
-    rn[2 * t] = nn; rn[2 * t + 1] = nb;
-    rn_prev = nn; rb_prev = nb;
+  for (int base = start; base < T; base += 32) {
+    const int t = base + lane;
+    const bool valid = t < T;
+    float phi = LZ, xc = 0.f, xb = 0.f;
+    if (valid) {
+      const float2 p = *reinterpret_cast<const float2 *>(rp + 2 * (t - 1));
+      phi = same ? p.y : logaddexpf_(p.x, p.y);
+      xc = __ldg(lpz + (size_t)t * V + c);
+      xb = __ldg(lpz + (size_t)t * V + blank);
+    }
+    const int n = min(32, T - base);
+    float my_n = LZ, my_b = LZ;
+    for (int i = 0; i < n; ++i) {
+      const float ph = __shfl_sync(0xffffffffu, phi, i), c_ = __shfl_sync(0xffffffffu, xc, i),
+                  b_ = __shfl_sync(0xffffffffu, xb, i);
+      const float nn = logaddexpf_(rn_prev, ph) + c_;
+      const float nb = logaddexpf_(rn_prev, rb_prev) + b_;
+      psi = logaddexpf_(psi, ph + c_);
+      if (lane == i) { my_n = nn; my_b = nb; }
+      rn_prev = nn; rb_prev = nb;
+    }
+    if (valid) *reinterpret_cast<float2 *>(rn + 2 * t) = make_float2(my_n, my_b);
   }
   if (c == eos) psi = logaddexpf_(rp[2 * (T - 1)], rp[2 * (T - 1) + 1]);
-  log_psi[idx] = psi;
+  if (lane == 0) log_psi[idx] = psi;
 }
 
 }  // namespace
@@ -678,7 +694,7 @@ extern "C" int re2e_ctc_prefix_score(const float *lpz, const float *r_prev, cons
   RE2E_CHECK_ARG(lpz && r_prev && cs && last && out_len && log_psi && r_new);
   RE2E_CHECK_ARG(T > 0 && V > 0 && H > 0 && Ccand > 0);
   const int n = H * Ccand;
-  ctc_prefix_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  ctc_prefix_kernel<<<(n + kPrefixWarps - 1) / kPrefixWarps, kPrefixWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       lpz, r_prev, cs, last, out_len, log_psi, r_new, T, V, H, Ccand, blank, eos);
   count_launch();
   return launch_status();

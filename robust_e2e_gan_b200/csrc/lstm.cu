@@ -65,8 +65,8 @@ constexpr int kBK = 320;       // reduction chunk
 constexpr int kBM = 32;        // rows per pass (lane <-> row)
 
 __global__ void __launch_bounds__(kBMN * 32) batch_nt_kernel(const float *__restrict__ X, const float *__restrict__ W,
-                                                            float *__restrict__ out, int M, int N, int K, int accumulate,
-                                                            int vec) {
+                                                            const float *__restrict__ bias, float *__restrict__ out, int M,
+                                                            int N, int K, int accumulate, int vec) {
   extern __shared__ __align__(16) float batch_smem[];
   float *x_s = batch_smem, *w_s = batch_smem + kBM * (kBK + 4);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kBMN * 32) batch_nt_kernel(const float *__rest
     }
     if (lane < rows && n < N) {
       float *o = out + (size_t)(m0 + lane) * N + n;
-      const float v = (a0 + a1) + (a2 + a3);
+      const float v = (a0 + a1) + (a2 + a3) + (bias ? __ldg(bias + n) : 0.f);
       *o = accumulate ? *o + v : v;
     }
   }
@@ -147,6 +147,7 @@ struct LstmStep {
   int pitch;                       // shared row pitch in floats: longest slice + 4 or + 8 so that pitch / 4 is odd
                                    // (conflict-free 128-bit reads with lane <-> row)
   const float *egate, *c_prev;     // forward epilogue
+  const int32_t *egate_row;        // row of `egate` for batch row m (NULL: m) -- the beam search looks the embedding half up by token
   float *act, *c_out, *h_out;
   int Z;
   float *out1, *out2;              // backward epilogue: columns [0,N1) -> out1 (M,N1), the rest -> out2 (M,NW-N1)
@@ -217,8 +218,9 @@ __global__ void __launch_bounds__(kSThreads) lstm_step_kernel(const LstmStep p) 
     if (m < rows && u < p.Z) {
       const size_t row = (size_t)(m0 + m);
       if (p.egate) {
+        const size_t erow = p.egate_row ? (size_t)__ldg(p.egate_row + row) : row;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) ep[g] = __ldg(p.egate + row * 4 * p.Z + (size_t)g * p.Z + u);
+        for (int g = 0; g < 4; ++g) ep[g] = __ldg(p.egate + erow * 4 * p.Z + (size_t)g * p.Z + u);
       }
       if (p.c_prev) ep[4] = __ldg(p.c_prev + row * p.Z + u);
     }
@@ -340,15 +342,15 @@ constexpr int kFwdCL = 4, kBwdCL = 8;
 
 using namespace re2e;
 
-extern "C" int re2e_batch_nt(const float *X, const float *W, float *out, int M, int N, int K, int accumulate,
-                             void *stream) {
+extern "C" int re2e_batch_nt(const float *X, const float *W, const float *bias, float *out, int M, int N, int K,
+                             int accumulate, void *stream) {
   RE2E_CHECK_ARG(X && W && out && M > 0 && N > 0 && K > 0);
   const int vec = !(K & 3) && aligned16(X) && aligned16(W);
   const size_t smem = sizeof(float) * (kBM * (kBK + 4) + kBMN * kBK);
   int rc = ensure_smem(reinterpret_cast<const void *>(batch_nt_kernel), smem);
   if (rc != RE2E_OK) return rc;
   batch_nt_kernel<<<(N + kBMN - 1) / kBMN, kBMN * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-      X, W, out, M, N, K, accumulate, vec);
+      X, W, bias, out, M, N, K, accumulate, vec);
   count_launch();
   return launch_status();
 }
@@ -359,14 +361,14 @@ extern "C" int re2e_lstm_step_supported(int B, int D, int Z) {
 }
 
 extern "C" int re2e_lstm_step_fwd(const float *ctx, const float *h_prev, const float *c_prev, const float *Wcat,
-                                  const float *egate, float *act, float *c_out, float *h_out, int B, int D, int Z,
-                                  void *stream) {
+                                  const float *egate, const int32_t *egate_row, float *act, float *c_out,
+                                  float *h_out, int B, int D, int Z, void *stream) {
   RE2E_CHECK_ARG(ctx && h_prev && Wcat && act && c_out && h_out && B > 0 && D > 0 && Z > 0);
   if (!re2e_lstm_step_supported(B, D, Z) || !aligned16(ctx) || !aligned16(h_prev) || !aligned16(Wcat))
     return RE2E_E_UNSUPPORTED;
   LstmStep p{};
   p.X1 = ctx; p.X2 = h_prev; p.W = Wcat; p.M = B; p.K1 = D; p.K2 = Z; p.NW = 4 * Z;
-  p.egate = egate; p.c_prev = c_prev; p.act = act; p.c_out = c_out; p.h_out = h_out; p.Z = Z;
+  p.egate = egate; p.egate_row = egate_row; p.c_prev = c_prev; p.act = act; p.c_out = c_out; p.h_out = h_out; p.Z = Z;
   return launch_lstm_step<true>(p, (Z + 7) / 8, kFwdCL, static_cast<cudaStream_t>(stream));
 }
 

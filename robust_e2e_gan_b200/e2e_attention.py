@@ -391,6 +391,18 @@ class AttLoc(torch.nn.Module):
                            self.mlp_att.weight, self.loc_conv.weight, self.gvec.weight, self.gvec.bias, att_prev,
                            scaling, bool(first_none))
 
+    def precompute(self, enc_hs_pad):
+        """mlp_enc(enc_h) of the utterance batch, once per reset() (e2e_attention.py:252-256); returns the per-batch
+        state (``pre``, ``enc``, contiguous weight views, dims) the step kernels read."""
+        if self.pre_compute_enc_h is None:
+            self._state = _State()
+            self.enc_h = enc_hs_pad
+            self.h_length = self.enc_h.size(1)
+            self.pre_compute_enc_h, self._anchor = _Precompute.apply(
+                enc_hs_pad, self.mlp_enc.weight, self.mlp_enc.bias, self.mlp_dec.weight, self.mlp_att.weight,
+                self.loc_conv.weight, self.gvec.weight, self.gvec.bias, self._state)
+        return self._state
+
     def forward(self, enc_hs_pad, enc_hs_len, dec_z, att_prev, scaling=2.0):
         '''AttLoc forward
 
@@ -408,14 +420,7 @@ class AttLoc(torch.nn.Module):
         if dev.type != 'cuda':
             raise RuntimeError("AttLoc parameters must live on a CUDA device (no CPU fallback)")
         batch = len(enc_hs_pad)
-        if self.pre_compute_enc_h is None:
-            self._state = _State()
-            self.enc_h = enc_hs_pad
-            self.h_length = self.enc_h.size(1)
-            self.pre_compute_enc_h, self._anchor = _Precompute.apply(
-                enc_hs_pad, self.mlp_enc.weight, self.mlp_enc.bias, self.mlp_dec.weight, self.mlp_att.weight,
-                self.loc_conv.weight, self.gvec.weight, self.gvec.bias, self._state)
-        st = self._state
+        st = self.precompute(enc_hs_pad)
         is_init = att_prev is None
         if is_init:
             # e2e_attention.py:264-268: uniform over enc_hs_len[b], zero padded

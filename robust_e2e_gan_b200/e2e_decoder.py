@@ -177,6 +177,87 @@ class Decoder(torch.nn.Module):
 
     # ------------------------------------------------------------------------------------------ beam search
     @torch.no_grad()
+    def _beam_tables(self):
+        """Per-model constants of the fused beam-search position, rebuilt when a parameter changes: the embedding half of
+        the LSTMCell input product for EVERY token (V, 4Z) = embed.weight @ W_ih[:, :E]^T + b_ih + b_hh (looked up by token
+        in the step kernel), the recurrent matrices side by side (4Z, D+Z), and the output layer."""
+        cell = self.decoder[0]
+        ps = (self.embed.weight, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, self.output.weight,
+              self.output.bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        tb = getattr(self, "_beam_tab", None)
+        if tb is None or tb[0] != key:
+            with torch.no_grad():
+                E = self.embed.weight.size(1)
+                eg = linear(_lib.f32c(self.embed.weight.detach()), cell.weight_ih.detach()[:, :E].contiguous(),
+                            (cell.bias_ih + cell.bias_hh).detach()).contiguous()
+                wcat = torch.cat((cell.weight_ih.detach()[:, E:], cell.weight_hh.detach()), 1).float().contiguous()
+                tb = (key, eg, wcat, _lib.f32c(self.output.weight.detach()), _lib.f32c(self.output.bias.detach()))
+            self._beam_tab = tb
+        return tb[1:]
+
+    def _fused_position(self, hb, lpz, ctl, sc, out, Cb, beam, ctc_weight):
+        """One output position for all W rows as seven launches of the library over static buffers (csrc/beam.cu): gather
+        the parents' states, AttLoc step, LSTMCell step (embedding half by token lookup), output layer, log-softmax +
+        top-Cb, CTC prefix scores, joint score + per-row top-beam.  Returns the step closure (same call shape as the
+        generic one; the first position needs no special case: the states start as every row's initial state)."""
+        import ctypes
+        lib = _lib.lib()
+        dev = hb.device
+        W, Th, D = hb.shape
+        Z, V = self.dunits, self.output.out_features
+        eg, wcat, w_out, b_out = self._beam_tables()
+        st = self.att.precompute(hb)
+        _, _, _, A, _, C, K = st.dims
+        W_dec, W_att, W_conv, gvec, gvec_b = st.weights
+        f = dict(device=dev, dtype=torch.float32)
+        z_st, c_st = torch.zeros(W, Z, **f), torch.zeros(W, Z, **f)
+        z_in, c_in = torch.empty(W, Z, **f), torch.empty(W, Z, **f)
+        a_st, a_in = torch.empty(W, Th, **f), torch.empty(W, Th, **f)
+        hl = torch.full((W,), Th, dtype=torch.int32, device=dev)
+        att_c, act, logits = torch.empty(W, D, **f), torch.empty(W, 4 * Z, **f), torch.empty(W, V, **f)
+        top_v, top_i = torch.empty(W, Cb, **f), torch.empty(W, Cb, dtype=torch.int32, device=dev)
+        segs = [(z_st, z_in, Z, 0), (c_st, c_in, Z, 0), (a_st, a_in, Th, 0)]
+        r_st = r_in = psi_st = psi_in = None
+        if lpz is not None:
+            r_st, r_in = torch.empty(W, Cb, Th, 2, **f), torch.empty(W, Th, 2, **f)
+            psi_st, psi_in = torch.zeros(W, Cb, **f), torch.empty(W, **f)
+            r0 = torch.full((Th, 2), -10000000000.0, **f)                 # CTCPrefixScore.initial_state
+            r0[:, 1] = torch.cumsum(lpz[:, 0], dim=0)
+            r_st[:, 0] = r0
+            segs += [(r_st, r_in, 2 * Th, Cb), (psi_st, psi_in, 1, Cb)]
+        n = len(segs)
+        src = (ctypes.c_void_p * n)(*[s[0].data_ptr() for s in segs])
+        dst = (ctypes.c_void_p * n)(*[s[1].data_ptr() for s in segs])
+        rowf = (ctypes.c_int * n)(*[s[2] for s in segs])
+        subc = (ctypes.c_int * n)(*[s[3] for s in segs])
+        keep = (segs, hl, eg, wcat, w_out, b_out)          # buffers a captured graph points into
+        w_att, w_ctc = float(1.0 - ctc_weight), float(ctc_weight)
+        P = _lib.ptr
+        with torch.cuda.device(dev):
+            _lib.check(lib.re2e_attloc_init_att(P(hl), P(a_st), W, Th, _lib.stream_ptr()), "re2e_attloc_init_att")
+
+        def step(_first):
+            sp = _lib.stream_ptr()
+            with torch.cuda.device(dev):
+                _lib.check(lib.re2e_beam_gather(P(ctl[0]), P(ctl[1]), W, n, src, dst, rowf, subc, sp), "re2e_beam_gather")
+                _lib.check(lib.re2e_attloc_step_fwd(P(st.pre), P(st.enc), P(z_in), P(a_in), P(W_dec), P(W_att), P(W_conv),
+                                                    P(gvec), P(gvec_b), 2.0, P(att_c), P(a_st), None, None, None,
+                                                    W, Th, D, A, Z, C, K, sp), "re2e_attloc_step_fwd")
+                _lib.check(lib.re2e_lstm_step_fwd(P(att_c), P(z_in), P(c_in), P(wcat), P(eg), P(ctl[2]), P(act), P(c_st),
+                                                  P(z_st), W, D, Z, sp), "re2e_lstm_step_fwd")
+                _lib.check(lib.re2e_batch_nt(P(z_st), P(w_out), P(b_out), P(logits), W, V, Z, 0, sp), "re2e_batch_nt")
+                _lib.check(lib.re2e_log_softmax_topk(P(logits), W, V, Cb, None, P(top_v), P(top_i), sp),
+                           "re2e_log_softmax_topk")
+                if lpz is not None:
+                    _lib.check(lib.re2e_ctc_prefix_score(P(lpz), P(r_in), P(top_i), P(ctl[2]), P(ctl[3]), P(psi_st),
+                                                         P(r_st), Th, V, W, Cb, 0, self.eos, sp), "re2e_ctc_prefix_score")
+                _lib.check(lib.re2e_beam_joint(P(top_v), P(top_i), P(psi_st), P(psi_in), P(sc), w_att, w_ctc, W, Cb, beam,
+                                               P(out), sp), "re2e_beam_joint")
+            return keep
+
+        return step
+
     def recognize_beam(self, h, lpz, recog_args, char_list=None, rnnlm=None, fstlm=None):
         """h (Th, D) encoder output of one utterance, lpz (Th, V) CTC log-probs or None.
         Returns the n-best list of dicts with 'score' (float) and 'yseq' (list of int, <sos> first)."""
@@ -214,12 +295,17 @@ class Decoder(torch.nn.Module):
         #      are replayed from a CUDA graph (captured once per utterance); the host only exchanges two small packed
         #      arrays per position (control in, candidates out) through pinned memory
         L = self.dlayers
-        ctl = torch.zeros(4, W, dtype=torch.long, device=dev)          # rows: parent, ctc candidate, token, position
+        Cb = ctc_beam if use_ctc else beam          # candidates scored per row
+        lib = _lib.lib()
+        fused = (bool(getattr(recog_args, "fused_position", True)) and L == 1 and beam <= Cb <= 32 and self.output.out_features <= 8192
+                 and bool(lib.re2e_lstm_step_supported(W, h.size(1), self.dunits)))
+        idt = torch.int32 if fused else torch.long
+        ctl = torch.zeros(4, W, dtype=idt, device=dev)                 # rows: parent, ctc candidate, token, position
         sc = torch.zeros(W, dtype=torch.float32, device=dev)           # accumulated scores of the rows
         out = torch.empty(3, W, beam, dtype=torch.float32, device=dev)   # candidate scores, token ids, ctc candidate idx
         pins = getattr(self, "_pinned", None)          # page-locked staging is expensive to allocate: keep it per beam
-        if pins is None or pins[0].shape[1] != W or pins[2].shape[2] != beam:
-            pins = (torch.zeros(4, W, dtype=torch.long).pin_memory(), torch.zeros(W, dtype=torch.float32).pin_memory(),
+        if pins is None or pins[0].shape[1] != W or pins[2].shape[2] != beam or pins[0].dtype != idt:
+            pins = (torch.zeros(4, W, dtype=idt).pin_memory(), torch.zeros(W, dtype=torch.float32).pin_memory(),
                     torch.empty(3, W, beam, dtype=torch.float32).pin_memory())
             self._pinned = pins
         ctl_h, sc_h, out_h = pins
@@ -271,6 +357,9 @@ class Decoder(torch.nn.Module):
             st_a.copy_(att_w)
             cand = sc.unsqueeze(1) + best_scores                                    # fp32, as hyp['score'] + tensor
             out.copy_(torch.stack((cand, best_ids.float(), joint.float()), 0))
+
+        if fused:
+            dev_step = self._fused_position(hb, lpz if use_ctc else None, ctl, sc, out, Cb, beam, ctc_weight)
 
         use_graph = bool(getattr(recog_args, "cuda_graph", True)) and maxlen >= 6
         graph = None

@@ -22,7 +22,7 @@ def _batch_nt(X, W, out, M, N, K, accumulate=False):
     """out[M,N] (+)= X[M,K] @ W[N,K]^T, M = batch rows (re2e_batch_nt: all SMs stream W once)."""
     L = _lib.lib()
     with torch.cuda.device(out.device):
-        _lib.check(L.re2e_batch_nt(_lib.ptr(X), _lib.ptr(W), _lib.ptr(out), M, N, K, int(accumulate),
+        _lib.check(L.re2e_batch_nt(_lib.ptr(X), _lib.ptr(W), None, _lib.ptr(out), M, N, K, int(accumulate),
                                    _lib.stream_ptr()), "re2e_batch_nt")
 
 
@@ -92,7 +92,7 @@ class _Step(torch.autograd.Function):
         with torch.cuda.device(dev):
             if state.Wcat is not None:
                 _lib.check(L.re2e_lstm_step_fwd(_lib.ptr(xc), _lib.ptr(hp), _lib.ptr(cp), _lib.ptr(state.Wcat), _lib.ptr(eg),
-                                                _lib.ptr(gates), _lib.ptr(c), _lib.ptr(h), B, D, Z, _lib.stream_ptr()),
+                                                None, _lib.ptr(gates), _lib.ptr(c), _lib.ptr(h), B, D, Z, _lib.stream_ptr()),
                            "re2e_lstm_step_fwd")
             else:
                 _batch_nt(xc, state.W_c, gates, B, 4 * Z, D)                     # context @ W_ih[:, Z:]^T

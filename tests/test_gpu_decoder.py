@@ -219,5 +219,93 @@ def test_batch_nt_product(M, N, K, acc):
     want32 = X @ W.t() + (O if acc else 0.0)
     Xd, Wd, Od = X.to(DEV), W.to(DEV), O.to(DEV)
     L = _lib.lib()
-    _lib.check(L.re2e_batch_nt(_lib.ptr(Xd), _lib.ptr(Wd), _lib.ptr(Od), M, N, K, int(acc), _lib.stream_ptr()), "batch_nt")
+    _lib.check(L.re2e_batch_nt(_lib.ptr(Xd), _lib.ptr(Wd), None, _lib.ptr(Od), M, N, K, int(acc), _lib.stream_ptr()), "batch_nt")
     helpers.assert_close(Od, want32, truth=want64, what="X @ W^T")
+
+
+@pytest.mark.parametrize("rows,V,k", [(10, 4233, 15), (1, 52, 1), (3, 8192, 32), (7, 1025, 10)])
+def test_log_softmax_topk(rows, V, k):
+    """re2e_log_softmax_topk against torch.topk(log_softmax) (model/e2e_decoder.py:262,276): ids identical, values and the
+    full log-softmax row to fp32 accuracy; duplicated maxima resolve to the lower index."""
+    from robust_e2e_gan_b200 import _lib
+    g = torch.Generator().manual_seed(rows * V + k)
+    x = torch.randn(rows, V, generator=g) * 3.0
+    if V > 60:
+        x[0, 50] = x[0, 7] = x[0].max() + 1.0          # a tie at the top
+    xd = x.to(DEV)
+    full = torch.empty(rows, V, device=DEV)
+    vals, ids = torch.empty(rows, k, device=DEV), torch.empty(rows, k, dtype=torch.int32, device=DEV)
+    _lib.check(_lib.lib().re2e_log_softmax_topk(_lib.ptr(xd), rows, V, k, _lib.ptr(full), _lib.ptr(vals), _lib.ptr(ids),
+                                                _lib.stream_ptr()), "log_softmax_topk")
+    want = torch.log_softmax(x.double(), 1)
+    helpers.assert_close(full, want.float(), truth=want, what="log-softmax rows")
+    wv, wi = torch.sort(want, dim=1, descending=True, stable=True)
+    assert ids.cpu().tolist() == wi[:, :k].tolist()
+    helpers.assert_close(vals, wv[:, :k].float(), truth=wv[:, :k], what="top-k values")
+
+
+def test_beam_gather_and_joint():
+    """re2e_beam_gather (parent / (parent, candidate) row gathers of several state tensors in one launch) and
+    re2e_beam_joint against the reference's tensor expressions (model/e2e_decoder.py:284-292), bit for bit."""
+    import ctypes
+    from robust_e2e_gan_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(3)
+    W, Cb, beam, Th, Z = 6, 9, 6, 37, 20
+    a, r = torch.randn(W, Z, generator=g).to(DEV), torch.randn(W, Cb, Th, 2, generator=g).to(DEV)
+    psi = torch.randn(W, Cb, generator=g).to(DEV)
+    parent = torch.randint(0, W, (W,), generator=g).int().to(DEV)
+    cand = torch.randint(0, Cb, (W,), generator=g).int().to(DEV)
+    a2, r2, p2 = torch.empty(W, Z, device=DEV), torch.empty(W, Th, 2, device=DEV), torch.empty(W, device=DEV)
+    src = (ctypes.c_void_p * 3)(a.data_ptr(), r.data_ptr(), psi.data_ptr())
+    dst = (ctypes.c_void_p * 3)(a2.data_ptr(), r2.data_ptr(), p2.data_ptr())
+    rowf, subc = (ctypes.c_int * 3)(Z, 2 * Th, 1), (ctypes.c_int * 3)(0, Cb, Cb)
+    _lib.check(L.re2e_beam_gather(_lib.ptr(parent), _lib.ptr(cand), W, 3, src, dst, rowf, subc, _lib.stream_ptr()), "gather")
+    pl, cl = parent.long(), cand.long()
+    assert torch.equal(a2, a[pl]) and torch.equal(r2, r[pl, cl]) and torch.equal(p2, psi[pl, cl])
+
+    att = torch.randn(W, Cb, generator=g).to(DEV)
+    ids = torch.randint(0, 4000, (W, Cb), generator=g).int().to(DEV)
+    prev, sc = torch.randn(W, generator=g).to(DEV), torch.randn(W, generator=g).to(DEV)
+    out = torch.empty(3, W, beam, device=DEV)
+    w = 0.3
+    _lib.check(L.re2e_beam_joint(_lib.ptr(att), _lib.ptr(ids), _lib.ptr(psi), _lib.ptr(prev), _lib.ptr(sc), 1.0 - w, w,
+                                 W, Cb, beam, _lib.ptr(out), _lib.stream_ptr()), "joint")
+    local = (1.0 - w) * att + w * (psi - prev.unsqueeze(1))
+    bs, bj = torch.topk(local, beam, dim=1)
+    assert torch.equal(out[0], sc.unsqueeze(1) + bs)
+    assert torch.equal(out[1], ids.long().gather(1, bj).float()) and torch.equal(out[2], bj.float())
+    _lib.check(L.re2e_beam_joint(_lib.ptr(att), _lib.ptr(ids), None, None, _lib.ptr(sc), 1.0, 0.0, W, Cb, beam,
+                                 _lib.ptr(out), _lib.stream_ptr()), "joint (attention only)")
+    bs, bj = torch.topk(att, beam, dim=1)
+    assert torch.equal(out[0], sc.unsqueeze(1) + bs) and torch.equal(out[2], bj.float())
+
+
+@pytest.mark.parametrize("ctc_weight,beam,Th", [(0.3, 10, 60), (0.0, 5, 40), (0.5, 1, 25)])
+def test_fused_beam_position_matches_generic_path(ctc_weight, beam, Th):
+    """The seven-launch fused position (csrc/beam.cu) and the generic tensor-op position of recognize_beam give the same
+    n-best list (tokens identical, scores to 1e-4), with and without CUDA-graph replay."""
+    helpers.BEAM_CASES["_tmp"] = dict(helpers.BEAM_CASES["beam_eos"], seed=31, beam=beam, ctc_weight=ctc_weight,
+                                      nbest=min(beam, 3), Th=Th)
+    try:
+        c, sd, h, _ = helpers.beam_case("_tmp")
+    finally:
+        del helpers.BEAM_CASES["_tmp"]
+    dec, ctc = build(c, sd)
+    hd = h.to(DEV)
+    lpz = ctc.log_softmax(hd.unsqueeze(0))[0] if ctc_weight > 0.0 else None
+    res = {}
+    for fused in (False, True):
+        for graph in (False, True):
+            ra = recog_args(c)
+            ra.fused_position, ra.cuda_graph = fused, graph
+            n0 = _lib_count()
+            with torch.no_grad():
+                res[fused, graph] = dec.recognize_beam(hd, lpz, ra, None)
+            if fused and not graph:
+                assert _lib_count() - n0 >= 6 * (len(res[fused, graph][0]["yseq"]) - 2)
+    ref = res[False, False]
+    for k, got in res.items():
+        assert [x["yseq"] for x in got] == [x["yseq"] for x in ref], "tokens differ for (fused, graph) = %s" % (k,)
+        for a, b in zip(got, ref):
+            assert abs(a["score"] - b["score"]) <= 1e-4 * abs(b["score"])

@@ -57,7 +57,7 @@ for M, N, K in [(32, 1200, 320), (32, 1200, 300), (32, 320, 1200), (32, 300, 120
     X, W, O = torch.randn(M, K, device=dev), torch.randn(N, K, device=dev), torch.zeros(M, N, device=dev)
     WT = W.t().contiguous()
     row = {"shape": (M, N, K),
-           "batch_nt": graph_time(lambda: L.re2e_batch_nt(_lib.ptr(X), _lib.ptr(W), _lib.ptr(O), M, N, K, 0, sp())),
+           "batch_nt": graph_time(lambda: L.re2e_batch_nt(_lib.ptr(X), _lib.ptr(W), None, _lib.ptr(O), M, N, K, 0, sp())),
            "gemm": graph_time(lambda: gemm_tf32x3(X, False, WT, True, O, M, N, K))}
     if K <= 320:
         row["skinny"] = graph_time(lambda: L.re2e_skinny_nt(_lib.ptr(X), _lib.ptr(W), _lib.ptr(O), M, N, K, 0, sp()))
@@ -71,7 +71,7 @@ eg, act = torch.randn(B, 4 * Z, device=dev), torch.empty(B, 4 * Z, device=dev)
 c, h = torch.empty(B, Z, device=dev), torch.empty(B, Z, device=dev)
 dg, dctx, dhp, dcp = torch.randn(B, 4 * Z, device=dev), torch.empty(B, D, device=dev), torch.empty(B, Z, device=dev), torch.empty(B, Z, device=dev)
 print({"lstm_step_fwd": round(graph_time(lambda: L.re2e_lstm_step_fwd(
-    _lib.ptr(xc), _lib.ptr(hp), _lib.ptr(cp), _lib.ptr(Wcat), _lib.ptr(eg), _lib.ptr(act), _lib.ptr(c), _lib.ptr(h), B, D, Z, sp())), 2),
+    _lib.ptr(xc), _lib.ptr(hp), _lib.ptr(cp), _lib.ptr(Wcat), _lib.ptr(eg), None, _lib.ptr(act), _lib.ptr(c), _lib.ptr(h), B, D, Z, sp())), 2),
     "lstm_step_bwd": round(graph_time(lambda: L.re2e_lstm_step_bwd(
         _lib.ptr(dg), _lib.ptr(WcatT), _lib.ptr(dctx), _lib.ptr(dhp), B, D, Z, sp())), 2),
     "pointwise_fwd": round(graph_time(lambda: L.re2e_lstm_pointwise_fwd(
