@@ -294,6 +294,14 @@ int re2e_log_softmax_topk(const float *logits, long long rows, int V, int k, flo
                           void *stream);
 int re2e_beam_joint(const float *att_top, const int32_t *ids, const float *log_psi, const float *psi_prev, const float *sc,
                     float w_att, float w_ctc, int W, int Cb, int beam, float *out, void *stream);
+/* Merge of one position on the device (model/e2e_decoder.py:296-333): the `beam` best of the first n_live x beam
+ * candidates of `out` (stable descending order), recorded in hist[pos] (4, beam) = {score, parent row, token, candidate
+ * index} for the host's hypothesis bookkeeping; the winners whose token is not <eos> become the rows of position pos+1
+ * (ctl (4,W) int32 = parent, candidate, token, position; sc (W) row scores), none survive at pos = maxlen-1.
+ * state int32[2] = {n_live, pos} is advanced.  With this the host reads the history back every few positions instead of
+ * synchronising at each one.  W, beam <= 32. */
+int re2e_beam_merge(const float *out, int32_t *state, int32_t *ctl, float *sc, float *hist, int W, int beam, int eos,
+                    int maxlen, void *stream);
 
 #ifdef __cplusplus
 }

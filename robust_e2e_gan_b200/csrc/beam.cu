@@ -162,10 +162,87 @@ __global__ void __launch_bounds__(128) beam_joint_kernel(const float *__restrict
   }
 }
 
+// ---- merge of the W x beam candidates of one position (model/e2e_decoder.py:296-333), one warp ---------------------
+// The reference extends the live hypotheses one by one and keeps a stable descending sort truncated to `beam`: that is
+// the `beam` best of the n_live x beam candidates in (row, rank) order, ties to the lower flat index.  The winners are
+// recorded for the host's bookkeeping (hist[pos]: score, parent row, token, candidate index); those that did not emit
+// <eos> become the rows of the next position, in order, spare rows repeating the last one.  state = {n_live, pos}.
+__global__ void __launch_bounds__(32) beam_merge_kernel(const float *__restrict__ out, int32_t *__restrict__ state,
+                                                        int32_t *__restrict__ ctl, float *__restrict__ sc,
+                                                        float *__restrict__ hist, int W, int beam, int eos, int maxlen) {
+  __shared__ float vals[1024];
+  __shared__ float row_sc[32];
+  __shared__ int row_p[32], row_j[32], row_t[32];
+  const int lane = threadIdx.x;
+  const int n = state[0], pos = state[1];
+  if (n <= 0 || pos >= maxlen) {
+    if (lane == 0) state[1] = pos + 1;
+    return;
+  }
+  const int total = n * beam;
+  for (int i = lane; i < total; i += 32) vals[i] = out[i];
+  __syncwarp();
+  float my_sc = 0.f;
+  int my_k = 0;
+  for (int b = 0; b < beam; ++b) {
+    float bv = -CUDART_INF_F;
+    int bk = 0x7fffffff;
+    for (int i = lane; i < total; i += 32) {
+      const float v = vals[i];
+      if (v > bv) { bv = v; bk = i; }
+    }
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, bv, of);
+      const int k2 = __shfl_xor_sync(0xffffffffu, bk, of);
+      if (v2 > bv || (v2 == bv && k2 < bk)) { bv = v2; bk = k2; }
+    }
+    if (bk == 0x7fffffff) bk = 0;                      // (every candidate -inf / NaN: keep indices valid)
+    if (lane == b) { my_sc = bv; my_k = bk; }
+    if (lane == 0) vals[bk] = -CUDART_INF_F;
+    __syncwarp();
+  }
+  // lane b < beam holds winner b
+  const bool have = lane < beam;
+  const int r = have ? my_k / beam : 0, j = have ? my_k - r * beam : 0;
+  const int tok = have ? (int)out[(size_t)(W + r) * beam + j] : eos;
+  const int joint = have ? (int)out[(size_t)(2 * W + r) * beam + j] : 0;
+  if (have) {
+    float *hp = hist + (size_t)pos * 4 * beam;
+    hp[lane] = my_sc;
+    hp[beam + lane] = (float)r;
+    hp[2 * beam + lane] = (float)tok;
+    hp[3 * beam + lane] = (float)joint;
+  }
+  const bool alive = have && tok != eos && pos != maxlen - 1;
+  const unsigned m = __ballot_sync(0xffffffffu, alive);
+  const int n2 = __popc(m), rank = __popc(m & ((1u << lane) - 1u));
+  if (alive) { row_sc[rank] = my_sc; row_p[rank] = r; row_j[rank] = joint; row_t[rank] = tok; }
+  __syncwarp();
+  if (n2 > 0 && lane < W) {
+    const int s = min(lane, n2 - 1);
+    ctl[lane] = row_p[s];
+    ctl[W + lane] = row_j[s];
+    ctl[2 * W + lane] = row_t[s];
+    ctl[3 * W + lane] = pos + 1;
+    sc[lane] = row_sc[s];
+  }
+  if (lane == 0) { state[0] = n2; state[1] = pos + 1; }
+}
+
 }  // namespace
 }  // namespace re2e
 
 using namespace re2e;
+
+extern "C" int re2e_beam_merge(const float *out, int32_t *state, int32_t *ctl, float *sc, float *hist, int W, int beam,
+                               int eos, int maxlen, void *stream) {
+  RE2E_CHECK_ARG(out && state && ctl && sc && hist && W > 0 && beam > 0 && maxlen > 0);
+  if (W > 32 || beam > 32) return RE2E_E_UNSUPPORTED;
+  beam_merge_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(out, state, ctl, sc, hist, W, beam, eos, maxlen);
+  count_launch();
+  return launch_status();
+}
 
 extern "C" int re2e_beam_gather(const int32_t *parent, const int32_t *cand, int W, int nseg, const float *const *src,
                                 float *const *dst, const int *row_floats, const int *sub_count, void *stream) {

@@ -258,6 +258,105 @@ class Decoder(torch.nn.Module):
 
         return step
 
+    def _host_merge(self, hyps, ended_hyps, entries, i, maxlen, minlen, penalty):
+        """The reference's bookkeeping for one position (model/e2e_decoder.py:296-333) given the merged candidates, best
+        first: ``entries`` = (score, index of the parent in ``hyps``, token, candidate index).  Appends finished
+        hypotheses to ``ended_hyps`` (length penalty added) and returns the ones that go on."""
+        new_hyps = [{'score': np.float32(s_), 'yseq': hyps[r]['yseq'] + [t], '_parent': r, '_j': j}
+                    for s_, r, t, j in entries]
+        if i == maxlen - 1:
+            for hyp in new_hyps:
+                hyp['yseq'].append(self.eos)
+        remained = []
+        for hyp in new_hyps:
+            if hyp['yseq'][-1] == self.eos:
+                if len(hyp['yseq']) > minlen:
+                    hyp['score'] = np.float32(hyp['score'] + np.float32((i + 1) * penalty))
+                    ended_hyps.append(hyp)
+            else:
+                remained.append(hyp)
+        return remained
+
+    def _recognize_fused(self, hb, lpz, recog_args, Cb, maxlen, minlen, chunk=8):
+        """Beam search with the whole position on the device: the seven launches of ``_fused_position`` plus
+        ``re2e_beam_merge`` (winners recorded in a history buffer, next rows written in place), replayed from one CUDA
+        graph.  The host reads the history back ``chunk`` positions at a time, two chunks in flight, and runs the
+        reference's bookkeeping (<eos>, length penalty, end_detect) on it; positions launched beyond the one where the
+        search ends are discarded (their rows are never read)."""
+        lib = _lib.lib()
+        dev = hb.device
+        W = hb.size(0)
+        beam = W
+        penalty = recog_args.penalty
+        ctl = torch.zeros(4, W, dtype=torch.int32, device=dev)        # rows: parent, ctc candidate, token, position
+        ctl[2] = self.sos
+        sc = torch.zeros(W, dtype=torch.float32, device=dev)
+        out = torch.empty(3, W, beam, dtype=torch.float32, device=dev)
+        state = torch.zeros(2, dtype=torch.int32, device=dev)        # {live hypotheses, position}
+        state[0] = 1
+        hist = torch.empty(maxlen, 4, beam, dtype=torch.float32, device=dev)
+        pin = getattr(self, "_hist_pin", None)
+        if pin is None or pin.shape[0] < maxlen or pin.shape[2] != beam:
+            pin = torch.empty(max(256, maxlen), 4, beam, dtype=torch.float32).pin_memory()
+            self._hist_pin = pin
+        hist_np = pin.numpy()
+        step = self._fused_position(hb, lpz, ctl, sc, out, Cb, beam, recog_args.ctc_weight)
+        P = _lib.ptr
+
+        def position():
+            step(False)
+            with torch.cuda.device(dev):
+                _lib.check(lib.re2e_beam_merge(P(out), P(state), P(ctl), P(sc), P(hist), W, beam, self.eos, maxlen,
+                                               _lib.stream_ptr()), "re2e_beam_merge")
+
+        use_graph = bool(getattr(recog_args, "cuda_graph", True)) and maxlen >= 6
+        graph = None
+        cur = torch.cuda.current_stream(dev)
+        hyps = [{'score': np.float32(0.0), 'yseq': [self.sos]}]     # hypothesis k lives in device row k
+        ended_hyps = []
+        launched = processed = 0
+        flights = []
+        stop = False
+        while not stop and processed < maxlen:
+            while launched < maxlen and launched < processed + 2 * chunk:
+                hi = min(maxlen, launched + chunk)
+                for i in range(launched, hi):
+                    if i == 0 or not use_graph:
+                        position()
+                    else:
+                        if graph is None:
+                            # raw capture_begin / capture_end on a side stream: the torch.cuda.graph context manager also
+                            # runs gc.collect() and empty_cache(), tens of milliseconds per utterance
+                            if getattr(self, "_cap_stream", None) is None or self._cap_stream.device != dev:
+                                self._cap_stream = torch.cuda.Stream(dev)
+                                self._graph_pool = torch.cuda.graph_pool_handle()
+                            self._cap_stream.wait_stream(cur)
+                            graph = torch.cuda.CUDAGraph()
+                            with torch.cuda.stream(self._cap_stream):
+                                graph.capture_begin(pool=self._graph_pool)
+                                position()
+                                graph.capture_end()
+                            cur.wait_stream(self._cap_stream)
+                            self._last_graph = graph
+                        graph.replay()
+                pin[launched:hi].copy_(hist[launched:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                flights.append((launched, hi, ev))
+                launched = hi
+            lo, hi, ev = flights.pop(0)
+            ev.synchronize()
+            for i in range(lo, hi):
+                rec = hist_np[i]
+                entries = [(rec[0, b], int(rec[1, b]), int(rec[2, b]), int(rec[3, b])) for b in range(beam)]
+                hyps = self._host_merge(hyps, ended_hyps, entries, i, maxlen, minlen, penalty)
+                if (end_detect(ended_hyps, i) and recog_args.maxlenratio == 0.0) or len(hyps) == 0:
+                    stop = True
+                    break
+            processed = hi
+        nbest = sorted(ended_hyps, key=lambda x: x['score'], reverse=True)[:min(len(ended_hyps), recog_args.nbest)]
+        return [{'score': float(x['score']), 'yseq': [int(t) for t in x['yseq']]} for x in nbest]
+
     def recognize_beam(self, h, lpz, recog_args, char_list=None, rnnlm=None, fstlm=None):
         """h (Th, D) encoder output of one utterance, lpz (Th, V) CTC log-probs or None.
         Returns the n-best list of dicts with 'score' (float) and 'yseq' (list of int, <sos> first)."""
@@ -274,9 +373,6 @@ class Decoder(torch.nn.Module):
         hb = h.unsqueeze(0).expand(W, Th, h.size(1)).contiguous()
         hlens = [Th] * W
         self.att.reset()
-        z = [h.new_zeros(W, self.dunits) for _ in range(self.dlayers)]
-        c = [h.new_zeros(W, self.dunits) for _ in range(self.dlayers)]
-        a_prev = None
         maxlen = Th if recog_args.maxlenratio == 0 else max(1, int(recog_args.maxlenratio * Th))
         minlen = int(recog_args.minlenratio * Th)
 
@@ -285,21 +381,26 @@ class Decoder(torch.nn.Module):
             lpz = _lib.f32c(lpz.detach(), dev)
             V = lpz.size(-1)
             ctc_beam = min(V, int(beam * CTC_SCORING_RATIO)) if ctc_weight != 1.0 else V
+        Cb = ctc_beam if use_ctc else beam          # candidates scored per row
+        if (bool(getattr(recog_args, "fused_position", True)) and self.dlayers == 1 and beam <= Cb <= 32 and W <= 32
+                and self.output.out_features <= 8192
+                and bool(_lib.lib().re2e_lstm_step_supported(W, h.size(1), self.dunits))):
+            return self._recognize_fused(hb, lpz if use_ctc else None, recog_args, Cb, maxlen, minlen)
+
+        # ---- generic position (any layer count / candidate width): tensor ops + the library's AttLoc / CTC kernels
+        z = [h.new_zeros(W, self.dunits) for _ in range(self.dlayers)]
+        c = [h.new_zeros(W, self.dunits) for _ in range(self.dlayers)]
+        if use_ctc:
             # CTCPrefixScore.initial_state (model/e2e_ctc.py:95-107), replicated for every row
             r0 = torch.full((Th, 2), -10000000000.0, device=dev, dtype=torch.float32)
             r0[:, 1] = torch.cumsum(lpz[:, 0], dim=0)
             r_prev = r0.unsqueeze(0).expand(W, Th, 2).contiguous()
             ctc_prev = torch.zeros(W, device=dev, dtype=torch.float32)
-
         # ---- static device buffers: one output position = one fixed sequence of launches over them, so positions >= 2
         #      are replayed from a CUDA graph (captured once per utterance); the host only exchanges two small packed
         #      arrays per position (control in, candidates out) through pinned memory
         L = self.dlayers
-        Cb = ctc_beam if use_ctc else beam          # candidates scored per row
-        lib = _lib.lib()
-        fused = (bool(getattr(recog_args, "fused_position", True)) and L == 1 and beam <= Cb <= 32 and self.output.out_features <= 8192
-                 and bool(lib.re2e_lstm_step_supported(W, h.size(1), self.dunits)))
-        idt = torch.int32 if fused else torch.long
+        idt = torch.long
         ctl = torch.zeros(4, W, dtype=idt, device=dev)                 # rows: parent, ctc candidate, token, position
         sc = torch.zeros(W, dtype=torch.float32, device=dev)           # accumulated scores of the rows
         out = torch.empty(3, W, beam, dtype=torch.float32, device=dev)   # candidate scores, token ids, ctc candidate idx
@@ -358,9 +459,6 @@ class Decoder(torch.nn.Module):
             cand = sc.unsqueeze(1) + best_scores                                    # fp32, as hyp['score'] + tensor
             out.copy_(torch.stack((cand, best_ids.float(), joint.float()), 0))
 
-        if fused:
-            dev_step = self._fused_position(hb, lpz if use_ctc else None, ctl, sc, out, Cb, beam, ctc_weight)
-
         use_graph = bool(getattr(recog_args, "cuda_graph", True)) and maxlen >= 6
         graph = None
         hyps = [{'score': np.float32(0.0), 'yseq': [self.sos]}]     # hypothesis k lives in device row k
@@ -401,22 +499,11 @@ class Decoder(torch.nn.Module):
             # the reference merges hypothesis by hypothesis with a stable descending sort truncated to `beam`
             # (model/e2e_decoder.py:296-314) == one stable descending sort over (hypothesis, rank) order
             order = np.argsort(-cand_h.reshape(-1), kind='stable')[:beam]
-            new_hyps = []
+            entries = []
             for k in order:
                 r, j = divmod(int(k), beam)
-                new_hyps.append({'score': np.float32(cand_h[r, j]), 'yseq': hyps[r]['yseq'] + [int(ids_h[r, j])],
-                                 '_parent': r, '_j': int(joint_h[r, j]) if use_ctc else j})
-            if i == maxlen - 1:
-                for hyp in new_hyps:
-                    hyp['yseq'].append(self.eos)
-            remained = []
-            for hyp in new_hyps:
-                if hyp['yseq'][-1] == self.eos:
-                    if len(hyp['yseq']) > minlen:
-                        hyp['score'] = np.float32(hyp['score'] + np.float32((i + 1) * penalty))
-                        ended_hyps.append(hyp)
-                else:
-                    remained.append(hyp)
+                entries.append((cand_h[r, j], r, int(ids_h[r, j]), int(joint_h[r, j]) if use_ctc else j))
+            remained = self._host_merge(hyps, ended_hyps, entries, i, maxlen, minlen, penalty)
             if end_detect(ended_hyps, i) and recog_args.maxlenratio == 0.0:
                 break
             hyps = remained

@@ -78,3 +78,50 @@ print({"lstm_step_fwd": round(graph_time(lambda: L.re2e_lstm_step_fwd(
         _lib.ptr(act), _lib.ptr(eg), _lib.ptr(cp), _lib.ptr(c), _lib.ptr(h), B, Z, sp())), 2),
     "pointwise_bwd": round(graph_time(lambda: L.re2e_lstm_pointwise_bwd(
         _lib.ptr(act), _lib.ptr(cp), _lib.ptr(c), _lib.ptr(h), _lib.ptr(c), _lib.ptr(dg), _lib.ptr(dcp), B, Z, sp())), 2)})
+
+# ---- the beam-search position (W = 10 rows, V = 4233, Th = 137), kernel by kernel
+import ctypes
+from robust_e2e_gan_b200 import AttLoc
+W, V, Th, Cb, beam, A, C, K = 10, 4233, 137, 15, 10, 320, 10, 201
+torch.manual_seed(0)
+att = AttLoc(D, Z, A, C, 100, "softmax").to(dev)
+hb = torch.tanh(torch.randn(1, Th, D, device=dev)).expand(W, Th, D).contiguous()
+with torch.no_grad():
+    st = att.precompute(hb)
+W_dec, W_att, W_conv, gvec, gvec_b = st.weights
+K = st.dims[6]
+P = _lib.ptr
+z_in, c_in, a_in = torch.randn(W, Z, device=dev), torch.randn(W, Z, device=dev), torch.softmax(torch.randn(W, Th, device=dev), 1)
+z_st, c_st, a_st, att_c = torch.empty(W, Z, device=dev), torch.empty(W, Z, device=dev), torch.empty(W, Th, device=dev), torch.empty(W, D, device=dev)
+EG = torch.randn(V, 4 * Z, device=dev) * 0.1
+tok = torch.randint(0, V, (W,), device=dev).int()
+pos = torch.full((W,), 20, device=dev).int()
+w_out, b_out, logits = torch.randn(V, Z, device=dev) * 0.05, torch.randn(V, device=dev), torch.empty(W, V, device=dev)
+top_v, top_i = torch.empty(W, Cb, device=dev), torch.empty(W, Cb, dtype=torch.int32, device=dev)
+lpz = torch.log_softmax(torch.randn(Th, V, device=dev), 1)
+r_st, r_in = torch.randn(W, Cb, Th, 2, device=dev) - 30, torch.randn(W, Th, 2, device=dev) - 30
+psi_st, psi_in, scr, outb = torch.randn(W, Cb, device=dev), torch.randn(W, device=dev), torch.randn(W, device=dev), torch.empty(3, W, beam, device=dev)
+parent, cand = torch.randint(0, W, (W,), device=dev).int(), torch.randint(0, Cb, (W,), device=dev).int()
+segs = [(z_in, z_st, Z, 0), (c_in, c_st, Z, 0), (a_in, a_st, Th, 0), (r_st, r_in, 2 * Th, Cb), (psi_st, psi_in, 1, Cb)]
+n = len(segs)
+src = (ctypes.c_void_p * n)(*[s[0].data_ptr() for s in segs]); dst = (ctypes.c_void_p * n)(*[s[1].data_ptr() for s in segs])
+rowf = (ctypes.c_int * n)(*[s[2] for s in segs]); subc = (ctypes.c_int * n)(*[s[3] for s in segs])
+steps = {
+    "beam_gather": lambda: L.re2e_beam_gather(P(parent), P(cand), W, n, src, dst, rowf, subc, sp()),
+    "attloc_step_fwd": lambda: L.re2e_attloc_step_fwd(P(st.pre), P(st.enc), P(z_in), P(a_in), P(W_dec), P(W_att), P(W_conv), P(gvec), P(gvec_b), 2.0, P(att_c), P(a_st), None, None, None, W, Th, D, A, Z, C, K, sp()),
+    "lstm_step_fwd": lambda: L.re2e_lstm_step_fwd(P(att_c), P(z_in), P(c_in), P(Wcat), P(EG), P(tok), P(act[:W]), P(c_st), P(z_st), W, D, Z, sp()),
+    "batch_nt(out)": lambda: L.re2e_batch_nt(P(z_st), P(w_out), P(b_out), P(logits), W, V, Z, 0, sp()),
+    "log_softmax_topk": lambda: L.re2e_log_softmax_topk(P(logits), W, V, Cb, None, P(top_v), P(top_i), sp()),
+    "ctc_prefix": lambda: L.re2e_ctc_prefix_score(P(lpz), P(r_in), P(top_i), P(tok), P(pos), P(psi_st), P(r_st), Th, V, W, Cb, 0, V - 1, sp()),
+    "beam_joint": lambda: L.re2e_beam_joint(P(top_v), P(top_i), P(psi_st), P(psi_in), P(scr), 0.7, 0.3, W, Cb, beam, P(outb), sp()),
+}
+res = {k: round(graph_time(f), 2) for k, f in steps.items()}
+
+
+def whole():
+    for f in steps.values():
+        f()
+
+
+res["position (7 launches)"] = round(graph_time(whole, n=20), 2)
+print(res)
