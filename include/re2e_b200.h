@@ -284,7 +284,7 @@ int re2e_ctc_prefix_score(const float *lpz, const float *r_prev, const int32_t *
  *   sub_count[s] > 0: the source has that many candidate sub-rows per parent row, e.g. the CTC states (W, ctc_beam, T, 2)).
  * re2e_log_softmax_topk: per row log-softmax (optionally written to `full` (rows,V)) and its k largest entries, sorted
  *   descending, ties to the lower index -- what torch.topk(log_softmax(x), k) returns (model/e2e_decoder.py:262,276).
- *   V <= 8192, else RE2E_E_UNSUPPORTED.
+ *   V <= 8192 and k <= 32, else RE2E_E_UNSUPPORTED.
  * re2e_beam_joint: local = w_att * att_top + w_ctc * (log_psi - psi_prev[row]) (log_psi NULL: local = att_top), the `beam`
  *   best of the Cb <= 32 candidates per row; out (3, W, beam) fp32 = {row score + local, token id, candidate index}
  *   (model/e2e_decoder.py:284-292). */

@@ -57,12 +57,23 @@ __device__ __forceinline__ float block_sum(float v, float *sh) {
   return r;
 }
 
+// float <-> unsigned key with the same order (so that redux.sync max does the arg-max in one instruction)
+__device__ __forceinline__ unsigned ord_key(float v) {
+  const unsigned u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_val(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Selection in two levels: every warp extracts the k best of its 256 entries (k rounds of a redux.sync arg-max, all 32
+// warps in parallel, no block barrier), then warp 0 merges the 32 sorted lists (lane <-> list, k rounds over the heads).
 __global__ void __launch_bounds__(kTkThreads) log_softmax_topk_kernel(const float *__restrict__ x, float *__restrict__ full,
                                                                       float *__restrict__ vals, int32_t *__restrict__ ids,
                                                                       int V, int k) {
   __shared__ float sh[32];
-  __shared__ int shi[32];
-  __shared__ int win;
+  __shared__ unsigned ckey[32][33];
+  __shared__ int cidx[32][33];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t row = blockIdx.x;
   const float *xr = x + row * V;
@@ -81,50 +92,44 @@ __global__ void __launch_bounds__(kTkThreads) log_softmax_topk_kernel(const floa
     if (tid + kTkThreads * i < V) s += expf(v[i] - m);
   s = block_sum(s, sh);
   const float lse = m + logf(s);
+  unsigned key[kTkVPT];
 #pragma unroll
   for (int i = 0; i < kTkVPT; ++i) {
     const int idx = tid + kTkThreads * i;
+    key[i] = 0u;                                   // below the key of every float
     if (idx < V) {
-      v[i] -= lse;
-      if (full) full[row * V + idx] = v[i];
+      const float o = v[i] - lse;
+      if (full) full[row * V + idx] = o;
+      key[i] = ord_key(o);
     }
   }
   for (int j = 0; j < k; ++j) {
-    float bv = -CUDART_INF_F;
+    unsigned bk = 0u;
     int bi = 0x7fffffff;
 #pragma unroll
-    for (int i = 0; i < kTkVPT; ++i) {
-      const int idx = tid + kTkThreads * i;
-      if (idx < V && v[i] > bv) { bv = v[i]; bi = idx; }
-    }
-#pragma unroll
-    for (int of = 16; of > 0; of >>= 1) {
-      const float v2 = __shfl_xor_sync(0xffffffffu, bv, of);
-      const int i2 = __shfl_xor_sync(0xffffffffu, bi, of);
-      if (v2 > bv || (v2 == bv && i2 < bi)) { bv = v2; bi = i2; }
-    }
-    if (lane == 0) { sh[warp] = bv; shi[warp] = bi; }
-    __syncthreads();
-    if (warp == 0) {
-      bv = sh[lane];
-      bi = shi[lane];
-#pragma unroll
-      for (int of = 16; of > 0; of >>= 1) {
-        const float v2 = __shfl_xor_sync(0xffffffffu, bv, of);
-        const int i2 = __shfl_xor_sync(0xffffffffu, bi, of);
-        if (v2 > bv || (v2 == bv && i2 < bi)) { bv = v2; bi = i2; }
-      }
-      if (lane == 0) {
-        win = bi;
-        vals[row * k + j] = bv;
-        ids[row * k + j] = bi;
-      }
-    }
-    __syncthreads();
-    const int w = win;
+    for (int i = 0; i < kTkVPT; ++i)
+      if (key[i] > bk) { bk = key[i]; bi = tid + kTkThreads * i; }
+    const unsigned mx = __reduce_max_sync(0xffffffffu, bk);
+    const int win = (int)__reduce_min_sync(0xffffffffu, bk == mx ? (unsigned)bi : 0x7fffffffu);
+    if (lane == 0) { ckey[warp][j] = mx; cidx[warp][j] = win; }
 #pragma unroll
     for (int i = 0; i < kTkVPT; ++i)
-      if (tid + kTkThreads * i == w) v[i] = -CUDART_INF_F;
+      if (tid + kTkThreads * i == win) key[i] = 0u;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int p = 0;                                     // head of list `lane`
+    for (int j = 0; j < k; ++j) {
+      const unsigned hk = p < k ? ckey[lane][p] : 0u;
+      const int hi = p < k ? cidx[lane][p] : 0x7fffffff;
+      const unsigned mx = __reduce_max_sync(0xffffffffu, hk);
+      const int win = (int)__reduce_min_sync(0xffffffffu, hk == mx ? (unsigned)hi : 0x7fffffffu);
+      if (hk == mx && hi == win) ++p;
+      if (lane == 0) {
+        vals[row * k + j] = ord_val(mx);
+        ids[row * k + j] = win;
+      }
+    }
   }
 }
 
@@ -265,7 +270,7 @@ extern "C" int re2e_beam_gather(const int32_t *parent, const int32_t *cand, int 
 extern "C" int re2e_log_softmax_topk(const float *logits, long long rows, int V, int k, float *full, float *vals,
                                      int32_t *ids, void *stream) {
   RE2E_CHECK_ARG(logits && vals && ids && rows > 0 && V > 0 && k > 0 && k <= V);
-  if (V > kTkThreads * kTkVPT) return RE2E_E_UNSUPPORTED;
+  if (V > kTkThreads * kTkVPT || k > 32) return RE2E_E_UNSUPPORTED;
   log_softmax_topk_kernel<<<(unsigned)rows, kTkThreads, 0, static_cast<cudaStream_t>(stream)>>>(logits, full, vals, ids,
                                                                                                 V, k);
   count_launch();

@@ -550,9 +550,20 @@ log_softmax_kernel(const float *__restrict__ x, float *__restrict__ out, int32_t
 // of lpz -- is fetched 32 frames at a time with lane <-> frame (coalesced); the recursion itself runs uniformly on all
 // lanes over values broadcast by shuffles (three independent logaddexp chains per frame: r^n, r^b, psi), and every lane
 // keeps the pair of its own frame so that r_new is written 32 frames per store.
-__device__ __forceinline__ float logaddexpf_(float a, float b) {
-  const float m = fmaxf(a, b), d = fminf(a, b) - m;
-  return m + __logf(1.0f + __expf(d));
+// The recursion runs in base-2 logarithms so that one logaddexp is FADD -> EX2 -> FADD -> LG2 -> FADD on the dependent
+// chain (no scale multiplies, raw MUFU approximations: relative error 2^-22, far inside the parity tolerance).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lae2(float a, float b) {      // log2(2^a + 2^b)
+  return fmaxf(a, b) + lg2_approx(1.0f + ex2_approx(-fabsf(a - b)));
 }
 constexpr int kPrefixWarps = 4;
 __global__ void __launch_bounds__(kPrefixWarps * 32)
@@ -565,40 +576,53 @@ ctc_prefix_kernel(const float *__restrict__ lpz, const float *__restrict__ r_pre
   if (idx >= H * Cc) return;
   const int h = idx / Cc;
   const int c = __ldg(cs + idx);
-  const float LZ = -10000000000.0f;
+  const float LZ = -10000000000.0f, L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   const int ol = __ldg(out_len + h);
   const float *rp = r_prev + (size_t)h * T * 2;
   float *rn = r_new + (size_t)idx * T * 2;
   const bool same = ol > 0 && c == __ldg(last + h);
   const int start = ol > 1 ? ol : 1;
   for (int t = lane; t < min(start - 1, T); t += 32) *reinterpret_cast<float2 *>(rn + 2 * t) = make_float2(LZ, LZ);
-  float rn_prev = ol == 0 ? __ldg(lpz + c) : LZ, rb_prev = LZ;
-  if (lane == 0 && start - 1 < T) *reinterpret_cast<float2 *>(rn + 2 * (start - 1)) = make_float2(rn_prev, rb_prev);
-  float psi = rn_prev;
+  const float r0 = ol == 0 ? __ldg(lpz + c) : LZ;
+  if (lane == 0 && start - 1 < T) *reinterpret_cast<float2 *>(rn + 2 * (start - 1)) = make_float2(r0, LZ);
+  float rn_prev = r0 * L2E, rb_prev = LZ * L2E, psi = r0 * L2E;      // base-2 from here on
+  // frame t of the current block, fetched one block ahead of the recursion
+  float2 p = make_float2(LZ, LZ);
+  float xc = 0.f, xb = 0.f;
+  if (start + lane < T) {
+    const int t = start + lane;
+    p = *reinterpret_cast<const float2 *>(rp + 2 * (t - 1));
+    xc = __ldg(lpz + (size_t)t * V + c);
+    xb = __ldg(lpz + (size_t)t * V + blank);
+  }
   for (int base = start; base < T; base += 32) {
     const int t = base + lane;
     const bool valid = t < T;
-    float phi = LZ, xc = 0.f, xb = 0.f;
-    if (valid) {
-      const float2 p = *reinterpret_cast<const float2 *>(rp + 2 * (t - 1));
-      phi = same ? p.y : logaddexpf_(p.x, p.y);
-      xc = __ldg(lpz + (size_t)t * V + c);
-      xb = __ldg(lpz + (size_t)t * V + blank);
+    const float phi = same ? p.y * L2E : lae2(p.x * L2E, p.y * L2E);
+    const float c2 = xc * L2E, b2 = xb * L2E;
+    if (t + 32 < T) {                                          // next block's operands
+      p = *reinterpret_cast<const float2 *>(rp + 2 * (t + 31));
+      xc = __ldg(lpz + (size_t)(t + 32) * V + c);
+      xb = __ldg(lpz + (size_t)(t + 32) * V + blank);
     }
     const int n = min(32, T - base);
     float my_n = LZ, my_b = LZ;
     for (int i = 0; i < n; ++i) {
-      const float ph = __shfl_sync(0xffffffffu, phi, i), c_ = __shfl_sync(0xffffffffu, xc, i),
-                  b_ = __shfl_sync(0xffffffffu, xb, i);
-      const float nn = logaddexpf_(rn_prev, ph) + c_;
-      const float nb = logaddexpf_(rn_prev, rb_prev) + b_;
-      psi = logaddexpf_(psi, ph + c_);
+      const float ph = __shfl_sync(0xffffffffu, phi, i), c_ = __shfl_sync(0xffffffffu, c2, i),
+                  b_ = __shfl_sync(0xffffffffu, b2, i);
+      const float nn = lae2(rn_prev, ph) + c_;
+      const float nb = lae2(rn_prev, rb_prev) + b_;
+      psi = lae2(psi, ph + c_);
       if (lane == i) { my_n = nn; my_b = nb; }
       rn_prev = nn; rb_prev = nb;
     }
-    if (valid) *reinterpret_cast<float2 *>(rn + 2 * t) = make_float2(my_n, my_b);
+    if (valid) *reinterpret_cast<float2 *>(rn + 2 * t) = make_float2(fmaxf(my_n * LN2, LZ), fmaxf(my_b * LN2, LZ));
   }
-  if (c == eos) psi = logaddexpf_(rp[2 * (T - 1)], rp[2 * (T - 1) + 1]);
+  psi = fmaxf(psi * LN2, LZ);
+  if (c == eos) {
+    const float a = rp[2 * (T - 1)], b = rp[2 * (T - 1) + 1];
+    psi = fmaxf(lae2(a * L2E, b * L2E) * LN2, LZ);
+  }
   if (lane == 0) log_psi[idx] = psi;
 }
 

@@ -55,71 +55,69 @@ __global__ void __launch_bounds__(256) lstm_pointwise_bwd_kernel(const float *__
   dc_prev[idx] = dct * f;
 }
 
-// out[m,n] (+)= sum_k X[m,k] * W[n,k]   for a batch-sized M (the decoder's per-position products: M = utterances or beam
-// rows, N up to 4Z = 1200, K up to 4Z).  One CTA per 8 output columns (150 CTAs for N = 1200: the 1.5 MB weight matrix is
-// streamed once, by all SMs), warp <-> column, lane <-> row; the reduction runs in chunks of kBK columns staged in shared
-// memory with 128-bit accesses on both sides: X rows at a pitch of kBK + 4 floats (conflict-free 128-bit reads with
-// lane <-> row), the warp's W row as broadcast reads.  Four independent FMA chains per thread.
-constexpr int kBMN = 8;        // columns (warps) per CTA
+// out[m,n] (+)= sum_k X[m,k] * W[n,k] (+ bias[n])   for a batch-sized M (the decoder's per-position products: M =
+// utterances or beam rows, N up to the vocabulary, K up to 4Z).  One CTA per 8 (or, for long N, 16) output columns so that
+// all SMs stream the weight matrix once; warp <-> column.  Within a warp lane <-> (row, slice of the reduction): with M
+// rows, 32 / M lanes share a row and split the staged chunk between them (M = 10 beam rows keep 30 lanes busy), combined
+// by shuffles at the end.  The reduction runs in chunks of kBK columns staged in shared memory with 128-bit accesses on
+// both sides: X rows at a pitch of kBK + 4 floats (conflict-free 128-bit reads with lane <-> row), the warp's W row as
+// broadcast reads.  Four independent FMA chains per thread.
 constexpr int kBK = 320;       // reduction chunk
-constexpr int kBM = 32;        // rows per pass (lane <-> row)
+constexpr int kBM = 32;        // rows per pass
 
-__global__ void __launch_bounds__(kBMN * 32) batch_nt_kernel(const float *__restrict__ X, const float *__restrict__ W,
-                                                            const float *__restrict__ bias, float *__restrict__ out, int M,
-                                                            int N, int K, int accumulate, int vec) {
+__global__ void __launch_bounds__(512) batch_nt_kernel(const float *__restrict__ X, const float *__restrict__ W,
+                                                      const float *__restrict__ bias, float *__restrict__ out, int M,
+                                                      int N, int K, int accumulate, int vec) {
   extern __shared__ __align__(16) float batch_smem[];
   float *x_s = batch_smem, *w_s = batch_smem + kBM * (kBK + 4);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = blockIdx.x * kBMN + warp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int n = blockIdx.x * nwarps + warp;
   for (int m0 = 0; m0 < M; m0 += kBM) {
     const int rows = min(kBM, M - m0);
+    const int G = 32 / rows;                                   // lanes per row
+    const int mrow = lane % rows, part = lane / rows;          // part >= G: idle lane
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     for (int k0 = 0; k0 < K; k0 += kBK) {
       const int kc = min(kBK, K - k0), kq = (kc + 3) >> 2;
       __syncthreads();                                         // previous chunk consumed
       if (vec) {                                               // K % 4 == 0, 16 B aligned operands
-        for (int i = tid; i < rows * kq; i += kBMN * 32) {
-          const int r = i / kq, q = i - r * kq;
-          *reinterpret_cast<float4 *>(x_s + r * (kBK + 4) + 4 * q) =
-              __ldg(reinterpret_cast<const float4 *>(X + (size_t)(m0 + r) * K + k0) + q);
-        }
-        for (int i = tid; i < kBMN * kq; i += kBMN * 32) {
-          const int r = i / kq, q = i - r * kq;
-          const int nn = blockIdx.x * kBMN + r;
-          *reinterpret_cast<float4 *>(w_s + r * kBK + 4 * q) =
-              nn < N ? __ldg(reinterpret_cast<const float4 *>(W + (size_t)nn * K + k0) + q)
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int r = warp; r < rows; r += nwarps)
+          for (int q = lane; q < kq; q += 32)
+            *reinterpret_cast<float4 *>(x_s + r * (kBK + 4) + 4 * q) =
+                __ldg(reinterpret_cast<const float4 *>(X + (size_t)(m0 + r) * K + k0) + q);
+        for (int q = lane; q < kq; q += 32)
+          *reinterpret_cast<float4 *>(w_s + warp * kBK + 4 * q) =
+              n < N ? __ldg(reinterpret_cast<const float4 *>(W + (size_t)n * K + k0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {                                                 // scalar staging, the chunk zero-padded to a quad
-        for (int i = tid; i < rows * 4 * kq; i += kBMN * 32) {
-          const int r = i / (4 * kq), k = i - r * 4 * kq;
-          x_s[r * (kBK + 4) + k] = k < kc ? __ldg(X + (size_t)(m0 + r) * K + k0 + k) : 0.f;
-        }
-        for (int i = tid; i < kBMN * 4 * kq; i += kBMN * 32) {
-          const int r = i / (4 * kq), k = i - r * 4 * kq;
-          const int nn = blockIdx.x * kBMN + r;
-          w_s[r * kBK + k] = (nn < N && k < kc) ? __ldg(W + (size_t)nn * K + k0 + k) : 0.f;
-        }
+        for (int r = warp; r < rows; r += nwarps)
+          for (int k = lane; k < 4 * kq; k += 32)
+            x_s[r * (kBK + 4) + k] = k < kc ? __ldg(X + (size_t)(m0 + r) * K + k0 + k) : 0.f;
+        for (int k = lane; k < 4 * kq; k += 32)
+          w_s[warp * kBK + k] = (n < N && k < kc) ? __ldg(W + (size_t)n * K + k0 + k) : 0.f;
       }
       __syncthreads();
-      if (lane < rows) {
-        const float4 *xr = reinterpret_cast<const float4 *>(x_s + lane * (kBK + 4));
+      if (part < G) {
+        const float4 *xr = reinterpret_cast<const float4 *>(x_s + mrow * (kBK + 4));
         const float4 *wr = reinterpret_cast<const float4 *>(w_s + warp * kBK);
 #pragma unroll 4
-        for (int q = 0; q < kq; ++q) {
+        for (int q = part; q < kq; q += G) {
           const float4 x = xr[q], w = wr[q];
           a0 = fmaf(x.x, w.x, a0); a1 = fmaf(x.y, w.y, a1); a2 = fmaf(x.z, w.z, a2); a3 = fmaf(x.w, w.w, a3);
         }
       }
     }
+    float v = (a0 + a1) + (a2 + a3);
+    for (int g = 1; g < G; ++g) {
+      const float o = __shfl_down_sync(0xffffffffu, v, g * rows);
+      if (lane < rows) v += o;
+    }
     if (lane < rows && n < N) {
       float *o = out + (size_t)(m0 + lane) * N + n;
-      const float v = (a0 + a1) + (a2 + a3) + (bias ? __ldg(bias + n) : 0.f);
+      v += bias ? __ldg(bias + n) : 0.f;
       *o = accumulate ? *o + v : v;
     }
   }
 }
-
 
 // ---- one LSTMCell position per launch -----------------------------------------------------------------------------
 // Both per-position products have batch-sized M (<= 32 rows per pass) against a 1.5-3 MB weight matrix that stays in
@@ -346,10 +344,11 @@ extern "C" int re2e_batch_nt(const float *X, const float *W, const float *bias, 
                              int accumulate, void *stream) {
   RE2E_CHECK_ARG(X && W && out && M > 0 && N > 0 && K > 0);
   const int vec = !(K & 3) && aligned16(X) && aligned16(W);
-  const size_t smem = sizeof(float) * (kBM * (kBK + 4) + kBMN * kBK);
+  const int cols = N >= 2048 ? 16 : 8;                         // columns (warps) per CTA
+  const size_t smem = sizeof(float) * (kBM * (kBK + 4) + cols * kBK);
   int rc = ensure_smem(reinterpret_cast<const void *>(batch_nt_kernel), smem);
   if (rc != RE2E_OK) return rc;
-  batch_nt_kernel<<<(N + kBMN - 1) / kBMN, kBMN * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+  batch_nt_kernel<<<(N + cols - 1) / cols, cols * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       X, W, bias, out, M, N, K, accumulate, vec);
   count_launch();
   return launch_status();
