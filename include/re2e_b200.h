@@ -302,6 +302,12 @@ int re2e_beam_joint(const float *att_top, const int32_t *ids, const float *log_p
  * synchronising at each one.  W, beam <= 32. */
 int re2e_beam_merge(const float *out, int32_t *state, int32_t *ctl, float *sc, float *hist, int W, int beam, int eos,
                     int maxlen, void *stream);
+/* re2e_beam_joint + re2e_beam_merge + re2e_beam_gather (for the NEXT position, with the rows just chosen) in one launch
+ * of one CTA: the tail of a position is a strictly serial chain of three tiny kernels, i.e. three launch latencies. */
+int re2e_beam_advance(const float *att_top, const int32_t *ids, const float *log_psi, const float *psi_prev, float *sc,
+                      float w_att, float w_ctc, int W, int Cb, int beam, int32_t *state, int32_t *ctl, float *hist,
+                      int eos, int maxlen, int nseg, const float *const *src, float *const *dst, const int *row_floats,
+                      const int *sub_count, void *stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,15 @@
 namespace re2e {
 namespace {
 
+// float <-> unsigned key with the same order (so that redux.sync max does the arg-max in one instruction)
+__device__ __forceinline__ unsigned ord_key(float v) {
+  const unsigned u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_val(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 constexpr int kMaxSeg = 8;
 struct GatherArgs {
   const float *src[kMaxSeg];
@@ -55,15 +64,6 @@ __device__ __forceinline__ float block_sum(float v, float *sh) {
   r = warp_sum(r);
   __syncthreads();
   return r;
-}
-
-// float <-> unsigned key with the same order (so that redux.sync max does the arg-max in one instruction)
-__device__ __forceinline__ unsigned ord_key(float v) {
-  const unsigned u = __float_as_uint(v);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float ord_val(unsigned k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
 // Selection in two levels: every warp extracts the k best of its 256 entries (k rounds of a redux.sync arg-max, all 32
@@ -235,6 +235,130 @@ __global__ void __launch_bounds__(32) beam_merge_kernel(const float *__restrict_
   if (lane == 0) { state[0] = n2; state[1] = pos + 1; }
 }
 
+// ---- joint + merge + gather of one position in ONE launch (one CTA, a warp per row) ---------------------------------
+// Phase 1 = beam_joint (candidates kept in shared memory), phase 2 = beam_merge on warp 0, phase 3 = beam_gather for the
+// NEXT position with the rows just chosen.  Three launch latencies of a strictly serial chain become one.
+struct AdvanceArgs {
+  const float *att_top, *log_psi, *psi_prev;
+  const int32_t *ids;
+  float *sc;
+  float w_att, w_ctc;
+  int W, Cb, beam, eos, maxlen;
+  int32_t *state, *ctl;
+  float *hist;
+  GatherArgs g;
+  int nseg;
+};
+
+__global__ void __launch_bounds__(1024) beam_advance_kernel(const AdvanceArgs a) {
+  __shared__ float s_out[3][1024];
+  __shared__ float row_sc[32];
+  __shared__ int row_p[32], row_j[32], row_t[32], s_ctl[2][32], s_n2, s_state[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int W = a.W, Cb = a.Cb, beam = a.beam;
+  if (threadIdx.x == 1023) { s_state[0] = a.state[0]; s_state[1] = a.state[1]; }     // (latency hidden behind phase 1)
+  // phase 1: joint scores of row `warp`, its `beam` best in descending order (arg-max by redux.sync on ordered keys)
+  if (warp < W) {
+    const int h = warp;
+    unsigned key = 0u;
+    if (lane < Cb) {
+      const float x = a.att_top[h * Cb + lane];
+      const float val = a.log_psi ? __fadd_rn(__fmul_rn(a.w_att, x),
+                                              __fmul_rn(a.w_ctc, __fsub_rn(a.log_psi[h * Cb + lane], a.psi_prev[h])))
+                                  : x;
+      key = ord_key(val);
+    }
+    const int my_id = lane < Cb ? a.ids[h * Cb + lane] : 0;
+    const float base = a.sc[h];
+    for (int b = 0; b < beam; ++b) {
+      const unsigned mx = __reduce_max_sync(0xffffffffu, key);
+      const int bj = (int)__reduce_min_sync(0xffffffffu, key == mx ? (unsigned)lane : 32u);
+      if (lane == bj) {
+        s_out[0][h * beam + b] = __fadd_rn(base, ord_val(mx));
+        s_out[1][h * beam + b] = (float)my_id;
+        s_out[2][h * beam + b] = (float)bj;
+        key = 0u;
+      }
+    }
+  }
+  __syncthreads();
+  // phase 2 (warp 0): the rows' lists are sorted, so the merge is a W-way merge over the list heads, lane <-> row
+  if (warp == 0) {
+    const int n = s_state[0], pos = s_state[1];
+    int n2 = 0;
+    if (n > 0 && pos < a.maxlen) {
+      int p = 0;
+      float my_sc = 0.f;
+      int my_k = 0;
+      for (int b = 0; b < beam; ++b) {
+        const bool live = lane < n && p < beam;
+        const unsigned hk = live ? ord_key(s_out[0][lane * beam + p]) : 0u;
+        const unsigned mx = __reduce_max_sync(0xffffffffu, hk);
+        const int wl = (int)__reduce_min_sync(0xffffffffu, (live && hk == mx) ? (unsigned)lane : 32u);   // lower flat index
+        const int wk = __shfl_sync(0xffffffffu, lane * beam + p, wl & 31);
+        if (lane == b) { my_sc = ord_val(mx); my_k = wk; }
+        if (lane == wl) ++p;
+      }
+      const bool have = lane < beam;
+      const int r = have ? my_k / beam : 0;
+      const int tok = have ? (int)s_out[1][my_k] : a.eos;
+      const int joint = have ? (int)s_out[2][my_k] : 0;
+      if (have) {
+        float *hp = a.hist + (size_t)pos * 4 * beam;
+        hp[lane] = my_sc;
+        hp[beam + lane] = (float)r;
+        hp[2 * beam + lane] = (float)tok;
+        hp[3 * beam + lane] = (float)joint;
+      }
+      const bool alive = have && tok != a.eos && pos != a.maxlen - 1;
+      const unsigned m = __ballot_sync(0xffffffffu, alive);
+      n2 = __popc(m);
+      const int rank = __popc(m & ((1u << lane) - 1u));
+      if (alive) { row_sc[rank] = my_sc; row_p[rank] = r; row_j[rank] = joint; row_t[rank] = tok; }
+      __syncwarp();
+      if (n2 > 0 && lane < W) {
+        const int s = min(lane, n2 - 1);
+        a.ctl[lane] = row_p[s];
+        a.ctl[W + lane] = row_j[s];
+        a.ctl[2 * W + lane] = row_t[s];
+        a.ctl[3 * W + lane] = pos + 1;
+        a.sc[lane] = row_sc[s];
+        s_ctl[0][lane] = row_p[s];
+        s_ctl[1][lane] = row_j[s];
+      }
+      if (lane == 0) a.state[0] = n2;
+    }
+    if (lane == 0) { a.state[1] = pos + 1; s_n2 = n2; }
+  }
+  __syncthreads();
+  // phase 3: the chosen rows' states -> working copies of the next position (four independent loads in flight per
+  // thread: the copy is latency-bound)
+  if (s_n2 <= 0) return;
+  const int nt = blockDim.x;
+  for (int s = 0; s < a.nseg; ++s) {
+    const int nf = a.g.row_floats[s], sub = a.g.sub_count[s], tot = W * nf;
+    const float *src = a.g.src[s];
+    float *dst = a.g.dst[s];
+    for (int e0 = threadIdx.x; e0 < tot; e0 += 4 * nt) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * nt;
+        if (e < tot) {
+          const int m = e / nf, i = e - m * nf;
+          const size_t srow = sub > 0 ? (size_t)s_ctl[0][m] * sub + s_ctl[1][m] : (size_t)s_ctl[0][m];
+          v[u] = __ldg(src + srow * nf + i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * nt;
+        if (e < tot) dst[e] = v[u];
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace re2e
 
@@ -284,6 +408,26 @@ extern "C" int re2e_beam_joint(const float *att_top, const int32_t *ids, const f
   if (Cb > 32) return RE2E_E_UNSUPPORTED;
   beam_joint_kernel<<<(W + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(att_top, ids, log_psi, psi_prev, sc, w_att,
                                                                               w_ctc, W, Cb, beam, out);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int re2e_beam_advance(const float *att_top, const int32_t *ids, const float *log_psi, const float *psi_prev,
+                                 float *sc, float w_att, float w_ctc, int W, int Cb, int beam, int32_t *state,
+                                 int32_t *ctl, float *hist, int eos, int maxlen, int nseg, const float *const *src,
+                                 float *const *dst, const int *row_floats, const int *sub_count, void *stream) {
+  RE2E_CHECK_ARG(att_top && ids && sc && state && ctl && hist && W > 0 && Cb > 0 && beam > 0 && beam <= Cb && maxlen > 0);
+  RE2E_CHECK_ARG((!log_psi || psi_prev) && nseg >= 0 && nseg <= kMaxSeg && (nseg == 0 || (src && dst && row_floats && sub_count)));
+  if (W > 32 || Cb > 32) return RE2E_E_UNSUPPORTED;
+  AdvanceArgs a{};
+  a.att_top = att_top; a.ids = ids; a.log_psi = log_psi; a.psi_prev = psi_prev; a.sc = sc;
+  a.w_att = w_att; a.w_ctc = w_ctc; a.W = W; a.Cb = Cb; a.beam = beam; a.eos = eos; a.maxlen = maxlen;
+  a.state = state; a.ctl = ctl; a.hist = hist; a.nseg = nseg;
+  for (int s = 0; s < nseg; ++s) {
+    RE2E_CHECK_ARG(src[s] && dst[s] && row_floats[s] > 0 && sub_count[s] >= 0);
+    a.g.src[s] = src[s]; a.g.dst[s] = dst[s]; a.g.row_floats[s] = row_floats[s]; a.g.sub_count[s] = sub_count[s];
+  }
+  beam_advance_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(a);
   count_launch();
   return launch_status();
 }

@@ -196,11 +196,12 @@ class Decoder(torch.nn.Module):
             self._beam_tab = tb
         return tb[1:]
 
-    def _fused_position(self, hb, lpz, ctl, sc, out, Cb, beam, ctc_weight):
-        """One output position for all W rows as seven launches of the library over static buffers (csrc/beam.cu): gather
-        the parents' states, AttLoc step, LSTMCell step (embedding half by token lookup), output layer, log-softmax +
-        top-Cb, CTC prefix scores, joint score + per-row top-beam.  Returns the step closure (same call shape as the
-        generic one; the first position needs no special case: the states start as every row's initial state)."""
+    def _fused_position(self, hb, lpz, Cb, beam, ctc_weight, maxlen, fused_tail=True):
+        """One output position for all W rows as launches of the library over static buffers (csrc/beam.cu):
+        AttLoc step, LSTMCell step (embedding half by token lookup), output layer, log-softmax + top-Cb, CTC prefix
+        scores, then joint score + merge + gather of the chosen rows' states for the next position (one launch,
+        ``re2e_beam_advance``; ``fused_tail=False`` runs them as three).  Returns (position closure, history buffer).
+        The first position needs no special case: the states start as every row's initial state."""
         import ctypes
         lib = _lib.lib()
         dev = hb.device
@@ -211,8 +212,15 @@ class Decoder(torch.nn.Module):
         _, _, _, A, _, C, K = st.dims
         W_dec, W_att, W_conv, gvec, gvec_b = st.weights
         f = dict(device=dev, dtype=torch.float32)
+        ctl = torch.zeros(4, W, dtype=torch.int32, device=dev)        # rows: parent, ctc candidate, token, position
+        ctl[2] = self.sos
+        sc = torch.zeros(W, **f)                                      # accumulated scores of the rows
+        out = torch.empty(3, W, beam, **f)
+        state = torch.zeros(2, dtype=torch.int32, device=dev)        # {live hypotheses, position}
+        state[0] = 1
+        hist = torch.empty(maxlen, 4, beam, **f)
         z_st, c_st = torch.zeros(W, Z, **f), torch.zeros(W, Z, **f)
-        z_in, c_in = torch.empty(W, Z, **f), torch.empty(W, Z, **f)
+        z_in, c_in = torch.zeros(W, Z, **f), torch.zeros(W, Z, **f)
         a_st, a_in = torch.empty(W, Th, **f), torch.empty(W, Th, **f)
         hl = torch.full((W,), Th, dtype=torch.int32, device=dev)
         att_c, act, logits = torch.empty(W, D, **f), torch.empty(W, 4 * Z, **f), torch.empty(W, V, **f)
@@ -231,32 +239,56 @@ class Decoder(torch.nn.Module):
         dst = (ctypes.c_void_p * n)(*[s[1].data_ptr() for s in segs])
         rowf = (ctypes.c_int * n)(*[s[2] for s in segs])
         subc = (ctypes.c_int * n)(*[s[3] for s in segs])
-        keep = (segs, hl, eg, wcat, w_out, b_out)          # buffers a captured graph points into
         w_att, w_ctc = float(1.0 - ctc_weight), float(ctc_weight)
         P = _lib.ptr
         with torch.cuda.device(dev):
-            _lib.check(lib.re2e_attloc_init_att(P(hl), P(a_st), W, Th, _lib.stream_ptr()), "re2e_attloc_init_att")
-
-        def step(_first):
             sp = _lib.stream_ptr()
-            with torch.cuda.device(dev):
-                _lib.check(lib.re2e_beam_gather(P(ctl[0]), P(ctl[1]), W, n, src, dst, rowf, subc, sp), "re2e_beam_gather")
-                _lib.check(lib.re2e_attloc_step_fwd(P(st.pre), P(st.enc), P(z_in), P(a_in), P(W_dec), P(W_att), P(W_conv),
-                                                    P(gvec), P(gvec_b), 2.0, P(att_c), P(a_st), None, None, None,
-                                                    W, Th, D, A, Z, C, K, sp), "re2e_attloc_step_fwd")
-                _lib.check(lib.re2e_lstm_step_fwd(P(att_c), P(z_in), P(c_in), P(wcat), P(eg), P(ctl[2]), P(act), P(c_st),
-                                                  P(z_st), W, D, Z, sp), "re2e_lstm_step_fwd")
-                _lib.check(lib.re2e_batch_nt(P(z_st), P(w_out), P(b_out), P(logits), W, V, Z, 0, sp), "re2e_batch_nt")
-                _lib.check(lib.re2e_log_softmax_topk(P(logits), W, V, Cb, None, P(top_v), P(top_i), sp),
-                           "re2e_log_softmax_topk")
-                if lpz is not None:
-                    _lib.check(lib.re2e_ctc_prefix_score(P(lpz), P(r_in), P(top_i), P(ctl[2]), P(ctl[3]), P(psi_st),
-                                                         P(r_st), Th, V, W, Cb, 0, self.eos, sp), "re2e_ctc_prefix_score")
-                _lib.check(lib.re2e_beam_joint(P(top_v), P(top_i), P(psi_st), P(psi_in), P(sc), w_att, w_ctc, W, Cb, beam,
-                                               P(out), sp), "re2e_beam_joint")
-            return keep
+            _lib.check(lib.re2e_attloc_init_att(P(hl), P(a_st), W, Th, sp), "re2e_attloc_init_att")
+            _lib.check(lib.re2e_beam_gather(P(ctl[0]), P(ctl[1]), W, n, src, dst, rowf, subc, sp), "re2e_beam_gather")
 
-        return step
+        def build(sp):
+            """The position's launches with their argument tuples, for one stream (everything else is constant)."""
+            calls = [
+                (lib.re2e_attloc_step_fwd, "re2e_attloc_step_fwd",
+                 (P(st.pre), P(st.enc), P(z_in), P(a_in), P(W_dec), P(W_att), P(W_conv), P(gvec), P(gvec_b), 2.0, P(att_c),
+                  P(a_st), None, None, None, W, Th, D, A, Z, C, K, sp)),
+                (lib.re2e_lstm_step_fwd, "re2e_lstm_step_fwd",
+                 (P(att_c), P(z_in), P(c_in), P(wcat), P(eg), P(ctl[2]), P(act), P(c_st), P(z_st), W, D, Z, sp)),
+                (lib.re2e_batch_nt, "re2e_batch_nt", (P(z_st), P(w_out), P(b_out), P(logits), W, V, Z, 0, sp)),
+                (lib.re2e_log_softmax_topk, "re2e_log_softmax_topk", (P(logits), W, V, Cb, None, P(top_v), P(top_i), sp)),
+            ]
+            if lpz is not None:
+                calls.append((lib.re2e_ctc_prefix_score, "re2e_ctc_prefix_score",
+                              (P(lpz), P(r_in), P(top_i), P(ctl[2]), P(ctl[3]), P(psi_st), P(r_st), Th, V, W, Cb, 0,
+                               self.eos, sp)))
+            if fused_tail:
+                calls.append((lib.re2e_beam_advance, "re2e_beam_advance",
+                              (P(top_v), P(top_i), P(psi_st), P(psi_in), P(sc), w_att, w_ctc, W, Cb, beam, P(state), P(ctl),
+                               P(hist), self.eos, maxlen, n, src, dst, rowf, subc, sp)))
+            else:
+                calls += [
+                    (lib.re2e_beam_joint, "re2e_beam_joint",
+                     (P(top_v), P(top_i), P(psi_st), P(psi_in), P(sc), w_att, w_ctc, W, Cb, beam, P(out), sp)),
+                    (lib.re2e_beam_merge, "re2e_beam_merge",
+                     (P(out), P(state), P(ctl), P(sc), P(hist), W, beam, self.eos, maxlen, sp)),
+                    (lib.re2e_beam_gather, "re2e_beam_gather", (P(ctl[0]), P(ctl[1]), W, n, src, dst, rowf, subc, sp))]
+            return calls
+
+        built = {}
+
+        def position():
+            key = torch.cuda.current_stream(dev).cuda_stream
+            calls = built.get(key)
+            if calls is None:
+                calls = built[key] = build(ctypes.c_void_p(key))
+            with torch.cuda.device(dev):
+                for fn, name, args in calls:
+                    rc = fn(*args)
+                    if rc != 0:
+                        _lib.check(rc, name)
+
+        position.keep = (segs, hl, eg, wcat, w_out, b_out, ctl, sc, out, state)   # buffers a captured graph points into
+        return position, hist
 
     def _host_merge(self, hyps, ended_hyps, entries, i, maxlen, minlen, penalty):
         """The reference's bookkeeping for one position (model/e2e_decoder.py:296-333) given the merged candidates, best
@@ -278,37 +310,24 @@ class Decoder(torch.nn.Module):
         return remained
 
     def _recognize_fused(self, hb, lpz, recog_args, Cb, maxlen, minlen, chunk=8):
-        """Beam search with the whole position on the device: the seven launches of ``_fused_position`` plus
-        ``re2e_beam_merge`` (winners recorded in a history buffer, next rows written in place), replayed from one CUDA
-        graph.  The host reads the history back ``chunk`` positions at a time, two chunks in flight, and runs the
-        reference's bookkeeping (<eos>, length penalty, end_detect) on it; positions launched beyond the one where the
-        search ends are discarded (their rows are never read)."""
-        lib = _lib.lib()
+        """Beam search with the whole position on the device (``_fused_position``), ``chunk`` positions per CUDA-graph
+        replay.  The winners of every position land in a history buffer; the host reads it back one chunk at a time, two
+        chunks in flight, and runs the reference's bookkeeping (<eos>, length penalty, end_detect) on it.  Positions
+        launched beyond the one where the search ends are discarded (past maxlen the merge is a no-op)."""
+        import time
+        prof = getattr(recog_args, "profile", None)       # optional dict: host seconds per phase (tools/recog_launches.py)
+        tick = time.perf_counter
+        t0 = tick()
         dev = hb.device
-        W = hb.size(0)
-        beam = W
+        beam = hb.size(0)
         penalty = recog_args.penalty
-        ctl = torch.zeros(4, W, dtype=torch.int32, device=dev)        # rows: parent, ctc candidate, token, position
-        ctl[2] = self.sos
-        sc = torch.zeros(W, dtype=torch.float32, device=dev)
-        out = torch.empty(3, W, beam, dtype=torch.float32, device=dev)
-        state = torch.zeros(2, dtype=torch.int32, device=dev)        # {live hypotheses, position}
-        state[0] = 1
-        hist = torch.empty(maxlen, 4, beam, dtype=torch.float32, device=dev)
+        position, hist = self._fused_position(hb, lpz, Cb, beam, recog_args.ctc_weight, maxlen,
+                                              bool(getattr(recog_args, "fused_tail", True)))
         pin = getattr(self, "_hist_pin", None)
         if pin is None or pin.shape[0] < maxlen or pin.shape[2] != beam:
             pin = torch.empty(max(256, maxlen), 4, beam, dtype=torch.float32).pin_memory()
             self._hist_pin = pin
         hist_np = pin.numpy()
-        step = self._fused_position(hb, lpz, ctl, sc, out, Cb, beam, recog_args.ctc_weight)
-        P = _lib.ptr
-
-        def position():
-            step(False)
-            with torch.cuda.device(dev):
-                _lib.check(lib.re2e_beam_merge(P(out), P(state), P(ctl), P(sc), P(hist), W, beam, self.eos, maxlen,
-                                               _lib.stream_ptr()), "re2e_beam_merge")
-
         use_graph = bool(getattr(recog_args, "cuda_graph", True)) and maxlen >= 6
         graph = None
         cur = torch.cuda.current_stream(dev)
@@ -317,35 +336,44 @@ class Decoder(torch.nn.Module):
         launched = processed = 0
         flights = []
         stop = False
+        t_setup = tick() - t0
+        t_capture = t_launch = t_wait = t_host = 0.0
         while not stop and processed < maxlen:
+            t1 = tick()
             while launched < maxlen and launched < processed + 2 * chunk:
-                hi = min(maxlen, launched + chunk)
-                for i in range(launched, hi):
-                    if i == 0 or not use_graph:
+                if launched == 0 or not use_graph:
+                    hi = 1 if use_graph else min(maxlen, launched + chunk)   # the first position also warms the kernels up
+                    for _ in range(launched, hi):
                         position()
-                    else:
-                        if graph is None:
-                            # raw capture_begin / capture_end on a side stream: the torch.cuda.graph context manager also
-                            # runs gc.collect() and empty_cache(), tens of milliseconds per utterance
-                            if getattr(self, "_cap_stream", None) is None or self._cap_stream.device != dev:
-                                self._cap_stream = torch.cuda.Stream(dev)
-                                self._graph_pool = torch.cuda.graph_pool_handle()
-                            self._cap_stream.wait_stream(cur)
-                            graph = torch.cuda.CUDAGraph()
-                            with torch.cuda.stream(self._cap_stream):
-                                graph.capture_begin(pool=self._graph_pool)
+                else:
+                    if graph is None:
+                        # raw capture_begin / capture_end on a side stream: the torch.cuda.graph context manager also runs
+                        # gc.collect() and empty_cache(), tens of milliseconds per utterance
+                        tc = tick()
+                        if getattr(self, "_cap_stream", None) is None or self._cap_stream.device != dev:
+                            self._cap_stream = torch.cuda.Stream(dev)
+                            self._graph_pool = torch.cuda.graph_pool_handle()
+                        self._cap_stream.wait_stream(cur)
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.stream(self._cap_stream):
+                            graph.capture_begin(pool=self._graph_pool)
+                            for _ in range(chunk):
                                 position()
-                                graph.capture_end()
-                            cur.wait_stream(self._cap_stream)
-                            self._last_graph = graph
-                        graph.replay()
+                            graph.capture_end()
+                        cur.wait_stream(self._cap_stream)
+                        self._last_graph = graph
+                        t_capture += tick() - tc
+                    graph.replay()
+                    hi = min(maxlen, launched + chunk)
                 pin[launched:hi].copy_(hist[launched:hi], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 flights.append((launched, hi, ev))
                 launched = hi
             lo, hi, ev = flights.pop(0)
+            t2 = tick()
             ev.synchronize()
+            t3 = tick()
             for i in range(lo, hi):
                 rec = hist_np[i]
                 entries = [(rec[0, b], int(rec[1, b]), int(rec[2, b]), int(rec[3, b])) for b in range(beam)]
@@ -354,6 +382,13 @@ class Decoder(torch.nn.Module):
                     stop = True
                     break
             processed = hi
+            t_launch += t2 - t1
+            t_wait += t3 - t2
+            t_host += tick() - t3
+        if prof is not None:
+            for k_, v_ in (("setup", t_setup), ("capture", t_capture), ("launch", t_launch - t_capture), ("wait", t_wait),
+                           ("host_merge", t_host), ("positions", float(processed))):
+                prof[k_] = prof.get(k_, 0.0) + v_
         nbest = sorted(ended_hyps, key=lambda x: x['score'], reverse=True)[:min(len(ended_hyps), recog_args.nbest)]
         return [{'score': float(x['score']), 'yseq': [int(t) for t in x['yseq']]} for x in nbest]
 

@@ -37,6 +37,12 @@ with torch.no_grad():
         n += len(decode(h)[0]["yseq"]) - 1
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    ra.profile = {}
+    for h in hs[1:3]:
+        decode(h)
+    torch.cuda.synchronize()
+    print("host seconds per phase over the same two utterances:", {k: round(v, 5) for k, v in ra.profile.items()})
+    del ra.profile
     print("wall: %.1f us per output position (%d positions, Th=%d)" % (dt * 1e6 / n, n, Th), flush=True)
     torch.cuda.cudart().cudaProfilerStart()
     decode(hs[3])
