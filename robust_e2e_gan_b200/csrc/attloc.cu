@@ -244,9 +244,9 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
 #pragma unroll
     for (int u = 0; u < IA; ++u) {
       const int i = tid + u * NT, t = i - filts;
-      va[u] = (i < g.App && t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
+      va[u] = (i < g.App && t >= 0 && t < Th) ? __ldcg(p.att_prev + (size_t)b * Th + t) : 0.0f;
     }
-    vz = (p.dec_z && tid < Z) ? __ldg(p.dec_z + (size_t)b * Z + tid) : 0.0f;
+    vz = (p.dec_z && tid < Z) ? __ldcg(p.dec_z + (size_t)b * Z + tid) : 0.0f;
 #pragma unroll
     for (int u = 0; u < IA; ++u)
       if (tid + u * NT < g.App) app[tid + u * NT] = va[u];
@@ -254,9 +254,9 @@ __global__ void __launch_bounds__(kFT, 1) attloc_fwd_kernel(const AttFwdParams p
     // remainders (shapes beyond the first block)
     for (int i = tid + IA * NT; i < g.App; i += NT) {
       const int t = i - filts;
-      app[i] = (t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
+      app[i] = (t >= 0 && t < Th) ? __ldcg(p.att_prev + (size_t)b * Th + t) : 0.0f;
     }
-    for (int i = tid + NT; i < Z; i += NT) dz_s[i] = p.dec_z ? __ldg(p.dec_z + (size_t)b * Z + i) : 0.0f;
+    for (int i = tid + NT; i < Z; i += NT) dz_s[i] = p.dec_z ? __ldcg(p.dec_z + (size_t)b * Z + i) : 0.0f;
   }
   __syncthreads();  // #1
   ATT_MARK(0, 1);
@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
 #pragma unroll
     for (int u = 0; u < IA; ++u) {
       const int i = tid + u * NT, t = i - filts;
-      va[u] = (i < g.App && t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
+      va[u] = (i < g.App && t >= 0 && t < Th) ? __ldcg(p.att_prev + (size_t)b * Th + t) : 0.0f;
     }
 #pragma unroll
     for (int u = 0; u < IC; ++u) {
@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
     if (tid < tloc) w_s[tid] = vws;
     for (int i = tid + IA * NT; i < g.App; i += NT) {
       const int t = i - filts;
-      app[i] = (t >= 0 && t < Th) ? __ldg(p.att_prev + (size_t)b * Th + t) : 0.0f;
+      app[i] = (t >= 0 && t < Th) ? __ldcg(p.att_prev + (size_t)b * Th + t) : 0.0f;
     }
     for (int i = tid + IC * NT; i < C * K; i += NT) wc_s[i] = __ldg(p.W_conv + i);
     for (int i = tid + IW * NT; i < A * C; i += NT) { const int a = i / C; watt_s[a * WP + (i - a * C)] = __ldg(p.W_att + i); }
@@ -741,8 +741,8 @@ __global__ void __launch_bounds__(kBT, 1) attloc_bwd_kernel(const AttBwdParams p
   pdl_launch_dependents();
   float dcr[DPL2];
 #pragma unroll
-  for (int j = 0; j < DPL2; ++j) dcr[j] = (p.dc && lane + 32 * j < D) ? __ldg(p.dc + (size_t)b * D + lane + 32 * j) : 0.0f;
-  for (int i = tid; i < tloc; i += NT) dwt_s[i] = p.dw ? __ldg(p.dw + (size_t)b * Th + t0 + i) : 0.0f;
+  for (int j = 0; j < DPL2; ++j) dcr[j] = (p.dc && lane + 32 * j < D) ? __ldcg(p.dc + (size_t)b * D + lane + 32 * j) : 0.0f;
+  for (int i = tid; i < tloc; i += NT) dwt_s[i] = p.dw ? __ldcg(p.dw + (size_t)b * Th + t0 + i) : 0.0f;
   __syncthreads();  // #1
   ATT_MARK(1, 1);
 
@@ -1278,11 +1278,6 @@ inline bool pick_geom_bwd(int B, int Th, int D, int A, int Z, int C, int K, int 
     if (CL >= 16 || B * CL * 2 > sms) return false;
     CL *= 2;
   }
-}
-
-inline bool pdl_enabled() {
-  static const bool on = [] { const char *e = getenv("RE2E_NO_PDL"); return !(e && e[0] == '1'); }();
-  return on;
 }
 
 template <typename Kern, typename Params>

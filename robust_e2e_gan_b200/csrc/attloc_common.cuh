@@ -65,15 +65,6 @@ __device__ __forceinline__ void st_async_f32x4(uint32_t remote_addr, float a, fl
                "r"(remote_bar)
                : "memory");
 }
-// Programmatic dependent launch (PDL).  The step kernels are launched with programmatic stream serialisation, so
-// a grid may become resident while its predecessor in the stream (normally the previous decoder step) is still
-// running.  Everything before pdl_wait() touches only memory that was final before the predecessor STARTED:
-// parameters, the per-utterance encoder tensors (pre, enc_h) and -- in the backward -- tensors saved by the
-// forward pass.  griddepcontrol.wait returns once the predecessor grid has completed and flushed; all global
-// writes and all reads of per-step inputs (att_prev / dec_z, dc / dw, accumulators) come after it.  A predecessor
-// that never executes launch_dependents (any foreign kernel) degrades to ordinary stream order.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void cluster_arrive_relaxed() {
   asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 }

@@ -77,12 +77,14 @@ __global__ void __launch_bounds__(kTkThreads) log_softmax_topk_kernel(const floa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t row = blockIdx.x;
   const float *xr = x + row * V;
+  pdl_wait();
+  pdl_launch_dependents();
   float v[kTkVPT];
   float m = -CUDART_INF_F;
 #pragma unroll
   for (int i = 0; i < kTkVPT; ++i) {
     const int idx = tid + kTkThreads * i;
-    v[i] = idx < V ? __ldg(xr + idx) : -CUDART_INF_F;
+    v[i] = idx < V ? __ldcg(xr + idx) : -CUDART_INF_F;
     m = fmaxf(m, v[i]);
   }
   m = block_max(m, sh);
@@ -256,20 +258,23 @@ __global__ void __launch_bounds__(1024) beam_advance_kernel(const AdvanceArgs a)
   __shared__ int row_p[32], row_j[32], row_t[32], s_ctl[2][32], s_n2, s_state[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int W = a.W, Cb = a.Cb, beam = a.beam;
-  if (threadIdx.x == 1023) { s_state[0] = a.state[0]; s_state[1] = a.state[1]; }     // (latency hidden behind phase 1)
+  pdl_wait();
+  pdl_launch_dependents();
+  if (threadIdx.x == 1023) { s_state[0] = __ldcg(a.state); s_state[1] = __ldcg(a.state + 1); }     // (latency hidden behind phase 1)
   // phase 1: joint scores of row `warp`, its `beam` best in descending order (arg-max by redux.sync on ordered keys)
   if (warp < W) {
     const int h = warp;
     unsigned key = 0u;
     if (lane < Cb) {
-      const float x = a.att_top[h * Cb + lane];
+      const float x = __ldcg(a.att_top + h * Cb + lane);
       const float val = a.log_psi ? __fadd_rn(__fmul_rn(a.w_att, x),
-                                              __fmul_rn(a.w_ctc, __fsub_rn(a.log_psi[h * Cb + lane], a.psi_prev[h])))
+                                              __fmul_rn(a.w_ctc, __fsub_rn(__ldcg(a.log_psi + h * Cb + lane),
+                                                                           __ldcg(a.psi_prev + h))))
                                   : x;
       key = ord_key(val);
     }
-    const int my_id = lane < Cb ? a.ids[h * Cb + lane] : 0;
-    const float base = a.sc[h];
+    const int my_id = lane < Cb ? __ldcg(a.ids + h * Cb + lane) : 0;
+    const float base = __ldcg(a.sc + h);
     for (int b = 0; b < beam; ++b) {
       const unsigned mx = __reduce_max_sync(0xffffffffu, key);
       const int bj = (int)__reduce_min_sync(0xffffffffu, key == mx ? (unsigned)lane : 32u);
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(1024) beam_advance_kernel(const AdvanceArgs a)
         if (e < tot) {
           const int m = e / nf, i = e - m * nf;
           const size_t srow = sub > 0 ? (size_t)s_ctl[0][m] * sub + s_ctl[1][m] : (size_t)s_ctl[0][m];
-          v[u] = __ldg(src + srow * nf + i);
+          v[u] = __ldcg(src + srow * nf + i);
         }
       }
 #pragma unroll
@@ -395,10 +400,10 @@ extern "C" int re2e_log_softmax_topk(const float *logits, long long rows, int V,
                                      int32_t *ids, void *stream) {
   RE2E_CHECK_ARG(logits && vals && ids && rows > 0 && V > 0 && k > 0 && k <= V);
   if (V > kTkThreads * kTkVPT || k > 32) return RE2E_E_UNSUPPORTED;
-  log_softmax_topk_kernel<<<(unsigned)rows, kTkThreads, 0, static_cast<cudaStream_t>(stream)>>>(logits, full, vals, ids,
-                                                                                                V, k);
+  cudaError_t e = launch_pdl(2, log_softmax_topk_kernel, dim3((unsigned)rows), dim3(kTkThreads), 0,
+                             static_cast<cudaStream_t>(stream), logits, full, vals, ids, V, k);
   count_launch();
-  return launch_status();
+  return e == cudaSuccess ? launch_status() : (int)e;
 }
 
 extern "C" int re2e_beam_joint(const float *att_top, const int32_t *ids, const float *log_psi, const float *psi_prev,
@@ -427,7 +432,7 @@ extern "C" int re2e_beam_advance(const float *att_top, const int32_t *ids, const
     RE2E_CHECK_ARG(src[s] && dst[s] && row_floats[s] > 0 && sub_count[s] >= 0);
     a.g.src[s] = src[s]; a.g.dst[s] = dst[s]; a.g.row_floats[s] = row_floats[s]; a.g.sub_count[s] = sub_count[s];
   }
-  beam_advance_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  cudaError_t e = launch_pdl(4, beam_advance_kernel, dim3(1), dim3(1024), 0, static_cast<cudaStream_t>(stream), a);
   count_launch();
-  return launch_status();
+  return e == cudaSuccess ? launch_status() : (int)e;
 }

@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <cstdlib>
+#include <utility>
 
 #include "re2e_b200.h"
 
@@ -36,6 +38,39 @@ inline int launch_status() {
 }
 
 int num_sms();   // SM count of the CURRENT device (cached per device); defined in api.cu
+
+// RE2E_NO_PDL=1 in the environment restores plain stream order (debugging / A-B timing)
+inline bool pdl_enabled() {
+  static const bool on = [] { const char *e = getenv("RE2E_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
+}
+// Launch sites of launch_pdl() are opt-in, one bit each in RE2E_PDL_MASK (default 0 = plain stream order): measured on
+// the beam-search position (six short kernels in a strictly serial chain) programmatic launches made the chain SLOWER
+// (70.2 vs 63.3 us per position: the early-resident successors take SM slots from the running kernel and the graph
+// capture costs 1.5x), so they stay off; the kernels keep the discipline that makes them legal (pdl_wait() first,
+// coherent __ldcg loads for everything an overlapping predecessor may write -- ld.global.nc / __ldg returned stale
+// lines there).
+inline unsigned pdl_mask() {
+  static const unsigned m = [] { const char *e = getenv("RE2E_PDL_MASK"); return e ? (unsigned)strtoul(e, nullptr, 0) : 0u; }();
+  return m;
+}
+// Launch with programmatic stream serialisation: the grid may become resident while its predecessor in the stream is
+// still running.  EVERY kernel launched this way must execute pdl_wait() before it reads or writes anything the
+// predecessor (or, transitively, anything earlier in the stream) may still touch.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int id, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_enabled() && ((pdl_mask() >> id) & 1)) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -92,6 +127,16 @@ __device__ __forceinline__ void st_stream4(float *p, float4 v) {
                "f"(v.z), "f"(v.w)
                : "memory");
 }
+
+// Programmatic dependent launch (PDL).  The step kernels are launched with programmatic stream serialisation, so
+// a grid may become resident while its predecessor in the stream (normally the previous decoder step) is still
+// running.  Everything before pdl_wait() touches only memory that was final before the predecessor STARTED:
+// parameters, the per-utterance encoder tensors (pre, enc_h) and -- in the backward -- tensors saved by the
+// forward pass.  griddepcontrol.wait returns once the predecessor grid has completed and flushed; all global
+// writes and all reads of per-step inputs (att_prev / dec_z, dc / dw, accumulators) come after it.  A predecessor
+// that never executes launch_dependents (any foreign kernel) degrades to ordinary stream order.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- mbarrier + bulk async copy (TMA 1-D, SASS UBLKCP) ----------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

@@ -573,14 +573,16 @@ ctc_prefix_kernel(const float *__restrict__ lpz, const float *__restrict__ r_pre
                   float *__restrict__ r_new, int T, int V, int H, int Cc, int blank, int eos) {
   const int lane = threadIdx.x & 31;
   const int idx = blockIdx.x * kPrefixWarps + (threadIdx.x >> 5);
+  pdl_wait();
+  pdl_launch_dependents();
   if (idx >= H * Cc) return;
   const int h = idx / Cc;
-  const int c = __ldg(cs + idx);
+  const int c = __ldcg(cs + idx);        // (candidates, states: results of kernels this grid may overlap)
   const float LZ = -10000000000.0f, L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-  const int ol = __ldg(out_len + h);
+  const int ol = __ldcg(out_len + h);
   const float *rp = r_prev + (size_t)h * T * 2;
   float *rn = r_new + (size_t)idx * T * 2;
-  const bool same = ol > 0 && c == __ldg(last + h);
+  const bool same = ol > 0 && c == __ldcg(last + h);
   const int start = ol > 1 ? ol : 1;
   for (int t = lane; t < min(start - 1, T); t += 32) *reinterpret_cast<float2 *>(rn + 2 * t) = make_float2(LZ, LZ);
   const float r0 = ol == 0 ? __ldg(lpz + c) : LZ;
@@ -591,7 +593,7 @@ ctc_prefix_kernel(const float *__restrict__ lpz, const float *__restrict__ r_pre
   float xc = 0.f, xb = 0.f;
   if (start + lane < T) {
     const int t = start + lane;
-    p = *reinterpret_cast<const float2 *>(rp + 2 * (t - 1));
+    p = __ldcg(reinterpret_cast<const float2 *>(rp + 2 * (t - 1)));
     xc = __ldg(lpz + (size_t)t * V + c);
     xb = __ldg(lpz + (size_t)t * V + blank);
   }
@@ -601,7 +603,7 @@ ctc_prefix_kernel(const float *__restrict__ lpz, const float *__restrict__ r_pre
     const float phi = same ? p.y * L2E : lae2(p.x * L2E, p.y * L2E);
     const float c2 = xc * L2E, b2 = xb * L2E;
     if (t + 32 < T) {                                          // next block's operands
-      p = *reinterpret_cast<const float2 *>(rp + 2 * (t + 31));
+      p = __ldcg(reinterpret_cast<const float2 *>(rp + 2 * (t + 31)));
       xc = __ldg(lpz + (size_t)(t + 32) * V + c);
       xb = __ldg(lpz + (size_t)(t + 32) * V + blank);
     }
@@ -620,7 +622,7 @@ ctc_prefix_kernel(const float *__restrict__ lpz, const float *__restrict__ r_pre
   }
   psi = fmaxf(psi * LN2, LZ);
   if (c == eos) {
-    const float a = rp[2 * (T - 1)], b = rp[2 * (T - 1) + 1];
+    const float a = __ldcg(rp + 2 * (T - 1)), b = __ldcg(rp + 2 * (T - 1) + 1);
     psi = fmaxf(lae2(a * L2E, b * L2E) * LN2, LZ);
   }
   if (lane == 0) log_psi[idx] = psi;
@@ -718,8 +720,9 @@ extern "C" int re2e_ctc_prefix_score(const float *lpz, const float *r_prev, cons
   RE2E_CHECK_ARG(lpz && r_prev && cs && last && out_len && log_psi && r_new);
   RE2E_CHECK_ARG(T > 0 && V > 0 && H > 0 && Ccand > 0);
   const int n = H * Ccand;
-  ctc_prefix_kernel<<<(n + kPrefixWarps - 1) / kPrefixWarps, kPrefixWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      lpz, r_prev, cs, last, out_len, log_psi, r_new, T, V, H, Ccand, blank, eos);
+  cudaError_t e = launch_pdl(3, ctc_prefix_kernel, dim3((unsigned)((n + kPrefixWarps - 1) / kPrefixWarps)),
+                             dim3(kPrefixWarps * 32), 0, static_cast<cudaStream_t>(stream), lpz, r_prev, cs, last, out_len,
+                             log_psi, r_new, T, V, H, Ccand, blank, eos);
   count_launch();
-  return launch_status();
+  return e == cudaSuccess ? launch_status() : (int)e;
 }

@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(512) batch_nt_kernel(const float *__restrict__
   float *x_s = batch_smem, *w_s = batch_smem + kBM * (kBK + 4);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int n = blockIdx.x * nwarps + warp;
+  pdl_wait();
+  pdl_launch_dependents();
   for (int m0 = 0; m0 < M; m0 += kBM) {
     const int rows = min(kBM, M - m0);
     const int G = 32 / rows;                                   // lanes per row
@@ -84,14 +86,14 @@ __global__ void __launch_bounds__(512) batch_nt_kernel(const float *__restrict__
         for (int r = warp; r < rows; r += nwarps)
           for (int q = lane; q < kq; q += 32)
             *reinterpret_cast<float4 *>(x_s + r * (kBK + 4) + 4 * q) =
-                __ldg(reinterpret_cast<const float4 *>(X + (size_t)(m0 + r) * K + k0) + q);
+                __ldcg(reinterpret_cast<const float4 *>(X + (size_t)(m0 + r) * K + k0) + q);   // (X: the predecessor's result)
         for (int q = lane; q < kq; q += 32)
           *reinterpret_cast<float4 *>(w_s + warp * kBK + 4 * q) =
               n < N ? __ldg(reinterpret_cast<const float4 *>(W + (size_t)n * K + k0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {                                                 // scalar staging, the chunk zero-padded to a quad
         for (int r = warp; r < rows; r += nwarps)
           for (int k = lane; k < 4 * kq; k += 32)
-            x_s[r * (kBK + 4) + k] = k < kc ? __ldg(X + (size_t)(m0 + r) * K + k0 + k) : 0.f;
+            x_s[r * (kBK + 4) + k] = k < kc ? __ldcg(X + (size_t)(m0 + r) * K + k0 + k) : 0.f;
         for (int k = lane; k < 4 * kq; k += 32)
           w_s[warp * kBK + k] = (n < N && k < kc) ? __ldg(W + (size_t)n * K + k0 + k) : 0.f;
       }
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(512) batch_nt_kernel(const float *__restrict__
     if (lane < rows && n < N) {
       float *o = out + (size_t)(m0 + lane) * N + n;
       v += bias ? __ldg(bias + n) : 0.f;
-      *o = accumulate ? *o + v : v;
+      *o = accumulate ? __ldcg(o) + v : v;
     }
   }
 }
@@ -192,23 +194,23 @@ __global__ void __launch_bounds__(kSThreads) lstm_step_kernel(const LstmStep p) 
   }
   cluster_arrive_relaxed();        // (rank 0's barrier is initialised before anyone signals it)
   __syncthreads();
-  if (tid < 128) {                 // one bulk copy per (row, half): threads 0-31 / 64-95 X rows, 32-63 / 96-127 W rows
-    const int half = tid >> 6, r = tid & 31, is_w = (tid >> 5) & 1;
-    const int off = half ? 4 * kq0 : 0, len = half ? 4 * (kq - kq0) : 4 * kq0;
+  // one bulk copy per (row, half): threads 0-31 / 64-95 X rows, 32-63 / 96-127 W rows.  The weights are constant, so their
+  // copies go out before the PDL boundary; the X rows (and every other input) are the predecessor's results.
+  const int half = (tid >> 6) & 1, r = tid & 31, is_w = (tid >> 5) & 1;
+  const int off = half ? 4 * kq0 : 0, len = half ? 4 * (kq - kq0) : 4 * kq0;
+  if (tid < 128 && len > 0) {
     const int wrow = FWD ? (r >> 3) * p.Z + tile * 8 + (r & 7) : tile * kST + r;
     const bool wvalid = FWD ? (tile * 8 + (r & 7) < p.Z) : (wrow < p.NW);
-    if (r == 0 && !is_w && len > 0) {
+    if (r == 0 && !is_w) {
       const int nw = FWD ? 4 * min(8, p.Z - tile * 8) : min(kST, p.NW - tile * kST);
       mbar_expect_tx(&bar[half], (uint32_t)(rows + nw) * (uint32_t)len * 4u);
     }
-    if (len > 0) {
-      if (!is_w) {
-        if (r < rows) bulk_g2s(x_s + r * pitch + off, X + (size_t)(m0 + r) * Ksrc + k0 + off, (uint32_t)len * 4u, &bar[half]);
-      } else if (wvalid) {
-        bulk_g2s(w_s + r * pitch + off, p.W + (size_t)wrow * ldw + wofs + off, (uint32_t)len * 4u, &bar[half]);
-      }
-    }
+    if (is_w && wvalid) bulk_g2s(w_s + r * pitch + off, p.W + (size_t)wrow * ldw + wofs + off, (uint32_t)len * 4u, &bar[half]);
   }
+  pdl_wait();
+  pdl_launch_dependents();
+  if (tid < 128 && len > 0 && !is_w && r < rows)
+    bulk_g2s(x_s + r * pitch + off, X + (size_t)(m0 + r) * Ksrc + k0 + off, (uint32_t)len * 4u, &bar[half]);
   // rank 0: this thread's epilogue inputs, fetched while the copies fly
   float ep[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   if (FWD && rank == 0) {
@@ -216,11 +218,11 @@ __global__ void __launch_bounds__(kSThreads) lstm_step_kernel(const LstmStep p) 
     if (m < rows && u < p.Z) {
       const size_t row = (size_t)(m0 + m);
       if (p.egate) {
-        const size_t erow = p.egate_row ? (size_t)__ldg(p.egate_row + row) : row;
+        const size_t erow = p.egate_row ? (size_t)__ldcg(p.egate_row + row) : row;
 #pragma unroll
         for (int g = 0; g < 4; ++g) ep[g] = __ldg(p.egate + erow * 4 * p.Z + (size_t)g * p.Z + u);
       }
-      if (p.c_prev) ep[4] = __ldg(p.c_prev + row * p.Z + u);
+      if (p.c_prev) ep[4] = __ldcg(p.c_prev + row * p.Z + u);
     }
   }
 
@@ -321,13 +323,15 @@ int launch_lstm_step(LstmStep prm, int tiles, int cl, cudaStream_t st) {
   cfg.blockDim = dim3((unsigned)kSThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)cl;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (pdl_enabled() && (pdl_mask() & 1)) ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, prm);
   count_launch();
   return e == cudaSuccess ? RE2E_OK : (int)e;
@@ -348,10 +352,10 @@ extern "C" int re2e_batch_nt(const float *X, const float *W, const float *bias, 
   const size_t smem = sizeof(float) * (kBM * (kBK + 4) + cols * kBK);
   int rc = ensure_smem(reinterpret_cast<const void *>(batch_nt_kernel), smem);
   if (rc != RE2E_OK) return rc;
-  batch_nt_kernel<<<(N + cols - 1) / cols, cols * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-      X, W, bias, out, M, N, K, accumulate, vec);
+  cudaError_t e = launch_pdl(1, batch_nt_kernel, dim3((unsigned)((N + cols - 1) / cols)), dim3((unsigned)(cols * 32)), smem,
+                             static_cast<cudaStream_t>(stream), X, W, bias, out, M, N, K, accumulate, vec);
   count_launch();
-  return launch_status();
+  return e == cudaSuccess ? launch_status() : (int)e;
 }
 
 extern "C" int re2e_lstm_step_supported(int B, int D, int Z) {

@@ -17,7 +17,7 @@ ctc = CTC(c["V"], c["D"], 0.0)
 dec.load_state_dict({k: v for k, v in sd.items() if not k.startswith("ctc_lo")})
 ctc.load_state_dict({k: v for k, v in sd.items() if k.startswith("ctc_lo")})
 dec, ctc = dec.to(dev).eval(), ctc.to(dev).eval()
-ra = types.SimpleNamespace(beam_size=10, penalty=0.0, ctc_weight=0.3, maxlenratio=0.0, minlenratio=0.0, nbest=1, lm_weight=0.0)
+ra = types.SimpleNamespace(cuda_graph=os.environ.get('RE2E_RECOG_GRAPH', '1') == '1', beam_size=10, penalty=0.0, ctc_weight=0.3, maxlenratio=0.0, minlenratio=0.0, nbest=1, lm_weight=0.0)
 g = torch.Generator().manual_seed(5001)
 Th = int(sys.argv[1]) if len(sys.argv) > 1 else 137
 hs = [torch.tanh(torch.randn(Th, c["D"], generator=g)).to(dev) for _ in range(4)]
