@@ -459,7 +459,8 @@ def decoder_forward_bench(cfg, dev, reps=5):
     rec = {"workload": "Decoder.forward + backward (teacher forcing), B=%d Th=%d U=%d V=%d" % (B, Th, U, V),
            "ms_eager": round(ms, 3), "utt_per_s_eager": round(B / (ms * 1e-3), 1), "our_kernel_launches": int(launches),
            "mode": "AttLoc per-step cluster kernels; LSTMCell = embedding-half gates of all positions in one tcgen05 GEMM + "
-                   "two batch-sized products and a fused pointwise kernel per position (lstm.py); one tcgen05 output-layer GEMM"}
+                   "ONE cluster kernel per position (both recurrent products, split-K over a 4-CTA cluster, pointwise cell as "
+                   "epilogue; backward: pointwise kernel + one 8-CTA-cluster product launch); one tcgen05 output-layer GEMM"}
     # the same forward + backward captured once into a CUDA graph (lengths as a device tensor: no host round trip
     # inside the loop) and replayed: what the loop costs on the GPU once the Python / launch overhead is gone
     try:
@@ -752,7 +753,10 @@ def main():
                                    "cover the set); seeded untrained weights never emit <eos>, so every search runs "
                                    "to maxlen = Th -- the longest case" % total_dec,
                          "workload": "BASELINE configs[4]: joint_recog beam search, Th~U(75,200), V=4233, D=A=320, "
-                                     "Z=300, sharded by utterance, no collective"}
+                                     "Z=300, sharded by utterance, no collective",
+                         "mode": "whole output position on the device: 6 library launches (AttLoc step, LSTM step, output "
+                                 "layer, log-softmax+top-k, CTC prefix scores, joint+merge+gather), 8 positions per graph "
+                                 "replay, host bookkeeping from a history buffer read back in chunks"}
     if rank == 0:
         if not args.no_kernels:
             ks = kernel_rooflines(hp, db, cfg, peak, dev)

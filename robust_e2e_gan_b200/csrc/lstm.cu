@@ -1,11 +1,12 @@
 // LSTMCell step of the attention decoder (model/e2e_decoder.py:128 `self.decoder[0](ey, (z_list[0], c_list[0]))`,
 // torch.nn.LSTMCell arithmetic, gate order i, f, g, o) as pieces that fit the decoder loop:
 //   * the embedding half of the input product, W_ih[:, :Z] . embed(y_s) + b_ih + b_hh, does not depend on the recurrence:
-//     ALL positions at once on the tensor-core GEMM before the loop (the caller);
-//   * per step only the two batch-sized products that do depend on it -- context . W_ih[:, Z:]^T and h . W_hh^T --
-//     (re2e_skinny_nt, accumulating into one gate buffer) and ONE fused pointwise kernel (this file);
-//   * backward per step: this file's pointwise kernel (gate gradients, d c_prev) + two re2e_skinny_nn products
-//     (d context, d h_prev); the weight gradients of all steps are two dense GEMMs after the loop.
+//     ALL positions at once on the tensor-core GEMM before the loop (training), or a per-token table (beam search);
+//   * per position ONE launch (lstm_step_kernel<true>): the two batch-sized products that do depend on it -- context .
+//     W_ih[:, Z:]^T and h . W_hh^T -- reduced across a 4-CTA cluster, with the pointwise cell as the epilogue;
+//   * backward per position: the pointwise kernel (gate gradients, d c_prev) + ONE product launch for d context | d h_prev
+//     (lstm_step_kernel<false>, 8-CTA clusters); the weight gradients of all positions are two dense GEMMs after the loop;
+//   * batch_nt_kernel: the generic batch-sized product (any dimensions; also the decoder's output layer in beam search).
 #include "attloc_common.cuh"
 #include "common.cuh"
 

@@ -11,17 +11,21 @@ state_dict keys as the reference's ``Decoder`` for the configuration the scripts
   state fed to step i depends on the context of step i-1 through the LSTMCell, so this loop calls the per-step AttLoc
   kernels (``AttLoc.forward_loop``, the persistent loop kernels, needs the states of all steps up front).
 * ``recognize_beam(h, lpz, recog_args, char_list, rnnlm=None, fstlm=None)`` -- hybrid CTC/attention beam search
-  (model/e2e_decoder.py:170-369) re-designed for the GPU: ALL live hypotheses advance together -- one AttLoc
-  step launch for the whole beam (B = beam instead of beam x (B = 1) launches), one LSTMCell / output GEMM, one
-  log-softmax launch, and ONE batched CTC prefix-score launch (hypotheses x ctc_beam candidates) whose forward
-  variables stay on the device (the reference copies ``lpz`` to the host and loops over T in numpy per
-  hypothesis, model/e2e_ctc.py:143-146).  All per-position device work runs over static buffers, so from the third
-  position on it is one CUDA-graph replay (captured once per utterance); per position the host writes one small
-  pinned control block (parent rows, CTC candidates, tokens, scores) and reads one block of beam x beam candidate
-  scores / ids back for the reference's own bookkeeping: stable descending sort, <eos> handling, length penalty,
-  ``end_detect``.  Scores accumulate in fp32 exactly as the reference's 0-dim tensors do.
+  (model/e2e_decoder.py:170-369) re-designed for the GPU: ALL live hypotheses advance together (B = beam instead of
+  beam x (B = 1) calls) and the whole output position runs on the device as SIX launches of the library over static
+  buffers (csrc/beam.cu): AttLoc step, LSTMCell step (one cluster kernel; the embedding half of its input product is a
+  per-token table looked up inside the kernel), output layer, log-softmax + top-``ctc_beam``, batched CTC prefix
+  scores whose forward variables never leave the device (the reference copies ``lpz`` to the host and loops over T in
+  numpy per hypothesis, model/e2e_ctc.py:143-146), and one kernel for joint score + merge of the beam x beam
+  candidates + gather of the chosen rows' states.  Eight positions are one CUDA-graph replay; the winners of every
+  position land in a history buffer that the host reads back a chunk at a time (two chunks in flight) to run the
+  reference's own bookkeeping -- <eos> handling, length penalty, ``end_detect`` -- so there is no host round trip per
+  position.  Scores accumulate in fp32 exactly as the reference's 0-dim tensors do.  Decoders the fused position does
+  not take (more than one LSTM layer, ctc_weight = 1 i.e. all V candidates, V > 8192, dunits or eprojs not a
+  multiple of 4) use the generic position: library AttLoc / prefix-score kernels + tensor ops, host merge per position.
 """
 import random
+import time
 
 import numpy as np
 import torch
@@ -76,6 +80,113 @@ def th_accuracy(y_all, pad_target, ignore_label):
     if y_all.is_cuda and torch.cuda.is_current_stream_capturing():
         return num.float() / den.float()
     return float(num) / float(den)
+
+
+class _FusedSearch(object):
+    """One utterance's beam search with the whole position on the device (``Decoder._fused_position``), as a resumable
+    object: ``pump()`` keeps two chunks of ``chunk`` positions in flight on ``stream`` (one CUDA-graph replay per chunk,
+    then an async copy of the chunk's history rows), ``poll()`` runs the reference's bookkeeping (<eos>, length penalty,
+    end_detect; model/e2e_decoder.py:296-333) on the oldest chunk that has arrived.  Positions launched beyond the one
+    where the search ends are discarded (past maxlen the merge kernel is a no-op)."""
+
+    def __init__(self, dec, hb, lpz, recog_args, Cb, maxlen, minlen, stream, slot, chunk=8):
+        self.dec, self.args, self.maxlen, self.minlen, self.chunk = dec, recog_args, maxlen, minlen, chunk
+        self.stream, self.dev = stream, hb.device
+        self.beam = hb.size(0)
+        self.prof = getattr(recog_args, "profile", None)   # optional dict: host seconds per phase
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            self.position, self.hist = dec._fused_position(hb, lpz, Cb, self.beam, recog_args.ctc_weight, maxlen,
+                                                           bool(getattr(recog_args, "fused_tail", True)))
+        pins = dec.__dict__.setdefault("_hist_pins", {})
+        pin = pins.get(slot)
+        if pin is None or pin.shape[0] < maxlen or pin.shape[2] != self.beam:
+            pin = pins[slot] = torch.empty(max(256, maxlen), 4, self.beam, dtype=torch.float32).pin_memory()
+        self.pin, self.hist_np = pin, pin.numpy()
+        self.use_graph = bool(getattr(recog_args, "cuda_graph", True)) and maxlen >= 6
+        self.graph = None
+        self.hyps = [{'score': np.float32(0.0), 'yseq': [dec.sos]}]     # hypothesis k lives in device row k
+        self.ended = []
+        self.launched = self.processed = 0
+        self.flights = []
+        self.done = False
+        self._t(t0, "setup")
+
+    def _t(self, t0, key):
+        if self.prof is not None:
+            self.prof[key] = self.prof.get(key, 0.0) + time.perf_counter() - t0
+
+    def _capture(self):
+        # raw capture_begin / capture_end on a side stream: the torch.cuda.graph context manager also runs gc.collect()
+        # and empty_cache(), tens of milliseconds per utterance.  Nothing is allocated during the capture.
+        t0 = time.perf_counter()
+        dec, dev = self.dec, self.dev
+        if getattr(dec, "_cap_stream", None) is None or dec._cap_stream.device != dev:
+            dec._cap_stream = torch.cuda.Stream(dev)
+        dec._cap_stream.wait_stream(self.stream)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(dec._cap_stream):
+            self.graph.capture_begin()
+            for _ in range(self.chunk):
+                self.position()
+            self.graph.capture_end()
+        self.stream.wait_stream(dec._cap_stream)
+        self._t(t0, "capture")
+
+    def pump(self):
+        if self.done:
+            return
+        t0 = time.perf_counter()
+        with torch.cuda.stream(self.stream):
+            while self.launched < self.maxlen and self.launched < self.processed + 2 * self.chunk:
+                lo = self.launched
+                if lo == 0 or not self.use_graph:
+                    hi = 1 if self.use_graph else min(self.maxlen, lo + self.chunk)   # position 0 also warms the kernels up
+                    for _ in range(lo, hi):
+                        self.position()
+                else:
+                    if self.graph is None:
+                        self._capture()
+                    self.graph.replay()
+                    hi = min(self.maxlen, lo + self.chunk)
+                self.pin[lo:hi].copy_(self.hist[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                self.flights.append((lo, hi, ev))
+                self.launched = hi
+        self._t(t0, "launch")
+
+    def poll(self, block):
+        """Book-keep the oldest chunk in flight if it has arrived (or wait for it); True if a chunk was processed."""
+        if self.done or not self.flights:
+            return False
+        lo, hi, ev = self.flights[0]
+        if not block and not ev.query():
+            return False
+        t0 = time.perf_counter()
+        ev.synchronize()
+        self._t(t0, "wait")
+        t0 = time.perf_counter()
+        self.flights.pop(0)
+        dec, args, beam = self.dec, self.args, self.beam
+        for i in range(lo, hi):
+            rec = self.hist_np[i]
+            entries = [(rec[0, b], int(rec[1, b]), int(rec[2, b]), int(rec[3, b])) for b in range(beam)]
+            self.hyps = dec._host_merge(self.hyps, self.ended, entries, i, self.maxlen, self.minlen, args.penalty)
+            if (end_detect(self.ended, i) and args.maxlenratio == 0.0) or len(self.hyps) == 0:
+                self.done = True
+                break
+        self.processed = hi
+        if hi >= self.maxlen:
+            self.done = True
+        self._t(t0, "host_merge")
+        if self.prof is not None:
+            self.prof["positions"] = self.prof.get("positions", 0.0) + (hi - lo)
+        return True
+
+    def result(self):
+        nbest = sorted(self.ended, key=lambda x: x['score'], reverse=True)[:min(len(self.ended), self.args.nbest)]
+        return [{'score': float(x['score']), 'yseq': [int(t) for t in x['yseq']]} for x in nbest]
 
 
 class Decoder(torch.nn.Module):
@@ -309,88 +420,85 @@ class Decoder(torch.nn.Module):
                 remained.append(hyp)
         return remained
 
-    def _recognize_fused(self, hb, lpz, recog_args, Cb, maxlen, minlen, chunk=8):
-        """Beam search with the whole position on the device (``_fused_position``), ``chunk`` positions per CUDA-graph
-        replay.  The winners of every position land in a history buffer; the host reads it back one chunk at a time, two
-        chunks in flight, and runs the reference's bookkeeping (<eos>, length penalty, end_detect) on it.  Positions
-        launched beyond the one where the search ends are discarded (past maxlen the merge is a no-op)."""
-        import time
-        prof = getattr(recog_args, "profile", None)       # optional dict: host seconds per phase (tools/recog_launches.py)
-        tick = time.perf_counter
-        t0 = tick()
-        dev = hb.device
-        beam = hb.size(0)
-        penalty = recog_args.penalty
-        position, hist = self._fused_position(hb, lpz, Cb, beam, recog_args.ctc_weight, maxlen,
-                                              bool(getattr(recog_args, "fused_tail", True)))
-        pin = getattr(self, "_hist_pin", None)
-        if pin is None or pin.shape[0] < maxlen or pin.shape[2] != beam:
-            pin = torch.empty(max(256, maxlen), 4, beam, dtype=torch.float32).pin_memory()
-            self._hist_pin = pin
-        hist_np = pin.numpy()
-        use_graph = bool(getattr(recog_args, "cuda_graph", True)) and maxlen >= 6
-        graph = None
+    def _recognize_fused(self, hb, lpz, recog_args, Cb, maxlen, minlen):
+        """Beam search with the whole position on the device, one utterance on the current stream (``_FusedSearch``)."""
+        search = _FusedSearch(self, hb, lpz, recog_args, Cb, maxlen, minlen, torch.cuda.current_stream(hb.device), 0)
+        while not search.done:
+            search.pump()
+            search.poll(block=True)
+        return search.result()
+
+    def _fused_plan(self, h, lpz, recog_args):
+        """Shapes of one utterance's search and whether the fused position takes it: (hb, lpz, Cb, maxlen, minlen) or None."""
+        dev = self.embed.weight.device
+        h = _lib.f32c(h.detach(), dev)
+        Th = h.size(0)
+        beam = int(recog_args.beam_size)
+        maxlen = Th if recog_args.maxlenratio == 0 else max(1, int(recog_args.maxlenratio * Th))
+        minlen = int(recog_args.minlenratio * Th)
+        Cb = beam
+        if lpz is not None:
+            lpz = _lib.f32c(lpz.detach(), dev)
+            V = lpz.size(-1)
+            Cb = min(V, int(beam * CTC_SCORING_RATIO)) if recog_args.ctc_weight != 1.0 else V
+        if not (bool(getattr(recog_args, "fused_position", True)) and self.dlayers == 1 and beam <= Cb <= 32
+                and self.output.out_features <= 8192
+                and bool(_lib.lib().re2e_lstm_step_supported(beam, h.size(1), self.dunits))):
+            return None
+        hb = h.unsqueeze(0).expand(beam, Th, h.size(1)).contiguous()
+        return hb, lpz, Cb, maxlen, minlen
+
+    def recognize_beam_batch(self, hs, lpzs, recog_args, char_list=None, rnnlm=None, fstlm=None, concurrency=4):
+        """``recognize_beam`` for a list of utterances (``hs[i]`` (Th_i, D), ``lpzs[i]`` (Th_i, V) or None); returns the list
+        of n-best lists, identical to calling ``recognize_beam`` per utterance.  An extension of the reference API
+        (joint_recog.py:143-149 decodes one utterance at a time): a single search is a strictly serial chain of short
+        kernels that leaves most of the GPU idle, so up to ``concurrency`` searches run interleaved, each with its own
+        static buffers, CUDA graph and stream; the host pumps them round-robin."""
+        if rnnlm is not None or fstlm is not None:
+            raise NotImplementedError("LM rescoring is outside the hot path (SURVEY.md section 8)")
+        n = len(hs)
+        results = [None] * n
+        dev = self.embed.weight.device
         cur = torch.cuda.current_stream(dev)
-        hyps = [{'score': np.float32(0.0), 'yseq': [self.sos]}]     # hypothesis k lives in device row k
-        ended_hyps = []
-        launched = processed = 0
-        flights = []
-        stop = False
-        t_setup = tick() - t0
-        t_capture = t_launch = t_wait = t_host = 0.0
-        while not stop and processed < maxlen:
-            t1 = tick()
-            while launched < maxlen and launched < processed + 2 * chunk:
-                if launched == 0 or not use_graph:
-                    hi = 1 if use_graph else min(maxlen, launched + chunk)   # the first position also warms the kernels up
-                    for _ in range(launched, hi):
-                        position()
-                else:
-                    if graph is None:
-                        # raw capture_begin / capture_end on a side stream: the torch.cuda.graph context manager also runs
-                        # gc.collect() and empty_cache(), tens of milliseconds per utterance
-                        tc = tick()
-                        if getattr(self, "_cap_stream", None) is None or self._cap_stream.device != dev:
-                            self._cap_stream = torch.cuda.Stream(dev)
-                            self._graph_pool = torch.cuda.graph_pool_handle()
-                        self._cap_stream.wait_stream(cur)
-                        graph = torch.cuda.CUDAGraph()
-                        with torch.cuda.stream(self._cap_stream):
-                            graph.capture_begin(pool=self._graph_pool)
-                            for _ in range(chunk):
-                                position()
-                            graph.capture_end()
-                        cur.wait_stream(self._cap_stream)
-                        self._last_graph = graph
-                        t_capture += tick() - tc
-                    graph.replay()
-                    hi = min(maxlen, launched + chunk)
-                pin[launched:hi].copy_(hist[launched:hi], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(cur)
-                flights.append((launched, hi, ev))
-                launched = hi
-            lo, hi, ev = flights.pop(0)
-            t2 = tick()
-            ev.synchronize()
-            t3 = tick()
-            for i in range(lo, hi):
-                rec = hist_np[i]
-                entries = [(rec[0, b], int(rec[1, b]), int(rec[2, b]), int(rec[3, b])) for b in range(beam)]
-                hyps = self._host_merge(hyps, ended_hyps, entries, i, maxlen, minlen, penalty)
-                if (end_detect(ended_hyps, i) and recog_args.maxlenratio == 0.0) or len(hyps) == 0:
-                    stop = True
-                    break
-            processed = hi
-            t_launch += t2 - t1
-            t_wait += t3 - t2
-            t_host += tick() - t3
-        if prof is not None:
-            for k_, v_ in (("setup", t_setup), ("capture", t_capture), ("launch", t_launch - t_capture), ("wait", t_wait),
-                           ("host_merge", t_host), ("positions", float(processed))):
-                prof[k_] = prof.get(k_, 0.0) + v_
-        nbest = sorted(ended_hyps, key=lambda x: x['score'], reverse=True)[:min(len(ended_hyps), recog_args.nbest)]
-        return [{'score': float(x['score']), 'yseq': [int(t) for t in x['yseq']]} for x in nbest]
+        streams = getattr(self, "_search_streams", None)
+        if streams is None or len(streams) < concurrency or streams[0].device != dev:
+            streams = self._search_streams = [torch.cuda.Stream(dev) for _ in range(concurrency)]
+        active = {}                       # slot -> (utterance index, search)
+        nxt = 0
+        while nxt < n or active:
+            for slot in range(concurrency):
+                if slot not in active and nxt < n:
+                    i, nxt = nxt, nxt + 1
+                    lp = lpzs[i] if lpzs is not None else None
+                    plan = self._fused_plan(hs[i], lp, recog_args)
+                    if plan is None:      # shapes the fused position does not take: the per-utterance path
+                        results[i] = self.recognize_beam(hs[i], lp, recog_args, char_list)
+                        continue
+                    for t in plan[:2]:    # made on the caller's stream, consumed on the search's
+                        if t is not None:
+                            t.record_stream(streams[slot])
+                    streams[slot].wait_stream(cur)
+                    self.att.reset()
+                    active[slot] = (i, _FusedSearch(self, plan[0], plan[1], recog_args, plan[2], plan[3], plan[4],
+                                                    streams[slot], slot))
+            progressed = False
+            for slot, (i, srch) in list(active.items()):
+                srch.pump()
+                progressed |= srch.poll(block=False)
+                if srch.done:
+                    results[i] = srch.result()
+                    del active[slot]
+                    progressed = True
+            if not progressed and active:
+                slot = next(iter(active))
+                i, srch = active[slot]
+                srch.poll(block=True)
+                if srch.done:
+                    results[i] = srch.result()
+                    del active[slot]
+        for st_ in streams[:concurrency]:
+            cur.wait_stream(st_)
+        return results
 
     def recognize_beam(self, h, lpz, recog_args, char_list=None, rnnlm=None, fstlm=None):
         """h (Th, D) encoder output of one utterance, lpz (Th, V) CTC log-probs or None.
@@ -398,6 +506,10 @@ class Decoder(torch.nn.Module):
         if rnnlm is not None or fstlm is not None:
             raise NotImplementedError("LM rescoring is outside the hot path (SURVEY.md section 8)")
         _lib.lib()
+        self.att.reset()
+        plan = self._fused_plan(h, lpz, recog_args)
+        if plan is not None:
+            return self._recognize_fused(*plan[:2], recog_args, *plan[2:])
         dev = self.embed.weight.device
         h = _lib.f32c(h.detach(), dev)
         Th = h.size(0)
@@ -407,20 +519,13 @@ class Decoder(torch.nn.Module):
         W = beam                                   # hypothesis rows on the device (constant -> one AttLoc cache shape)
         hb = h.unsqueeze(0).expand(W, Th, h.size(1)).contiguous()
         hlens = [Th] * W
-        self.att.reset()
         maxlen = Th if recog_args.maxlenratio == 0 else max(1, int(recog_args.maxlenratio * Th))
         minlen = int(recog_args.minlenratio * Th)
-
         use_ctc = lpz is not None
         if use_ctc:
             lpz = _lib.f32c(lpz.detach(), dev)
             V = lpz.size(-1)
             ctc_beam = min(V, int(beam * CTC_SCORING_RATIO)) if ctc_weight != 1.0 else V
-        Cb = ctc_beam if use_ctc else beam          # candidates scored per row
-        if (bool(getattr(recog_args, "fused_position", True)) and self.dlayers == 1 and beam <= Cb <= 32 and W <= 32
-                and self.output.out_features <= 8192
-                and bool(_lib.lib().re2e_lstm_step_supported(W, h.size(1), self.dunits))):
-            return self._recognize_fused(hb, lpz if use_ctc else None, recog_args, Cb, maxlen, minlen)
 
         # ---- generic position (any layer count / candidate width): tensor ops + the library's AttLoc / CTC kernels
         z = [h.new_zeros(W, self.dunits) for _ in range(self.dlayers)]

@@ -310,3 +310,24 @@ def test_fused_beam_position_matches_generic_path(ctc_weight, beam, Th):
         assert [x["yseq"] for x in got] == [x["yseq"] for x in ref], "tokens differ for (fused, graph, fused tail) = %s" % (k,)
         for a, b in zip(got, ref):
             assert abs(a["score"] - b["score"]) <= 1e-4 * abs(b["score"])
+
+
+def test_recognize_beam_batch_equals_per_utterance():
+    """recognize_beam_batch (interleaved searches on their own streams and graphs) returns, for every utterance, exactly
+    what recognize_beam returns for it alone: lengths differ, some searches end early through <eos> / end_detect."""
+    helpers.BEAM_CASES["_tmp"] = dict(helpers.BEAM_CASES["beam_eos"], seed=41, beam=5, ctc_weight=0.3, nbest=2, Th=30)
+    try:
+        c, sd, h, _ = helpers.beam_case("_tmp")
+    finally:
+        del helpers.BEAM_CASES["_tmp"]
+    dec, ctc = build(c, sd)
+    g = torch.Generator().manual_seed(99)
+    hs = [torch.tanh(torch.randn(int(t), c["D"], generator=g)).to(DEV) for t in (30, 12, 47, 8, 25, 33, 6)]
+    with torch.no_grad():
+        lpzs = [ctc.log_softmax(x.unsqueeze(0))[0] for x in hs]
+        one = [dec.recognize_beam(x, l, recog_args(c), None) for x, l in zip(hs, lpzs)]
+        for conc in (1, 3):
+            got = dec.recognize_beam_batch(hs, lpzs, recog_args(c), None, concurrency=conc)
+            assert got == one, "concurrency %d" % conc
+        att_only = [dec.recognize_beam(x, None, recog_args(c), None) for x in hs[:3]]
+        assert dec.recognize_beam_batch(hs[:3], None, recog_args(c), None, concurrency=2) == att_only

@@ -44,6 +44,16 @@ with torch.no_grad():
     print("host seconds per phase over the same two utterances:", {k: round(v, 5) for k, v in ra.profile.items()})
     del ra.profile
     print("wall: %.1f us per output position (%d positions, Th=%d)" % (dt * 1e6 / n, n, Th), flush=True)
+    hs8 = [torch.tanh(torch.randn(Th, c["D"], generator=g)).to(dev) for _ in range(16)]
+    lp8 = [ctc.log_softmax(h.unsqueeze(0))[0] for h in hs8]
+    for conc in (1, 2, 4, 6):
+        dec.recognize_beam_batch(hs8[:conc], lp8[:conc], ra, None, concurrency=conc)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = dec.recognize_beam_batch(hs8, lp8, ra, None, concurrency=conc)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        print("batch of 16, %d concurrent searches: %.2f ms per utterance (%.1f utt/s)" % (conc, dt * 1e3 / 16, 16 / dt), flush=True)
     torch.cuda.cudart().cudaProfilerStart()
     decode(hs[3])
     torch.cuda.synchronize()
