@@ -377,6 +377,9 @@ def kernel_specs(hp, db, cfg, dev):
     return specs
 
 
+RECOG_CONCURRENCY = 4
+
+
 def recog_bench(rank, world, dev, total_utts=1000, per_rank_cap=125):
     """BASELINE configs[4] (joint_recog.py:143-149, run.sh:199-226): hybrid CTC/attention beam search, beam 10,
     ctc_weight 0.3, maxlenratio = minlenratio = 0 (end_detect), nbest 1, over a seeded set of 1000 synthetic utterances
@@ -408,17 +411,19 @@ def recog_bench(rank, world, dev, total_utts=1000, per_rank_cap=125):
     ra = types.SimpleNamespace(beam_size=c["beam"], penalty=c["penalty"], ctc_weight=c["ctc_weight"],
                                maxlenratio=c["maxlenratio"], minlenratio=c["minlenratio"], nbest=c["nbest"], lm_weight=0.0)
 
-    def decode(i):
-        h = hs[i].to(dev, non_blocking=True)
-        lpz = ctc.log_softmax(h.unsqueeze(0))[0]
-        return dec.recognize_beam(h, lpz, ra, None)
+    def decode(idx):
+        """A group of utterances through Decoder.recognize_beam_batch (4 searches interleaved on their own streams)."""
+        with torch.no_grad():
+            hd = [hs[i].to(dev, non_blocking=True) for i in idx]
+            lp = [ctc.log_softmax(h.unsqueeze(0))[0] for h in hd]
+            return dec.recognize_beam_batch(hd, lp, ra, None, concurrency=RECOG_CONCURRENCY)
 
-    decode(lo)                                     # warm-up (allocator, shared-memory attributes)
+    decode(list(range(lo, min(hi, lo + RECOG_CONCURRENCY))))      # warm-up (allocator, shared-memory attributes, streams)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     toks = 0
-    for i in range(lo, hi):
-        toks += len(decode(i)[0]["yseq"]) - 1
+    for nb in decode(list(range(lo, hi))):
+        toks += len(nb[0]["yseq"]) - 1
     torch.cuda.synchronize()
     return hi - lo, time.perf_counter() - t0, toks
 

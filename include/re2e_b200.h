@@ -288,6 +288,11 @@ int re2e_ctc_prefix_score(const float *lpz, const float *r_prev, const int32_t *
  * re2e_beam_joint: local = w_att * att_top + w_ctc * (log_psi - psi_prev[row]) (log_psi NULL: local = att_top), the `beam`
  *   best of the Cb <= 32 candidates per row; out (3, W, beam) fp32 = {row score + local, token id, candidate index}
  *   (model/e2e_decoder.py:284-292). */
+/* Initial working state of a search (model/e2e_decoder.py:205-231): z_in = c_in = 0 (W,Z), a_in uniform over Th (W,Th),
+ * r_in (W,Th,2) = CTCPrefixScore.initial_state (model/e2e_ctc.py:95-107; r_in / psi_in / lpz NULL without CTC), psi_in = 0,
+ * ctl = {parent 0, candidate 0, token sos, position 0}, sc = 0, state = {1 live hypothesis, position 0}. */
+int re2e_beam_init(float *z_in, float *c_in, float *a_in, float *r_in, float *psi_in, const float *lpz, int32_t *ctl,
+                   float *sc, int32_t *state, int W, int Z, int Th, int V, int blank, int sos, void *stream);
 int re2e_beam_gather(const int32_t *parent, const int32_t *cand, int W, int nseg, const float *const *src,
                      float *const *dst, const int *row_floats, const int *sub_count, void *stream);
 int re2e_log_softmax_topk(const float *logits, long long rows, int V, int k, float *full, float *vals, int32_t *ids,

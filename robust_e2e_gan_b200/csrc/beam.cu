@@ -364,6 +364,39 @@ __global__ void __launch_bounds__(1024) beam_advance_kernel(const AdvanceArgs a)
   }
 }
 
+// ---- initial state of a search: the working copies every row starts from (model/e2e_decoder.py:205-231) -----------
+// z = c = 0, alignment uniform over the Th frames (e2e_attention.py:264-268), CTC state r0 = (logzero, running sum of the
+// blank column) (model/e2e_ctc.py:95-107, sequential fp32 as the reference's loop), row 0 live with token <sos>.
+__global__ void __launch_bounds__(1024) beam_init_kernel(float *__restrict__ z_in, float *__restrict__ c_in,
+                                                         float *__restrict__ a_in, float *__restrict__ r_in,
+                                                         float *__restrict__ psi_in, const float *__restrict__ lpz,
+                                                         int32_t *__restrict__ ctl, float *__restrict__ sc,
+                                                         int32_t *__restrict__ state, int W, int Z, int Th, int V,
+                                                         int blank, int sos) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < W * Z; i += nt) { z_in[i] = 0.f; c_in[i] = 0.f; }
+  const float u = 1.0f / (float)Th;
+  for (int i = tid; i < W * Th; i += nt) a_in[i] = u;
+  if (tid < W) {
+    ctl[tid] = 0; ctl[W + tid] = 0; ctl[2 * W + tid] = sos; ctl[3 * W + tid] = 0;
+    sc[tid] = 0.f;
+    if (psi_in) psi_in[tid] = 0.f;
+  }
+  if (tid == 0) { state[0] = 1; state[1] = 0; }
+  if (r_in) {
+    if (tid == 0) {
+      float acc = 0.f;
+      for (int t = 0; t < Th; ++t) {
+        acc = t == 0 ? __ldg(lpz + blank) : acc + __ldg(lpz + (size_t)t * V + blank);
+        r_in[2 * t] = -10000000000.0f;
+        r_in[2 * t + 1] = acc;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < (W - 1) * 2 * Th; i += nt) r_in[2 * Th + i] = r_in[i % (2 * Th)];
+  }
+}
+
 }  // namespace
 }  // namespace re2e
 
@@ -435,4 +468,15 @@ extern "C" int re2e_beam_advance(const float *att_top, const int32_t *ids, const
   cudaError_t e = launch_pdl(4, beam_advance_kernel, dim3(1), dim3(1024), 0, static_cast<cudaStream_t>(stream), a);
   count_launch();
   return e == cudaSuccess ? launch_status() : (int)e;
+}
+
+extern "C" int re2e_beam_init(float *z_in, float *c_in, float *a_in, float *r_in, float *psi_in, const float *lpz,
+                              int32_t *ctl, float *sc, int32_t *state, int W, int Z, int Th, int V, int blank, int sos,
+                              void *stream) {
+  RE2E_CHECK_ARG(z_in && c_in && a_in && ctl && sc && state && W > 0 && Z > 0 && Th > 0 && (!r_in || (lpz && psi_in && V > 0)));
+  if (W > 1024) return RE2E_E_UNSUPPORTED;
+  beam_init_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(z_in, c_in, a_in, r_in, psi_in, lpz, ctl, sc, state, W,
+                                                                      Z, Th, V, blank, sos);
+  count_launch();
+  return launch_status();
 }

@@ -95,20 +95,23 @@ class _FusedSearch(object):
         self.beam = hb.size(0)
         self.prof = getattr(recog_args, "profile", None)   # optional dict: host seconds per phase
         t0 = time.perf_counter()
-        with torch.cuda.stream(stream):
-            self.position, self.hist = dec._fused_position(hb, lpz, Cb, self.beam, recog_args.ctc_weight, maxlen,
-                                                           bool(getattr(recog_args, "fused_tail", True)))
         pins = dec.__dict__.setdefault("_hist_pins", {})
         pin = pins.get(slot)
-        if pin is None or pin.shape[0] < maxlen or pin.shape[2] != self.beam:
-            pin = pins[slot] = torch.empty(max(256, maxlen), 4, self.beam, dtype=torch.float32).pin_memory()
-        self.pin, self.hist_np = pin, pin.numpy()
+        if pin is None or pin[0].shape[0] < maxlen or pin[0].shape[2] != self.beam:
+            pin = pins[slot] = (torch.empty(max(256, maxlen), 4, self.beam, dtype=torch.float32).pin_memory(),
+                                [torch.cuda.Event() for _ in range(3)])
+        self.pin, self.events = pin
+        self.hist_np = self.pin.numpy()
+        with torch.cuda.stream(stream):
+            self.position = dec._fused_position(hb, lpz, Cb, self.beam, recog_args.ctc_weight, maxlen, self.pin,
+                                                bool(getattr(recog_args, "fused_tail", True)))
         self.use_graph = bool(getattr(recog_args, "cuda_graph", True)) and maxlen >= 6
         self.graph = None
-        self.hyps = [{'score': np.float32(0.0), 'yseq': [dec.sos]}]     # hypothesis k lives in device row k
+        self.hyps = [(np.float32(0.0), dec.sos, None, 1)]               # hypothesis k lives in device row k
         self.ended = []
         self.launched = self.processed = 0
         self.flights = []
+        self._evi = 0
         self.done = False
         self._t(t0, "setup")
 
@@ -149,8 +152,8 @@ class _FusedSearch(object):
                         self._capture()
                     self.graph.replay()
                     hi = min(self.maxlen, lo + self.chunk)
-                self.pin[lo:hi].copy_(self.hist[lo:hi], non_blocking=True)
-                ev = torch.cuda.Event()
+                ev = self.events[self._evi]              # (three events, at most two chunks in flight)
+                self._evi = (self._evi + 1) % 3
                 ev.record(self.stream)
                 self.flights.append((lo, hi, ev))
                 self.launched = hi
@@ -169,9 +172,10 @@ class _FusedSearch(object):
         t0 = time.perf_counter()
         self.flights.pop(0)
         dec, args, beam = self.dec, self.args, self.beam
+        recs = self.hist_np[lo:hi].tolist()
         for i in range(lo, hi):
-            rec = self.hist_np[i]
-            entries = [(rec[0, b], int(rec[1, b]), int(rec[2, b]), int(rec[3, b])) for b in range(beam)]
+            sc_, par, tok, cj = recs[i - lo]
+            entries = [(sc_[b], int(par[b]), int(tok[b]), int(cj[b])) for b in range(beam)]
             self.hyps = dec._host_merge(self.hyps, self.ended, entries, i, self.maxlen, self.minlen, args.penalty)
             if (end_detect(self.ended, i) and args.maxlenratio == 0.0) or len(self.hyps) == 0:
                 self.done = True
@@ -307,11 +311,12 @@ class Decoder(torch.nn.Module):
             self._beam_tab = tb
         return tb[1:]
 
-    def _fused_position(self, hb, lpz, Cb, beam, ctc_weight, maxlen, fused_tail=True):
+    def _fused_position(self, hb, lpz, Cb, beam, ctc_weight, maxlen, hist, fused_tail=True):
         """One output position for all W rows as launches of the library over static buffers (csrc/beam.cu):
         AttLoc step, LSTMCell step (embedding half by token lookup), output layer, log-softmax + top-Cb, CTC prefix
         scores, then joint score + merge + gather of the chosen rows' states for the next position (one launch,
-        ``re2e_beam_advance``; ``fused_tail=False`` runs them as three).  Returns (position closure, history buffer).
+        ``re2e_beam_advance``; ``fused_tail=False`` runs them as three).  ``hist`` (>= maxlen, 4, beam): page-locked host
+        tensor the winners of every position are written to.  Returns the position closure.
         The first position needs no special case: the states start as every row's initial state."""
         import ctypes
         lib = _lib.lib()
@@ -322,28 +327,28 @@ class Decoder(torch.nn.Module):
         st = self.att.precompute(hb)
         _, _, _, A, _, C, K = st.dims
         W_dec, W_att, W_conv, gvec, gvec_b = st.weights
-        f = dict(device=dev, dtype=torch.float32)
-        ctl = torch.zeros(4, W, dtype=torch.int32, device=dev)        # rows: parent, ctc candidate, token, position
-        ctl[2] = self.sos
-        sc = torch.zeros(W, **f)                                      # accumulated scores of the rows
-        out = torch.empty(3, W, beam, **f)
-        state = torch.zeros(2, dtype=torch.int32, device=dev)        # {live hypotheses, position}
-        state[0] = 1
-        hist = torch.empty(maxlen, 4, beam, **f)
-        z_st, c_st = torch.zeros(W, Z, **f), torch.zeros(W, Z, **f)
-        z_in, c_in = torch.zeros(W, Z, **f), torch.zeros(W, Z, **f)
-        a_st, a_in = torch.empty(W, Th, **f), torch.empty(W, Th, **f)
-        hl = torch.full((W,), Th, dtype=torch.int32, device=dev)
-        att_c, act, logits = torch.empty(W, D, **f), torch.empty(W, 4 * Z, **f), torch.empty(W, V, **f)
-        top_v, top_i = torch.empty(W, Cb, **f), torch.empty(W, Cb, dtype=torch.int32, device=dev)
+        # every buffer of the search carved out of two allocations (fp32 / int32); `hist` is page-locked HOST memory that
+        # the merge kernel writes directly (160 B per position over the bus: no copy, the host just waits for an event)
+        use_ctc = lpz is not None
+        sizes = [("sc", W), ("out", 3 * W * beam), ("z_st", W * Z), ("c_st", W * Z), ("z_in", W * Z), ("c_in", W * Z),
+                 ("a_st", W * Th), ("a_in", W * Th), ("att_c", W * D), ("act", W * 4 * Z), ("logits", W * V),
+                 ("top_v", W * Cb)]
+        if use_ctc:
+            sizes += [("r_st", W * Cb * Th * 2), ("r_in", W * Th * 2), ("psi_st", W * Cb), ("psi_in", W)]
+        flat = torch.empty(sum((n_ + 3) // 4 * 4 for _, n_ in sizes), device=dev, dtype=torch.float32)
+        bufs, o = {}, 0
+        for name, n_ in sizes:
+            bufs[name] = flat[o:o + n_]
+            o += (n_ + 3) // 4 * 4
+        ints = torch.empty(4 * W + 4 + W * Cb, device=dev, dtype=torch.int32)
+        ctl, state, top_i = ints[:4 * W].view(4, W), ints[4 * W:4 * W + 2], ints[4 * W + 4:]
+        sc, out = bufs["sc"], bufs["out"]
+        z_st, c_st, z_in, c_in = bufs["z_st"], bufs["c_st"], bufs["z_in"], bufs["c_in"]
+        a_st, a_in, att_c, act, logits, top_v = (bufs[k_] for k_ in ("a_st", "a_in", "att_c", "act", "logits", "top_v"))
         segs = [(z_st, z_in, Z, 0), (c_st, c_in, Z, 0), (a_st, a_in, Th, 0)]
         r_st = r_in = psi_st = psi_in = None
-        if lpz is not None:
-            r_st, r_in = torch.empty(W, Cb, Th, 2, **f), torch.empty(W, Th, 2, **f)
-            psi_st, psi_in = torch.zeros(W, Cb, **f), torch.empty(W, **f)
-            r0 = torch.full((Th, 2), -10000000000.0, **f)                 # CTCPrefixScore.initial_state
-            r0[:, 1] = torch.cumsum(lpz[:, 0], dim=0)
-            r_st[:, 0] = r0
+        if use_ctc:
+            r_st, r_in, psi_st, psi_in = bufs["r_st"], bufs["r_in"], bufs["psi_st"], bufs["psi_in"]
             segs += [(r_st, r_in, 2 * Th, Cb), (psi_st, psi_in, 1, Cb)]
         n = len(segs)
         src = (ctypes.c_void_p * n)(*[s[0].data_ptr() for s in segs])
@@ -353,9 +358,8 @@ class Decoder(torch.nn.Module):
         w_att, w_ctc = float(1.0 - ctc_weight), float(ctc_weight)
         P = _lib.ptr
         with torch.cuda.device(dev):
-            sp = _lib.stream_ptr()
-            _lib.check(lib.re2e_attloc_init_att(P(hl), P(a_st), W, Th, sp), "re2e_attloc_init_att")
-            _lib.check(lib.re2e_beam_gather(P(ctl[0]), P(ctl[1]), W, n, src, dst, rowf, subc, sp), "re2e_beam_gather")
+            _lib.check(lib.re2e_beam_init(P(z_in), P(c_in), P(a_in), P(r_in), P(psi_in), P(lpz), P(ctl), P(sc), P(state), W, Z,
+                                          Th, V, 0, self.sos, _lib.stream_ptr()), "re2e_beam_init")
 
         def build(sp):
             """The position's launches with their argument tuples, for one stream (everything else is constant)."""
@@ -398,26 +402,32 @@ class Decoder(torch.nn.Module):
                     if rc != 0:
                         _lib.check(rc, name)
 
-        position.keep = (segs, hl, eg, wcat, w_out, b_out, ctl, sc, out, state)   # buffers a captured graph points into
-        return position, hist
+        position.keep = (flat, ints, eg, wcat, w_out, b_out, lpz, st)   # buffers a captured graph points into
+        return position
 
     def _host_merge(self, hyps, ended_hyps, entries, i, maxlen, minlen, penalty):
         """The reference's bookkeeping for one position (model/e2e_decoder.py:296-333) given the merged candidates, best
         first: ``entries`` = (score, index of the parent in ``hyps``, token, candidate index).  Appends finished
-        hypotheses to ``ended_hyps`` (length penalty added) and returns the ones that go on."""
-        new_hyps = [{'score': np.float32(s_), 'yseq': hyps[r]['yseq'] + [t], '_parent': r, '_j': j}
-                    for s_, r, t, j in entries]
-        if i == maxlen - 1:
-            for hyp in new_hyps:
-                hyp['yseq'].append(self.eos)
+        hypotheses to ``ended_hyps`` (length penalty added) and returns the ones that go on.  Live hypotheses are
+        (score, token, parent hypothesis, length) tuples -- the token sequence is only materialised for the ones that
+        end (the reference copies ``yseq`` for every candidate at every position)."""
         remained = []
-        for hyp in new_hyps:
-            if hyp['yseq'][-1] == self.eos:
-                if len(hyp['yseq']) > minlen:
-                    hyp['score'] = np.float32(hyp['score'] + np.float32((i + 1) * penalty))
-                    ended_hyps.append(hyp)
+        last = i == maxlen - 1
+        for s_, r, t, j in entries:
+            parent = hyps[r]
+            n = parent[3] + 1
+            if last or t == self.eos:
+                if n + (1 if last else 0) > minlen:
+                    yseq = [self.eos] if last else []
+                    yseq.append(t)
+                    node = parent
+                    while node is not None:
+                        yseq.append(node[1])
+                        node = node[2]
+                    yseq.reverse()
+                    ended_hyps.append({'score': np.float32(np.float32(s_) + np.float32((i + 1) * penalty)), 'yseq': yseq})
             else:
-                remained.append(hyp)
+                remained.append((np.float32(s_), t, parent, n, r, j))
         return remained
 
     def _recognize_fused(self, hb, lpz, recog_args, Cb, maxlen, minlen):
@@ -601,11 +611,11 @@ class Decoder(torch.nn.Module):
 
         use_graph = bool(getattr(recog_args, "cuda_graph", True)) and maxlen >= 6
         graph = None
-        hyps = [{'score': np.float32(0.0), 'yseq': [self.sos]}]     # hypothesis k lives in device row k
+        hyps = [(np.float32(0.0), self.sos, None, 1)]               # (score, token, parent, length, row, ctc candidate)
         ended_hyps = []
         for i in range(maxlen):
             n = len(hyps)
-            ctl_np[2, :] = [hyps[min(k, n - 1)]['yseq'][i] for k in range(W)]
+            ctl_np[2, :] = [hyps[min(k, n - 1)][1] for k in range(W)]
             ctl_np[3, :] = i
             ctl.copy_(ctl_h, non_blocking=True)
             sc.copy_(sc_h, non_blocking=True)
@@ -652,8 +662,8 @@ class Decoder(torch.nn.Module):
             # control block of the next position: parent row, ctc candidate and score of every surviving hypothesis
             # (spare rows repeat the last one)
             rows = [hyps[min(k, len(hyps) - 1)] for k in range(W)]
-            ctl_np[0, :] = [hk['_parent'] for hk in rows]
-            ctl_np[1, :] = [hk['_j'] if use_ctc else 0 for hk in rows]
-            sc_np[:] = [hk['score'] for hk in rows]
+            ctl_np[0, :] = [hk[4] for hk in rows]
+            ctl_np[1, :] = [hk[5] if use_ctc else 0 for hk in rows]
+            sc_np[:] = [hk[0] for hk in rows]
         nbest = sorted(ended_hyps, key=lambda x: x['score'], reverse=True)[:min(len(ended_hyps), recog_args.nbest)]
         return [{'score': float(x['score']), 'yseq': [int(t) for t in x['yseq']]} for x in nbest]
