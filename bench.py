@@ -761,7 +761,9 @@ def main():
                                      "Z=300, sharded by utterance, no collective",
                          "mode": "whole output position on the device: 6 library launches (AttLoc step, LSTM step, output "
                                  "layer, log-softmax+top-k, CTC prefix scores, joint+merge+gather), 8 positions per graph "
-                                 "replay, host bookkeeping from a history buffer read back in chunks"}
+                                 "replay, winners written to a page-locked history buffer that the host book-keeps in chunks; "
+                                 "%d utterances' searches interleaved on their own streams "
+                                 "(Decoder.recognize_beam_batch)" % RECOG_CONCURRENCY}
     if rank == 0:
         if not args.no_kernels:
             ks = kernel_rooflines(hp, db, cfg, peak, dev)
