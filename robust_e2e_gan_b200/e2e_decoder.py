@@ -64,10 +64,34 @@ def mask_by_length(xs, length, fill=0):
         keep = torch.arange(xs.size(1), device=xs.device)[None, :] < length.to(xs.device)[:, None]
         keep = keep.view(keep.shape + (1,) * (xs.dim() - 2))
         return torch.where(keep, xs, xs.new_full((), fill))
+    if xs.is_cuda:
+        # same values as the reference's per-utterance slice copies, as ONE select (whose backward is one kernel instead
+        # of a zero-fill + copy + add of the whole batch tensor per utterance)
+        return mask_by_length(xs, torch.as_tensor([int(l) for l in length], dtype=torch.int64).to(xs.device), fill)
     ret = xs.new_full(xs.size(), fill)
     for i, l in enumerate(length):
         ret[i, :l] = xs[i, :l]
     return ret
+
+
+def _label_batches(ys, sos, eos, ignore_id, keep):
+    """pad_ys_in = pad([<sos>, y...], <eos>) and pad_ys_out = pad([y..., <eos>], ignore_id) of model/e2e_decoder.py:88-97
+    for label tensors that already live on the device: one concatenation and two gathers through host-built index
+    tables (copied from page-locked memory, so the sequence is CUDA-graph capturable; ``keep`` holds the host side)
+    instead of two concatenations and two slice copies per utterance."""
+    dev, dt = ys[0].device, ys[0].dtype
+    lens = [int(y.size(0)) for y in ys]
+    n, B, U1 = sum(lens), len(ys), max(lens) + 1
+    off = np.concatenate(([0], np.cumsum(lens)[:-1]))
+    j = np.arange(U1)[None, :]
+    ln, of = np.asarray(lens)[:, None], off[:, None]
+    idx = np.stack((np.where(j == 0, n, np.where(j - 1 < ln, of + j - 1, n + 1)),          # n: <sos>, n+1: <eos>
+                    np.where(j < ln, of + j, np.where(j == ln, n + 1, n + 2)))).astype(np.int64)   # n+2: ignore_id
+    pin, spec = torch.from_numpy(idx).pin_memory(), torch.tensor([sos, eos, ignore_id], dtype=dt).pin_memory()
+    keep.append((pin, spec))                        # (alive as long as a captured graph may replay the two copies)
+    ext = torch.cat(list(ys) + [spec.to(dev, non_blocking=True)])
+    out = ext[pin.to(dev, non_blocking=True).view(-1)].view(2, B, U1)
+    return out[0], out[1]
 
 
 def th_accuracy(y_all, pad_target, ignore_label):
@@ -234,12 +258,20 @@ class Decoder(torch.nn.Module):
         hpad = mask_by_length(hpad.to(dev), hlen, 0)
         self.loss = None
         ys = [y.to(dev) for y in ys]
-        eos = torch.full((1,), self.eos, dtype=ys[0].dtype, device=ys[0].device)    # (fill kernels: graph capturable)
-        sos = torch.full((1,), self.sos, dtype=ys[0].dtype, device=ys[0].device)
-        ys_in = [torch.cat([sos, y], dim=0) for y in ys]
-        ys_out = [torch.cat([y, eos], dim=0) for y in ys]
-        pad_ys_in = pad_list(ys_in, self.eos)
-        pad_ys_out = pad_list(ys_out, self.ignore_id)
+        if ys[0].is_cuda:
+            if not hasattr(self, "_label_tables"):
+                import collections
+                self._label_tables = collections.deque(maxlen=16)
+            pad_ys_in, pad_ys_out = _label_batches(ys, self.sos, self.eos, self.ignore_id, self._label_tables)
+            ys_in_lens = [int(y.size(0)) + 1 for y in ys]
+        else:
+            eos = torch.full((1,), self.eos, dtype=ys[0].dtype, device=ys[0].device)
+            sos = torch.full((1,), self.sos, dtype=ys[0].dtype, device=ys[0].device)
+            ys_in = [torch.cat([sos, y], dim=0) for y in ys]
+            ys_out = [torch.cat([y, eos], dim=0) for y in ys]
+            pad_ys_in = pad_list(ys_in, self.eos)
+            pad_ys_out = pad_list(ys_out, self.ignore_id)
+            ys_in_lens = [len(x) for x in ys_in]
         batch, olength = pad_ys_out.size(0), pad_ys_out.size(1)
         c_list = [self.zero_state(hpad) for _ in range(self.dlayers)]
         z_list = [self.zero_state(hpad) for _ in range(self.dlayers)]
@@ -281,12 +313,12 @@ class Decoder(torch.nn.Module):
         else:
             y_all = torch.stack(y_all, dim=0).transpose(0, 1).contiguous().view(batch * olength, -1)
         self.loss = F.cross_entropy(y_all, pad_ys_out.view(-1), ignore_index=self.ignore_id, reduction='mean')
-        self.loss = self.loss * (np.mean([len(x) for x in ys_in]) - 1)   # quirk 7 of SURVEY.md 8a
+        self.loss = self.loss * (np.mean(ys_in_lens) - 1)   # quirk 7 of SURVEY.md 8a
         acc = th_accuracy(y_all, pad_ys_out, ignore_label=self.ignore_id)
         if self.labeldist is not None:
             if self.vlabeldist is None:
                 self.vlabeldist = torch.from_numpy(self.labeldist).to(dev)
-            loss_reg = -torch.sum((F.log_softmax(y_all, dim=1) * self.vlabeldist).view(-1), dim=0) / len(ys_in)
+            loss_reg = -torch.sum((F.log_softmax(y_all, dim=1) * self.vlabeldist).view(-1), dim=0) / len(ys_in_lens)
             self.loss = (1. - self.lsm_weight) * self.loss + self.lsm_weight * loss_reg
         return self.loss, acc
 
