@@ -49,11 +49,15 @@ with torch.no_grad():
     for conc in (1, 2, 4, 6):
         dec.recognize_beam_batch(hs8[:conc], lp8[:conc], ra, None, concurrency=conc)
         torch.cuda.synchronize()
+        ra.profile = {}
         t0 = time.perf_counter()
         out = dec.recognize_beam_batch(hs8, lp8, ra, None, concurrency=conc)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        print("batch of 16, %d concurrent searches: %.2f ms per utterance (%.1f utt/s)" % (conc, dt * 1e3 / 16, 16 / dt), flush=True)
+        print("batch of 16, %d concurrent searches: %.2f ms per utterance (%.1f utt/s); host ms per utterance by phase: %s"
+              % (conc, dt * 1e3 / 16, 16 / dt, {k: round(v * 1e3 / 16, 3) for k, v in ra.profile.items() if k != "positions"}),
+              flush=True)
+        del ra.profile
     torch.cuda.cudart().cudaProfilerStart()
     decode(hs[3])
     torch.cuda.synchronize()
