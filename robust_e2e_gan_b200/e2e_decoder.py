@@ -161,8 +161,8 @@ class _FusedSearch(object):
         self._t(t0, "capture")
 
     def pump(self):
-        if self.done:
-            return
+        if self.done or self.launched >= self.maxlen or self.launched >= self.processed + 2 * self.chunk:
+            return                      # (nothing to launch: do not pay for the stream switch)
         t0 = time.perf_counter()
         with torch.cuda.stream(self.stream):
             while self.launched < self.maxlen and self.launched < self.processed + 2 * self.chunk:
@@ -174,7 +174,9 @@ class _FusedSearch(object):
                 else:
                     if self.graph is None:
                         self._capture()
+                    t1 = time.perf_counter()
                     self.graph.replay()
+                    self._t(t1, "replay")
                     hi = min(self.maxlen, lo + self.chunk)
                 ev = self.events[self._evi]              # (three events, at most two chunks in flight)
                 self._evi = (self._evi + 1) % 3
@@ -196,10 +198,11 @@ class _FusedSearch(object):
         t0 = time.perf_counter()
         self.flights.pop(0)
         dec, args, beam = self.dec, self.args, self.beam
-        recs = self.hist_np[lo:hi].tolist()
+        blk = self.hist_np[lo:hi]
+        scs, idx = blk[:, 0].tolist(), blk[:, 1:].astype(np.int64).tolist()
         for i in range(lo, hi):
-            sc_, par, tok, cj = recs[i - lo]
-            entries = [(sc_[b], int(par[b]), int(tok[b]), int(cj[b])) for b in range(beam)]
+            par, tok, cj = idx[i - lo]
+            entries = list(zip(scs[i - lo], par, tok, cj))
             self.hyps = dec._host_merge(self.hyps, self.ended, entries, i, self.maxlen, self.minlen, args.penalty)
             if (end_detect(self.ended, i) and args.maxlenratio == 0.0) or len(self.hyps) == 0:
                 self.done = True
