@@ -274,6 +274,16 @@ int re2e_ctc_prefix_score(const float *lpz, const float *r_prev, const int32_t *
                           float *r_new, int T, int V, int H, int Ccand, int blank, int eos,
                           void *stream);
 
+/* Cross-entropy of the attention decoder (model/e2e_decoder.py:155-157: F.cross_entropy, ignore_index, mean) in one pass
+ * per direction.  logits (rows, V) with row pitch ld floats; target int64 (rows); rows whose target is ignore_id (or out
+ * of range) contribute nll = 0 / a zero gradient row.  fwd: lse (rows), nll (rows) = lse - logits[target], best (rows)
+ * = arg-max (NULL to skip; th_accuracy of model/e2e_common.py:198-205).  bwd: dlogits (rows, V) pitch ldd =
+ * (softmax - onehot) * *scale, scale a device scalar (incoming gradient / number of labelled rows). */
+int re2e_cross_entropy_fwd(const float *logits, long long ld, const long long *target, long long ignore_id, long long rows,
+                           int V, float *lse, float *nll, int32_t *best, void *stream);
+int re2e_cross_entropy_bwd(const float *logits, long long ld, const long long *target, long long ignore_id, long long rows,
+                           int V, const float *lse, const float *scale, float *dlogits, long long ldd, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Beam search, one output position for all W = beam hypothesis rows (model/e2e_decoder.py:233-314).
  * The reference advances one hypothesis at a time (beam x B=1 calls) and scores CTC prefixes in a host loop over T;

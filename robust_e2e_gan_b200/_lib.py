@@ -54,6 +54,8 @@ SIGNATURES = {
     "re2e_beam_gather": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "re2e_log_softmax_topk": (_I, [_P, _LL, _I, _I, _P, _P, _P, _P]),
     "re2e_beam_advance": (_I, [_P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "re2e_cross_entropy_fwd": (_I, [_P, _LL, _P, _LL, _LL, _I, _P, _P, _P, _P]),
+    "re2e_cross_entropy_bwd": (_I, [_P, _LL, _P, _LL, _LL, _I, _P, _P, _P, _LL, _P]),
     "re2e_beam_init": (_I, [_P] * 9 + [_I] * 6 + [_P]),
     "re2e_beam_merge": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "re2e_beam_joint": (_I, [_P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P]),

@@ -545,6 +545,57 @@ log_softmax_kernel(const float *__restrict__ x, float *__restrict__ out, int32_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// Cross-entropy of the attention decoder (model/e2e_decoder.py:155-157, F.cross_entropy with ignore_index, mean over
+// the labelled positions) without materialising log-softmax: one pass per row gives lse, the row's nll and its arg-max
+// (th_accuracy, model/e2e_common.py:198-205); the backward writes (softmax - onehot) * scale in one pass.  Rows may be
+// pitched (`ld`, the padded layout the tensor-core GEMM writes).  One warp per row.
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+ce_fwd_kernel(const float *__restrict__ x, long long ld, const long long *__restrict__ target, long long ignore_id,
+              long long rows, int V, float *__restrict__ lse, float *__restrict__ nll, int32_t *__restrict__ best) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float *xr = x + row * ld;
+  float m = -CUDART_INF_F, s = 0.f, av = -CUDART_INF_F;
+  int am = 0x7fffffff;
+  for (int i = lane; i < V; i += 32) {
+    const float v = xr[i];
+    lse_push(m, s, v);
+    if (v > av) { av = v; am = i; }
+  }
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, of), s2 = __shfl_xor_sync(0xffffffffu, s, of);
+    lse_merge(m, s, m2, s2);
+    const float av2 = __shfl_xor_sync(0xffffffffu, av, of);
+    const int am2 = __shfl_xor_sync(0xffffffffu, am, of);
+    if (av2 > av || (av2 == av && am2 < am)) { av = av2; am = am2; }
+  }
+  if (lane == 0) {
+    const float l = m + logf(s);
+    const long long t = target[row];
+    lse[row] = l;
+    nll[row] = (t == ignore_id || t < 0 || t >= V) ? 0.f : l - xr[t];
+    if (best) best[row] = am;
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+ce_bwd_kernel(const float *__restrict__ x, long long ld, const long long *__restrict__ target, long long ignore_id,
+              long long rows, int V, const float *__restrict__ lse, const float *__restrict__ scale,
+              float *__restrict__ dx, long long ldd) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long t = target[row];
+  const bool on = !(t == ignore_id || t < 0 || t >= V);
+  const float l = lse[row], sc = on ? __ldg(scale) : 0.f;
+  const float *xr = x + row * ld;
+  float *dr = dx + row * ldd;
+  for (int i = lane; i < V; i += 32) dr[i] = on ? (expf(xr[i] - l) - (i == t ? 1.f : 0.f)) * sc : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Batched prefix scoring (model/e2e_ctc.py:109-155): one WARP per (hypothesis h, candidate j).  Everything that does not
 // depend on the recursion -- phi[t-1] = logaddexp(r_prev[t-1]) (or its blank half for a repeated token), the two columns
 // of lpz -- is fetched 32 frames at a time with lane <-> frame (coalesced); the recursion itself runs uniformly on all
@@ -709,6 +760,27 @@ extern "C" int re2e_log_softmax(const float *logits, float *out, int32_t *best, 
   const int grid = (int)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
   log_softmax_kernel<<<grid, kWarpsPerCta * 32, 0, static_cast<cudaStream_t>(stream)>>>(logits, out, best,
                                                                                        rows, V);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int re2e_cross_entropy_fwd(const float *logits, long long ld, const long long *target, long long ignore_id,
+                                      long long rows, int V, float *lse, float *nll, int32_t *best, void *stream) {
+  RE2E_CHECK_ARG(logits && target && lse && nll && rows > 0 && V > 0 && ld >= V);
+  const int grid = (int)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
+  ce_fwd_kernel<<<grid, kWarpsPerCta * 32, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, target, ignore_id, rows, V,
+                                                                                  lse, nll, best);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int re2e_cross_entropy_bwd(const float *logits, long long ld, const long long *target, long long ignore_id,
+                                      long long rows, int V, const float *lse, const float *scale, float *dlogits,
+                                      long long ldd, void *stream) {
+  RE2E_CHECK_ARG(logits && target && lse && scale && dlogits && rows > 0 && V > 0 && ld >= V && ldd >= V);
+  const int grid = (int)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
+  ce_bwd_kernel<<<grid, kWarpsPerCta * 32, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, target, ignore_id, rows, V,
+                                                                                  lse, scale, dlogits, ldd);
   count_launch();
   return launch_status();
 }

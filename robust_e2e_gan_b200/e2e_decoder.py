@@ -94,16 +94,60 @@ def _label_batches(ys, sos, eos, ignore_id, keep):
     return out[0], out[1]
 
 
-def th_accuracy(y_all, pad_target, ignore_label):
+def th_accuracy(y_all, pad_target, ignore_label, pred=None):
     """model/e2e_common.py:198-205.  Returns a Python float like the reference, except while a CUDA graph is being
-    captured (no device-to-host read is possible there): then the 0-dim device tensor."""
-    pad_pred = y_all.detach().view(pad_target.size(0), pad_target.size(1), y_all.size(1)).max(2)[1]
+    captured (no device-to-host read is possible there): then the 0-dim device tensor.  ``pred``: the rows' arg-max
+    when the caller already has it."""
+    pad_pred = pred if pred is not None else \
+        y_all.detach().reshape(pad_target.size(0), pad_target.size(1), y_all.size(1)).max(2)[1]
     mask = pad_target != ignore_label
     num = torch.sum((pad_pred == pad_target) & mask)
     den = torch.sum(mask)
     if y_all.is_cuda and torch.cuda.is_current_stream_capturing():
         return num.float() / den.float()
     return float(num) / float(den)
+
+
+class _CrossEntropy(torch.autograd.Function):
+    """F.cross_entropy(y_all, target, ignore_index, reduction='mean') of model/e2e_decoder.py:155 on the library's
+    kernels: no log-softmax tensor, the arg-max of every row (for th_accuracy) from the same pass, the gradient written
+    in the row-padded layout the dense layer's backward reads without a copy."""
+
+    @staticmethod
+    def forward(ctx, y_all, target, ignore_id):
+        L = _lib.lib()
+        x = y_all.detach()
+        if x.dtype != torch.float32 or x.stride(1) != 1:
+            x = x.float().contiguous()
+        rows, V = x.shape
+        dev = x.device
+        tgt = target.contiguous()
+        lse = torch.empty(rows, device=dev, dtype=torch.float32)
+        nll = torch.empty(rows, device=dev, dtype=torch.float32)
+        best = torch.empty(rows, device=dev, dtype=torch.int32)
+        with torch.cuda.device(dev):
+            _lib.check(L.re2e_cross_entropy_fwd(_lib.ptr(x), x.stride(0), _lib.ptr(tgt), int(ignore_id), rows, V,
+                                                _lib.ptr(lse), _lib.ptr(nll), _lib.ptr(best), _lib.stream_ptr()),
+                       "re2e_cross_entropy_fwd")
+        count = (tgt != ignore_id).sum().to(torch.float32)
+        ctx.save_for_backward(x, tgt, lse, count)
+        ctx.ignore_id = int(ignore_id)
+        ctx.mark_non_differentiable(best)
+        return nll.sum() / count, best
+
+    @staticmethod
+    def backward(ctx, g, _gbest):
+        L = _lib.lib()
+        x, tgt, lse, count = ctx.saved_tensors
+        rows, V = x.shape
+        scale = (g.to(torch.float32) / count).contiguous()
+        ldd = (V + 3) // 4 * 4
+        dx = torch.empty(rows, ldd, device=x.device, dtype=torch.float32)[:, :V]
+        with torch.cuda.device(x.device):
+            _lib.check(L.re2e_cross_entropy_bwd(_lib.ptr(x), x.stride(0), _lib.ptr(tgt), ctx.ignore_id, rows, V,
+                                                _lib.ptr(lse), _lib.ptr(scale), _lib.ptr(dx), ldd, _lib.stream_ptr()),
+                       "re2e_cross_entropy_bwd")
+        return dx, None, None
 
 
 class _FusedSearch(object):
@@ -315,9 +359,15 @@ class Decoder(torch.nn.Module):
             y_all = linear(z_all, self.output.weight, self.output.bias).reshape(batch * olength, -1)
         else:
             y_all = torch.stack(y_all, dim=0).transpose(0, 1).contiguous().view(batch * olength, -1)
-        self.loss = F.cross_entropy(y_all, pad_ys_out.view(-1), ignore_index=self.ignore_id, reduction='mean')
-        self.loss = self.loss * (np.mean(ys_in_lens) - 1)   # quirk 7 of SURVEY.md 8a
-        acc = th_accuracy(y_all, pad_ys_out, ignore_label=self.ignore_id)
+        if y_all.is_cuda and pad_ys_out.dtype == torch.int64:
+            # cross-entropy + the arg-max for th_accuracy from one pass over the logits (csrc/ctc.cu)
+            self.loss, best = _CrossEntropy.apply(y_all, pad_ys_out.reshape(-1), self.ignore_id)
+            self.loss = self.loss * (np.mean(ys_in_lens) - 1)   # quirk 7 of SURVEY.md 8a
+            acc = th_accuracy(y_all, pad_ys_out, ignore_label=self.ignore_id, pred=best.view(pad_ys_out.shape))
+        else:
+            self.loss = F.cross_entropy(y_all, pad_ys_out.view(-1), ignore_index=self.ignore_id, reduction='mean')
+            self.loss = self.loss * (np.mean(ys_in_lens) - 1)   # quirk 7 of SURVEY.md 8a
+            acc = th_accuracy(y_all, pad_ys_out, ignore_label=self.ignore_id)
         if self.labeldist is not None:
             if self.vlabeldist is None:
                 self.vlabeldist = torch.from_numpy(self.labeldist).to(dev)

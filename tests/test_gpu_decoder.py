@@ -331,3 +331,58 @@ def test_recognize_beam_batch_equals_per_utterance():
             assert got == one, "concurrency %d" % conc
         att_only = [dec.recognize_beam(x, None, recog_args(c), None) for x in hs[:3]]
         assert dec.recognize_beam_batch(hs[:3], None, recog_args(c), None, concurrency=2) == att_only
+
+
+def test_label_batches_and_length_mask_match_the_list_formulation():
+    """_label_batches (one concatenation + two gathers) == the reference's per-utterance cat / pad_list construction
+    (model/e2e_decoder.py:88-97); mask_by_length as one select == the per-utterance slice copies, values and gradient."""
+    from robust_e2e_gan_b200.e2e_common import pad_list
+    from robust_e2e_gan_b200.e2e_decoder import _label_batches, mask_by_length
+    g = torch.Generator().manual_seed(5)
+    ys = [torch.randint(0, 50, (int(n),), generator=g).to(DEV) for n in (7, 1, 12, 4, 12)]
+    sos, eos, ign = 51, 52, -1
+    keep = []
+    pin, pout = _label_batches(ys, sos, eos, ign, keep)
+    s_, e_ = torch.full((1,), sos, device=DEV), torch.full((1,), eos, device=DEV)
+    assert torch.equal(pin, pad_list([torch.cat([s_, y]) for y in ys], eos))
+    assert torch.equal(pout, pad_list([torch.cat([y, e_]) for y in ys], ign))
+    x = torch.randn(4, 9, 6, generator=g).to(DEV).requires_grad_(True)
+    lens = [9, 3, 1, 6]
+    got = mask_by_length(x, lens, 0)
+    want = x.detach().clone()
+    for i, l in enumerate(lens):
+        want[i, l:] = 0
+    assert torch.equal(got, want)
+    w = torch.randn(4, 9, 6, generator=g).to(DEV)
+    (got * w).sum().backward()
+    gw = w.clone()
+    for i, l in enumerate(lens):
+        gw[i, l:] = 0
+    assert torch.equal(x.grad, gw)
+
+
+@pytest.mark.parametrize("rows,V,pitched", [(1312, 4233, True), (7, 52, False), (33, 1000, True)])
+def test_cross_entropy_kernels_match_torch(rows, V, pitched):
+    """_CrossEntropy (re2e_cross_entropy_fwd / _bwd) == F.cross_entropy(ignore_index, mean) in value and gradient (fp64 as
+    tie-breaker), arg-max == torch's, on contiguous and row-pitched logits; ignored rows get a zero gradient row."""
+    from robust_e2e_gan_b200.e2e_decoder import _CrossEntropy
+    g = torch.Generator().manual_seed(rows + V)
+    x = torch.randn(rows, V, generator=g) * 2.0
+    t = torch.randint(0, V, (rows,), generator=g)
+    t[::5] = -1
+    ld = (V + 3) // 4 * 4 if pitched else V
+    buf = torch.zeros(rows, ld, device=DEV)
+    buf[:, :V] = x.to(DEV)
+    xd = buf[:, :V].detach().requires_grad_(True)
+    loss, best = _CrossEntropy.apply(xd, t.to(DEV), -1)
+    (loss * 3.0).backward()
+    refs = []
+    for dt in (torch.float32, torch.float64):
+        xr = x.detach().clone().to(dt).requires_grad_(True)
+        lr = torch.nn.functional.cross_entropy(xr, t, ignore_index=-1, reduction='mean')
+        (lr * 3.0).backward()
+        refs.append((lr.detach(), xr.grad))
+    helpers.assert_close(loss.detach(), refs[0][0], truth=refs[1][0], what="cross-entropy")
+    helpers.assert_close(xd.grad, refs[0][1], truth=refs[1][1], what="d logits")
+    assert torch.equal(best.cpu().long(), x.argmax(1))
+    assert float(xd.grad[::5].abs().max()) == 0.0

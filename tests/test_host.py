@@ -159,3 +159,46 @@ def test_cmvn_statistics_are_reduced_over_ranks_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_beam_bookkeeping_matches_the_reference_formulation():
+    """Decoder._host_merge (linked hypotheses, token lists only for finished ones) against the reference's bookkeeping
+    written out literally (model/e2e_decoder.py:296-333: copy yseq per candidate, append <eos> at the last position, move
+    <eos> hypotheses longer than minlen to the ended list with the length penalty) on random candidate streams."""
+    from robust_e2e_gan_b200.e2e_decoder import Decoder
+    dec = Decoder.__new__(Decoder)          # bookkeeping only: no parameters needed
+    eos, sos, beam = 7, 7, 4
+    dec.eos, dec.sos = eos, sos
+    rng = np.random.RandomState(0)
+    for maxlen, minlen, penalty in ((9, 0, 0.0), (6, 3, 0.25), (12, 5, -0.1)):
+        hyps = [(np.float32(0.0), sos, None, 1)]
+        ref_hyps = [{'score': np.float32(0.0), 'yseq': [sos]}]
+        ended, ref_ended = [], []
+        for i in range(maxlen):
+            n = len(hyps)
+            entries = [(np.float32(rng.randn()), int(rng.randint(n)), int(rng.randint(5, 9)), int(rng.randint(6)))
+                       for _ in range(beam)]
+            hyps = dec._host_merge(hyps, ended, entries, i, maxlen, minlen, penalty)
+            new = [{'score': np.float32(s), 'yseq': ref_hyps[r]['yseq'] + [t]} for s, r, t, _ in entries]
+            if i == maxlen - 1:
+                for h in new:
+                    h['yseq'].append(eos)
+            ref_rem = []
+            for h in new:
+                if h['yseq'][-1] == eos:
+                    if len(h['yseq']) > minlen:
+                        h['score'] = np.float32(h['score'] + np.float32((i + 1) * penalty))
+                        ref_ended.append(h)
+                else:
+                    ref_rem.append(h)
+            ref_hyps = ref_rem
+            assert len(hyps) == len(ref_hyps)
+            for a, b in zip(hyps, ref_hyps):
+                seq, node = [], a
+                while node is not None:
+                    seq.append(node[1])
+                    node = node[2]
+                assert seq[::-1] == b['yseq'] and a[0] == b['score'] and a[3] == len(b['yseq'])
+            assert ended == ref_ended
+            if not hyps:
+                break
