@@ -596,13 +596,17 @@ ce_bwd_kernel(const float *__restrict__ x, long long ld, const long long *__rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// Batched prefix scoring (model/e2e_ctc.py:109-155): one WARP per (hypothesis h, candidate j).  Everything that does not
-// depend on the recursion -- phi[t-1] = logaddexp(r_prev[t-1]) (or its blank half for a repeated token), the two columns
-// of lpz -- is fetched 32 frames at a time with lane <-> frame (coalesced); the recursion itself runs uniformly on all
-// lanes over values broadcast by shuffles (three independent logaddexp chains per frame: r^n, r^b, psi), and every lane
-// keeps the pair of its own frame so that r_new is written 32 frames per store.
-// The recursion runs in base-2 logarithms so that one logaddexp is FADD -> EX2 -> FADD -> LG2 -> FADD on the dependent
-// chain (no scale multiplies, raw MUFU approximations: relative error 2^-22, far inside the parity tolerance).
+// Batched prefix scoring (model/e2e_ctc.py:109-155): one WARP per (hypothesis h, candidate j), lane <-> frame, 32 frames
+// per block.  The recursion
+//     r^n_t = (r^n_{t-1} + phi_{t-1}) x_t ,   r^b_t = (r^n_{t-1} + r^b_{t-1}) y_t        (probability domain)
+// is linear in the state (r^n, r^b, 1): frame t is the matrix [[x, 0, x phi], [y, y, 0], [0, 0, 1]] and products of such
+// matrices keep the shape [[a, 0, p], [b, d, q], [0, 0, 1]].  So instead of a 32-step dependent chain per block the warp
+// runs an inclusive SCAN over the frames' matrices in the log semiring (5 shuffle steps, 4 logaddexp each) and applies
+// every lane's prefix product to the state carried in from the previous block: ~12 dependent logaddexp per 32 frames
+// instead of 32.  psi = logsumexp_t(phi_{t-1} + x_t) is a plain warp reduction.  Everything that does not depend on the
+// recursion (phi, the two columns of lpz) is fetched one block ahead, coalesced.
+// Arithmetic in base-2 logs with raw MUFU approximations (relative error 2^-22, far inside the parity tolerance);
+// "log 0" is the reference's logzero, which absorbs every finite addend in fp32 exactly as it does there.
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -629,7 +633,7 @@ ctc_prefix_kernel(const float *__restrict__ lpz, const float *__restrict__ r_pre
   if (idx >= H * Cc) return;
   const int h = idx / Cc;
   const int c = __ldcg(cs + idx);        // (candidates, states: results of kernels this grid may overlap)
-  const float LZ = -10000000000.0f, L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  const float LZ = -10000000000.0f, L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f, LZ2 = LZ * L2E;
   const int ol = __ldcg(out_len + h);
   const float *rp = r_prev + (size_t)h * T * 2;
   float *rn = r_new + (size_t)idx * T * 2;
@@ -638,39 +642,54 @@ ctc_prefix_kernel(const float *__restrict__ lpz, const float *__restrict__ r_pre
   for (int t = lane; t < min(start - 1, T); t += 32) *reinterpret_cast<float2 *>(rn + 2 * t) = make_float2(LZ, LZ);
   const float r0 = ol == 0 ? __ldg(lpz + c) : LZ;
   if (lane == 0 && start - 1 < T) *reinterpret_cast<float2 *>(rn + 2 * (start - 1)) = make_float2(r0, LZ);
-  float rn_prev = r0 * L2E, rb_prev = LZ * L2E, psi = r0 * L2E;      // base-2 from here on
-  // frame t of the current block, fetched one block ahead of the recursion
-  float2 p = make_float2(LZ, LZ);
+  float n_in = r0 * L2E, b_in = LZ2;               // state after frame base-1, base-2 logs
+  float psi = LZ2;                                 // this lane's share of logsumexp_t(phi_{t-1} + x_t)
+  // operands of frame t of the current block, fetched one block ahead of their use
+  float2 pv = make_float2(LZ, LZ);
   float xc = 0.f, xb = 0.f;
   if (start + lane < T) {
     const int t = start + lane;
-    p = __ldcg(reinterpret_cast<const float2 *>(rp + 2 * (t - 1)));
+    pv = __ldcg(reinterpret_cast<const float2 *>(rp + 2 * (t - 1)));
     xc = __ldg(lpz + (size_t)t * V + c);
     xb = __ldg(lpz + (size_t)t * V + blank);
   }
   for (int base = start; base < T; base += 32) {
     const int t = base + lane;
     const bool valid = t < T;
-    const float phi = same ? p.y * L2E : lae2(p.x * L2E, p.y * L2E);
-    const float c2 = xc * L2E, b2 = xb * L2E;
-    if (t + 32 < T) {                                          // next block's operands
-      p = __ldcg(reinterpret_cast<const float2 *>(rp + 2 * (t + 31)));
+    const float phi = same ? pv.y * L2E : lae2(pv.x * L2E, pv.y * L2E);
+    const float x = xc * L2E, y = xb * L2E;
+    if (t + 32 < T) {                              // next block's operands
+      pv = __ldcg(reinterpret_cast<const float2 *>(rp + 2 * (t + 31)));
       xc = __ldg(lpz + (size_t)(t + 32) * V + c);
       xb = __ldg(lpz + (size_t)(t + 32) * V + blank);
     }
-    const int n = min(32, T - base);
-    float my_n = LZ, my_b = LZ;
-    for (int i = 0; i < n; ++i) {
-      const float ph = __shfl_sync(0xffffffffu, phi, i), c_ = __shfl_sync(0xffffffffu, c2, i),
-                  b_ = __shfl_sync(0xffffffffu, b2, i);
-      const float nn = lae2(rn_prev, ph) + c_;
-      const float nb = lae2(rn_prev, rb_prev) + b_;
-      psi = lae2(psi, ph + c_);
-      if (lane == i) { my_n = nn; my_b = nb; }
-      rn_prev = nn; rb_prev = nb;
+    // this frame's matrix (identity beyond T): [[a, 0, p], [b, d, q], [0, 0, 1]] in logs
+    float a = valid ? x : 0.f, b = valid ? y : LZ2, d = valid ? y : 0.f, p = valid ? x + phi : LZ2, q = LZ2;
+    if (valid) psi = lae2(psi, x + phi);
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {       // mine (later frames) x theirs (earlier frames)
+      const float a0 = __shfl_up_sync(0xffffffffu, a, off), b0 = __shfl_up_sync(0xffffffffu, b, off),
+                  d0 = __shfl_up_sync(0xffffffffu, d, off), p0 = __shfl_up_sync(0xffffffffu, p, off),
+                  q0 = __shfl_up_sync(0xffffffffu, q, off);
+      if (lane >= off) {
+        const float qn = lae2(lae2(b + p0, d + q0), q);
+        const float bn = lae2(b + a0, d + b0);
+        p = lae2(a + p0, p);
+        a += a0;
+        d += d0;
+        b = bn;
+        q = qn;
+      }
     }
-    if (valid) *reinterpret_cast<float2 *>(rn + 2 * t) = make_float2(fmaxf(my_n * LN2, LZ), fmaxf(my_b * LN2, LZ));
+    const float nn = lae2(a + n_in, p);
+    const float nb = lae2(lae2(b + n_in, d + b_in), q);
+    if (valid) *reinterpret_cast<float2 *>(rn + 2 * t) = make_float2(fmaxf(nn * LN2, LZ), fmaxf(nb * LN2, LZ));
+    n_in = __shfl_sync(0xffffffffu, nn, 31);
+    b_in = __shfl_sync(0xffffffffu, nb, 31);
   }
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) psi = lae2(psi, __shfl_xor_sync(0xffffffffu, psi, of));
+  psi = lae2(psi, r0 * L2E);                       // the t = start-1 term the reference starts from
   psi = fmaxf(psi * LN2, LZ);
   if (c == eos) {
     const float a = __ldcg(rp + 2 * (T - 1)), b = __ldcg(rp + 2 * (T - 1) + 1);
