@@ -232,6 +232,9 @@ def test_log_softmax_topk(rows, V, k):
     x = torch.randn(rows, V, generator=g) * 3.0
     if V > 60:
         x[0, 50] = x[0, 7] = x[0].max() + 1.0          # a tie at the top
+    if rows > 1 and V > 1100:
+        x[1, :24] += 40.0                              # the k best all in ONE warp's slice (the selection's slow path)
+        x[1, 1024:1030] += 30.0
     xd = x.to(DEV)
     full = torch.empty(rows, V, device=DEV)
     vals, ids = torch.empty(rows, k, device=DEV), torch.empty(rows, k, dtype=torch.int32, device=DEV)
@@ -281,7 +284,8 @@ def test_beam_gather_and_joint():
     assert torch.equal(out[0], sc.unsqueeze(1) + bs) and torch.equal(out[2], bj.float())
 
 
-@pytest.mark.parametrize("ctc_weight,beam,Th", [(0.3, 10, 60), (0.0, 5, 40), (0.5, 1, 25)])
+@pytest.mark.parametrize("ctc_weight,beam,Th", [(0.3, 10, 60), (0.0, 5, 40), (0.5, 1, 25), (0.3, 4, 2), (0.3, 6, 7),
+                                                 (0.7, 3, 11)])
 def test_fused_beam_position_matches_generic_path(ctc_weight, beam, Th):
     """The fused position (csrc/beam.cu; tail as one launch or as joint / merge / gather) and the generic tensor-op
     position of recognize_beam give the same n-best list (tokens identical, scores to 1e-4), with and without CUDA-graph
