@@ -390,3 +390,37 @@ def test_cross_entropy_kernels_match_torch(rows, V, pitched):
     helpers.assert_close(xd.grad, refs[0][1], truth=refs[1][1], what="d logits")
     assert torch.equal(best.cpu().long(), x.argmax(1))
     assert float(xd.grad[::5].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dlayers,lsm", [(2, 0.0), (1, 0.1)])
+def test_decoder_forward_variants_agree_with_the_library_free_path(dlayers, lsm):
+    """Two decoder layers (only the first LSTMCell runs on the cluster kernel) and label smoothing (the extra
+    F.log_softmax term of model/e2e_decoder.py:160-164): the fused path (LSTM step kernel, batched output layer,
+    cross-entropy kernels) against the same module with torch.nn.LSTMCell + per-position output layer + F.cross_entropy
+    (scheduled_sampling_rate just above 0 selects that loop; the draw never fires), loss and all gradients."""
+    from robust_e2e_gan_b200 import AttLoc, Decoder
+    torch.manual_seed(11)
+    V, D, Z, A, C, filts, B, Th = 37, 64, 48, 64, 4, 5, 4, 17
+    ld = np.full(V, 1.0 / V, dtype=np.float32) if lsm > 0 else None
+    dec = Decoder(D, V, dlayers, Z, V - 1, V - 1, AttLoc(D, Z, A, C, filts, "softmax"), labeldist=ld, lsm_weight=lsm).to(DEV)
+    dec.train()
+    g = torch.Generator().manual_seed(3)
+    hpad = torch.tanh(torch.randn(B, Th, D, generator=g)).to(DEV)
+    hlen = [17, 12, 9, 17]
+    ys = [torch.randint(0, V - 1, (n,), generator=g).to(DEV) for n in (5, 3, 4, 6)]
+    res = []
+    for rate in (0.0, 1e-12):
+        dec.zero_grad(set_to_none=True)
+        h = hpad.clone().requires_grad_(True)
+        loss, acc = dec(h, hlen, ys, rate)
+        loss.backward()
+        res.append((loss.detach(), acc, h.grad, {k: p.grad.clone() for k, p in dec.named_parameters() if p.grad is not None}))
+    (l0, a0, h0, g0), (l1, a1, h1, g1) = res
+    helpers.assert_close(l0, l1, what="loss")
+    assert a0 == pytest.approx(a1)
+    helpers.assert_close(h0, h1, what="d hpad")
+    assert set(g0) == set(g1)
+    for k in g0:
+        if k == "att.gvec.bias":
+            continue
+        helpers.assert_close(g0[k], g1[k], what="d " + k)
