@@ -117,8 +117,43 @@ def check(rc, what=""):
         raise RuntimeError("%s failed: %s (code %d)" % (what or "re2e call", msg, rc))
 
 
+_get_device = getattr(torch._C, "_cuda_getDevice", None)
+_set_device = getattr(torch._C, "_cuda_setDevice", None)
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr():
+    """Handle of torch's current stream on the current device.  The raw query is ~40x cheaper than
+    torch.cuda.current_stream() (which builds a Stream object and resolves the device index in Python); a decoder loop
+    makes several hundred of these calls per step."""
+    if _raw_stream is not None and _get_device is not None:
+        return ctypes.c_void_p(_raw_stream(_get_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class on(object):
+    """``with on(device):`` -- make ``device`` current for the calls inside, like torch.cuda.device(device) but free when
+    it already is (the usual case: one process per GPU)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index if isinstance(device, torch.device) else int(device)
+        self.prev = -1
+
+    def __enter__(self):
+        if self.idx is None or _get_device is None:
+            return self
+        cur = _get_device()
+        if cur != self.idx:
+            self.prev = cur
+            _set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            _set_device(self.prev)
+            self.prev = -1
+        return False
 
 
 def ptr(t):

@@ -106,7 +106,7 @@ class _Precompute(torch.autograd.Function):
                 d_enc = torch.zeros(B, Th, D, device=dev, dtype=torch.float32)
             w_all = torch.stack(st.bwd_w, 0).contiguous()
             dc_all = torch.stack(st.bwd_dc, 0).contiguous()
-            with torch.cuda.device(dev):
+            with _lib.on(dev):
                 _lib.check(L.re2e_attloc_enc_grad(_lib.ptr(w_all), _lib.ptr(dc_all), _lib.ptr(d_enc),
                                                   w_all.shape[0], B, Th, D, 1, _lib.stream_ptr()),
                            "re2e_attloc_enc_grad")
@@ -119,7 +119,7 @@ class _Precompute(torch.autograd.Function):
             dW_dec = torch.zeros(A, Z, device=dev, dtype=torch.float32)
         if st.acc is not None:
             tot = torch.empty(A * C + C * K + A + 1, device=dev, dtype=torch.float32)
-            with torch.cuda.device(dev):
+            with _lib.on(dev):
                 _lib.check(L.re2e_attloc_acc_reduce(_lib.ptr(st.acc), st.acc_nslots, _lib.ptr(tot), A, C, K,
                                                     _lib.stream_ptr()), "re2e_attloc_acc_reduce")
             dW_att = tot[:A * C].view(A, C)
@@ -145,7 +145,7 @@ class _Step(torch.autograd.Function):
         need_bwd = any(ctx.needs_input_grad[:3])
         conv = torch.empty(B, Th, C, device=dev, dtype=torch.float32) if need_bwd else None
         xsave = torch.empty(B, Th, A, device=dev, dtype=torch.float32) if need_bwd else None
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             _lib.check(L.re2e_attloc_step_fwd(_lib.ptr(st.pre), _lib.ptr(st.enc), _lib.ptr(dz), _lib.ptr(ap),
                                               _lib.ptr(W_dec), _lib.ptr(W_att), _lib.ptr(W_conv), _lib.ptr(gvec),
                                               _lib.ptr(gvec_b), float(scaling), _lib.ptr(c), _lib.ptr(w),
@@ -183,7 +183,7 @@ class _Step(torch.autograd.Function):
         d_prev = torch.empty(B, Th, device=dev, dtype=torch.float32) if want_dprev else None
         d_dz = (torch.empty(B, Z, device=dev, dtype=torch.float32)
                 if (ctx.has_dz and ctx.needs_input_grad[1]) else None)
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             _lib.check(L.re2e_attloc_step_bwd(
                 _lib.ptr(dc), _lib.ptr(dw), _lib.ptr(xsave), _lib.ptr(st.enc), _lib.ptr(ap), _lib.ptr(w),
                 _lib.ptr(conv), _lib.ptr(W_dec), _lib.ptr(st.W_decT), _lib.ptr(W_att), _lib.ptr(W_conv),
@@ -234,7 +234,7 @@ class _Loop(torch.autograd.Function):
         c_all = torch.empty(S, B, D, device=dev, dtype=torch.float32)
         w_all = torch.empty(S, B, Th, device=dev, dtype=torch.float32)
         conv_all = torch.empty(S, B, Th, C, device=dev, dtype=torch.float32) if need_bwd else None
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             _lib.check(L.re2e_attloc_loop_fwd(_lib.ptr(pre), _lib.ptr(enc), _lib.ptr(dec_proj), _lib.ptr(att0),
                                               _lib.ptr(Wa), _lib.ptr(Wc), _lib.ptr(gw), _lib.ptr(gb), float(scaling),
                                               _lib.ptr(c_all), _lib.ptr(w_all), _lib.ptr(conv_all), S, B, Th, D, A, C, K,
@@ -263,7 +263,7 @@ class _Loop(torch.autograd.Function):
         acc = torch.empty(nslots, stride, device=dev, dtype=torch.float32)
         d_pre = torch.empty(B, Th, A, device=dev, dtype=torch.float32)
         d_decproj = torch.empty(S, B, A, device=dev, dtype=torch.float32)
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             _lib.check(L.re2e_attloc_loop_bwd(_lib.ptr(pre), _lib.ptr(enc), _lib.ptr(dec_proj), _lib.ptr(att0),
                                               _lib.ptr(w_all), _lib.ptr(conv_all), _lib.ptr(dc_all), _lib.ptr(dw_all),
                                               _lib.ptr(Wa), _lib.ptr(Wc), _lib.ptr(gw), ctx.scaling, _lib.ptr(d_pre),
@@ -275,7 +275,7 @@ class _Loop(torch.autograd.Function):
             d_enc = torch.empty(B, Th, D, device=dev, dtype=torch.float32)
             gemm_tf32x3(dp2, False, We, True, d_enc.view(B * Th, D), B * Th, D, A)         # d_pre @ W_enc
             if dc_all is not None:                                                          # + sum_i w_i (x) dc_i
-                with torch.cuda.device(dev):
+                with _lib.on(dev):
                     _lib.check(L.re2e_attloc_enc_grad(_lib.ptr(w_all), _lib.ptr(dc_all), _lib.ptr(d_enc), S, B, Th, D, 1,
                                                       _lib.stream_ptr()), "re2e_attloc_enc_grad")
         if need[2]:
@@ -295,7 +295,7 @@ class _Loop(torch.autograd.Function):
             else:
                 dW_dec.zero_()
         tot = torch.empty(A * C + C * K + A + 1, device=dev, dtype=torch.float32)
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             _lib.check(L.re2e_attloc_acc_reduce(_lib.ptr(acc), nslots, _lib.ptr(tot), A, C, K, _lib.stream_ptr()),
                        "re2e_attloc_acc_reduce")
         dW_att = tot[:A * C].view(A, C)
@@ -384,7 +384,7 @@ class AttLoc(torch.nn.Module):
             else:
                 hl = torch.from_numpy(np.fromiter((int(l) for l in enc_hs_len), dtype=np.int32)).to(dev, non_blocking=True)
             att_prev = torch.empty(batch, h_length, device=dev, dtype=torch.float32)
-            with torch.cuda.device(dev):
+            with _lib.on(dev):
                 _lib.check(L.re2e_attloc_init_att(_lib.ptr(hl), _lib.ptr(att_prev), batch, h_length, _lib.stream_ptr()),
                            "re2e_attloc_init_att")
         return _Loop.apply(enc_hs_pad, dec_z_all, self.mlp_enc.weight, self.mlp_enc.bias, self.mlp_dec.weight,
@@ -432,7 +432,7 @@ class AttLoc(torch.nn.Module):
                     st.hlens_dev = torch.from_numpy(
                         np.fromiter((int(l) for l in enc_hs_len), dtype=np.int32)).to(dev, non_blocking=True)
             att_prev = torch.empty(batch, self.h_length, device=dev, dtype=torch.float32)
-            with torch.cuda.device(dev):
+            with _lib.on(dev):
                 _lib.check(L.re2e_attloc_init_att(_lib.ptr(st.hlens_dev), _lib.ptr(att_prev), batch,
                                                   self.h_length, _lib.stream_ptr()), "re2e_attloc_init_att")
         if dec_z is not None:

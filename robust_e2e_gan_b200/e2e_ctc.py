@@ -58,7 +58,7 @@ class _CTCLossFunction(torch.autograd.Function):
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
         nll = torch.empty(B, device=dev, dtype=torch.float32)
         loss = torch.empty(1, device=dev, dtype=torch.float32)
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             _lib.check(L.re2e_ctc_loss_fwd(_lib.ptr(x), sb, st, _lib.ptr(tgt.labels), _lib.ptr(tgt.offs),
                                            _lib.ptr(tgt.lens), _lib.ptr(hlens_dev), int(blank), _lib.ptr(nll),
                                            _lib.ptr(loss), _lib.ptr(ws), nbytes, B, Th, V, tgt.umax,
@@ -78,7 +78,7 @@ class _CTCLossFunction(torch.autograd.Function):
         # same (possibly row-padded) layout as the logits: the tcgen05 backward GEMMs read it through TMA
         grad = torch.empty_strided((B, Th, V), x.stride(), device=x.device, dtype=torch.float32)
         g = _lib.f32c(g.reshape(-1)[:1], x.device)
-        with torch.cuda.device(x.device):
+        with _lib.on(x.device):
             _lib.check(L.re2e_ctc_loss_bwd(_lib.ptr(x), sb, st, _lib.ptr(labels), _lib.ptr(offs),
                                            _lib.ptr(lens), _lib.ptr(hlens_dev), blank, _lib.ptr(nll), _lib.ptr(g),
                                            _lib.ptr(ws), ws.numel(), _lib.ptr(grad), B, Th, V, umax,
@@ -114,7 +114,7 @@ def log_softmax_rows(logits, want_best=False):
     rows = x.numel() // V
     out = torch.empty_like(x)
     best = torch.empty(x.shape[:-1], device=x.device, dtype=torch.int32) if want_best else None
-    with torch.cuda.device(x.device):
+    with _lib.on(x.device):
         _lib.check(L.re2e_log_softmax(_lib.ptr(x), _lib.ptr(out), _lib.ptr(best), rows, V, _lib.stream_ptr()),
                    "re2e_log_softmax")
     return (out, best) if want_best else out
@@ -168,7 +168,7 @@ def ctc_prefix_score_batch(lpz, r_prev, cs, last, out_len, blank, eos):
     dev = lpz.device
     log_psi = torch.empty(H, C, device=dev, dtype=torch.float32)
     r_new = torch.empty(H, C, T, 2, device=dev, dtype=torch.float32)
-    with torch.cuda.device(dev):
+    with _lib.on(dev):
         _lib.check(L.re2e_ctc_prefix_score(_lib.ptr(lpz), _lib.ptr(r_prev), _lib.ptr(cs), _lib.ptr(last),
                                            _lib.ptr(out_len), _lib.ptr(log_psi), _lib.ptr(r_new), T, V, H, C,
                                            int(blank), int(eos), _lib.stream_ptr()), "re2e_ctc_prefix_score")

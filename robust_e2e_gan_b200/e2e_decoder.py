@@ -125,7 +125,7 @@ class _CrossEntropy(torch.autograd.Function):
         lse = torch.empty(rows, device=dev, dtype=torch.float32)
         nll = torch.empty(rows, device=dev, dtype=torch.float32)
         best = torch.empty(rows, device=dev, dtype=torch.int32)
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             _lib.check(L.re2e_cross_entropy_fwd(_lib.ptr(x), x.stride(0), _lib.ptr(tgt), int(ignore_id), rows, V,
                                                 _lib.ptr(lse), _lib.ptr(nll), _lib.ptr(best), _lib.stream_ptr()),
                        "re2e_cross_entropy_fwd")
@@ -143,7 +143,7 @@ class _CrossEntropy(torch.autograd.Function):
         scale = (g.to(torch.float32) / count).contiguous()
         ldd = (V + 3) // 4 * 4
         dx = torch.empty(rows, ldd, device=x.device, dtype=torch.float32)[:, :V]
-        with torch.cuda.device(x.device):
+        with _lib.on(x.device):
             _lib.check(L.re2e_cross_entropy_bwd(_lib.ptr(x), x.stride(0), _lib.ptr(tgt), ctx.ignore_id, rows, V,
                                                 _lib.ptr(lse), _lib.ptr(scale), _lib.ptr(dx), ldd, _lib.stream_ptr()),
                        "re2e_cross_entropy_bwd")
@@ -442,7 +442,7 @@ class Decoder(torch.nn.Module):
         subc = (ctypes.c_int * n)(*[s[3] for s in segs])
         w_att, w_ctc = float(1.0 - ctc_weight), float(ctc_weight)
         P = _lib.ptr
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             _lib.check(lib.re2e_beam_init(P(z_in), P(c_in), P(a_in), P(r_in), P(psi_in), P(lpz), P(ctl), P(sc), P(state), W, Z,
                                           Th, V, 0, self.sos, _lib.stream_ptr()), "re2e_beam_init")
 
@@ -481,7 +481,7 @@ class Decoder(torch.nn.Module):
             calls = built.get(key)
             if calls is None:
                 calls = built[key] = build(ctypes.c_void_p(key))
-            with torch.cuda.device(dev):
+            with _lib.on(dev):
                 for fn, name, args in calls:
                     rc = fn(*args)
                     if rc != 0:

@@ -143,7 +143,7 @@ class _FbankFunction(torch.autograd.Function):
         G = torch.empty(B, T, M, device=dev, dtype=torch.float32) if need_grad else None
         enh = torch.empty(B, T, F, device=dev, dtype=torch.float32) if (want_enh and mask is not None) else None
         band = _band_for(fc, B, T) if enh is None else None
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             if band is not None:      # banded (mel) bank: the streaming kernels
                 _lib.check(L.re2e_fbank_band_fwd(_lib.ptr(mask), int(mask_is_logit), _lib.ptr(mag), None,
                                                  _lib.ptr(band[0]), _lib.ptr(band[1]), _lib.ptr(cm), _lib.ptr(ln),
@@ -174,7 +174,7 @@ class _FbankFunction(torch.autograd.Function):
         d_in = torch.empty(B, T, F, device=dev, dtype=torch.float32) if want_in else None
         dfc = torch.zeros(F, M, device=dev, dtype=torch.float32) if ctx.needs_input_grad[2] else None
         band = ctx.band
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             if band is not None and d_in is not None:      # banded bank: d_in from the streaming kernel
                 _lib.check(L.re2e_fbank_band_bwd(_lib.ptr(dY), _lib.ptr(G), _lib.ptr(mask), ctx.mask_is_logit,
                                                  _lib.ptr(mag), _lib.ptr(band[2]), _lib.ptr(band[3]), _lib.ptr(ln),
@@ -209,7 +209,7 @@ class _FbankJoint(torch.autograd.Function):
         need_grad = ctx.needs_input_grad[0]
         Y, Ym, Yc = (torch.empty(B, T, M, device=dev, dtype=torch.float32) for _ in range(3))
         G = torch.empty(B, T, M, device=dev, dtype=torch.float32) if need_grad else None
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             _lib.check(L.re2e_fbank_band_fwd(_lib.ptr(mask), 1, _lib.ptr(mix), _lib.ptr(clean), _lib.ptr(band[0]),
                                              _lib.ptr(band[1]), _lib.ptr(cm), _lib.ptr(ln), _lib.ptr(Y), _lib.ptr(G),
                                              _lib.ptr(Ym), _lib.ptr(Yc), B, T, F, M, _lib.stream_ptr()),
@@ -226,7 +226,7 @@ class _FbankJoint(torch.autograd.Function):
         B, T, F = mix.shape
         M = G.shape[2]
         d_mask = torch.empty(B, T, F, device=mix.device, dtype=torch.float32)
-        with torch.cuda.device(mix.device):
+        with _lib.on(mix.device):
             _lib.check(L.re2e_fbank_band_bwd(_lib.ptr(_lib.f32c(dY, mix.device)), _lib.ptr(G), _lib.ptr(mask), 1,
                                              _lib.ptr(mix), _lib.ptr(mlo), _lib.ptr(bw), _lib.ptr(ln), _lib.ptr(d_mask),
                                              B, T, F, M, _lib.stream_ptr()), "re2e_fbank_band_bwd")
@@ -304,7 +304,7 @@ class FFTModel(ModelBase):
                 self._dev_frames = torch.zeros(1, device=dev, dtype=torch.int64)
             sizes = torch.as_tensor(np.asarray(input_sizes)).to(torch.int32)
             ln = sizes.to(dev, non_blocking=True).contiguous()
-            with torch.cuda.device(dev):
+            with _lib.on(dev):
                 _lib.check(L.re2e_cmvn_stats(_lib.ptr(features.detach()), _lib.ptr(ln),
                                              _lib.ptr(self._dev_sum[0]), _lib.ptr(self._dev_sum[1]),
                                              _lib.ptr(self._dev_frames), B, T, M, _lib.stream_ptr()),
@@ -389,7 +389,7 @@ class _MaskApply(torch.autograd.Function):
         ln = lens.to(dev, torch.int32, non_blocking=True).contiguous()
         B, T, F = lo.shape
         out = torch.empty_like(lo)
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             _lib.check(L.re2e_mask_apply_fwd(_lib.ptr(lo), _lib.ptr(mx), _lib.ptr(ln), _lib.ptr(out), B, T, F,
                                              _lib.stream_ptr()), "re2e_mask_apply_fwd")
         ctx.save_for_backward(lo, mx, ln)
@@ -401,7 +401,7 @@ class _MaskApply(torch.autograd.Function):
         lo, mx, ln = ctx.saved_tensors
         B, T, F = lo.shape
         d = torch.empty_like(lo)
-        with torch.cuda.device(lo.device):
+        with _lib.on(lo.device):
             _lib.check(L.re2e_mask_apply_bwd(_lib.ptr(_lib.f32c(d_enh, lo.device)), _lib.ptr(lo), _lib.ptr(mx),
                                              _lib.ptr(ln), _lib.ptr(d), B, T, F, _lib.stream_ptr()),
                        "re2e_mask_apply_bwd")

@@ -20,7 +20,7 @@ def gemm_tf32x3(A, a_mn, B, b_mn, C, M, N, K, bias=None, accumulate=False):
     """C[M,N] (+)= Aop[M,K] Bop[N,K]^T (+bias).  A: [M][lda] (a_mn False) or [K][lda] (a_mn True); same for B."""
     L = _lib.lib()
     lda, ldb, ldc = _ld(A), _ld(B), _ld(C)
-    with torch.cuda.device(C.device):
+    with _lib.on(C.device):
         _lib.check(L.re2e_gemm_tf32x3(_lib.ptr(A), lda, int(a_mn), _lib.ptr(B), ldb, int(b_mn), _lib.ptr(C), ldc,
                                       _lib.ptr(bias), M, N, K, int(accumulate), _lib.stream_ptr()), "re2e_gemm_tf32x3")
     return C
@@ -35,7 +35,7 @@ def colsum(g):
     nrb = int(L.re2e_colsum_blocks(rows))
     partial = torch.empty(nrb, cols, device=g.device, dtype=torch.float32)
     out = torch.empty(cols, device=g.device, dtype=torch.float32)
-    with torch.cuda.device(g.device):
+    with _lib.on(g.device):
         _lib.check(L.re2e_colsum(_lib.ptr(g), ld, rows, cols, _lib.ptr(partial), _lib.ptr(out), _lib.stream_ptr()),
                    "re2e_colsum")
     return out

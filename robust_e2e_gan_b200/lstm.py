@@ -21,7 +21,7 @@ from .linear import gemm_tf32x3, linear
 def _batch_nt(X, W, out, M, N, K, accumulate=False):
     """out[M,N] (+)= X[M,K] @ W[N,K]^T, M = batch rows (re2e_batch_nt: all SMs stream W once)."""
     L = _lib.lib()
-    with torch.cuda.device(out.device):
+    with _lib.on(out.device):
         _lib.check(L.re2e_batch_nt(_lib.ptr(X), _lib.ptr(W), None, _lib.ptr(out), M, N, K, int(accumulate),
                                    _lib.stream_ptr()), "re2e_batch_nt")
 
@@ -89,7 +89,7 @@ class _Step(torch.autograd.Function):
         D = xc.shape[1]
         gates = torch.empty(B, 4 * Z, device=dev, dtype=torch.float32)
         h, c = torch.empty_like(hp), torch.empty_like(hp)
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             if state.Wcat is not None:
                 _lib.check(L.re2e_lstm_step_fwd(_lib.ptr(xc), _lib.ptr(hp), _lib.ptr(cp), _lib.ptr(state.Wcat), _lib.ptr(eg),
                                                 None, _lib.ptr(gates), _lib.ptr(c), _lib.ptr(h), B, D, Z, _lib.stream_ptr()),
@@ -118,7 +118,7 @@ class _Step(torch.autograd.Function):
         dc = _lib.f32c(dc, dev) if dc is not None else None
         dg = torch.empty(B, 4 * Z, device=dev, dtype=torch.float32)
         dcp = torch.empty(B, Z, device=dev, dtype=torch.float32)
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             _lib.check(L.re2e_lstm_pointwise_bwd(_lib.ptr(act), _lib.ptr(cp), _lib.ptr(c), _lib.ptr(dh), _lib.ptr(dc),
                                                  _lib.ptr(dg), _lib.ptr(dcp), B, Z, _lib.stream_ptr()),
                        "re2e_lstm_pointwise_bwd")
@@ -127,7 +127,7 @@ class _Step(torch.autograd.Function):
         if st.Wcat is not None:
             if st.WcatT is None:     # once per loop: the transposed copy makes the backward's product row-streamed as well
                 st.WcatT = st.Wcat.t().contiguous()
-            with torch.cuda.device(dev):
+            with _lib.on(dev):
                 _lib.check(L.re2e_lstm_step_bwd(_lib.ptr(dg), _lib.ptr(st.WcatT), _lib.ptr(d_ctx), _lib.ptr(d_hp), B, D, Z,
                                                 _lib.stream_ptr()), "re2e_lstm_step_bwd")
         else:
