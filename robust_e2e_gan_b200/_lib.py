@@ -157,10 +157,9 @@ class on(object):
 
 
 def ptr(t):
-    """Raw device pointer of a tensor (None -> NULL).  Tensors must be CUDA fp32/int32 contiguous."""
-    if t is None:
-        return None
-    return ctypes.c_void_p(t.data_ptr())
+    """Raw device pointer of a tensor (None -> NULL) as a plain int (ctypes converts it for the declared void* argument).
+    Tensors must be CUDA fp32/int32 contiguous."""
+    return None if t is None else t.data_ptr()
 
 
 def launch_count():
