@@ -658,12 +658,21 @@ __global__ void __launch_bounds__(kLT, 1) attloc_loop_bwd_kernel(const LoopBwdPa
     float ddp[APL];
 #pragma unroll
     for (int j = 0; j < APL; ++j) ddp[j] = 0.0f;
+    // `pre` of chunk q+1 is requested from TMEM while chunk q is processed (the wait at the top of an iteration then
+    // finds the data there); the empty asm pins the prefetch registers behind the wait
+    float pn[APL];
+    tmem_load<APL>(tcol_pre, pn);
 #pragma unroll 1
     for (int q = 0; q < nchx; ++q) {
       const int tl = kLP * q + pair;
-      float pv[APL];
-      tmem_load<APL>(tcol_pre + (uint32_t)(q * APL), pv);
       tmem_wait_ld();
+      float pv[APL];
+#pragma unroll
+      for (int j = 0; j < APL; ++j) {
+        asm volatile("" : "+f"(pn[j]));
+        pv[j] = pn[j];
+      }
+      if (q + 1 < nchx) tmem_load<APL>(tcol_pre + (uint32_t)((q + 1) * APL), pn);
       if (tl < tloc) {
         const float de = de_s[tl];
         const float *cvp = conv_s + tl * CPP;
