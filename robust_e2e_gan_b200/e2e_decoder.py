@@ -180,6 +180,7 @@ class _FusedSearch(object):
         self.launched = self.processed = 0
         self.flights = []
         self._evi = 0
+        self.lazy = True              # no hypothesis has ended yet (see poll)
         self.done = False
         self._t(t0, "setup")
 
@@ -243,6 +244,26 @@ class _FusedSearch(object):
         self.flights.pop(0)
         dec, args, beam = self.dec, self.args, self.beam
         blk = self.hist_np[lo:hi]
+        if self.lazy:
+            # As long as no hypothesis has ended the beam simply extends (every winner survives, its parent index is its
+            # position in the previous winners' list), so a chunk in which no <eos> was emitted needs no bookkeeping at
+            # all: the history buffer IS the search state.  The first chunk with an <eos> (or the last position)
+            # rebuilds the linked hypotheses from the history once and continues position by position.
+            if hi < self.maxlen and not (blk[:, 2] == float(dec.eos)).any():
+                self.processed = hi
+                self._t(t0, "host_merge")
+                if self.prof is not None:
+                    self.prof["positions"] = self.prof.get("positions", 0.0) + (hi - lo)
+                return True
+            self.lazy = False
+            if lo > 0:
+                past = self.hist_np[:lo]
+                psc, pidx = past[:, 0].tolist(), past[:, 1:].astype(np.int64).tolist()
+                nodes = [self.hyps[0]]
+                for i in range(lo):
+                    par, tok, cj = pidx[i]
+                    nodes = [(np.float32(psc[i][b]), tok[b], nodes[par[b]], i + 2, par[b], cj[b]) for b in range(beam)]
+                self.hyps = nodes
         scs, idx = blk[:, 0].tolist(), blk[:, 1:].astype(np.int64).tolist()
         for i in range(lo, hi):
             par, tok, cj = idx[i - lo]
